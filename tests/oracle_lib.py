@@ -1,0 +1,124 @@
+"""ctypes loader for the CPU checkers under oracle/ (TEST INFRASTRUCTURE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from pagan2_msa_b200 import abi
+
+ORACLE_DIR = os.path.join(abi.REPO_ROOT, "oracle")
+REF_SRC = "/root/reference/src"
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+
+
+def build_ref():
+    """Builds oracle/_ref when the reference sources are present (this container only)."""
+    subprocess.check_call(["make", "-s", "-j8", "-C", ORACLE_DIR, "ref"])
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "libviterbi_oracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        lib = C.CDLL(path)
+        lib.pg2o_align.restype = C.c_int
+        lib.pg2o_align.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.ModelDesc), C.POINTER(C.c_double),
+                                   C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        _oracle = lib
+    return _oracle
+
+
+def oracle_align(job):
+    """Runs the C restatement on one FlatJob -> (status, score, steps[STEP_DTYPE], cells)."""
+    lib = oracle()
+    cap = job.left.n_sites + job.right.n_sites + 2
+    steps = np.zeros(cap, dtype=abi.STEP_DTYPE)
+    js = job.as_struct()
+    ms = job.model.as_struct()
+    score = C.c_double()
+    n = C.c_int32()
+    cells = C.c_int64()
+    rc = lib.pg2o_align(C.byref(js), C.byref(ms), C.byref(score), steps.ctypes.data, cap, C.byref(n), C.byref(cells))
+    if rc < 0:
+        raise RuntimeError("oracle: capacity/allocation failure")
+    return rc, score.value, steps[: n.value].copy(), cells.value
+
+
+def ref_available():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libpagan2ref.so"))
+
+
+def ref_binary():
+    return os.path.join(ORACLE_DIR, "_ref", "pagan2_ref")
+
+
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libpagan2ref.so"))
+        i32p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_float)
+        lib.pagan2_ref_align_flat.restype = C.c_int
+        lib.pagan2_ref_align_flat.argtypes = [C.c_int, f32p, f32p,
+                                              C.c_int, i32p, i32p, i32p, f32p, i32p,
+                                              C.c_int, i32p, i32p, i32p, f32p, i32p,
+                                              i32p, i32p, C.c_int,
+                                              C.POINTER(C.c_double), i32p, C.POINTER(C.c_double), C.c_int, i32p]
+        _ref = lib
+    return _ref
+
+
+def ref_align_flat(job):
+    """Runs the REFERENCE's Viterbi_alignment::align on one FlatJob -> (score, path(n,6), path_score)."""
+    lib = ref_lib()
+    cap = job.left.n_sites + job.right.n_sites + 2
+    path = np.zeros(cap * 6, np.int32)
+    ps = np.zeros(cap, np.float64)
+    score = C.c_double()
+    n = C.c_int32()
+    p = abi._ptr
+    L, R, m = job.left, job.right, job.model
+    up = p(job.upper, C.c_int32) if job.upper is not None else None
+    lo = p(job.lower, C.c_int32) if job.lower is not None else None
+    rc = lib.pagan2_ref_align_flat(m.fas, p(m.table, C.c_float), p(m.scalars, C.c_float),
+                                   L.n_sites, p(L.state, C.c_int32), p(L.off, C.c_int32), p(L.start, C.c_int32),
+                                   p(L.logw, C.c_float), p(L.eidx, C.c_int32),
+                                   R.n_sites, p(R.state, C.c_int32), p(R.off, C.c_int32), p(R.start, C.c_int32),
+                                   p(R.logw, C.c_float), p(R.eidx, C.c_int32),
+                                   up, lo, job.flags, C.byref(score), p(path, C.c_int32), p(ps, C.c_double), cap, C.byref(n))
+    if rc != 0:
+        raise RuntimeError("reference path longer than capacity")
+    return score.value, path[: n.value * 6].reshape(-1, 6).copy(), ps[: n.value].copy()
+
+
+def steps_equal(steps, path, path_score):
+    """Bit-exact comparison of STEP_DTYPE steps with reference (n,6) path + scores; returns list of diffs."""
+    diffs = []
+    if len(steps) != len(path):
+        return ["length %d vs %d" % (len(steps), len(path))]
+    cols = ["matrix", "x_ind", "y_ind", "x_edge_ind", "y_edge_ind", "real_site"]
+    for c, name in enumerate(cols):
+        bad = np.nonzero(steps[name] != path[:, c])[0]
+        if len(bad):
+            diffs.append("%s differs at %d steps (first %d: %d vs %d)" % (name, len(bad), bad[0], steps[name][bad[0]], path[bad[0], c]))
+    if path_score is not None:
+        a = steps["score"].view(np.uint64)
+        b = np.asarray(path_score, dtype=np.float64).view(np.uint64)
+        bad = np.nonzero(a != b)[0]
+        if len(bad):
+            diffs.append("score bits differ at %d steps (first %d: %r vs %r)" % (len(bad), bad[0], steps["score"][bad[0]], path_score[bad[0]]))
+    return diffs
