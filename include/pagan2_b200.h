@@ -154,6 +154,20 @@ int pg2_model_release(pg2_ctx *ctx, int32_t handle);
 int pg2_align_batch(pg2_ctx *ctx, int32_t n_jobs, const pg2_job *jobs, pg2_result *results,
                     uint32_t *steps, int64_t step_cap);
 
+/* The same call split in three, for callers that keep a launch batch resident in HBM (and for
+ * measurement: bench.py times pg2_batch_run alone for the device-resident figure):
+ *   pg2_batch_create  validates O(1) properties, packs the jobs into pinned staging (graphs that share
+ *                     host arrays are packed once);
+ *   pg2_batch_run     uploads on first use, then validation + fill + traceback kernels; may be repeated;
+ *   pg2_batch_fetch   copies results and packed pointers back (step_cap >= pg2_batch_step_capacity).
+ * One batch per ctx at a time; the job arrays must stay valid until pg2_batch_create returns. */
+typedef struct pg2_batch pg2_batch;
+int pg2_batch_create(pg2_ctx *ctx, int32_t n_jobs, const pg2_job *jobs, pg2_batch **out);
+int pg2_batch_run(pg2_ctx *ctx, pg2_batch *batch);
+int pg2_batch_fetch(pg2_ctx *ctx, pg2_batch *batch, pg2_result *results, uint32_t *steps, int64_t step_cap);
+int64_t pg2_batch_step_capacity(const pg2_batch *batch);
+void pg2_batch_destroy(pg2_ctx *ctx, pg2_batch *batch);
+
 /* Host-side unpacker: rebuilds the reference's forward path (backtrack_new_path,
  * viterbi_alignment.cpp:1038-1189, incl. the real_site=false steps of insert_preexisting_gap,
  * viterbi_alignment.h:146-193) from one job's packed pointers, replaying the score of every element in

@@ -1,0 +1,104 @@
+// pg2_device.cuh -- device-side data layout shared by the fill, traceback and validation kernels.
+//
+// HBM layout of one launch batch (all arrays are flat, one allocation each, jobs index into them):
+//   d_state[]   int32   Site::character_state of every distinct graph, back to back
+//   d_off[]     int32   CSR offsets (graph-relative, n_sites+1 per graph)
+//   d_estart[]  int32   Edge::start_site_index per backward edge, reference list order
+//   d_elogw[]   float   Edge::log_posterior_weight per backward edge
+//   d_slot[]    int32   per site: saved-row slot when the site is the source of a long-span edge, else -1
+//   d_blo/d_bhi int32   clipped anchor band per row (banded jobs only; tunnel_matrix.h:194)
+//   d_dlo       int32   first row on each anti-diagonal   (banded jobs only)
+//   d_doff      int64   cell offset of each anti-diagonal (banded jobs only)
+//   scores      double4 {X,Y,M,-} per in-band cell, ANTI-DIAGONAL-MAJOR (wavefront kernel scratch)
+//   ptrs        uint32 / uint16 packed back-pointers per in-band cell (streamed once, read by traceback)
+//   steps       uint32  packed pointers along each job's Viterbi path, walk order
+#pragma once
+#include <stdint.h>
+#ifdef PG2_HOST_EMU
+#include "pg2_emu_runtime.h"  // tests/emu: CPU test build only, never the product
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace pg2 {
+
+constexpr int X_MAT = 0, Y_MAT = 1, M_MAT = 2, NO_MAT = 3;
+constexpr unsigned FLAG_NO_TERMINAL_EDGES = 1u, FLAG_REDUCED = 2u;
+
+// job status (mirrors PG2_JOB_* in include/pagan2_b200.h)
+constexpr int JOB_OK = 0, JOB_NO_PATH = 1, JOB_BAD_BAND = 2, JOB_BAD_GRAPH = 3, JOB_BROKEN_PATH = 4,
+              JOB_UNSUPPORTED = 5;
+
+struct DevGraph {
+    int n_sites;
+    int state_base;  // into d_state
+    int off_base;    // into d_off
+    int edge_base;   // into d_estart / d_elogw
+    int max_indeg;   // filled by the validation kernel
+    int simple;      // 1: every site s>=1 has exactly one backward edge, from s-1 (plain leaf / read graph)
+    int n_slots;     // saved-row slots the strip kernel needs when this graph is the row graph
+    int pad;
+};
+
+struct DevModel {
+    const float *table;  // [fas*fas] column-major log_score[l + r*fas]
+    int fas;
+    float open, ext, end_ext, brk, lng;
+};
+
+struct DevJob {
+    int lx, ly;          // DP matrix dims = n_sites-1 of left / right (viterbi_alignment.cpp:243)
+    int left, right;     // indices into the DevGraph array
+    int model;           // index into the DevModel array
+    unsigned flags;
+    int banded;
+    int kernel;          // 0 wavefront, 1 strip
+    long long band_base; // into d_blo / d_bhi (lx entries)
+    long long diag_base; // into d_dlo / d_doff (lx+ly-1 entries)
+    long long cell_base; // into the group's score / ptr buffers
+    long long cells;     // in-band DP cells (the algorithmic count)
+    long long ptr_cells; // pointer-buffer entries this job occupies in its kernel's layout
+    long long step_base; // into the steps buffer
+    int step_cap;
+    int strip_k;         // strip kernel: columns per lane
+};
+
+struct DevResult {
+    double score;
+    unsigned end_ptr;
+    int n_steps;
+    int status;
+    int pad;
+};
+
+// ---- packed back-pointers -------------------------------------------------------------------
+// API encoding of ONE pointer: bits 0-1 source matrix, 2-7 left edge ordinal, 8-13 right edge ordinal.
+__host__ __device__ inline unsigned pack_ptr(int mat, int lord, int rord) {
+    return (unsigned)mat | ((unsigned)lord << 2) | ((unsigned)rord << 8);
+}
+// wavefront kernel cell word: X pointer in bits 0-7 (mat | lord<<2), Y pointer in bits 8-15
+// (mat | rord<<2), M pointer in bits 16-29 (mat | lord<<2 | rord<<8).
+__host__ __device__ inline unsigned cell_word(unsigned px, unsigned py, unsigned pm) {
+    return (px & 0xffu) | ((py & 0xffu) << 8) | ((pm & 0x3fffu) << 16);
+}
+__host__ __device__ inline unsigned word_ptr(unsigned w, int mat) {
+    if (mat == X_MAT) return w & 0xffu;                                    // mat | lord<<2
+    if (mat == Y_MAT) { unsigned y = (w >> 8) & 0xffu; return (y & 3u) | ((y >> 2) << 8); }
+    return (w >> 16) & 0x3fffu;
+}
+
+// ---- anti-diagonal-major cell indexing (unbanded closed form) --------------------------------
+// cells with i+j < s in an n x m matrix
+__host__ __device__ inline long long diag_cum(long long s, long long n, long long m) {
+    long long a = n < m ? n : m, b = n < m ? m : n;
+    if (s <= a) return s * (s + 1) / 2;
+    if (s <= b) return a * (a + 1) / 2 + (s - a) * a;
+    long long t = s - b;
+    return a * (a + 1) / 2 + (b - a) * a + t * (a - 1) - t * (t - 1) / 2;
+}
+__host__ __device__ inline int diag_lo(int s, int m) { return s - (m - 1) > 0 ? s - (m - 1) : 0; }
+__host__ __device__ inline int diag_hi(int s, int n) { return s < n - 1 ? s : n - 1; }
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+}  // namespace pg2

@@ -1,0 +1,654 @@
+// pg2_engine.cu -- host side of the C-ABI (include/pagan2_b200.h): context, model staging, batch packing,
+// launch grouping, result fetch.  No DP arithmetic happens on the host; without a CUDA device every
+// computing entry point fails (PG2_ERR_NO_DEVICE) -- there is no CPU fallback.
+//
+// Launch batch = the unit the schedulers hand over (a guide-tree wave, node.cpp:240-264, or the trial /
+// final alignments of many reads, reads_aligner.cpp:983-1216).  Jobs are packed into flat arrays
+// (pg2_device.cuh), graphs shared between jobs (same host arrays) are uploaded once, and jobs are cut
+// into groups that fit the scratch budget; each group is one fill launch + one traceback launch.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pagan2_b200.h"
+#include "pg2_device.cuh"
+#include "pg2_strip_geom.cuh"
+
+namespace pg2 {
+void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
+                     const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
+                     DevResult *results, cudaStream_t stream);
+void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
+                           const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
+                           const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores,
+                           unsigned *ptrs, DevResult *results, cudaStream_t stream);
+void launch_strip_fill(int K, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
+                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_slot,
+                       unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
+                       long long bcol_per_warp, int *queue, int n_warps, cudaStream_t stream);
+int strip_warps_per_sm();
+bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
+void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_off,
+                      const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
+                      const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps, DevResult *results, cudaStream_t stream);
+}  // namespace pg2
+
+using namespace pg2;
+
+static thread_local std::string g_last_error = "";
+
+static int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a, b);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) return fail(PG2_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// grow-only device buffer
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return PG2_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        if (cudaMalloc((void **)&p, want * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            if (cudaMalloc((void **)&p, n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); p = nullptr; return PG2_ERR_NOMEM; }
+            want = n;
+        }
+        cap = want;
+        return PG2_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// grow-only pinned host staging vector
+template <class T> struct PinVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t nc = std::max(want, cap * 2 + 1024);
+        T *q = nullptr;
+        if (cudaMallocHost((void **)&q, nc * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (n) memcpy(q, p, n * sizeof(T));
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = nc;
+        return true;
+    }
+    T *extend(size_t k) {
+        if (!reserve(n + k)) return nullptr;
+        T *r = p + n;
+        n += k;
+        return r;
+    }
+    void clear() { n = 0; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
+};
+
+struct ModelRec {
+    bool live = false;
+    int fas = 0;
+    float *d_table = nullptr;
+    DevModel dev;
+};
+
+struct Group {
+    int kernel;        // 0 wavefront, 1 strip
+    int strip_k;       // strip kernel: columns per lane (all jobs of the group share it)
+    int first, count;  // range in batch->order
+    long long cells;   // pointer-buffer entries of the group
+    int max_diag;
+    int max_slots, max_lx;  // strip kernel per-warp scratch: saved rows, boundary column
+};
+
+struct pg2_batch {
+    int n_jobs = 0, n_graphs = 0;
+    std::vector<DevJob> jobs;
+    std::vector<DevGraph> graphs;
+    std::vector<int> order;  // job ids sorted by (kernel, -cells)
+    std::vector<Group> groups;
+    long long total_steps = 0;
+    long long total_cells = 0;
+    long long h2d_bytes = 0;
+    size_t n_state = 0, n_off = 0, n_edge = 0, n_band = 0, n_diag = 0;
+    bool uploaded = false, ran = false;
+};
+
+struct pg2_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    cudaDeviceProp prop;
+    std::vector<ModelRec> models;
+    bool models_dirty = true;
+    size_t scratch_bytes = (size_t)16 << 30;
+    bool force_wavefront = false;  // PG2_FORCE_WAVEFRONT=1: route every job through the general kernel (tests)
+    // staging (pinned) and device arrays of the current batch
+    PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_slot;
+    PinVec<float> h_elogw;
+    PinVec<long long> h_doff;
+    DevBuf<int> d_state, d_off, d_estart, d_blo, d_bhi, d_dlo, d_order, d_graph_status, d_slot, d_queue;
+    DevBuf<double4> d_saved, d_bcol;
+    DevBuf<float> d_elogw;
+    DevBuf<long long> d_doff;
+    DevBuf<DevJob> d_jobs;
+    DevBuf<DevGraph> d_graphs;
+    DevBuf<DevModel> d_models;
+    DevBuf<DevResult> d_results;
+    DevBuf<double4> d_scores;
+    DevBuf<unsigned> d_ptr32, d_steps;
+    DevBuf<unsigned short> d_ptr16;
+    PinVec<DevResult> h_results;
+    cudaEvent_t ev[8];
+    pg2_stats stats;
+    pg2_batch *current = nullptr;
+};
+
+extern "C" int pg2_abi_version(void) { return PG2_ABI_VERSION; }
+extern "C" const char *pg2_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
+    if (!out) return fail(PG2_ERR_INVALID, "pg2_ctx_create: null out pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(PG2_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    }
+    if (device < 0 || device >= n) return fail(PG2_ERR_NO_DEVICE, "device index out of range");
+    CU(cudaSetDevice(device));
+    pg2_ctx *c = new pg2_ctx();
+    c->device = device;
+    if (cudaGetDeviceProperties(&c->prop, device) != cudaSuccess) { delete c; return fail(PG2_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+    if (c->prop.major < 10) {
+        delete c;
+        return fail(PG2_ERR_NO_DEVICE, "device is not sm_100 class; the kernels are built for sm_100a only");
+    }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(PG2_ERR_CUDA, "stream creation failed"); }
+    for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
+    const char *fw = getenv("PG2_FORCE_WAVEFRONT");
+    c->force_wavefront = fw && atoi(fw) != 0;
+    const char *mb = getenv("PG2_SCRATCH_MB");
+    if (mb && atoll(mb) > 0) c->scratch_bytes = (size_t)atoll(mb) << 20;
+    size_t half = c->prop.totalGlobalMem / 2;
+    if (c->scratch_bytes > half) c->scratch_bytes = half;
+    memset(&c->stats, 0, sizeof c->stats);
+    *out = c;
+    return PG2_OK;
+}
+
+extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &m : c->models) if (m.live && m.d_table) cudaFree(m.d_table);
+    c->h_state.release(); c->h_off.release(); c->h_estart.release(); c->h_blo.release(); c->h_bhi.release(); c->h_dlo.release();
+    c->h_elogw.release(); c->h_doff.release(); c->h_results.release(); c->h_slot.release();
+    c->d_slot.release(); c->d_queue.release(); c->d_saved.release(); c->d_bcol.release();
+    c->d_state.release(); c->d_off.release(); c->d_estart.release(); c->d_blo.release(); c->d_bhi.release(); c->d_dlo.release();
+    c->d_order.release(); c->d_graph_status.release(); c->d_elogw.release(); c->d_doff.release(); c->d_jobs.release();
+    c->d_graphs.release(); c->d_models.release(); c->d_results.release(); c->d_scores.release(); c->d_ptr32.release();
+    c->d_steps.release(); c->d_ptr16.release();
+    for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int pg2_model_upload(pg2_ctx *c, const pg2_model_desc *d, int32_t *handle_out) {
+    if (!c || !d || !handle_out || !d->log_score || d->fas <= 0) return fail(PG2_ERR_INVALID, "pg2_model_upload: bad argument");
+    CU(cudaSetDevice(c->device));
+    ModelRec r;
+    r.live = true;
+    r.fas = d->fas;
+    size_t n = (size_t)d->fas * d->fas;
+    if (cudaMalloc((void **)&r.d_table, n * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return fail(PG2_ERR_NOMEM, "model table allocation failed"); }
+    CU(cudaMemcpyAsync(r.d_table, d->log_score, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    r.dev.table = r.d_table;
+    r.dev.fas = d->fas;
+    r.dev.open = d->log_gap_open;
+    r.dev.ext = d->log_gap_ext;
+    r.dev.end_ext = d->log_gap_end_ext;
+    r.dev.brk = d->log_gap_break_ext;
+    r.dev.lng = d->log_non_gap;
+    int h = -1;
+    for (size_t i = 0; i < c->models.size(); i++) if (!c->models[i].live) { h = (int)i; break; }
+    if (h < 0) { h = (int)c->models.size(); c->models.push_back(r); } else c->models[h] = r;
+    c->models_dirty = true;
+    *handle_out = h;
+    return PG2_OK;
+}
+
+extern "C" int pg2_model_release(pg2_ctx *c, int32_t h) {
+    if (!c || h < 0 || h >= (int)c->models.size() || !c->models[h].live) return fail(PG2_ERR_INVALID, "pg2_model_release: bad handle");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->models[h].d_table);
+    c->models[h] = ModelRec();
+    c->models_dirty = true;
+    return PG2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch packing
+// ------------------------------------------------------------------------------------------------
+struct GraphKey {
+    const void *a, *b, *c, *d;
+    int n;
+    bool operator==(const GraphKey &o) const { return a == o.a && b == o.b && c == o.c && d == o.d && n == o.n; }
+};
+struct GraphKeyHash {
+    size_t operator()(const GraphKey &k) const {
+        size_t h = (size_t)k.a * 1000003u ^ (size_t)k.b * 10007u ^ (size_t)k.c * 31u ^ (size_t)k.d ^ (size_t)k.n;
+        return h;
+    }
+};
+
+static int pack_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unordered_map<GraphKey, int, GraphKeyHash> &seen, int *gid) {
+    if (g.n_sites < 2 || !g.state || !g.bwd_off || (g.n_edges > 0 && (!g.edge_start || !g.edge_logw || !g.edge_index)))
+        return fail(PG2_ERR_INVALID, "graph with null arrays or fewer than 2 sites");
+    GraphKey key = {g.state, g.bwd_off, g.edge_start, g.edge_logw, g.n_sites};
+    auto it = seen.find(key);
+    if (it != seen.end()) { *gid = it->second; return PG2_OK; }
+    int n_edges = g.bwd_off[g.n_sites];
+    if (n_edges < 0 || n_edges != g.n_edges) return fail(PG2_ERR_INVALID, "graph: n_edges does not match bwd_off[n_sites]");
+    DevGraph dg;
+    dg.n_sites = g.n_sites;
+    dg.state_base = (int)c->h_state.n;
+    dg.off_base = (int)c->h_off.n;
+    dg.edge_base = (int)c->h_estart.n;
+    if ((long long)c->h_state.n + g.n_sites > 0x7fffffffLL || (long long)c->h_estart.n + n_edges > 0x7fffffffLL)
+        return fail(PG2_ERR_INVALID, "batch too large: more than 2^31 sites or edges; split the batch");
+    int *ps = c->h_state.extend(g.n_sites), *po = c->h_off.extend(g.n_sites + 1), *pe = c->h_estart.extend(n_edges);
+    int *pslot = c->h_slot.extend(g.n_sites);
+    float *pw = c->h_elogw.extend(n_edges);
+    if (!ps || !po || !pe || !pw || !pslot) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    memcpy(ps, g.state, sizeof(int) * g.n_sites);
+    memcpy(po, g.bwd_off, sizeof(int) * (g.n_sites + 1));
+    if (n_edges) {
+        memcpy(pe, g.edge_start, sizeof(int) * n_edges);
+        memcpy(pw, g.edge_logw, sizeof(float) * n_edges);
+    }
+    // shape summary used to pick the fill kernel (the device re-validates everything)
+    int simple = 1, maxdeg = 0;
+    for (int s = 0; s < g.n_sites; s++) {
+        int k0 = po[s], k1 = po[s + 1];
+        if (k1 < k0 || k1 > n_edges || k0 < 0) { simple = 0; maxdeg = 1 << 30; break; }  // malformed: device flags it
+        int deg = k1 - k0;
+        if (deg > maxdeg) maxdeg = deg;
+        if (s > 0 && (deg != 1 || pe[k0] != s - 1)) simple = 0;
+        if (s == 0 && deg != 0) simple = 0;
+    }
+    if (maxdeg == (1 << 30)) {
+        // keep offsets in range so that no kernel reads out of bounds: collapse to an edgeless graph, flagged bad
+        for (int s = 0; s <= g.n_sites; s++) po[s] = 0;
+        po[0] = 1;  // off[0] != 0 => validation marks JOB_BAD_GRAPH
+        maxdeg = 0;
+    }
+    dg.max_indeg = maxdeg;
+    dg.simple = simple;
+    dg.pad = 0;
+    // Saved-row slots for the strip kernel: a DP row p (site p < n_sites-1) that is the source of an edge
+    // p -> s with s - p >= 2 (s a DP row too) must stay addressable until row s is done.  A slot is reused
+    // two rows after its last reader (the skewed sweep reads it one step late on the next lane).
+    for (int s = 0; s < g.n_sites; s++) pslot[s] = -1;
+    dg.n_slots = 0;
+    if (!simple && maxdeg > 0) {
+        std::vector<int> last_use(g.n_sites, -1);
+        for (int s = 1; s < g.n_sites - 1; s++)
+            for (int k = po[s]; k < po[s + 1]; k++) {
+                int p = pe[k];
+                if (p >= 0 && p < s && s - p >= 2 && last_use[p] < s) last_use[p] = s;
+            }
+        std::vector<int> free_slots;
+        std::vector<std::vector<int> > release(g.n_sites + 3);
+        int n_slots = 0;
+        for (int s = 0; s < g.n_sites - 1; s++) {
+            for (size_t r = 0; r < release[s].size(); r++) free_slots.push_back(release[s][r]);
+            release[s].clear();
+            if (last_use[s] > 0) {
+                int slot;
+                if (!free_slots.empty()) { slot = free_slots.back(); free_slots.pop_back(); }
+                else slot = n_slots++;
+                pslot[s] = slot;
+                release[std::min(last_use[s] + 2, g.n_sites + 2)].push_back(slot);
+            }
+        }
+        dg.n_slots = n_slots;
+    }
+    *gid = (int)b->graphs.size();
+    b->graphs.push_back(dg);
+    seen.emplace(key, *gid);
+    return PG2_OK;
+}
+
+// clipped band + anti-diagonal geometry of one banded job (host, O(lx+ly))
+static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t *lower) {
+    const int lx = J.lx, ly = J.ly, nd = lx + ly - 1;
+    J.band_base = (long long)c->h_blo.n;
+    J.diag_base = (long long)c->h_dlo.n;
+    int *blo = c->h_blo.extend(lx), *bhi = c->h_bhi.extend(lx), *dlo = c->h_dlo.extend(nd + 1);
+    long long *doff = c->h_doff.extend(nd + 1);
+    if (!blo || !bhi || !dlo || !doff) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    bool ok = true;
+    for (int i = 0; i < lx; i++) {
+        blo[i] = upper[i] > 0 ? upper[i] : 0;                  // tunnel_matrix.h:194
+        bhi[i] = lower[i] < ly - 1 ? lower[i] : ly - 1;
+        if (bhi[i] < blo[i]) ok = false;
+        if (i && (blo[i] < blo[i - 1] || bhi[i] < bhi[i - 1])) ok = false;
+    }
+    if (blo[0] > 0) ok = false;
+    long long cells = 0;
+    if (ok) {
+        // rows on diagonal s: blo[i]+i <= s <= bhi[i]+i, both strictly increasing in i
+        int first = 0, last = -1;
+        for (int s = 0; s < nd; s++) {
+            while (last + 1 < lx && blo[last + 1] + (last + 1) <= s) ++last;
+            while (first < lx && bhi[first] + first < s) ++first;
+            dlo[s] = first;
+            doff[s] = cells;
+            if (last >= first) cells += last - first + 1;
+        }
+        dlo[nd] = 0;
+        doff[nd] = cells;
+    } else {
+        // invalid band: the validation kernel reports PG2_JOB_BAD_BAND from the same blo/bhi; the job is
+        // skipped by the fill, so any in-range geometry will do
+        for (int s = 0; s <= nd; s++) { dlo[s] = 0; doff[s] = s ? 1 : 0; }
+        cells = 1;
+    }
+    J.cells = cells;
+    return PG2_OK;
+}
+
+extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_batch **out) {
+    if (!c || !out || n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail(PG2_ERR_INVALID, "pg2_batch_create: bad argument");
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    if (c->current) return fail(PG2_ERR_INVALID, "pg2_batch_create: another batch is live on this ctx (destroy it first)");
+    pg2_batch *b = new pg2_batch();
+    b->n_jobs = n_jobs;
+    b->jobs.resize(n_jobs);
+    c->h_state.clear(); c->h_off.clear(); c->h_estart.clear(); c->h_elogw.clear(); c->h_slot.clear();
+    c->h_blo.clear(); c->h_bhi.clear(); c->h_dlo.clear(); c->h_doff.clear();
+    std::unordered_map<GraphKey, int, GraphKeyHash> seen;
+    seen.reserve((size_t)n_jobs * 2 + 16);
+    long long step_base = 0;
+    for (int t = 0; t < n_jobs; t++) {
+        const pg2_job &j = jobs[t];
+        DevJob &J = b->jobs[t];
+        memset(&J, 0, sizeof J);
+        if (j.model < 0 || j.model >= (int)c->models.size() || !c->models[j.model].live) { delete b; return fail(PG2_ERR_INVALID, "job names an unknown model handle"); }
+        if ((j.upper == nullptr) != (j.lower == nullptr)) { delete b; return fail(PG2_ERR_INVALID, "job band needs both upper and lower (or neither)"); }
+        int rc = pack_graph(c, b, j.left, seen, &J.left);
+        if (rc == PG2_OK) rc = pack_graph(c, b, j.right, seen, &J.right);
+        if (rc != PG2_OK) { delete b; return rc; }
+        J.lx = j.left.n_sites - 1;
+        J.ly = j.right.n_sites - 1;
+        J.model = j.model;
+        J.flags = j.flags;
+        J.banded = j.upper != nullptr;
+        J.band_base = J.diag_base = -1;
+        if (J.banded) {
+            rc = pack_band(c, J, j.upper, j.lower);
+            if (rc != PG2_OK) { delete b; return rc; }
+        } else {
+            J.cells = (long long)J.lx * J.ly;
+        }
+        const DevGraph &GL = b->graphs[J.left], &GR = b->graphs[J.right];
+        J.kernel = strip_eligible(J.lx, J.ly, J.banded != 0, GL.simple, GR.simple, GL.max_indeg, GR.max_indeg, c->models[j.model].fas) ? 1 : 0;
+        if (c->force_wavefront) J.kernel = 0;
+        J.strip_k = J.kernel == 1 ? strip_pick_k(J.ly) : 0;
+        J.ptr_cells = J.kernel == 1 ? strip_cells(J.lx, J.ly, J.strip_k) : J.cells;
+        J.step_base = step_base;
+        J.step_cap = j.left.n_sites + j.right.n_sites;
+        step_base += J.step_cap;
+        b->total_cells += J.cells;
+    }
+    b->total_steps = step_base;
+    b->n_graphs = (int)b->graphs.size();
+
+    // order: strip jobs first, larger jobs first inside a class (tail balance)
+    b->order.resize(n_jobs);
+    for (int t = 0; t < n_jobs; t++) b->order[t] = t;
+    std::stable_sort(b->order.begin(), b->order.end(), [&](int x, int y) {
+        const DevJob &A = b->jobs[x], &B = b->jobs[y];
+        if (A.kernel != B.kernel) return A.kernel > B.kernel;
+        if (A.strip_k != B.strip_k) return A.strip_k < B.strip_k;
+        return A.cells > B.cells;
+    });
+    // groups under the scratch budget: wavefront 36 B/cell (scores + pointer word), strip 2 B/cell
+    size_t pos = 0;
+    while (pos < b->order.size()) {
+        Group g;
+        g.kernel = b->jobs[b->order[pos]].kernel;
+        g.strip_k = b->jobs[b->order[pos]].strip_k;
+        g.first = (int)pos;
+        g.count = 0;
+        g.cells = 0;
+        g.max_diag = 1;
+        g.max_slots = 0;
+        g.max_lx = 1;
+        size_t per_cell = g.kernel == 0 ? 36 : 2;
+        while (pos < b->order.size()) {
+            DevJob &J = b->jobs[b->order[pos]];
+            if (J.kernel != g.kernel || J.strip_k != g.strip_k) break;
+            long long padded = (J.ptr_cells + 7) & ~7LL;
+            if (g.count > 0 && (size_t)(g.cells + padded) * per_cell > c->scratch_bytes) break;
+            J.cell_base = g.cells;
+            g.cells += padded;
+            g.max_diag = std::max(g.max_diag, std::min(J.lx, J.ly));
+            g.max_slots = std::max(g.max_slots, b->graphs[J.left].n_slots);
+            g.max_lx = std::max(g.max_lx, J.lx);
+            g.count++;
+            pos++;
+        }
+        b->groups.push_back(g);
+    }
+    c->current = b;
+    *out = b;
+    return PG2_OK;
+}
+
+static int upload_batch(pg2_ctx *c, pg2_batch *b) {
+    int rc;
+#define ENS(buf, n) if ((rc = (buf).ensure(n)) != PG2_OK) return fail(rc, "device allocation failed (%s)", #buf)
+    ENS(c->d_slot, c->h_slot.n + 1); ENS(c->d_queue, 4);
+    ENS(c->d_state, c->h_state.n + 1); ENS(c->d_off, c->h_off.n + 1); ENS(c->d_estart, c->h_estart.n + 1); ENS(c->d_elogw, c->h_elogw.n + 1);
+    ENS(c->d_blo, c->h_blo.n + 1); ENS(c->d_bhi, c->h_bhi.n + 1); ENS(c->d_dlo, c->h_dlo.n + 1); ENS(c->d_doff, c->h_doff.n + 1);
+    ENS(c->d_jobs, b->jobs.size() + 1); ENS(c->d_graphs, b->graphs.size() + 1); ENS(c->d_order, b->order.size() + 1);
+    ENS(c->d_graph_status, b->graphs.size() + 1); ENS(c->d_results, b->jobs.size() + 1); ENS(c->d_steps, (size_t)b->total_steps + 1);
+    ENS(c->d_models, c->models.size() + 1);
+    long long bytes = 0;
+#define H2D(dst, src, n, T)                                                                                 \
+    if ((n) > 0) { CU(cudaMemcpyAsync((dst).p, (src), (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, c->stream)); bytes += (long long)(n) * sizeof(T); }
+    H2D(c->d_state, c->h_state.p, c->h_state.n, int);
+    H2D(c->d_off, c->h_off.p, c->h_off.n, int);
+    H2D(c->d_slot, c->h_slot.p, c->h_slot.n, int);
+    H2D(c->d_estart, c->h_estart.p, c->h_estart.n, int);
+    H2D(c->d_elogw, c->h_elogw.p, c->h_elogw.n, float);
+    H2D(c->d_blo, c->h_blo.p, c->h_blo.n, int);
+    H2D(c->d_bhi, c->h_bhi.p, c->h_bhi.n, int);
+    H2D(c->d_dlo, c->h_dlo.p, c->h_dlo.n, int);
+    H2D(c->d_doff, c->h_doff.p, c->h_doff.n, long long);
+    H2D(c->d_jobs, b->jobs.data(), b->jobs.size(), DevJob);
+    H2D(c->d_graphs, b->graphs.data(), b->graphs.size(), DevGraph);
+    H2D(c->d_order, b->order.data(), b->order.size(), int);
+    {
+        std::vector<DevModel> dm(c->models.size());
+        for (size_t i = 0; i < dm.size(); i++) dm[i] = c->models[i].dev;
+        if (!dm.empty()) {
+            CU(cudaMemcpyAsync(c->d_models.p, dm.data(), dm.size() * sizeof(DevModel), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));  // dm is a stack temporary
+        }
+        c->models_dirty = false;
+    }
+    b->h2d_bytes = bytes;
+    b->uploaded = true;
+    return PG2_OK;
+#undef ENS
+#undef H2D
+}
+
+// Upload (if needed) and enqueue validation + every group's fill and traceback on the ctx stream.
+extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
+    if (!c || !b || c->current != b) return fail(PG2_ERR_INVALID, "pg2_batch_run: bad batch");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    pg2_stats &st = c->stats;
+    if (!b->uploaded) {
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        if ((rc = upload_batch(c, b)) != PG2_OK) return rc;
+        CU(cudaEventRecord(c->ev[1], c->stream));
+        CU(cudaEventSynchronize(c->ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        st.h2d_ms = ms;
+        st.h2d_bytes = b->h2d_bytes;
+    }
+    // scratch for the largest group of each class
+    long long max_w = 0, max_s = 0;
+    for (auto &g : b->groups) (g.kernel == 0 ? max_w : max_s) = std::max(g.kernel == 0 ? max_w : max_s, g.cells);
+    if (max_w > 0) {
+        if ((rc = c->d_scores.ensure((size_t)max_w)) != PG2_OK) return fail(rc, "score scratch allocation failed");
+        if ((rc = c->d_ptr32.ensure((size_t)max_w)) != PG2_OK) return fail(rc, "pointer buffer allocation failed");
+    }
+    if (max_s > 0 && (rc = c->d_ptr16.ensure((size_t)max_s)) != PG2_OK) return fail(rc, "pointer buffer allocation failed");
+#ifdef PG2_HOST_EMU
+    const int resident_warps = 1;
+#else
+    const int resident_warps = c->prop.multiProcessorCount * strip_warps_per_sm();
+#endif
+    for (auto &g : b->groups)
+        if (g.kernel == 1) {
+            int warps = std::min(resident_warps, std::max(g.count, 1));
+            size_t saved = (size_t)std::max(g.max_slots, 1) * 32 * g.strip_k * warps;
+            size_t bcol = (size_t)g.max_lx * 2 * warps;
+            if ((rc = c->d_saved.ensure(saved)) != PG2_OK) return fail(rc, "saved-row scratch allocation failed");
+            if ((rc = c->d_bcol.ensure(bcol)) != PG2_OK) return fail(rc, "boundary-column scratch allocation failed");
+        }
+
+    launch_validate(b->n_graphs, b->n_jobs, c->d_graphs.p, c->d_jobs.p, c->d_models.p, c->d_state.p, c->d_off.p, c->d_estart.p,
+                    c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, c->stream);
+    st.fill_ms = st.traceback_ms = 0;
+    st.fill_launches = st.traceback_launches = 0;
+    st.jobs_wavefront = st.jobs_strip = 0;
+    st.cells = b->total_cells;
+    st.traceback_bytes = 0;
+    // events: per group fill start/stop + traceback stop are accumulated after a final sync to keep the
+    // stream free of host round trips; with many groups we sync per group (bounded by scratch anyway)
+    for (auto &g : b->groups) {
+        const int *ids = c->d_order.p + g.first;
+        CU(cudaEventRecord(c->ev[2], c->stream));
+        if (g.kernel == 0) {
+            int threads = g.max_diag <= 32 ? 32 : g.max_diag <= 64 ? 64 : g.max_diag <= 128 ? 128 : g.max_diag <= 256 ? 256
+                          : g.max_diag <= 512 ? 512 : 1024;
+            launch_wavefront_fill(g.count, threads, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
+                                  c->d_estart.p, c->d_elogw.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_scores.p,
+                                  c->d_ptr32.p, c->d_results.p, c->stream);
+            st.jobs_wavefront += g.count;
+            st.traceback_bytes += g.cells * 4;
+        } else {
+            int warps = std::min(resident_warps, std::max(g.count, 1));
+            launch_strip_fill(g.strip_k, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
+                              c->d_estart.p, c->d_elogw.p, c->d_slot.p, c->d_ptr16.p, c->d_results.p, c->d_saved.p,
+                              (long long)std::max(g.max_slots, 1) * 32 * g.strip_k, c->d_bcol.p, (long long)g.max_lx, c->d_queue.p,
+                              warps, c->stream);
+            st.jobs_strip += g.count;
+            st.traceback_bytes += g.cells * 2;
+        }
+        CU(cudaEventRecord(c->ev[3], c->stream));
+        launch_traceback(g.count, ids, c->d_jobs.p, c->d_graphs.p, c->d_off.p, c->d_estart.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p,
+                         c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_steps.p, c->d_results.p, c->stream);
+        CU(cudaEventRecord(c->ev[4], c->stream));
+        CU(cudaEventSynchronize(c->ev[4]));
+        CU(cudaGetLastError());
+        float f = 0, t = 0;
+        cudaEventElapsedTime(&f, c->ev[2], c->ev[3]);
+        cudaEventElapsedTime(&t, c->ev[3], c->ev[4]);
+        st.fill_ms += f;
+        st.traceback_ms += t;
+        st.fill_launches++;
+        st.traceback_launches++;
+    }
+    b->ran = true;
+    return PG2_OK;
+}
+
+extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, uint32_t *steps, int64_t step_cap) {
+    if (!c || !b || c->current != b || !b->ran || (b->n_jobs > 0 && (!results || !steps))) return fail(PG2_ERR_INVALID, "pg2_batch_fetch: bad argument or batch not run");
+    CU(cudaSetDevice(c->device));
+    if (step_cap < b->total_steps) {
+        for (int t = 0; t < b->n_jobs; t++) results[t].n_steps = b->jobs[t].step_cap;
+        return fail(PG2_ERR_CAPACITY, "step buffer too small");
+    }
+    c->h_results.clear();
+    DevResult *hr = c->h_results.extend((size_t)b->n_jobs + 1);
+    if (!hr) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    CU(cudaEventRecord(c->ev[5], c->stream));
+    if (b->n_jobs > 0) {
+        CU(cudaMemcpyAsync(hr, c->d_results.p, sizeof(DevResult) * b->n_jobs, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(steps, c->d_steps.p, sizeof(unsigned) * (size_t)b->total_steps, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaEventRecord(c->ev[6], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]);
+    c->stats.d2h_ms = ms;
+    c->stats.d2h_bytes = (long long)sizeof(DevResult) * b->n_jobs + (long long)sizeof(unsigned) * b->total_steps;
+    for (int t = 0; t < b->n_jobs; t++) {
+        const DevJob &J = b->jobs[t];
+        pg2_result &r = results[t];
+        r.score = hr[t].score;
+        r.cells = J.cells;
+        r.step_off = J.step_base;
+        r.n_steps = hr[t].n_steps;
+        r.status = hr[t].status == JOB_UNSUPPORTED ? PG2_JOB_BAD_GRAPH : hr[t].status;
+        r.end_ptr = hr[t].end_ptr;
+        r.kernel = J.kernel;
+        if (hr[t].status == JOB_UNSUPPORTED) { g_last_error = "a graph exceeds PG2_MAX_IN_DEGREE backward edges per site"; }
+    }
+    return PG2_OK;
+}
+
+extern "C" void pg2_batch_destroy(pg2_ctx *c, pg2_batch *b) {
+    if (!b) return;
+    if (c) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        if (c->current == b) c->current = nullptr;
+    }
+    delete b;
+}
+
+extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint32_t *steps, int64_t step_cap) {
+    pg2_batch *b = nullptr;
+    int rc = pg2_batch_create(c, n_jobs, jobs, &b);
+    if (rc != PG2_OK) return rc;
+    rc = pg2_batch_run(c, b);
+    if (rc == PG2_OK) rc = pg2_batch_fetch(c, b, results, steps, step_cap);
+    pg2_batch_destroy(c, b);
+    return rc;
+}
+
+extern "C" int64_t pg2_batch_step_capacity(const pg2_batch *b) { return b ? b->total_steps : 0; }
+
+extern "C" int pg2_get_stats(pg2_ctx *c, pg2_stats *out) {
+    if (!c || !out) return fail(PG2_ERR_INVALID, "pg2_get_stats: bad argument");
+    *out = c->stats;
+    return PG2_OK;
+}

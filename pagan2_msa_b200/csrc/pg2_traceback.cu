@@ -1,0 +1,258 @@
+// pg2_traceback.cu -- validation prepass and the backtrack kernel.
+//
+// validate_kernel: one warp per distinct graph / per job checks what the reference takes for granted
+// (edges point to earlier sites, states index the substitution table, in-degree fits the packed pointer,
+// the band is monotone and contains (0,0); tunnel_matrix.h:163-168).  Failing jobs get a status and are
+// skipped by the fill kernels -- the host never walks the graphs.
+//
+// traceback_kernel: walks the packed back-pointers from the end corner to (0,0) exactly as
+// backtrack_new_path does (reference src/main/viterbi_alignment.cpp:1038-1189) and emits the pointer of
+// every visited cell in walk order.  The host unpacker (pg2_expand.cpp) turns that into the reference's
+// vector<Path_pointer>, including the skipped-site steps of insert_preexisting_gap.
+#include "pg2_device.cuh"
+#include "pg2_strip_geom.cuh"
+
+namespace pg2 {
+
+// per-lane partial check of one graph: lanes stride over the sites
+__device__ __forceinline__ void check_graph_lane(const DevGraph &G, const int *d_off, const int *d_estart, int lane, int nlanes,
+                                                 int &bad, int &maxdeg, int &simple) {
+    const int *off = d_off + G.off_base;
+    const int *es = d_estart + G.edge_base;
+    bad = 0; maxdeg = 0; simple = 1;
+    if (G.n_sites < 2) { bad = 1; return; }
+    for (int s = lane; s < G.n_sites; s += nlanes) {
+        int k0 = off[s], k1 = off[s + 1];
+        if (k1 < k0 || (s == 0 && k0 != 0)) { bad = 1; break; }
+        int deg = k1 - k0;
+        if (deg > maxdeg) maxdeg = deg;
+        if (s == 0) { if (deg != 0) bad = 1; }
+        else if (deg != 1 || es[k0] != s - 1) simple = 0;
+        for (int k = k0; k < k1; ++k) {
+            int p = es[k];
+            if (p < 0 || p >= s) bad = 1;
+        }
+    }
+}
+
+__device__ __forceinline__ void finish_graph(DevGraph *graphs, int *graph_status, int g, int bad, int maxdeg, int simple) {
+    graphs[g].max_indeg = maxdeg;
+    graphs[g].simple = simple && !bad;
+    graph_status[g] = bad ? JOB_BAD_GRAPH : (maxdeg > 63 ? JOB_UNSUPPORTED : JOB_OK);
+}
+
+// per-lane partial check of one job; returns 1 when this lane saw a problem of the given kind
+__device__ __forceinline__ int check_states_lane(const DevJob &J, const DevGraph *graphs, const DevModel *models, const int *d_state,
+                                                 int lane, int nlanes) {
+    // states of real sites must index the table (model->log_score, evol_model.h:80)
+    const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+    int fas = models[J.model].fas;
+    int bad = 0;
+    for (int s = 1 + lane; s < GL.n_sites - 1; s += nlanes) {
+        int st = d_state[GL.state_base + s];
+        if (st < 0 || st >= fas) bad = 1;
+    }
+    for (int s = 1 + lane; s < GR.n_sites - 1; s += nlanes) {
+        int st = d_state[GR.state_base + s];
+        if (st < 0 || st >= fas) bad = 1;
+    }
+    return bad;
+}
+
+__device__ __forceinline__ int check_band_lane(const DevJob &J, const int *d_blo, const int *d_bhi, int lane, int nlanes) {
+    // d_blo/d_bhi hold the CLIPPED band; monotone + (0,0) inside (tunnel_matrix.h:163-168, viterbi_alignment.cpp:729)
+    const int *lo = d_blo + J.band_base, *hi = d_bhi + J.band_base;
+    int bad = 0;
+    for (int i = lane; i < J.lx; i += nlanes) {
+        if (lo[i] > hi[i]) bad = 1;
+        if (i == 0) { if (lo[0] > 0) bad = 1; }
+        else if (lo[i] < lo[i - 1] || hi[i] < hi[i - 1]) bad = 1;
+    }
+    return bad;
+}
+
+__device__ __forceinline__ void finish_job(DevResult *results, int jid, int status) {
+    results[jid].status = status;
+    results[jid].score = neg_inf();
+    results[jid].end_ptr = NO_MAT;
+    results[jid].n_steps = 0;
+}
+
+#ifndef PG2_HOST_EMU
+__global__ void validate_graphs_kernel(int n_graphs, DevGraph *graphs, const int *d_state, const int *d_off, const int *d_estart,
+                                       int *graph_status) {
+    int g = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+    int lane = threadIdx.x & 31;
+    if (g >= n_graphs) return;
+    int bad, maxdeg, simple;
+    check_graph_lane(graphs[g], d_off, d_estart, lane, 32, bad, maxdeg, simple);
+    for (int o = 16; o; o >>= 1) {
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+        simple &= __shfl_xor_sync(0xffffffffu, simple, o);
+    }
+    if (lane == 0) finish_graph(graphs, graph_status, g, bad, maxdeg, simple);
+}
+
+__global__ void validate_jobs_kernel(int n_jobs, const DevJob *jobs, const DevGraph *graphs, const DevModel *models,
+                                     const int *graph_status, const int *d_state, const int *d_blo, const int *d_bhi,
+                                     DevResult *results) {
+    int jid = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+    int lane = threadIdx.x & 31;
+    if (jid >= n_jobs) return;
+    const DevJob J = jobs[jid];
+    int status = JOB_OK;
+    int gs_l = graph_status[J.left], gs_r = graph_status[J.right];
+    if (gs_l != JOB_OK) status = gs_l;
+    else if (gs_r != JOB_OK) status = gs_r;
+    if (status == JOB_OK && __any_sync(0xffffffffu, check_states_lane(J, graphs, models, d_state, lane, 32))) status = JOB_BAD_GRAPH;
+    if (status == JOB_OK && J.banded && __any_sync(0xffffffffu, check_band_lane(J, d_blo, d_bhi, lane, 32))) status = JOB_BAD_BAND;
+    if (lane == 0) finish_job(results, jid, status);
+}
+#endif
+
+// Cell pointer lookup for both fill kernels' layouts.
+struct TraceCtx {
+    const DevJob *J;
+    const int *blo, *bhi, *dlo;
+    const long long *doff;
+    const unsigned *ptr32;        // wavefront layout: anti-diagonal-major, one word per cell
+    const unsigned short *ptr16;  // strip layout: row-major [i][j], one half-word per cell
+};
+
+__device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int j, unsigned &out) {
+    const DevJob &J = *t.J;
+    if (i < 0 || j < 0 || i >= J.lx || j >= J.ly) return false;
+    if (J.kernel == 0) {
+        long long idx;
+        if (J.banded) {
+            if (j < t.blo[i] || j > t.bhi[i]) return false;
+            int s = i + j;
+            idx = t.doff[s] + (i - t.dlo[s]);
+        } else {
+            int s = i + j;
+            idx = diag_cum(s, J.lx, J.ly) + (i - diag_lo(s, J.ly));
+        }
+        out = word_ptr(t.ptr32[J.cell_base + idx], mat);
+    } else {
+        // strip kernel half-word: X ptr bits 0-5 (mat | lord<<2), Y ptr bits 6-7 (mat), M ptr bits 8-13 (mat | lord<<2)
+        unsigned w = t.ptr16[J.cell_base + strip_ptr_index(J.lx, J.ly, J.strip_k, i, j)];
+        if (mat == X_MAT) out = w & 0x3fu;
+        else if (mat == Y_MAT) out = (w >> 6) & 3u;
+        else out = (w >> 8) & 0x3fu;
+    }
+    return true;
+}
+
+__device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graphs, const int *d_off,
+                              const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo,
+                              const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps,
+                              DevResult *results) {
+    const DevJob &J = jobs[jid];
+    DevResult *res = results + jid;
+    if (res->status != JOB_OK) return;
+    const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+    const int *l_off = d_off + GL.off_base, *r_off = d_off + GR.off_base;
+    const int *l_es = d_estart + GL.edge_base, *r_es = d_estart + GR.edge_base;
+    TraceCtx tc;
+    tc.J = &J;
+    tc.blo = J.banded ? d_blo + J.band_base : nullptr;
+    tc.bhi = J.banded ? d_bhi + J.band_base : nullptr;
+    tc.dlo = J.banded ? d_dlo + J.diag_base : nullptr;
+    tc.doff = J.banded ? d_doff + J.diag_base : nullptr;
+    tc.ptr32 = ptr32;
+    tc.ptr16 = ptr16;
+    unsigned *out = steps + J.step_base;
+    int n = 0;
+
+    // end pointer -> last alignment column (viterbi_alignment.cpp:1047-1069)
+    unsigned p = res->end_ptr;
+    int vit = (int)(p & 3u);
+    int i, j;
+    if (vit == M_MAT) { i = l_es[l_off[J.lx] + ((p >> 2) & 63u)]; j = r_es[r_off[J.ly] + ((p >> 8) & 63u)]; }
+    else if (vit == X_MAT) { i = l_es[l_off[J.lx] + ((p >> 2) & 63u)]; j = J.ly - 1; }
+    else if (vit == Y_MAT) { i = J.lx - 1; j = r_es[r_off[J.ly] + ((p >> 8) & 63u)]; }
+    else { res->status = JOB_NO_PATH; return; }
+    out[n++] = p;
+
+    int status = JOB_OK;
+    // the reference loop ends when (i<1 && j<1) AFTER reading the cell it stands on (:1073-1181)
+    for (;;) {
+        unsigned q;
+        if (vit == NO_MAT || !fetch_ptr(tc, vit, i, j, q)) { status = JOB_BROKEN_PATH; break; }
+        if (n >= J.step_cap) { status = JOB_BROKEN_PATH; break; }
+        out[n++] = q;
+        int src = (int)(q & 3u);
+        if (vit == M_MAT) {
+            int ni = (src == NO_MAT) ? -1 : l_es[l_off[i] + ((q >> 2) & 63u)];
+            int nj = (src == NO_MAT) ? -1 : r_es[r_off[j] + ((q >> 8) & 63u)];
+            i = ni; j = nj;
+        } else if (vit == X_MAT) {
+            i = (src == NO_MAT) ? -1 : l_es[l_off[i] + ((q >> 2) & 63u)];
+        } else {
+            j = (src == NO_MAT) ? -1 : r_es[r_off[j] + ((q >> 8) & 63u)];
+        }
+        vit = src;
+        if (i < 1 && j < 1) break;
+    }
+    res->n_steps = n;
+    res->status = status;
+}
+
+#ifndef PG2_HOST_EMU
+__global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_off,
+                                 const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo,
+                                 const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps,
+                                 DevResult *results) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_jobs) return;
+    traceback_one(job_ids[t], jobs, graphs, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+}
+#endif
+
+void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
+                     const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
+                     DevResult *results, cudaStream_t stream) {
+#ifndef PG2_HOST_EMU
+    const int warps = 8;
+    if (n_graphs > 0)
+        validate_graphs_kernel<<<(n_graphs + warps - 1) / warps, warps * 32, 0, stream>>>(n_graphs, graphs, d_state, d_off, d_estart,
+                                                                                         graph_status);
+    if (n_jobs > 0)
+        validate_jobs_kernel<<<(n_jobs + warps - 1) / warps, warps * 32, 0, stream>>>(n_jobs, jobs, graphs, models, graph_status,
+                                                                                     d_state, d_blo, d_bhi, results);
+#else
+    (void)stream;
+    for (int g = 0; g < n_graphs; ++g) {
+        int bad, maxdeg, simple;
+        check_graph_lane(graphs[g], d_off, d_estart, 0, 1, bad, maxdeg, simple);
+        finish_graph(graphs, graph_status, g, bad, maxdeg, simple);
+    }
+    for (int jid = 0; jid < n_jobs; ++jid) {
+        const DevJob J = jobs[jid];
+        int status = JOB_OK;
+        if (graph_status[J.left] != JOB_OK) status = graph_status[J.left];
+        else if (graph_status[J.right] != JOB_OK) status = graph_status[J.right];
+        if (status == JOB_OK && check_states_lane(J, graphs, models, d_state, 0, 1)) status = JOB_BAD_GRAPH;
+        if (status == JOB_OK && J.banded && check_band_lane(J, d_blo, d_bhi, 0, 1)) status = JOB_BAD_BAND;
+        finish_job(results, jid, status);
+    }
+#endif
+}
+
+void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_off,
+                      const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
+                      const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps, DevResult *results, cudaStream_t stream) {
+    if (n_jobs <= 0) return;
+#ifndef PG2_HOST_EMU
+    const int threads = 64;
+    traceback_kernel<<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_off, d_estart, d_blo,
+                                                                              d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+#else
+    (void)stream;
+    for (int t = 0; t < n_jobs; ++t)
+        traceback_one(job_ids[t], jobs, graphs, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+#endif
+}
+
+}  // namespace pg2

@@ -1,0 +1,272 @@
+// pg2_wavefront.cu -- general fill kernel: one CTA per alignment, anti-diagonal wavefront.
+//
+// Handles every job shape (arbitrary in-degree and edge spans on both graphs, anchor bands).  Scores
+// live in an anti-diagonal-major double4 scratch in HBM/L2 so that the common predecessors (i-1,j),
+// (i-1,j-1), (i,j-1) of consecutive threads sit in consecutive cells (coalesced), and long-span
+// predecessors are still addressable.  One packed 32-bit word of back-pointers per cell is streamed out
+// for the traceback kernel.
+//
+// Restates compute_fwd_scores / iterate_bwd_edges_for_gap / iterate_bwd_edges_for_match /
+// iterate_bwd_edges_for_end_corner (reference src/main/viterbi_alignment.cpp:856-971, 1328-1552,
+// 2029-2255).  Candidate order and FP64 association follow the reference exactly; ties keep the first
+// candidate (strict '>', basic_alignment.h:449-462).
+#include "pg2_device.cuh"
+
+namespace pg2 {
+
+struct WaveCtx {
+    const DevJob *job;
+    const int *l_state, *l_off, *l_estart;
+    const float *l_elogw;
+    const int *r_state, *r_off, *r_estart;
+    const float *r_elogw;
+    const int *blo, *bhi, *dlo;
+    const long long *doff;
+    double4 *scores;
+    int lx, ly;
+    bool banded;
+};
+
+__device__ __forceinline__ long long cell_index(const WaveCtx &c, int p, int q) {
+    int s = p + q;
+    if (c.banded) return c.doff[s] + (p - c.dlo[s]);
+    return diag_cum(s, c.lx, c.ly) + (p - diag_lo(s, c.ly));
+}
+
+// Tunnel_slice::at (utils/tunnel_matrix.h:85-98): -inf outside the band
+__device__ __forceinline__ double4 load_cell(const WaveCtx &c, int p, int q) {
+    if (c.banded && (q < c.blo[p] || q > c.bhi[p])) {
+        double ninf = neg_inf();
+        return make_double4(ninf, ninf, ninf, 0.0);
+    }
+    const double4 *ptr = c.scores + cell_index(c, p, q);
+    double2 a = __ldcg(reinterpret_cast<const double2 *>(ptr));
+    double2 b = __ldcg(reinterpret_cast<const double2 *>(ptr) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// One gap cell (X when is_x, else Y).  Returns score, writes packed pointer (mat | ord<<2).
+template <bool IS_X>
+__device__ __forceinline__ double gap_cell(const WaveCtx &c, const DevModel &m, int i, int j, bool end_gap, bool reduced,
+                                           unsigned &ptr_out) {
+    const int *off = IS_X ? c.l_off : c.r_off;
+    const int *es = IS_X ? c.l_estart : c.r_estart;
+    int site = IS_X ? i : j;
+    int k0 = off[site], k1 = off[site + 1];
+    double best = neg_inf();
+    unsigned ptr = NO_MAT;
+    double ext = (double)(end_gap ? m.end_ext : m.ext);
+    double open = (double)m.open, lng = (double)m.lng;
+    for (int k = k0; k < k1; ++k) {
+        int p = es[k];
+        double4 v = IS_X ? load_cell(c, p, j) : load_cell(c, i, p);
+        double same = IS_X ? v.x : v.y, other = IS_X ? v.y : v.x;
+        unsigned ord = (unsigned)(k - k0) << 2;
+        double s = __dadd_rn(same, ext);                       // score_gap_ext    :2116-2149
+        if (s > best) { best = s; ptr = (IS_X ? X_MAT : Y_MAT) | ord; }
+        s = __dadd_rn(__dadd_rn(other, 0.0), open);            // score_gap_double :2158-2180
+        if (s > best) { best = s; ptr = (IS_X ? Y_MAT : X_MAT) | ord; }
+        double pen = (reduced && p == 0) ? 0.0 : open;         // get_log_gap_open_penalty basic_alignment.h:490
+        s = __dadd_rn(__dadd_rn(v.z, lng), pen);               // score_gap_open   :2190-2211
+        if (s > best) { best = s; ptr = M_MAT | ord; }
+    }
+    ptr_out = ptr;
+    return best;
+}
+
+__device__ __forceinline__ void match_pairs(const WaveCtx &c, int kl0, int kl1, int kr0, int kr1, double m_log, double x_log,
+                                            double y_log, bool end_corner, double &best, unsigned &ptr) {
+    for (int kl = kl0; kl < kl1; ++kl) {
+        int pl = c.l_estart[kl];
+        double wl = (double)c.l_elogw[kl];
+        for (int kr = kr0; kr < kr1; ++kr) {
+            int pr = c.r_estart[kr];
+            double wr = (double)c.r_elogw[kr];
+            double4 v = load_cell(c, pl, pr);
+            unsigned ord = ((unsigned)(kl - kl0) << 2) | ((unsigned)(kr - kr0) << 8);
+            double s = __dadd_rn(__dadd_rn(__dadd_rn(v.z, m_log), wl), wr);  // score_m_match :2029-2056
+            if (s > best) { best = s; ptr = M_MAT | ord; }
+            if (!end_corner) {
+                s = __dadd_rn(__dadd_rn(__dadd_rn(v.x, x_log), wl), wr);     // score_x_match :2058-2084
+                if (s > best) { best = s; ptr = X_MAT | ord; }
+                s = __dadd_rn(__dadd_rn(__dadd_rn(v.y, y_log), wl), wr);     // score_y_match :2086-2112
+                if (s > best) { best = s; ptr = Y_MAT | ord; }
+            }
+        }
+    }
+}
+
+// iterate_bwd_edges_for_end_corner (:1440-1552).  Run by one thread after the last anti-diagonal.
+__device__ void end_corner(const WaveCtx &c, const DevModel &m, DevResult *res) {
+    int kl0 = c.l_off[c.lx], kl1 = c.l_off[c.lx + 1], kr0 = c.r_off[c.ly], kr1 = c.r_off[c.ly + 1];
+    double best = neg_inf();
+    unsigned ptr = NO_MAT;
+    if (kl1 > kl0 && kr1 > kr0) {
+        double m_log = (double)m.lng;
+        // The reference interleaves M-pair and gap-close candidates; every candidate is compared with
+        // strict '>' against the running maximum, so the visiting order below is what matters.
+        auto m_pair = [&](int kl, int kr) {
+            double4 v = load_cell(c, c.l_estart[kl], c.r_estart[kr]);
+            double s = __dadd_rn(__dadd_rn(__dadd_rn(v.z, m_log), (double)c.l_elogw[kl]), (double)c.r_elogw[kr]);
+            if (s > best) { best = s; ptr = pack_ptr(M_MAT, kl - kl0, kr - kr0); }
+        };
+        auto x_close = [&](int kl) {  // score_gap_close :2221-2255, close penalty 0
+            double4 v = load_cell(c, c.l_estart[kl], c.ly - 1);
+            double s = __dadd_rn(v.x, 0.0);
+            if (s > best) { best = s; ptr = pack_ptr(X_MAT, kl - kl0, 0); }
+        };
+        auto y_close = [&](int kr) {
+            double4 v = load_cell(c, c.lx - 1, c.r_estart[kr]);
+            double s = __dadd_rn(v.y, 0.0);
+            if (s > best) { best = s; ptr = pack_ptr(Y_MAT, 0, kr - kr0); }
+        };
+        m_pair(kl0, kr0);
+        x_close(kl0);
+        y_close(kr0);
+        for (int kr = kr0 + 1; kr < kr1; ++kr) { m_pair(kl0, kr); y_close(kr); }
+        for (int kl = kl0 + 1; kl < kl1; ++kl) {
+            m_pair(kl, kr0);
+            x_close(kl);
+            for (int kr = kr0 + 1; kr < kr1; ++kr) { m_pair(kl, kr); y_close(kr); }
+        }
+    }
+    res->score = best;
+    res->end_ptr = ptr;
+    res->status = (best == neg_inf()) ? JOB_NO_PATH : JOB_OK;
+}
+
+// Per-job setup shared by the kernel and the CPU test emulation.
+__device__ __forceinline__ void make_wave_ctx(WaveCtx &c, const DevJob &J, const DevGraph &GL, const DevGraph &GR, const int *d_state,
+                                              const int *d_off, const int *d_estart, const float *d_elogw, const int *d_blo,
+                                              const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores) {
+    c.job = &J;
+    c.l_state = d_state + GL.state_base;
+    c.l_off = d_off + GL.off_base;
+    c.l_estart = d_estart + GL.edge_base;
+    c.l_elogw = d_elogw + GL.edge_base;
+    c.r_state = d_state + GR.state_base;
+    c.r_off = d_off + GR.off_base;
+    c.r_estart = d_estart + GR.edge_base;
+    c.r_elogw = d_elogw + GR.edge_base;
+    c.lx = J.lx;
+    c.ly = J.ly;
+    c.banded = J.banded != 0;
+    c.blo = c.banded ? d_blo + J.band_base : nullptr;
+    c.bhi = c.banded ? d_bhi + J.band_base : nullptr;
+    c.dlo = c.banded ? d_dlo + J.diag_base : nullptr;
+    c.doff = c.banded ? d_doff + J.diag_base : nullptr;
+    c.scores = scores + J.cell_base;
+}
+
+// initialise_array_corner (:725-733)
+__device__ __forceinline__ void wave_init(const WaveCtx &c, unsigned *P) {
+    double ninf = neg_inf();
+    double2 *s0 = reinterpret_cast<double2 *>(c.scores);
+    s0[0] = make_double2(ninf, ninf);
+    s0[1] = make_double2(0.0, 0.0);
+    P[0] = cell_word(NO_MAT, NO_MAT, NO_MAT);
+}
+
+__device__ __forceinline__ void diag_geometry(const WaveCtx &c, int s, int &ilo, int &ihi, long long &base) {
+    if (c.banded) {
+        ilo = c.dlo[s];
+        base = c.doff[s];
+        ihi = ilo + (int)(c.doff[s + 1] - base) - 1;
+    } else {
+        ilo = diag_lo(s, c.ly);
+        ihi = diag_hi(s, c.lx);
+        base = diag_cum(s, c.lx, c.ly);
+    }
+}
+
+// compute_fwd_scores (:856-971) for one cell
+__device__ __forceinline__ void wave_cell(const WaveCtx &c, const DevModel &m, unsigned flags, float lng2, int i, int j, long long idx,
+                                          unsigned *P) {
+    const bool term = !(flags & FLAG_NO_TERMINAL_EDGES);
+    const bool reduced = (flags & FLAG_REDUCED) != 0;
+    const double ninf = neg_inf();
+    double sx = ninf, sy = ninf, sm = ninf;
+    unsigned px = NO_MAT, py = NO_MAT, pm = NO_MAT;
+    if (i > 0) sx = gap_cell<true>(c, m, i, j, term && (j == 0 || j == c.ly - 1), reduced, px);
+    if (j > 0) sy = gap_cell<false>(c, m, i, j, term && (i == 0 || i == c.lx - 1), reduced, py);
+    if (i > 0 && j > 0) {
+        double ls = (double)__ldg(m.table + (size_t)c.l_state[i] + (size_t)c.r_state[j] * (size_t)m.fas);
+        double m_log = __dadd_rn((double)lng2, ls);
+        double x_log = __dadd_rn((double)m.lng, ls);
+        match_pairs(c, c.l_off[i], c.l_off[i + 1], c.r_off[j], c.r_off[j + 1], m_log, x_log, x_log, false, sm, pm);
+    }
+    double2 *dst = reinterpret_cast<double2 *>(c.scores + idx);
+    dst[0] = make_double2(sx, sy);
+    dst[1] = make_double2(sm, 0.0);
+    // gap_cell returns (mat | ord<<2) for both X and Y, which is the in-word form
+    P[idx] = cell_word(px, py, pm);
+}
+
+#ifndef PG2_HOST_EMU
+__global__ void __launch_bounds__(1024, 1)
+wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models, const int *d_state,
+                      const int *d_off, const int *d_estart, const float *d_elogw, const int *d_blo, const int *d_bhi,
+                      const int *d_dlo, const long long *d_doff, double4 *scores, unsigned *ptrs, DevResult *results) {
+    const int jid = job_ids[blockIdx.x];
+    const DevJob &J = jobs[jid];
+    DevResult *res = results + jid;
+    if (res->status != JOB_OK) return;  // rejected by the validation kernel
+    const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+    const DevModel m = models[J.model];
+    WaveCtx c;
+    make_wave_ctx(c, J, GL, GR, d_state, d_off, d_estart, d_elogw, d_blo, d_bhi, d_dlo, d_doff, scores);
+    unsigned *P = ptrs + J.cell_base;
+    const unsigned flags = J.flags;
+    const float lng2 = __fmul_rn(2.0f, m.lng);  // 2*model->log_non_gap() stays float (:1364)
+
+    if (threadIdx.x == 0) wave_init(c, P);
+    __syncthreads();
+
+    const int n_diag = c.lx + c.ly - 1;
+    for (int s = 1; s < n_diag; ++s) {
+        int ilo, ihi;
+        long long base;
+        diag_geometry(c, s, ilo, ihi, base);
+        for (int i = ilo + (int)threadIdx.x; i <= ihi; i += (int)blockDim.x)
+            wave_cell(c, m, flags, lng2, i, s - i, base + (i - ilo), P);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) end_corner(c, m, res);
+}
+#endif
+
+void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
+                           const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
+                           const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores,
+                           unsigned *ptrs, DevResult *results, cudaStream_t stream) {
+    if (n_jobs <= 0) return;
+#ifndef PG2_HOST_EMU
+    wavefront_fill_kernel<<<n_jobs, threads, 0, stream>>>(jobs, job_ids, graphs, models, d_state, d_off, d_estart, d_elogw, d_blo,
+                                                          d_bhi, d_dlo, d_doff, scores, ptrs, results);
+#else
+    // CPU test emulation: anti-diagonals in order, cells of one diagonal in any order
+    (void)threads; (void)stream;
+    for (int b = 0; b < n_jobs; ++b) {
+        const int jid = job_ids[b];
+        const DevJob &J = jobs[jid];
+        DevResult *res = results + jid;
+        if (res->status != JOB_OK) continue;
+        const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+        const DevModel m = models[J.model];
+        WaveCtx c;
+        make_wave_ctx(c, J, GL, GR, d_state, d_off, d_estart, d_elogw, d_blo, d_bhi, d_dlo, d_doff, scores);
+        unsigned *P = ptrs + J.cell_base;
+        const float lng2 = __fmul_rn(2.0f, m.lng);
+        wave_init(c, P);
+        for (int s = 1; s < c.lx + c.ly - 1; ++s) {
+            int ilo, ihi;
+            long long base;
+            diag_geometry(c, s, ilo, ihi, base);
+            for (int i = ihi; i >= ilo; --i) wave_cell(c, m, J.flags, lng2, i, s - i, base + (i - ilo), P);
+        }
+        end_corner(c, m, res);
+    }
+#endif
+}
+
+}  // namespace pg2
