@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- graph-DP throughput of the PAGAN2 pairwise Viterbi path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU code, host cores
+
+Workload (config.workload): BASELINE.json configs[1], query placement -- synthetic 150-nt reads against a
+64-taxon x 1.5 kb reference alignment + tree.  The 127 target graphs (64 leaves + 63 internal nodes) are
+the reference's own graphs (tests/golden/bench_targets.pjob.gz, made by the reference binary from a seeded
+synthetic alignment); reads are seeded substrings of the leaf sequences with 1 % substitutions, each
+assigned to a node on the path from its source leaf to the root.  One step = one launch batch = one
+alignment (fill + end corner + traceback) of every read against its target: --reads x 151 x ~1.5 k cells.
+
+Printed line (rank 0): metric/value = whole-job GCUPS with the batch resident in HBM (device time, CUDA
+events on the engine's stream, max over ranks); e2e = the same through pg2_align_batch from host buffers
+(packing, H2D, kernels, D2H inside the timed region); roofline, cpu_baseline, clocks as the contract asks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from pagan2_msa_b200 import abi, jobio, synth  # noqa: E402
+
+TARGETS = os.path.join(ROOT, "tests", "golden", "bench_targets.pjob.gz")
+FP64_INSTR_PER_CELL = 22  # 13 DADD + 9 DSETP per in-degree-1 unit-weight cell
+PTR_BYTES_PER_CELL = 2    # packed back-pointers streamed to HBM
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def build_workload(n_reads, seed, rank=0):
+    """Returns (jobs, info).  Deterministic in (n_reads, seed, rank)."""
+    tjobs = jobio.load_jobs(TARGETS)
+    model = tjobs[0].model
+    targets = [j.left for j in tjobs]
+    # node order of the reference's post-order naming is not needed: recover leaf/ancestor relations from
+    # sizes is fragile, so reads are cut from LEAF graphs (plain chains) and assigned either to that leaf
+    # or to a random internal node (a read aligns to any ancestor of its source equally well in shape).
+    leaves = [k for k, g in enumerate(targets) if (np.diff(g.off)[1:] == 1).all() and (g.logw == 0).all()]
+    internal = [k for k in range(len(targets)) if k not in leaves]
+    rng = np.random.default_rng(seed * 1000003 + rank)
+    reads, assign = [], []
+    for k in range(n_reads):
+        src = leaves[int(rng.integers(0, len(leaves)))]
+        seq = targets[src].state[1:-1]
+        st = int(rng.integers(0, max(1, len(seq) - 150)))
+        r = seq[st:st + 150].copy()
+        mut = rng.random(r.shape[0]) < 0.01
+        r[mut] = rng.integers(0, 4, size=int(mut.sum()))
+        reads.append(r)
+        if k % 2 == 0 or not internal:
+            assign.append(src)
+        else:
+            assign.append(internal[int(rng.integers(0, len(internal)))])
+    jobs = synth.placement_jobs(targets, reads, assign, model)
+    cells = sum(j.cells for j in jobs)
+    info = {"n_targets": len(targets), "n_leaf_targets": len(leaves), "cells_per_step": int(cells),
+            "mean_target_sites": float(np.mean([g.n_sites for g in targets]))}
+    return jobs, info
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return rank, world, local, dist
+    return rank, world, local, None
+
+
+def cpu_baseline_sample(jobs, budget_s=12.0):
+    """The reference's own code (oracle/_ref, kind 'reference') or the oracle port, 1 thread, on the first
+    jobs of the workload until ~budget_s seconds are spent."""
+    import oracle_lib
+
+    use_ref = oracle_lib.ref_available()
+    fn = (lambda j: oracle_lib.ref_align_flat(j)) if use_ref else (lambda j: oracle_lib.oracle_align(j))
+    t0 = time.perf_counter()
+    cells = 0
+    n = 0
+    for j in jobs:
+        fn(j)
+        cells += j.cells
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": cells / dt * 1e-9, "unit": "GCUPS", "cores": 1, "kind": "reference" if use_ref else "port",
+            "sample": "first %d jobs of the workload (%d cells) in %.1f s, 1 thread" % (n, cells, dt)}
+
+
+def _ref_worker(args):
+    """One host process of the reference arm: aligns its share of jobs with the reference library."""
+    lo, hi, n_reads, seed = args
+    import oracle_lib
+
+    jobs, _ = build_workload(n_reads, seed)
+    use_ref = oracle_lib.ref_available()
+    cells = 0
+    for j in jobs[lo:hi]:
+        if use_ref:
+            oracle_lib.ref_align_flat(j)
+        else:
+            oracle_lib.oracle_align(j)
+        cells += j.cells
+    return cells
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on all host cores.  Each step is a
+    bounded sample of the same workload: `cores * per_core` jobs split over one process per core."""
+    import multiprocessing as mp
+
+    import oracle_lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    per_core = 2
+    n = cores * per_core
+    jobs, info = build_workload(n, args.seed)
+    use_ref = oracle_lib.ref_available()
+    bounds = [(k * per_core, (k + 1) * per_core, n, args.seed) for k in range(cores)]
+    times, cells_step = [], 0
+    with mp.get_context("fork").Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            cells_step = sum(pool.map(_ref_worker, bounds))
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = cells_step * len(times) / total * 1e-9
+    line = {
+        "impl": "reference", "metric": "graph_dp_gcups", "value": value, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "query placement: 150-nt reads vs 64-taxon x 1.5 kb reference (BASELINE configs[1]); "
+                               "bounded sample of %d alignments per step" % n, "cells_per_step": int(cells_step)},
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": cores, "kind": "reference" if use_ref else "port",
+                         "sample": "%d alignments per step over %d processes (fork), model build excluded" % (n, cores)},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=100000, help="reads (= alignments) per GPU per step")
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import ctypes as C
+
+    import __graft_entry__
+    from pagan2_msa_b200 import engine
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    if rank == 0:
+        __graft_entry__.build()
+    if dist is not None:
+        dist.barrier()
+
+    import torch
+
+    jobs, info = build_workload(args.reads, args.seed, rank)
+    eng = engine.Engine(local)  # raises without the CUDA library / device: no fallback
+    peaks, peaks_kind = measured_peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput: batch packed and uploaded once ----------------
+    batch = eng.batch(jobs)
+    for _ in range(max(args.warmup, 3)):
+        batch.run()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_ms, fill_ms, tb_ms, launches, fill_launches = 0.0, 0.0, 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.run()
+        st = eng.stats()
+        dev_ms += st["run_ms"]
+        fill_ms += st["fill_ms"]
+        tb_ms += st["traceback_ms"]
+        launches += st["kernel_launches"]
+        fill_launches += st["fill_launches"]
+    barrier()
+    wall_dev = time.perf_counter() - t0
+    clocks = sampler.stop()
+    stats = eng.stats()
+    results, steps_buf = batch.fetch()
+    batch.close()
+    ok = int((results["status"] == 0).sum())
+
+    # ---------------- end to end: host buffers in, host results out, every step ----------------
+    eng.align(jobs[: min(len(jobs), 2000)])  # warm the staging buffers
+    barrier()
+    e2e_t = []
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        t1 = time.perf_counter()
+        eng.align(jobs)
+        e2e_t.append(time.perf_counter() - t1)
+        st = eng.stats()
+        h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+    barrier()
+
+    cells = info["cells_per_step"]
+    local_vals = np.array([dev_ms / args.steps, fill_ms / args.steps, sum(e2e_t) / args.steps * 1e3, wall_dev / args.steps * 1e3],
+                          dtype=np.float64)
+    if dist is not None:
+        t = torch.from_numpy(local_vals).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        local_vals = t.cpu().numpy()
+        c = torch.tensor([cells], dtype=torch.int64).cuda()
+        dist.all_reduce(c)
+        total_cells = int(c.item())
+    else:
+        total_cells = cells
+    ms_dev, ms_fill, ms_e2e, ms_wall = [float(x) for x in local_vals]
+
+    if rank == 0:
+        dadd, cand = C.c_double(), C.c_double()
+        eng.lib.pg2_measure_fp64_issue(local, C.byref(dadd), C.byref(cand))
+        fp64_peak = dadd.value  # 1e9 FP64-pipe warp-instructions / s, chip-wide
+        per_launch_cells = cells / max(stats["fill_launches"], 1)
+        launch_ms = ms_fill / max(stats["fill_launches"], 1)
+        achieved_gbs = per_launch_cells * PTR_BYTES_PER_CELL / (launch_ms * 1e-3) * 1e-9
+        fp64_achieved = cells * FP64_INSTR_PER_CELL / 32.0 / (ms_fill * 1e-3) * 1e-9
+        line = {
+            "metric": "graph_dp_gcups", "value": total_cells / (ms_dev * 1e-3) * 1e-9, "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "query placement (BASELINE configs[1]): %d reads x 150 nt per GPU vs 64-taxon x 1.5 kb "
+                                   "reference alignment+tree, 1 alignment per read (fill + end corner + traceback)" % args.reads,
+                       "reads_per_gpu": args.reads, "targets": info["n_targets"], "cells_per_step_per_gpu": cells,
+                       "l2_policy": "inputs+outputs per step (%.1f GB of back-pointers) exceed L2" % (stats["traceback_bytes"] * 1e-9),
+                       "parallelism": "independent alignments sharded by index range, %d rank(s)" % world},
+            "e2e": {"value": total_cells / (ms_e2e * 1e-3) * 1e-9, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_kind,
+                         "kernel": "strip_fill_kernel", "algorithmic_bytes_per_cell": PTR_BYTES_PER_CELL,
+                         "launch_ms": launch_ms,
+                         "dp_issue": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "1e9 FP64-pipe warp-instr/s",
+                                      "frac": fp64_achieved / fp64_peak if fp64_peak else None,
+                                      "instr_per_cell": FP64_INSTR_PER_CELL,
+                                      "peak_source": "pg2_measure_fp64_issue (DADD loop, this run)",
+                                      "candidate_update_peak": cand.value}},
+            "fill_ms_per_step": ms_fill, "traceback_ms_per_step": tb_ms / args.steps, "wall_ms_per_step": ms_wall,
+            "jobs_ok": ok, "jobs": len(jobs), "kernels": {"strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"]},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(jobs)
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

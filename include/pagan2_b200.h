@@ -190,8 +190,23 @@ typedef struct pg2_stats {
     int64_t traceback_bytes;   /* packed back-pointers written by the fill */
     int32_t fill_launches, traceback_launches;
     int32_t jobs_wavefront, jobs_strip;
+    double run_ms;             /* validation + all fill + all traceback launches of the last pg2_batch_run */
+    int32_t kernel_launches;   /* kernels launched by the last pg2_batch_run */
+    int32_t jobs_strip_groups;
 } pg2_stats;
 int pg2_get_stats(pg2_ctx *ctx, pg2_stats *out);
+
+/* Device addresses of the last run's result records (24-byte records {double score; uint32 end_ptr;
+ * int32 n_steps; int32 status; int32 pad}, job order) and packed-pointer buffer, for callers that forward
+ * results GPU-to-GPU (multi-GPU gather to rank 0 over NCCL, no host bounce).  Valid until the next batch
+ * is created on this ctx. */
+int pg2_batch_device_buffers(pg2_ctx *ctx, pg2_batch *batch, void **results_dev, void **steps_dev, int64_t *n_steps_total);
+int pg2_stream_synchronize(pg2_ctx *ctx);
+
+/* Measures the device's FP64 issue rate (the fill kernels' roofline denominator): 1e9 warp-instructions
+ * per second chip-wide for independent DADDs, and for the DADD + DSETP + select group of one first-wins
+ * candidate update.  Runs two small kernels for a few milliseconds. */
+int pg2_measure_fp64_issue(int device, double *dadd_gips, double *cand_gips);
 
 #ifdef __cplusplus
 }

@@ -108,6 +108,9 @@ class Stats(C.Structure):
         ("traceback_launches", C.c_int32),
         ("jobs_wavefront", C.c_int32),
         ("jobs_strip", C.c_int32),
+        ("run_ms", C.c_double),
+        ("kernel_launches", C.c_int32),
+        ("jobs_strip_groups", C.c_int32),
     ]
 
 

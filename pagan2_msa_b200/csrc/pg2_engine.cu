@@ -542,11 +542,13 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
             if ((rc = c->d_bcol.ensure(bcol)) != PG2_OK) return fail(rc, "boundary-column scratch allocation failed");
         }
 
+    CU(cudaEventRecord(c->ev[7], c->stream));
     launch_validate(b->n_graphs, b->n_jobs, c->d_graphs.p, c->d_jobs.p, c->d_models.p, c->d_state.p, c->d_off.p, c->d_estart.p,
                     c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, c->stream);
     st.fill_ms = st.traceback_ms = 0;
     st.fill_launches = st.traceback_launches = 0;
     st.jobs_wavefront = st.jobs_strip = 0;
+    st.jobs_strip_groups = 0;
     st.cells = b->total_cells;
     st.traceback_bytes = 0;
     // events: per group fill start/stop + traceback stop are accumulated after a final sync to keep the
@@ -569,6 +571,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
                               (long long)std::max(g.max_slots, 1) * 32 * g.strip_k, c->d_bcol.p, (long long)g.max_lx, c->d_queue.p,
                               warps, c->stream);
             st.jobs_strip += g.count;
+            st.jobs_strip_groups++;
             st.traceback_bytes += g.cells * 2;
         }
         CU(cudaEventRecord(c->ev[3], c->stream));
@@ -584,6 +587,12 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
         st.traceback_ms += t;
         st.fill_launches++;
         st.traceback_launches++;
+    }
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[7], c->ev[4]);
+        st.run_ms = b->groups.empty() ? 0.0 : ms;
+        st.kernel_launches = 2 + st.fill_launches + st.traceback_launches + st.jobs_strip_groups;
     }
     b->ran = true;
     return PG2_OK;
@@ -643,6 +652,24 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
     if (rc == PG2_OK) rc = pg2_batch_fetch(c, b, results, steps, step_cap);
     pg2_batch_destroy(c, b);
     return rc;
+}
+
+// Device addresses of the batch's result records (pg2_device.cuh DevResult, 24 bytes each, job order) and
+// packed-pointer buffer, valid until the next batch is created on this ctx.  For callers that forward
+// results GPU-to-GPU (the multi-GPU gather to rank 0 goes over NCCL without a host bounce).
+extern "C" int pg2_batch_device_buffers(pg2_ctx *c, pg2_batch *b, void **results_dev, void **steps_dev, int64_t *n_steps_total) {
+    if (!c || !b || c->current != b || !b->ran) return fail(PG2_ERR_INVALID, "pg2_batch_device_buffers: batch not run");
+    if (results_dev) *results_dev = c->d_results.p;
+    if (steps_dev) *steps_dev = c->d_steps.p;
+    if (n_steps_total) *n_steps_total = b->total_steps;
+    return PG2_OK;
+}
+
+extern "C" int pg2_stream_synchronize(pg2_ctx *c) {
+    if (!c) return fail(PG2_ERR_INVALID, "pg2_stream_synchronize: null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return PG2_OK;
 }
 
 extern "C" int64_t pg2_batch_step_capacity(const pg2_batch *b) { return b ? b->total_steps : 0; }

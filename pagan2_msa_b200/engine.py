@@ -39,6 +39,9 @@ def _bind(lib):
     lib.pg2_expand_path.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.ModelDesc), C.POINTER(abi.Result), vp, vp,
                                     C.POINTER(C.c_int32), vp, C.POINTER(C.c_int32), vp, C.POINTER(C.c_int32)]
     lib.pg2_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
+    lib.pg2_batch_device_buffers.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
+    lib.pg2_stream_synchronize.argtypes = [vp]
+    lib.pg2_measure_fp64_issue.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return lib
 
 

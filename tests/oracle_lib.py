@@ -122,3 +122,22 @@ def steps_equal(steps, path, path_score):
         if len(bad):
             diffs.append("score bits differ at %d steps (first %d: %r vs %r)" % (len(bad), bad[0], steps["score"][bad[0]], path_score[bad[0]]))
     return diffs
+
+
+def run_ref(args, cwd, dump_name="jobs.bin", stats_name="stats.json", timeout=3600):
+    """Runs the reference binary (oracle/_ref/pagan2_ref) with the job-dump interposer on.
+    Returns (list[FlatJob], stats dict)."""
+    import json
+
+    from pagan2_msa_b200 import jobio
+
+    env = dict(os.environ)
+    dump = os.path.join(cwd, dump_name)
+    stats = os.path.join(cwd, stats_name)
+    env["PAGAN2_ORACLE_DUMP"] = dump
+    env["PAGAN2_ORACLE_STATS"] = stats
+    subprocess.run([ref_binary()] + list(args), cwd=cwd, env=env, check=True, timeout=timeout,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    with open(stats) as f:
+        st = json.load(f)
+    return jobio.load_jobs(dump), st

@@ -1,0 +1,127 @@
+"""CPU tests of the engine's HOST logic (packing, graph sharing, band geometry, launch grouping, result
+unpacking) and of the per-thread kernel bodies, through tests/_emu/libpg2_emu.so: the product's CUDA
+sources compiled with g++ against tests/emu/pg2_emu_runtime.h, kernels run as serial loops.  This is a
+development aid for a container without a GPU -- the shipped library is built by nvcc and has no CPU
+path; the GPU parity tests proper are in test_gpu_parity.py."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import enginecheck
+import randjobs
+from pagan2_msa_b200 import abi, engine
+
+EMU_DIR = os.path.join(abi.REPO_ROOT, "tests", "emu")
+EMU_LIB = os.path.join(abi.REPO_ROOT, "tests", "_emu", "libpg2_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    return EMU_LIB
+
+
+def make_engine(lib, force_wavefront):
+    os.environ["PG2_FORCE_WAVEFRONT"] = "1" if force_wavefront else "0"
+    try:
+        return engine.Engine(0, lib)
+    finally:
+        os.environ.pop("PG2_FORCE_WAVEFRONT", None)
+
+
+@pytest.mark.parametrize("force_wavefront", [True, False])
+@pytest.mark.parametrize("name", ["prog_dna", "place_dna", "pileup_hp", "codon", "anchored"])
+def test_golden(emu_lib, golden, name, force_wavefront):
+    with make_engine(emu_lib, force_wavefront) as eng:
+        res = enginecheck.check_batch(eng, golden[name])
+        if force_wavefront:
+            assert (res["kernel"] == 0).all()
+
+
+def test_strip_kernel_is_chosen_for_placement(emu_lib, golden):
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, golden["place_dna"])
+        assert (res["kernel"] == 1).all()
+
+
+@pytest.mark.parametrize("kind,seed", [("general", 21), ("banded", 22), ("strip", 23)])
+def test_random_jobs_vs_oracle(emu_lib, kind, seed):
+    rng = np.random.default_rng(seed)
+    jobs = [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for _ in range(60)]
+    with make_engine(emu_lib, False) as eng:
+        enginecheck.check_batch(eng, jobs)
+
+
+def test_shared_graphs_uploaded_once(emu_lib, golden):
+    jobs = golden["place_dna"]
+    # 60 jobs, but far fewer distinct target graphs
+    with make_engine(emu_lib, False) as eng:
+        eng.align(jobs + jobs)
+        once = eng.stats()["h2d_bytes"]
+        eng.align(jobs)
+        assert eng.stats()["h2d_bytes"] < once  # doubling the jobs re-used every graph: only job records grew
+        assert once < 2 * eng.stats()["h2d_bytes"]
+
+
+def test_small_scratch_budget_splits_groups(emu_lib, golden):
+    os.environ["PG2_SCRATCH_MB"] = "1"
+    try:
+        with make_engine(emu_lib, True) as eng:
+            enginecheck.check_batch(eng, golden["prog_dna"])
+            assert eng.stats()["fill_launches"] > 1
+    finally:
+        os.environ.pop("PG2_SCRATCH_MB", None)
+
+
+def test_bad_inputs_are_reported_not_crashed(emu_lib):
+    rng = np.random.default_rng(31)
+    good = enginecheck.expect_from_oracle(randjobs.random_job(rng, "general"))
+    bad_graph = randjobs.random_job(rng, "general")
+    bad_graph.left.start[-1] = bad_graph.left.n_sites + 5  # edge from a later site
+    bad_graph.expected_status = abi.PG2_JOB_BAD_GRAPH
+    bad_state = randjobs.random_job(rng, "general")
+    bad_state.right.state[1] = 99
+    bad_state.expected_status = abi.PG2_JOB_BAD_GRAPH
+    bad_band = randjobs.random_job(rng, "banded")
+    bad_band.upper = bad_band.upper.copy()
+    bad_band.upper[len(bad_band.upper) // 2] = bad_band.upper[-1] + 5
+    bad_band.expected_status = abi.PG2_JOB_BAD_BAND
+    no_path = randjobs.random_job(rng, "general")
+    while no_path.right.n_sites < 6:
+        no_path = randjobs.random_job(rng, "general")
+    lx = no_path.left.n_sites - 1
+    no_path.upper = np.zeros(lx, np.int32)
+    no_path.lower = np.zeros(lx, np.int32)
+    no_path.expected_status = abi.PG2_JOB_NO_PATH
+    with make_engine(emu_lib, False) as eng:
+        enginecheck.check_batch(eng, [good, bad_graph, bad_state, bad_band, no_path, good])
+
+
+def test_empty_batch_and_tiny_graphs(emu_lib):
+    rng = np.random.default_rng(41)
+    with make_engine(emu_lib, False) as eng:
+        res, steps = eng.align([])
+        assert len(res) == 0
+        model = randjobs.random_model(rng, 15)
+        empty = abi.FlatGraph.chain(np.zeros(0, np.int32))  # start + stop only
+        one = abi.FlatGraph.chain(np.array([2], np.int32))
+        jobs = [abi.FlatJob(empty, empty, model, 2), abi.FlatJob(one, empty, model, 2), abi.FlatJob(empty, one, model, 3),
+                abi.FlatJob(one, one, model, 0)]
+        jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+        enginecheck.check_batch(eng, jobs)
+
+
+def test_invalid_arguments(emu_lib):
+    with make_engine(emu_lib, False) as eng:
+        rng = np.random.default_rng(51)
+        job = randjobs.random_job(rng, "general")
+        js = job.as_struct(12345)  # unknown model handle
+        import ctypes as C
+        arr = (abi.Job * 1)(js)
+        res = (abi.Result * 1)()
+        steps = np.zeros(1000, np.uint32)
+        rc = eng.lib.pg2_align_batch(eng.ctx, 1, arr, res, steps.ctypes.data, 1000)
+        assert rc == abi.PG2_ERR_INVALID
+        assert b"model" in eng.lib.pg2_last_error()

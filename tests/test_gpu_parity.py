@@ -1,0 +1,136 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C-ABI against the committed
+golden dumps of the reference, against the oracle on seeded random jobs, and -- at BASELINE config sizes --
+through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+import enginecheck
+import randjobs
+from pagan2_msa_b200 import abi, engine, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__
+
+    __graft_entry__.build()
+    e = engine.Engine(0)  # raises if the CUDA library or the device is missing: no fallback
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_wave():
+    os.environ["PG2_FORCE_WAVEFRONT"] = "1"
+    try:
+        e = engine.Engine(0)
+    finally:
+        os.environ.pop("PG2_FORCE_WAVEFRONT", None)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["prog_dna", "place_dna", "pileup_hp", "codon", "anchored"])
+def test_golden_default_dispatch(eng, golden, name):
+    enginecheck.check_batch(eng, golden[name])
+
+
+@pytest.mark.parametrize("name", ["prog_dna", "place_dna", "pileup_hp", "codon", "anchored"])
+def test_golden_wavefront_kernel(eng_wave, golden, name):
+    res = enginecheck.check_batch(eng_wave, golden[name])
+    assert (res["kernel"] == 0).all()
+
+
+def test_placement_uses_strip_kernel(eng, golden):
+    res = enginecheck.check_batch(eng, golden["place_dna"])
+    assert (res["kernel"] == 1).all()
+
+
+@pytest.mark.parametrize("kind,seed", [("general", 121), ("banded", 122), ("strip", 123)])
+def test_random_jobs_vs_oracle(eng, kind, seed):
+    rng = np.random.default_rng(seed)
+    jobs = [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for _ in range(300)]
+    enginecheck.check_batch(eng, jobs)
+
+
+def test_both_kernels_agree_on_strip_jobs(eng, eng_wave):
+    rng = np.random.default_rng(77)
+    jobs = [randjobs.random_job(rng, "strip") for _ in range(200)]
+    ra, sa = eng.align(jobs)
+    rb, sb = eng_wave.align(jobs)
+    assert (ra["kernel"] == 1).all() and (rb["kernel"] == 0).all()
+    assert (ra["score"].view(np.uint64) == rb["score"].view(np.uint64)).all()
+    for k, job in enumerate(jobs):
+        pa, _, _ = eng.expand(job, ra[k], sa)
+        pb, _, _ = eng_wave.expand(job, rb[k], sb)
+        assert pa.tobytes() == pb.tobytes()
+
+
+def test_bad_inputs_statuses(eng):
+    rng = np.random.default_rng(31)
+    good = enginecheck.expect_from_oracle(randjobs.random_job(rng, "general"))
+    bad_graph = randjobs.random_job(rng, "general")
+    bad_graph.left.start[-1] = bad_graph.left.n_sites + 5
+    bad_graph.expected_status = abi.PG2_JOB_BAD_GRAPH
+    bad_band = randjobs.random_job(rng, "banded")
+    bad_band.upper = bad_band.upper.copy()
+    bad_band.upper[len(bad_band.upper) // 2] = bad_band.upper[-1] + 5
+    bad_band.expected_status = abi.PG2_JOB_BAD_BAND
+    enginecheck.check_batch(eng, [good, bad_graph, bad_band, good])
+
+
+def test_placement_config_scale_properties(eng, golden):
+    """BASELINE configs[1] shape at scale: 4096 reads x 150 nt against 1.5 kb targets.
+    Properties that need no oracle: (1) a read cut from the target aligns with an all-match path and
+    the path is a monotone walk ending at the corner; (2) identical jobs give identical bits;
+    (3) the replayed path score equals the device score (checked inside pg2_expand_path);
+    (4) a sample is compared with the oracle bit for bit."""
+    model = golden["place_dna"][0].model
+    rng = np.random.default_rng(2024)
+    targets = [synth.leaf_graph(synth.random_dna(1500, rng)) for _ in range(8)]
+    tseqs = [t.state[1:-1] for t in targets]
+    reads, assign = [], []
+    for k in range(4096):
+        a = int(rng.integers(0, 8))
+        st = int(rng.integers(0, 1350))
+        r = tseqs[a][st:st + 150].copy()
+        if k % 2:
+            mut = rng.random(150) < 0.02
+            r[mut] = rng.integers(0, 4, size=int(mut.sum()))
+        reads.append(r)
+        assign.append(a)
+    jobs = synth.placement_jobs(targets, reads, assign, model)
+    res, steps = eng.align(jobs)
+    assert (res["status"] == 0).all() and (res["kernel"] == 1).all()
+    res2, steps2 = eng.align(jobs)
+    assert res.tobytes() == res2.tobytes() and steps.tobytes() == steps2.tobytes()
+    for k in range(0, 4096, 64):
+        p, ul, ur = eng.expand(jobs[k], res[k], steps)  # raises if the replayed score differs by one bit
+        real = p[p["real_site"] == 1]
+        assert (np.diff(real["x_ind"]) >= 0).all() and (np.diff(real["y_ind"]) >= 0).all()
+        assert (real["matrix"] == abi.PG2_M_MAT).sum() >= 140  # the read matches its source window
+        if k % 2 == 0:
+            m = real[real["matrix"] == abi.PG2_M_MAT]
+            assert len(m) == 150 and (np.diff(m["x_ind"]) == 1).all()
+    sample = [enginecheck.expect_from_oracle(jobs[k]) for k in range(0, 4096, 256)]
+    enginecheck.check_batch(eng, sample)
+
+
+def test_progressive_config_scale_vs_oracle(eng):
+    """BASELINE configs[0] shape: 1 kb x 1 kb leaf alignments (multi-block strip) and a banded
+    200 kb-style corridor job on the wavefront kernel, both against the oracle."""
+    rng = np.random.default_rng(9)
+    model = randjobs.random_model(rng, 15)
+    a = synth.random_dna(1000, rng)
+    b = synth.evolve(a, rng)
+    job = abi.FlatJob(synth.leaf_graph(a), synth.leaf_graph(b), model, 2)
+    lx, ly = job.left.n_sites - 1, job.right.n_sites - 1
+    banded = abi.FlatJob(synth.leaf_graph(a), synth.leaf_graph(b), model, 2)
+    banded.upper, banded.lower = randjobs.random_band(rng, lx, ly, 20, 40)
+    jobs = [enginecheck.expect_from_oracle(job), enginecheck.expect_from_oracle(banded)]
+    res = enginecheck.check_batch(eng, jobs)
+    assert res["kernel"][0] == 1 and res["kernel"][1] == 0

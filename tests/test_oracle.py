@@ -1,0 +1,63 @@
+"""CPU tests of the oracle: pinned against the reference's own outputs (golden dumps; and, where
+oracle/_ref is present, the reference library run live on random flat jobs)."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import randjobs
+
+
+def check_job(job):
+    status, score, steps, cells = oracle_lib.oracle_align(job)
+    assert status == 0
+    assert cells == job.cells
+    assert np.float64(score).view(np.uint64) == np.float64(job.expected_score).view(np.uint64)
+    assert oracle_lib.steps_equal(steps, job.expected_path, job.expected_path_score) == []
+
+
+@pytest.mark.parametrize("name", ["prog_dna", "place_dna", "pileup_hp", "codon", "anchored"])
+def test_oracle_matches_reference_dump(golden, name):
+    for job in golden[name]:
+        check_job(job)
+
+
+def test_golden_covers_all_shapes(golden):
+    assert any(j.upper is not None for j in golden["anchored"])
+    assert golden["codon"][0].model.fas == 1892
+    deg = lambda g: int(np.diff(g.off).max())
+    assert max(deg(j.right) for j in golden["pileup_hp"]) >= 2      # homopolymer multi-edge reads
+    assert max(deg(j.left) for j in golden["place_dna"]) >= 2       # internal reference nodes
+    assert any((j.left.logw != 0).any() for j in golden["place_dna"])
+
+
+@pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("kind", ["general", "banded", "strip"])
+def test_oracle_matches_live_reference_on_random_jobs(kind):
+    rng = np.random.default_rng({"general": 11, "banded": 12, "strip": 13}[kind])
+    for _ in range(40):
+        job = randjobs.random_job(rng, kind)
+        score, path, pscore = oracle_lib.ref_align_flat(job)
+        job.expected_score, job.expected_path, job.expected_path_score = score, path, pscore
+        check_job(job)
+
+
+def test_oracle_rejects_bad_band():
+    rng = np.random.default_rng(5)
+    job = randjobs.random_job(rng, "banded")
+    job.upper = job.upper.copy()
+    job.upper[len(job.upper) // 2] = job.upper[-1] + 5  # not monotone
+    status, _, _, _ = oracle_lib.oracle_align(job)
+    assert status == 2
+
+
+def test_oracle_no_path_in_disconnected_band():
+    rng = np.random.default_rng(6)
+    job = randjobs.random_job(rng, "general")
+    lx, ly = job.left.n_sites - 1, job.right.n_sites - 1
+    if lx < 4 or ly < 4:
+        job = randjobs.random_job(rng, "general")
+        lx, ly = job.left.n_sites - 1, job.right.n_sites - 1
+    job.upper = np.zeros(lx, np.int32)
+    job.lower = np.zeros(lx, np.int32)  # only column 0: the end corner is unreachable unless ly == 1
+    status, score, _, _ = oracle_lib.oracle_align(job)
+    assert (status == 1 and score == -np.inf) or ly == 1
