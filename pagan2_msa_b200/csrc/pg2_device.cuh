@@ -5,7 +5,7 @@
 //   d_off[]     int32   CSR offsets (graph-relative, n_sites+1 per graph)
 //   d_estart[]  int32   Edge::start_site_index per backward edge, reference list order
 //   d_elogw[]   float   Edge::log_posterior_weight per backward edge
-//   d_slot[]    int32   per site: saved-row slot when the site is the source of a long-span edge, else -1
+//   d_rowinfo[] int32   per site: state | fast-row flag | zero-weight flag | saved-row slot (pg2_strip_geom.cuh)
 //   d_blo/d_bhi int32   clipped anchor band per row (banded jobs only; tunnel_matrix.h:194)
 //   d_dlo       int32   first row on each anti-diagonal   (banded jobs only)
 //   d_doff      int64   cell offset of each anti-diagonal (banded jobs only)
@@ -37,7 +37,7 @@ struct DevGraph {
     int max_indeg;   // filled by the validation kernel
     int simple;      // 1: every site s>=1 has exactly one backward edge, from s-1 (plain leaf / read graph)
     int n_slots;     // saved-row slots the strip kernel needs when this graph is the row graph
-    int pad;
+    int zero_w;      // 1: every edge has log weight +0.0 (weight 1)
 };
 
 struct DevModel {
@@ -52,7 +52,8 @@ struct DevJob {
     int model;           // index into the DevModel array
     unsigned flags;
     int banded;
-    int kernel;          // 0 wavefront, 1 strip
+    short kernel;        // 0 wavefront, 1 strip
+    short strip_general; // strip kernel: 1 = left graph needs the general row body, 0 = plain unit-weight chain
     long long band_base; // into d_blo / d_bhi (lx entries)
     long long diag_base; // into d_dlo / d_doff (lx+ly-1 entries)
     long long cell_base; // into the group's score / ptr buffers

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -26,8 +27,8 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
                            const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                            const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores,
                            unsigned *ptrs, DevResult *results, cudaStream_t stream);
-void launch_strip_fill(int K, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
-                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_slot,
+void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
+                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
                        unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
                        long long bcol_per_warp, int *queue, int n_warps, cudaStream_t stream);
 int strip_warps_per_sm();
@@ -110,6 +111,7 @@ struct ModelRec {
 struct Group {
     int kernel;        // 0 wavefront, 1 strip
     int strip_k;       // strip kernel: columns per lane (all jobs of the group share it)
+    int strip_general; // strip kernel: general row body needed
     int first, count;  // range in batch->order
     long long cells;   // pointer-buffer entries of the group
     int max_diag;
@@ -301,11 +303,12 @@ static int pack_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unorder
     }
     dg.max_indeg = maxdeg;
     dg.simple = simple;
-    dg.pad = 0;
+    dg.zero_w = 1;
+    for (int k = 0; k < n_edges; k++) if (pw[k] != 0.0f || (pw[k] == 0.0f && std::signbit(pw[k]))) dg.zero_w = 0;
     // Saved-row slots for the strip kernel: a DP row p (site p < n_sites-1) that is the source of an edge
     // p -> s with s - p >= 2 (s a DP row too) must stay addressable until row s is done.  A slot is reused
     // two rows after its last reader (the skewed sweep reads it one step late on the next lane).
-    for (int s = 0; s < g.n_sites; s++) pslot[s] = -1;
+    std::vector<int> slot_of(g.n_sites, -1);
     dg.n_slots = 0;
     if (!simple && maxdeg > 0) {
         std::vector<int> last_use(g.n_sites, -1);
@@ -324,11 +327,29 @@ static int pack_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unorder
                 int slot;
                 if (!free_slots.empty()) { slot = free_slots.back(); free_slots.pop_back(); }
                 else slot = n_slots++;
-                pslot[s] = slot;
+                slot_of[s] = slot;
                 release[std::min(last_use[s] + 2, g.n_sites + 2)].push_back(slot);
             }
         }
         dg.n_slots = n_slots;
+    }
+    // rowinfo word per site (pg2_strip_geom.cuh)
+    for (int s = 0; s < g.n_sites; s++) {
+        int st = ps[s] < 0 ? 0 : (ps[s] & ROWINFO_STATE_MASK);
+        int k0 = po[s], k1 = po[s + 1];
+        bool ok = k0 >= 0 && k1 >= k0 && k1 <= n_edges;
+        bool fast = s == 0 ? (ok && k1 == k0) : (ok && k1 - k0 == 1 && pe[k0] == s - 1);
+        bool zw = true;
+        if (ok) for (int k = k0; k < k1; k++) if (pw[k] != 0.0f || std::signbit(pw[k])) zw = false;
+        pslot[s] = st | (fast ? ROWINFO_FAST : 0) | (zw ? ROWINFO_ZERO_W : 0) | ((slot_of[s] + 1) << ROWINFO_SLOT_SHIFT);
+    }
+    // rows the end corner reads: predecessors of the stop site and the last DP row (Y close, :1468-1469)
+    if (g.n_sites >= 2) {
+        int stop = g.n_sites - 1;
+        pslot[stop - 1] |= ROWINFO_ENDPRED;
+        if (po[stop] >= 0 && po[stop + 1] <= n_edges)
+            for (int k = po[stop]; k < po[stop + 1]; k++)
+                if (pe[k] >= 0 && pe[k] < stop) pslot[pe[k]] |= ROWINFO_ENDPRED;
     }
     *gid = (int)b->graphs.size();
     b->graphs.push_back(dg);
@@ -413,6 +434,8 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         J.kernel = strip_eligible(J.lx, J.ly, J.banded != 0, GL.simple, GR.simple, GL.max_indeg, GR.max_indeg, c->models[j.model].fas) ? 1 : 0;
         if (c->force_wavefront) J.kernel = 0;
         J.strip_k = J.kernel == 1 ? strip_pick_k(J.ly) : 0;
+        J.strip_general = (J.kernel == 1 && !(GL.simple && GL.zero_w)) ? 1 : 0;
+        if (J.kernel == 1 && c->models[j.model].fas <= STRIP_SMALL_FAS) J.strip_general |= 2;  // bit 1: shared-table variant
         J.ptr_cells = J.kernel == 1 ? strip_cells(J.lx, J.ly, J.strip_k) : J.cells;
         J.step_base = step_base;
         J.step_cap = j.left.n_sites + j.right.n_sites;
@@ -429,6 +452,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         const DevJob &A = b->jobs[x], &B = b->jobs[y];
         if (A.kernel != B.kernel) return A.kernel > B.kernel;
         if (A.strip_k != B.strip_k) return A.strip_k < B.strip_k;
+        if (A.strip_general != B.strip_general) return A.strip_general < B.strip_general;
         return A.cells > B.cells;
     });
     // groups under the scratch budget: wavefront 36 B/cell (scores + pointer word), strip 2 B/cell
@@ -437,6 +461,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         Group g;
         g.kernel = b->jobs[b->order[pos]].kernel;
         g.strip_k = b->jobs[b->order[pos]].strip_k;
+        g.strip_general = b->jobs[b->order[pos]].strip_general;
         g.first = (int)pos;
         g.count = 0;
         g.cells = 0;
@@ -446,7 +471,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         size_t per_cell = g.kernel == 0 ? 36 : 2;
         while (pos < b->order.size()) {
             DevJob &J = b->jobs[b->order[pos]];
-            if (J.kernel != g.kernel || J.strip_k != g.strip_k) break;
+            if (J.kernel != g.kernel || J.strip_k != g.strip_k || J.strip_general != g.strip_general) break;
             long long padded = (J.ptr_cells + 7) & ~7LL;
             if (g.count > 0 && (size_t)(g.cells + padded) * per_cell > c->scratch_bytes) break;
             J.cell_base = g.cells;
@@ -566,7 +591,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
             st.traceback_bytes += g.cells * 4;
         } else {
             int warps = std::min(resident_warps, std::max(g.count, 1));
-            launch_strip_fill(g.strip_k, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
+            launch_strip_fill(g.strip_k, (g.strip_general & 1) != 0, (g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
                               c->d_estart.p, c->d_elogw.p, c->d_slot.p, c->d_ptr16.p, c->d_results.p, c->d_saved.p,
                               (long long)std::max(g.max_slots, 1) * 32 * g.strip_k, c->d_bcol.p, (long long)g.max_lx, c->d_queue.p,
                               warps, c->stream);

@@ -12,20 +12,32 @@
 // written to a per-warp boundary column (next block's left neighbour, and what the end corner reads).
 // Back-pointers: one uint16 per cell, written step-major so that every step is one coalesced store.
 //
+// Two row bodies.  fast_row: the row has exactly one backward edge, from the row above (every row of a
+// leaf graph, ~90 % of the rows of an ancestor graph) -- scores are updated in place, no staging.
+// general_row: any in-degree / span, sources staged from registers or the saved-row scratch.  The choice
+// is warp-uniform per step (one __any_sync), so a warp never executes both bodies for one step.
+//
 // Arithmetic follows the reference candidate by candidate (src/main/viterbi_alignment.cpp:856-971,
 // 1328-1436, 2029-2219): same order, same FP64 association, strict '>' (first candidate wins ties).
-// "+ 0.0" terms (log_gap_close == 0) are dropped: x + 0.0 == x for every x the DP can produce.
+// "+ 0.0" terms (log_gap_close == 0, zero log edge weights) are dropped: x + 0.0 == x for every x the DP
+// can produce (no -0.0 arises: the corner is +0.0 and RN sums give -0.0 only from two -0.0 addends).
+// A cell whose candidates are all -inf keeps an arbitrary pointer in fast_row: such a cell cannot lie on
+// the Viterbi path, so the traceback never reads it.
 #include "pg2_device.cuh"
 #include "pg2_strip_geom.cuh"
+#ifdef PG2_HOST_EMU
+#include <vector>
+#endif
 
 namespace pg2 {
 
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas) {
-    (void)l_simple; (void)r_maxdeg; (void)fas;
+    (void)l_simple; (void)r_maxdeg;
     if (banded) return false;
     if (!r_simple) return false;
     if (l_maxdeg > STRIP_MAX_LEFT_INDEG) return false;
     if (lx < 1 || ly < 1) return false;
+    if (fas > ROWINFO_STATE_MASK) return false;
     return true;
 }
 
@@ -33,21 +45,21 @@ template <int K> struct LaneState {
     double X[K], Y[K], M[K];     // own strip, row this lane handled in the previous step
     double bX, bY, bM;           // left neighbour column (c0-1) of that same row
     double extX[K];              // log_gap_ext / log_gap_end_ext per column (X moves, :864-868)
-    double penY[K];              // gap-open penalty for Y moves from column j-1 (0 when j-1 == 0 and reduced)
     double wr[K];                // log weight of the column edge into site j
-    int colbase[K];              // state_r[j] * fas
-    bool valid[K];
+    double penY1;                // gap-open penalty of the Y move out of column 0 (k == 1 of lane 0, block 0)
+    int colbase[K];              // state_r[j] * fas (0 for padding columns)
 };
 
 struct StripCtx {
     // row graph (left)
-    const int *l_state, *l_off, *l_estart, *l_slot;
+    const int *l_rowinfo, *l_off, *l_estart;
     const float *l_elogw;
     // model
-    const float *table;
+    const float *table;          // global float table (any alphabet)
+    const double2 *stab;         // shared {2*lng + ls, lng + ls} table, or nullptr when the alphabet is too big
     int fas;
     double open, ext, end_ext, lng, lng2;
-    bool term, reduced;
+    bool term, reduced, wr_zero;
     int lx, ly;
     // per-warp scratch
     double4 *saved;   // [n_slots][W]
@@ -57,96 +69,164 @@ struct StripCtx {
     bool first_block;
 };
 
-// One row of one lane's strip.  recv* = (X,Y,M) of column c0-1 on this row (from lane l-1, or the
-// previous block's boundary column for lane 0).  On return st holds this row.
-template <int K>
-__device__ __forceinline__ void strip_row(const StripCtx &c, LaneState<K> &st, int lane, int i, double recvX, double recvY,
-                                          double recvM, unsigned short *out_words) {
-    const double ninf = neg_inf();
-    const int c0 = c.c_block + lane * K;
-    double nX[K], nM[K], nY[K];
-    unsigned pX[K], pM[K], pY[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) { nX[k] = ninf; nM[k] = ninf; pX[k] = NO_MAT; pM[k] = NO_MAT; }
+// {m_log, x_log} of one cell: 2*log_non_gap + log_score and log_non_gap + log_score (:1363-1367).
+// SMALLTAB: both terms come precomputed from the per-warp shared table (alphabets up to STRIP_SMALL_FAS).
+template <bool SMALLTAB>
+__device__ __forceinline__ void subst_terms(const StripCtx &c, int sl, int colbase, double &mlog, double &xlog) {
+    if (SMALLTAB) {
+        double2 v = c.stab[sl + colbase];
+        mlog = v.x;
+        xlog = v.y;
+    } else {
+        double ls = (double)__ldg(c.table + sl + colbase);
+        mlog = __dadd_rn(c.lng2, ls);
+        xlog = __dadd_rn(c.lng, ls);
+    }
+}
 
-    const int k0 = c.l_off[i], k1 = c.l_off[i + 1];
-    const int sl = (i > 0) ? c.l_state[i] : 0;
-    // substitution terms of this row (only rows i >= 1 have candidates)
-    double mlog[K], xlog[K];
-    if (k1 > k0) {
+// Fast-row pointer half-word: bit 14 set, bits 0-5 the raw comparison outcomes
+//   bit0/1 X: (double > ext), (open > max of the first two)      candidates in order X, Y, M
+//   bit2/3 Y: (open > double), (that winner > ext)                candidates in order Y, X, M
+//   bit4/5 M: (X > M), (Y > max of the first two)                 candidates in order M, X, Y
+// decoded by strip_fast_ptr() in pg2_strip_geom.cuh.  A cell whose candidates are all -inf gets
+// arbitrary bits: it cannot lie on the Viterbi path.
+//
+// Row with a single backward edge from row i-1: in-place update of the lane's strip.
+template <int K, bool WEIGHTS, bool SMALLTAB>
+__device__ __forceinline__ void fast_row(const StripCtx &c, LaneState<K> &st, int i, int sl, double wl, bool corner, double recvX,
+                                         double recvY, double recvM, unsigned short *out_words) {
+    const double pen = (c.reduced && i == 1) ? 0.0 : c.open;  // open penalty out of row p = i-1 (basic_alignment.h:490-513)
+    unsigned bits[K];
+    // descending k: X(i,j) reads (i-1,j), M(i,j) reads (i-1,j-1); both still hold row i-1
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double ls = st.valid[k] ? (double)__ldg(c.table + sl + st.colbase[k]) : 0.0;
-            mlog[k] = __dadd_rn(c.lng2, ls);   // 2*log_non_gap + log_score  (:1364)
-            xlog[k] = __dadd_rn(c.lng, ls);    // close(=0) + log_non_gap + log_score (:1366-1367)
+    for (int k = K - 1; k >= 0; --k) {
+        const double qX = k ? st.X[k - 1] : st.bX, qY = k ? st.Y[k - 1] : st.bY, qM = k ? st.M[k - 1] : st.bM;
+        // X: ext, double, open (:2116-2211)
+        double a = __dadd_rn(st.X[k], st.extX[k]);
+        double b = __dadd_rn(st.Y[k], c.open);
+        double d = __dadd_rn(__dadd_rn(st.M[k], c.lng), pen);
+        bool p1 = b > a;
+        double t = p1 ? b : a;
+        bool p2 = d > t;
+        const double nx = p2 ? d : t;
+        unsigned w = (p1 ? 1u : 0u) | (p2 ? 2u : 0u);
+        // M: from M, X, Y (:2029-2112)
+        double mlog, xlog;
+        subst_terms<SMALLTAB>(c, sl, st.colbase[k], mlog, xlog);
+        a = __dadd_rn(qM, mlog);
+        b = __dadd_rn(qX, xlog);
+        d = __dadd_rn(qY, xlog);
+        if (WEIGHTS) {
+            a = __dadd_rn(__dadd_rn(a, wl), st.wr[k]);
+            b = __dadd_rn(__dadd_rn(b, wl), st.wr[k]);
+            d = __dadd_rn(__dadd_rn(d, wl), st.wr[k]);
         }
+        p1 = b > a;
+        t = p1 ? b : a;
+        p2 = d > t;
+        const double nm = p2 ? d : t;
+        w |= (p1 ? 16u : 0u) | (p2 ? 32u : 0u);
+        bits[k] = w;
+        st.X[k] = nx;
+        st.M[k] = nm;
     }
-    for (int e = k0; e < k1; ++e) {
-        const int p = c.l_estart[e];
-        const double wl = (double)c.l_elogw[e];
-        const unsigned ord = (unsigned)(e - k0) << 2;
-        // source row p: columns c0-1 .. c0+K-1
-        double sX[K + 1], sY[K + 1], sM[K + 1];
-        if (p == i - 1) {
-            sX[0] = st.bX; sY[0] = st.bY; sM[0] = st.bM;
-#pragma unroll
-            for (int k = 0; k < K; ++k) { sX[k + 1] = st.X[k]; sY[k + 1] = st.Y[k]; sM[k + 1] = st.M[k]; }
-        } else {
-            const int slot = c.l_slot[p];
-            const double4 *row = c.saved + (long long)slot * c.W + lane * K;
-            double4 b;
-            if (lane > 0) b = row[-1];
-            else if (!c.first_block) b = c.bcol_prev[p];
-            else b = make_double4(ninf, ninf, ninf, 0.0);
-            sX[0] = b.x; sY[0] = b.y; sM[0] = b.z;
-#pragma unroll
-            for (int k = 0; k < K; ++k) { double4 v = row[k]; sX[k + 1] = v.x; sY[k + 1] = v.y; sM[k + 1] = v.z; }
-        }
-        const double pen = (c.reduced && p == 0) ? 0.0 : c.open;  // get_log_gap_open_penalty (basic_alignment.h:490-513)
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            // X(i,j) from (p,j): ext, double, open  (:2116-2211)
-            double s = __dadd_rn(sX[k + 1], st.extX[k]);
-            if (s > nX[k]) { nX[k] = s; pX[k] = X_MAT | ord; }
-            s = __dadd_rn(sY[k + 1], c.open);
-            if (s > nX[k]) { nX[k] = s; pX[k] = Y_MAT | ord; }
-            s = __dadd_rn(__dadd_rn(sM[k + 1], c.lng), pen);
-            if (s > nX[k]) { nX[k] = s; pX[k] = M_MAT | ord; }
-            // M(i,j) from (p,j-1): M, X, Y  (:2029-2112)
-            s = __dadd_rn(__dadd_rn(__dadd_rn(sM[k], mlog[k]), wl), st.wr[k]);
-            if (s > nM[k]) { nM[k] = s; pM[k] = M_MAT | ord; }
-            s = __dadd_rn(__dadd_rn(__dadd_rn(sX[k], xlog[k]), wl), st.wr[k]);
-            if (s > nM[k]) { nM[k] = s; pM[k] = X_MAT | ord; }
-            s = __dadd_rn(__dadd_rn(__dadd_rn(sY[k], xlog[k]), wl), st.wr[k]);
-            if (s > nM[k]) { nM[k] = s; pM[k] = Y_MAT | ord; }
-        }
-    }
-    // column 0 has no M (compute_fwd_scores :956-969); cell (0,0) is the start corner (:725-733)
-    if (c0 == 0) {
-        nM[0] = (i == 0) ? 0.0 : ninf;
-        pM[0] = NO_MAT;
-    }
-    // Y(i,j) from (i,j-1): ext, double, open -- sequential along the row
+    // Column 0 needs no special case for i > 0: its M sources are the -inf boundary, so M(i,0) = -inf falls
+    // out of the arithmetic.  Row 0 has no edges but its sources are the -inf initial strip, so X(0,j) =
+    // M(0,j) = -inf fall out as well; only the start corner M(0,0) = 0 (:725-733) is planted here.
+    if (corner) st.M[0] = 0.0;
+    // Y(i,j) from (i,j-1): ext, double, open.  The two chain-independent candidates are folded first;
+    // (g > a ? g : a) with g = first-wins(double, open) equals the sequential first-wins over all three.
     const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : c.ext;
     double lX = recvX, lY = recvY, lM = recvM;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
+        const double penY = (k == 1) ? st.penY1 : c.open;
+        const double b = __dadd_rn(lX, c.open);
+        const double d = __dadd_rn(__dadd_rn(lM, c.lng), penY);
+        const bool p2 = d > b;
+        const double g = p2 ? d : b;
+        const double a = __dadd_rn(lY, extY);
+        const bool p1 = g > a;
+        const double ny = p1 ? g : a;
+        out_words[k] = (unsigned short)(bits[k] | (p2 ? 4u : 0u) | (p1 ? 8u : 0u) | 0x4000u);
+        lX = st.X[k];
+        lM = st.M[k];
+        lY = ny;
+        st.Y[k] = ny;
+    }
+    st.bX = recvX; st.bY = recvY; st.bM = recvM;
+}
+
+// Any in-degree / span: sources come from the previous-row registers or the saved-row scratch.
+template <int K, bool SMALLTAB>
+__device__ __forceinline__ void general_row(const StripCtx &c, LaneState<K> &st, int lane, int i, int sl, double recvX, double recvY,
+                                         double recvM, unsigned short *out_words) {
+    const double ninf = neg_inf();
+    const int c0 = c.c_block + lane * K;
+    double nX[K], nM[K];
+    unsigned pX[K], pM[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { nX[k] = ninf; nM[k] = ninf; pX[k] = NO_MAT; pM[k] = NO_MAT; }
+    const int k0 = c.l_off[i], k1 = c.l_off[i + 1];
+    for (int e = k0; e < k1; ++e) {
+        const int p = c.l_estart[e];
+        const double wl = (double)c.l_elogw[e];
+        const unsigned ord = (unsigned)(e - k0) << 2;
+        const bool from_regs = (p == i - 1);
+        const double4 *row = nullptr;
+        double4 bnd = make_double4(ninf, ninf, ninf, 0.0);
+        if (from_regs) {
+            bnd = make_double4(st.bX, st.bY, st.bM, 0.0);
+        } else {
+            const int slot = (int)((unsigned)c.l_rowinfo[p] >> ROWINFO_SLOT_SHIFT) - 1;
+            row = c.saved + (long long)slot * c.W + lane * K;
+            if (lane > 0) bnd = row[-1];
+            else if (!c.first_block) bnd = c.bcol_prev[p];
+        }
+        const double pen = (c.reduced && p == 0) ? 0.0 : c.open;
+        double qX = bnd.x, qY = bnd.y, qM = bnd.z;  // (p, j-1), walking right
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double sX, sY, sM;  // (p, j)
+            if (from_regs) { sX = st.X[k]; sY = st.Y[k]; sM = st.M[k]; }
+            else { double4 v = row[k]; sX = v.x; sY = v.y; sM = v.z; }
+            double s = __dadd_rn(sX, st.extX[k]);
+            if (s > nX[k]) { nX[k] = s; pX[k] = X_MAT | ord; }
+            s = __dadd_rn(sY, c.open);
+            if (s > nX[k]) { nX[k] = s; pX[k] = Y_MAT | ord; }
+            s = __dadd_rn(__dadd_rn(sM, c.lng), pen);
+            if (s > nX[k]) { nX[k] = s; pX[k] = M_MAT | ord; }
+            double mlog, xlog;
+            subst_terms<SMALLTAB>(c, sl, st.colbase[k], mlog, xlog);
+            s = __dadd_rn(__dadd_rn(__dadd_rn(qM, mlog), wl), st.wr[k]);
+            if (s > nM[k]) { nM[k] = s; pM[k] = M_MAT | ord; }
+            s = __dadd_rn(__dadd_rn(__dadd_rn(qX, xlog), wl), st.wr[k]);
+            if (s > nM[k]) { nM[k] = s; pM[k] = X_MAT | ord; }
+            s = __dadd_rn(__dadd_rn(__dadd_rn(qY, xlog), wl), st.wr[k]);
+            if (s > nM[k]) { nM[k] = s; pM[k] = Y_MAT | ord; }
+            qX = sX; qY = sY; qM = sM;
+        }
+    }
+    if (c0 == 0) {
+        nM[0] = (i == 0) ? 0.0 : ninf;
+        pM[0] = NO_MAT;
+    }
+    const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : c.ext;
+    double lX = recvX, lY = recvY, lM = recvM;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double penY = (k == 1) ? st.penY1 : c.open;
         double best = ninf;
         unsigned ptr = NO_MAT;
         double s = __dadd_rn(lY, extY);
         if (s > best) { best = s; ptr = Y_MAT; }
         s = __dadd_rn(lX, c.open);
         if (s > best) { best = s; ptr = X_MAT; }
-        s = __dadd_rn(__dadd_rn(lM, c.lng), st.penY[k]);
+        s = __dadd_rn(__dadd_rn(lM, c.lng), penY);
         if (s > best) { best = s; ptr = M_MAT; }
-        nY[k] = best;
-        pY[k] = ptr;
+        out_words[k] = (unsigned short)strip_word(pX[k], ptr, pM[k]);
         lX = nX[k]; lY = best; lM = nM[k];
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        st.X[k] = nX[k]; st.Y[k] = nY[k]; st.M[k] = nM[k];
-        out_words[k] = (unsigned short)strip_word(pX[k], pY[k], pM[k]);
+        st.X[k] = nX[k]; st.Y[k] = best; st.M[k] = nM[k];
     }
     st.bX = recvX; st.bY = recvY; st.bM = recvM;
 }
@@ -161,14 +241,13 @@ __device__ __forceinline__ void strip_init_lane(const StripCtx &c, LaneState<K> 
     for (int k = 0; k < K; ++k) {
         int j = c0 + k;
         bool v = j < c.ly;
-        st.valid[k] = v;
         st.X[k] = st.Y[k] = st.M[k] = ninf;
         st.extX[k] = (c.term && (j == 0 || j == c.ly - 1)) ? c.end_ext : c.ext;
-        st.penY[k] = (c.reduced && j == 1) ? 0.0 : c.open;
         // column j >= 1 is entered by the chain edge (j-1 -> j), CSR position j-1
         st.wr[k] = (v && j >= 1) ? (double)r_elogw[j - 1] : 0.0;
         st.colbase[k] = (v && j >= 1) ? r_state[j] * c.fas : 0;
     }
+    st.penY1 = (c.reduced && c0 == 0) ? 0.0 : c.open;  // Y move out of column j-1 == 0 (basic_alignment.h:494)
     st.bX = st.bY = st.bM = ninf;
 }
 
@@ -196,15 +275,15 @@ __device__ __forceinline__ void strip_end_corner(const StripCtx &c, const double
     res->status = (best == ninf) ? JOB_NO_PATH : JOB_OK;
 }
 
-__device__ __forceinline__ void strip_make_ctx(StripCtx &c, const DevJob &J, const DevGraph &GL, const DevModel &m, const int *d_state,
-                                               const int *d_off, const int *d_estart, const float *d_elogw, const int *d_slot,
+__device__ __forceinline__ void strip_make_ctx(StripCtx &c, const DevJob &J, const DevGraph &GL, const DevGraph &GR, const DevModel &m,
+                                               const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
                                                int K) {
-    c.l_state = d_state + GL.state_base;
+    c.l_rowinfo = d_rowinfo + GL.state_base;
     c.l_off = d_off + GL.off_base;
     c.l_estart = d_estart + GL.edge_base;
     c.l_elogw = d_elogw + GL.edge_base;
-    c.l_slot = d_slot + GL.state_base;
     c.table = m.table;
+    c.stab = nullptr;
     c.fas = m.fas;
     c.open = (double)m.open;
     c.ext = (double)m.ext;
@@ -213,24 +292,47 @@ __device__ __forceinline__ void strip_make_ctx(StripCtx &c, const DevJob &J, con
     c.lng2 = (double)__fmul_rn(2.0f, m.lng);
     c.term = !(J.flags & FLAG_NO_TERMINAL_EDGES);
     c.reduced = (J.flags & FLAG_REDUCED) != 0;
+    c.wr_zero = GR.zero_w != 0;
     c.lx = J.lx;
     c.ly = J.ly;
     c.W = 32 * K;
 }
 
+// One step of one lane: pick the row body.  `all_fast` / `any_weights` are warp-uniform.
+template <int K, bool GENERAL, bool SMALLTAB>
+__device__ __forceinline__ void strip_lane_step(const StripCtx &c, LaneState<K> &st, int lane, int i, int info, bool all_fast,
+                                                bool any_weights, double wl, double rX, double rY, double rM,
+                                                unsigned short *w) {
+    const int sl = info & ROWINFO_STATE_MASK;
+    if (!GENERAL || all_fast) {
+        const bool corner = (i == 0) && (c.c_block + lane * K == 0);  // row 0 is a fast row
+        if (any_weights) fast_row<K, true, SMALLTAB>(c, st, i, sl, wl, corner, rX, rY, rM, w);
+        else fast_row<K, false, SMALLTAB>(c, st, i, sl, wl, corner, rX, rY, rM, w);
+    } else {
+        general_row<K, SMALLTAB>(c, st, lane, i, sl, rX, rY, rM, w);
+    }
+}
+
 #ifndef PG2_HOST_EMU
-template <int K>
-__global__ void __launch_bounds__(128)
+// keeps a per-job constant in a register: without the barrier ptxas re-derives the doubles from the
+// float model parameters (F2F) inside the step loop whenever registers get tight
+__device__ __forceinline__ void pin(double &v) { asm volatile("" : "+d"(v)); }
+
+template <int K, bool GENERAL, bool SMALLTAB>
+__global__ void __launch_bounds__(128, 4)
 strip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
-                  const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_slot,
+                  const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
                   unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
                   long long bcol_per_warp, int *queue) {
+    __shared__ double2 s_tab[SMALLTAB ? 4 : 1][SMALLTAB ? STRIP_SMALL_FAS * STRIP_SMALL_FAS : 1];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double4 *saved = saved_all + (long long)warp_global * saved_per_warp;
     double4 *bcol0 = bcol_all + (long long)warp_global * bcol_per_warp * 2;
     double4 *bcol1 = bcol0 + bcol_per_warp;
     const double ninf = neg_inf();
+    int tab_model = -1;
 
     for (;;) {
         int q = 0;
@@ -244,13 +346,29 @@ strip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevG
         const DevGraph GL = graphs[J.left], GR = graphs[J.right];
         const DevModel m = models[J.model];
         StripCtx c;
-        strip_make_ctx(c, J, GL, m, d_state, d_off, d_estart, d_elogw, d_slot, K);
+        strip_make_ctx(c, J, GL, GR, m, d_off, d_estart, d_elogw, d_rowinfo, K);
+        pin(c.open); pin(c.ext); pin(c.end_ext); pin(c.lng);
         c.saved = saved;
         c.ptr = ptrs + J.cell_base;
+        if (SMALLTAB) {
+            if (tab_model != J.model) {
+                __syncwarp();
+                for (int e = lane; e < m.fas * m.fas; e += 32) {
+                    double ls = (double)m.table[e];
+                    s_tab[wib][e] = make_double2(__dadd_rn(c.lng2, ls), __dadd_rn(c.lng, ls));
+                }
+                __syncwarp();
+                tab_model = J.model;
+            }
+            c.stab = s_tab[wib];
+        }
         const int *r_state = d_state + GR.state_base;
         const float *r_elogw = d_elogw + GR.edge_base;
         const int n_blocks = (c.ly + c.W - 1) / c.W;
         constexpr int KS = (K + 1) & ~1;
+        // GENERAL == false: the engine only sends jobs whose left graph is a plain chain with unit weights,
+        // so every row is a fast row and the general body is not even compiled in
+        const bool left_fast = !GENERAL || (GL.simple != 0 && GL.zero_w != 0);
 
         for (int b = 0; b < n_blocks; ++b) {
             c.c_block = b * c.W;
@@ -259,37 +377,56 @@ strip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevG
             c.bcol_cur = (b & 1) ? bcol1 : bcol0;
             LaneState<K> st;
             strip_init_lane<K>(c, st, lane, r_state, r_elogw);
-            // lane that owns the block's last valid column writes the boundary column
+#pragma unroll
+            for (int k = 0; k < K; ++k) pin(st.extX[k]);
+            pin(st.penY1);
+            // the lane that owns the block's last valid column feeds the boundary column: every row when
+            // another block follows, else only the rows the end corner reads (predecessors of the stop site)
             const int last_col = min(c.c_block + c.W, c.ly) - 1;
             const int last_lane = (last_col - c.c_block) / K, last_k = (last_col - c.c_block) % K;
+            const int bcol_need = (b + 1 < n_blocks) ? ~0 : ROWINFO_ENDPRED;
+            // lane 0 of the first block has no left neighbour: adding -inf to whatever the shuffle delivers
+            // (its own column) yields the -inf boundary on the FP64 pipe, no selects
+            double lane0_mask = (lane == 0 && c.first_block) ? ninf : 0.0;
+            pin(lane0_mask);
             unsigned short *out = c.ptr + ((long long)b * (c.lx + 31) * 32 + lane) * KS;
             const int n_steps = c.lx + 31;
             for (int t = 0; t < n_steps; ++t) {
                 // hand the previous step's last column to the next lane
-                double rX = __shfl_up_sync(0xffffffffu, st.X[K - 1], 1);
-                double rY = __shfl_up_sync(0xffffffffu, st.Y[K - 1], 1);
-                double rM = __shfl_up_sync(0xffffffffu, st.M[K - 1], 1);
+                double rX = __dadd_rn(__shfl_up_sync(0xffffffffu, st.X[K - 1], 1), lane0_mask);
+                double rY = __dadd_rn(__shfl_up_sync(0xffffffffu, st.Y[K - 1], 1), lane0_mask);
+                double rM = __dadd_rn(__shfl_up_sync(0xffffffffu, st.M[K - 1], 1), lane0_mask);
                 const int i = t - lane;
-                if (i >= 0 && i < c.lx) {
-                    if (lane == 0) {
-                        if (c.first_block) { rX = rY = rM = ninf; }
-                        else { double4 v = c.bcol_prev[i]; rX = v.x; rY = v.y; rM = v.z; }
-                    }
+                const bool active = (i >= 0 && i < c.lx);
+                int info = ROWINFO_FAST | ROWINFO_ZERO_W;
+                double wl = 0.0;
+                if (active) info = c.l_rowinfo[i];
+                bool all_fast = true, any_weights = !c.wr_zero;
+                if (GENERAL && !left_fast) {
+                    all_fast = !__any_sync(0xffffffffu, !(info & ROWINFO_FAST));
+                    const bool lane_w = !(info & ROWINFO_ZERO_W);
+                    any_weights = __any_sync(0xffffffffu, lane_w) || !c.wr_zero;
+                    if (active && all_fast && lane_w) wl = (double)c.l_elogw[c.l_off[i]];
+                }
+                if (active) {
+                    if (lane == 0 && !c.first_block) { double4 v = c.bcol_prev[i]; rX = v.x; rY = v.y; rM = v.z; }
                     unsigned short w[KS];
                     if (KS > K) w[KS - 1] = 0;
-                    strip_row<K>(c, st, lane, i, rX, rY, rM, w);
+                    strip_lane_step<K, GENERAL, SMALLTAB>(c, st, lane, i, info, all_fast, any_weights, wl, rX, rY, rM, w);
                     // coalesced pointer store: KS half-words per lane, step-major
                     unsigned *dst = reinterpret_cast<unsigned *>(out + (long long)t * 32 * KS);
 #pragma unroll
                     for (int h = 0; h < KS / 2; ++h) dst[h] = (unsigned)w[2 * h] | ((unsigned)w[2 * h + 1] << 16);
                     // park rows that feed long-span edges
-                    const int slot = c.l_slot[i];
-                    if (slot >= 0) {
-                        double4 *row = c.saved + (long long)slot * c.W + lane * K;
+                    if (GENERAL) {
+                        const int slot = (int)((unsigned)info >> ROWINFO_SLOT_SHIFT) - 1;
+                        if (slot >= 0) {
+                            double4 *row = c.saved + (long long)slot * c.W + lane * K;
 #pragma unroll
-                        for (int k = 0; k < K; ++k) row[k] = make_double4(st.X[k], st.Y[k], st.M[k], 0.0);
+                            for (int k = 0; k < K; ++k) row[k] = make_double4(st.X[k], st.Y[k], st.M[k], 0.0);
+                        }
                     }
-                    if (lane == last_lane) {
+                    if (lane == last_lane && (info & bcol_need)) {
                         double vx = ninf, vy = ninf, vm = ninf;
 #pragma unroll
                         for (int k = 0; k < K; ++k) if (k == last_k) { vx = st.X[k]; vy = st.Y[k]; vm = st.M[k]; }
@@ -309,22 +446,33 @@ strip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevG
 }
 #endif
 
-// CPU test emulation of one warp (tests/emu): the same strip_row / init / end-corner bodies, lanes run
-// one after the other inside a step with the shuffle replaced by a snapshot of the previous step.
+// CPU test emulation of one warp (tests/emu): the same row bodies, lanes run one after the other inside
+// a step with the shuffle replaced by a snapshot of the previous step.
 template <int K>
 static void strip_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &GR, const DevModel &m, const int *d_state,
-                              const int *d_off, const int *d_estart, const float *d_elogw, const int *d_slot,
+                              const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
                               unsigned short *ptrs, DevResult *res, double4 *saved, double4 *bcol0, double4 *bcol1) {
 #ifdef PG2_HOST_EMU
     const double ninf = neg_inf();
     StripCtx c;
-    strip_make_ctx(c, J, GL, m, d_state, d_off, d_estart, d_elogw, d_slot, K);
+    strip_make_ctx(c, J, GL, GR, m, d_off, d_estart, d_elogw, d_rowinfo, K);
     c.saved = saved;
     c.ptr = ptrs + J.cell_base;
+    std::vector<double2> tab;
+    const bool smalltab = m.fas <= STRIP_SMALL_FAS;
+    if (smalltab) {
+        tab.resize((size_t)m.fas * m.fas);
+        for (int e = 0; e < m.fas * m.fas; ++e) {
+            double ls = (double)m.table[e];
+            tab[e] = make_double2(c.lng2 + ls, c.lng + ls);
+        }
+        c.stab = tab.data();
+    }
     const int *r_state = d_state + GR.state_base;
     const float *r_elogw = d_elogw + GR.edge_base;
     const int n_blocks = (c.ly + c.W - 1) / c.W;
     const int KS = strip_ks(K);
+    const bool left_fast = GL.simple != 0 && GL.zero_w != 0;
     for (int b = 0; b < n_blocks; ++b) {
         c.c_block = b * c.W;
         c.first_block = (b == 0);
@@ -336,7 +484,17 @@ static void strip_emulate_job(const DevJob &J, const DevGraph &GL, const DevGrap
         const int last_lane = (last_col - c.c_block) / K, last_k = (last_col - c.c_block) % K;
         for (int t = 0; t < c.lx + 31; ++t) {
             double sx[32], sy[32], sm[32];
-            for (int l = 0; l < 32; ++l) { sx[l] = st[l].X[K - 1]; sy[l] = st[l].Y[K - 1]; sm[l] = st[l].M[K - 1]; }
+            int info[32];
+            bool all_fast = true, any_weights = !c.wr_zero;
+            for (int l = 0; l < 32; ++l) {
+                sx[l] = st[l].X[K - 1]; sy[l] = st[l].Y[K - 1]; sm[l] = st[l].M[K - 1];
+                const int i = t - l;
+                info[l] = (i >= 0 && i < c.lx) ? c.l_rowinfo[i] : (ROWINFO_FAST | ROWINFO_ZERO_W);
+                if (!left_fast) {
+                    if (!(info[l] & ROWINFO_FAST)) all_fast = false;
+                    if (!(info[l] & ROWINFO_ZERO_W)) any_weights = true;
+                }
+            }
             for (int l = 0; l < 32; ++l) {
                 const int i = t - l;
                 if (i < 0 || i >= c.lx) continue;
@@ -345,22 +503,27 @@ static void strip_emulate_job(const DevJob &J, const DevGraph &GL, const DevGrap
                     if (c.first_block) rX = rY = rM = ninf;
                     else { double4 v = c.bcol_prev[i]; rX = v.x; rY = v.y; rM = v.z; }
                 } else { rX = sx[l - 1]; rY = sy[l - 1]; rM = sm[l - 1]; }
+                double wl = 0.0;
+                if (!left_fast && all_fast && !(info[l] & ROWINFO_ZERO_W)) wl = (double)c.l_elogw[c.l_off[i]];
                 unsigned short w[8];
-                strip_row<K>(c, st[l], l, i, rX, rY, rM, w);
+                if (smalltab) strip_lane_step<K, true, true>(c, st[l], l, i, info[l], all_fast, any_weights, wl, rX, rY, rM, w);
+                else strip_lane_step<K, true, false>(c, st[l], l, i, info[l], all_fast, any_weights, wl, rX, rY, rM, w);
                 unsigned short *out = c.ptr + (((long long)b * (c.lx + 31) + t) * 32 + l) * KS;
                 for (int k = 0; k < K; ++k) out[k] = w[k];
-                const int slot = c.l_slot[i];
+                const int slot = (int)((unsigned)info[l] >> ROWINFO_SLOT_SHIFT) - 1;
                 if (slot >= 0) {
                     double4 *row = c.saved + (long long)slot * c.W + l * K;
                     for (int k = 0; k < K; ++k) row[k] = make_double4(st[l].X[k], st[l].Y[k], st[l].M[k], 0.0);
                 }
-                if (l == last_lane) c.bcol_cur[i] = make_double4(st[l].X[last_k], st[l].Y[last_k], st[l].M[last_k], 0.0);
+                const int bcol_need = (b + 1 < n_blocks) ? ~0 : ROWINFO_ENDPRED;
+                if (l == last_lane && (info[l] & bcol_need))
+                    c.bcol_cur[i] = make_double4(st[l].X[last_k], st[l].Y[last_k], st[l].M[last_k], 0.0);
             }
         }
     }
     strip_end_corner(c, ((n_blocks - 1) & 1) ? bcol1 : bcol0, r_elogw, res);
 #else
-    (void)J; (void)GL; (void)GR; (void)m; (void)d_state; (void)d_off; (void)d_estart; (void)d_elogw; (void)d_slot; (void)ptrs;
+    (void)J; (void)GL; (void)GR; (void)m; (void)d_state; (void)d_off; (void)d_estart; (void)d_elogw; (void)d_rowinfo; (void)ptrs;
     (void)res; (void)saved; (void)bcol0; (void)bcol1;
 #endif
 }
@@ -368,8 +531,8 @@ static void strip_emulate_job(const DevJob &J, const DevGraph &GL, const DevGrap
 // Launch one group of strip jobs that share the strip width K.  saved/bcol scratch is per resident warp.
 int strip_warps_per_sm() { return 16; }
 
-void launch_strip_fill(int K, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
-                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_slot,
+void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
+                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
                        unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
                        long long bcol_per_warp, int *queue, int n_warps, cudaStream_t stream) {
     if (n_jobs <= 0) return;
@@ -377,19 +540,25 @@ void launch_strip_fill(int K, int n_jobs, const DevJob *jobs, const int *job_ids
     cudaMemsetAsync(queue, 0, sizeof(int), stream);
     const int threads = 128;
     const int blocks = (n_warps * 32 + threads - 1) / threads;
-#define PG2_STRIP_CASE(KK)                                                                                                   \
-    case KK:                                                                                                                 \
-        strip_fill_kernel<KK><<<blocks, threads, 0, stream>>>(n_jobs, jobs, job_ids, graphs, models, d_state, d_off, d_estart, \
-                                                              d_elogw, d_slot, ptrs, results, saved_all, saved_per_warp,    \
-                                                              bcol_all, bcol_per_warp, queue);                               \
+#define PG2_STRIP_LAUNCH(KK, G, S)                                                                                            \
+    strip_fill_kernel<KK, G, S><<<blocks, threads, 0, stream>>>(n_jobs, jobs, job_ids, graphs, models, d_state, d_off, d_estart, \
+                                                                d_elogw, d_rowinfo, ptrs, results, saved_all, saved_per_warp,  \
+                                                                bcol_all, bcol_per_warp, queue)
+#define PG2_STRIP_CASE(KK)                                         \
+    case KK:                                                       \
+        if (general && smalltab) PG2_STRIP_LAUNCH(KK, true, true);  \
+        else if (general) PG2_STRIP_LAUNCH(KK, true, false);        \
+        else if (smalltab) PG2_STRIP_LAUNCH(KK, false, true);       \
+        else PG2_STRIP_LAUNCH(KK, false, false);                    \
         break;
     switch (K) {
         PG2_STRIP_CASE(2) PG2_STRIP_CASE(3) PG2_STRIP_CASE(4) PG2_STRIP_CASE(5) PG2_STRIP_CASE(6) PG2_STRIP_CASE(8)
         default: break;
     }
 #undef PG2_STRIP_CASE
+#undef PG2_STRIP_LAUNCH
 #else
-    (void)queue; (void)n_warps; (void)stream;
+    (void)queue; (void)n_warps; (void)stream; (void)general; (void)smalltab;
     for (int q = 0; q < n_jobs; ++q) {
         const int jid = job_ids[q];
         const DevJob &J = jobs[jid];
@@ -397,7 +566,7 @@ void launch_strip_fill(int K, int n_jobs, const DevJob *jobs, const int *job_ids
         if (res->status != JOB_OK) continue;
         double4 *bcol0 = bcol_all, *bcol1 = bcol_all + bcol_per_warp;
         switch (K) {
-#define PG2_STRIP_CASE(KK) case KK: strip_emulate_job<KK>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_slot, ptrs, res, saved_all, bcol0, bcol1); break;
+#define PG2_STRIP_CASE(KK) case KK: strip_emulate_job<KK>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_rowinfo, ptrs, res, saved_all, bcol0, bcol1); break;
             PG2_STRIP_CASE(2) PG2_STRIP_CASE(3) PG2_STRIP_CASE(4) PG2_STRIP_CASE(5) PG2_STRIP_CASE(6) PG2_STRIP_CASE(8)
 #undef PG2_STRIP_CASE
             default: break;

@@ -135,11 +135,9 @@ __device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int
         }
         out = word_ptr(t.ptr32[J.cell_base + idx], mat);
     } else {
-        // strip kernel half-word: X ptr bits 0-5 (mat | lord<<2), Y ptr bits 6-7 (mat), M ptr bits 8-13 (mat | lord<<2)
+        if (i == 0 && j == 0) { out = NO_MAT; return true; }  // start corner: no predecessor
         unsigned w = t.ptr16[J.cell_base + strip_ptr_index(J.lx, J.ly, J.strip_k, i, j)];
-        if (mat == X_MAT) out = w & 0x3fu;
-        else if (mat == Y_MAT) out = (w >> 6) & 3u;
-        else out = (w >> 8) & 0x3fu;
+        out = strip_decode_ptr(w, mat);
     }
     return true;
 }

@@ -132,8 +132,9 @@ class Engine:
     def batch(self, jobs):
         return Batch(self, jobs)
 
-    def align(self, jobs):
-        """pg2_align_batch on a list of FlatJob -> (results[RESULT_DTYPE], packed steps uint32)."""
+    def prepare(self, jobs):
+        """Builds the pg2_job array (the caller-side host buffers of the C-ABI) once; the arrays of the
+        FlatJob objects stay owned by `jobs`.  Returns an opaque tuple for align_prepared()."""
         n = len(jobs)
         structs = (abi.Job * max(n, 1))()
         cap = 0
@@ -142,9 +143,18 @@ class Engine:
             cap += j.left.n_sites + j.right.n_sites
         results = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
         steps = np.zeros(max(cap, 1), dtype=np.uint32)
+        return (n, structs, results, steps, jobs)
+
+    def align_prepared(self, prep):
+        """One pg2_align_batch call: host job arrays in, host results + packed steps out."""
+        n, structs, results, steps, _ = prep
         self._check(self.lib.pg2_align_batch(self.ctx, n, structs, results.ctypes.data_as(C.POINTER(abi.Result)),
                                              steps.ctypes.data, steps.shape[0]))
         return results[:n], steps
+
+    def align(self, jobs):
+        """pg2_align_batch on a list of FlatJob -> (results[RESULT_DTYPE], packed steps uint32)."""
+        return self.align_prepared(self.prepare(jobs))
 
     def expand(self, job, result, steps):
         """pg2_expand_path -> (steps[STEP_DTYPE] forward order, used_left, used_right)."""
