@@ -137,7 +137,7 @@ struct pg2_ctx {
     cudaDeviceProp prop;
     std::vector<ModelRec> models;
     bool models_dirty = true;
-    size_t scratch_bytes = (size_t)16 << 30;
+    size_t scratch_bytes = (size_t)64 << 30;  // pointer/score scratch per launch group (PG2_SCRATCH_MB overrides)
     bool force_wavefront = false;  // PG2_FORCE_WAVEFRONT=1: route every job through the general kernel (tests)
     // staging (pinned) and device arrays of the current batch
     PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_slot;
@@ -186,8 +186,8 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
     c->force_wavefront = fw && atoi(fw) != 0;
     const char *mb = getenv("PG2_SCRATCH_MB");
     if (mb && atoll(mb) > 0) c->scratch_bytes = (size_t)atoll(mb) << 20;
-    size_t half = c->prop.totalGlobalMem / 2;
-    if (c->scratch_bytes > half) c->scratch_bytes = half;
+    size_t cap = c->prop.totalGlobalMem / 100 * 45;  // leave room for inputs, steps and the caller
+    if (c->scratch_bytes > cap) c->scratch_bytes = cap;
     memset(&c->stats, 0, sizeof c->stats);
     *out = c;
     return PG2_OK;
