@@ -5,7 +5,8 @@
 //   d_off[]     int32   CSR offsets (graph-relative, n_sites+1 per graph)
 //   d_estart[]  int32   Edge::start_site_index per backward edge, reference list order
 //   d_elogw[]   float   Edge::log_posterior_weight per backward edge
-//   d_rowinfo[] int32   per site: state | fast-row flag | zero-weight flag | saved-row slot (pg2_strip_geom.cuh)
+//   d_vrow[]    int4    strip kernel row program: one entry per (DP row, backward edge) of a row graph
+//   d_vlast[]   int32   per site of a row graph: index of the virtual row that completes the site
 //   d_blo/d_bhi int32   clipped anchor band per row (banded jobs only; tunnel_matrix.h:194)
 //   d_dlo       int32   first row on each anti-diagonal   (banded jobs only)
 //   d_doff      int64   cell offset of each anti-diagonal (banded jobs only)
@@ -38,6 +39,10 @@ struct DevGraph {
     int simple;      // 1: every site s>=1 has exactly one backward edge, from s-1 (plain leaf / read graph)
     int n_slots;     // saved-row slots the strip kernel needs when this graph is the row graph
     int zero_w;      // 1: every edge has log weight +0.0 (weight 1)
+    int vrow_base;   // into d_vrow (int4 units); -1 until the graph is used as a strip row graph
+    int n_vrows;     // virtual rows: one per (DP row, backward edge), edgeless rows count once
+    int vlast_base;  // into d_vlast: per site, the virtual row that completes it
+    int pad;
 };
 
 struct DevModel {

@@ -28,12 +28,12 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
                            const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores,
                            unsigned *ptrs, DevResult *results, cudaStream_t stream);
 void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
-                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
+                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
                        unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
                        long long bcol_per_warp, int *queue, int n_warps, cudaStream_t stream);
 int strip_warps_per_sm();
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
-void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_off,
+void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
                       const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps, DevResult *results, cudaStream_t stream);
 }  // namespace pg2
@@ -140,10 +140,10 @@ struct pg2_ctx {
     size_t scratch_bytes = (size_t)64 << 30;  // pointer/score scratch per launch group (PG2_SCRATCH_MB overrides)
     bool force_wavefront = false;  // PG2_FORCE_WAVEFRONT=1: route every job through the general kernel (tests)
     // staging (pinned) and device arrays of the current batch
-    PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_slot;
+    PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_vrow, h_vlast;
     PinVec<float> h_elogw;
     PinVec<long long> h_doff;
-    DevBuf<int> d_state, d_off, d_estart, d_blo, d_bhi, d_dlo, d_order, d_graph_status, d_slot, d_queue;
+    DevBuf<int> d_state, d_off, d_estart, d_blo, d_bhi, d_dlo, d_order, d_graph_status, d_vrow, d_vlast, d_queue;
     DevBuf<double4> d_saved, d_bcol;
     DevBuf<float> d_elogw;
     DevBuf<long long> d_doff;
@@ -199,8 +199,8 @@ extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (auto &m : c->models) if (m.live && m.d_table) cudaFree(m.d_table);
     c->h_state.release(); c->h_off.release(); c->h_estart.release(); c->h_blo.release(); c->h_bhi.release(); c->h_dlo.release();
-    c->h_elogw.release(); c->h_doff.release(); c->h_results.release(); c->h_slot.release();
-    c->d_slot.release(); c->d_queue.release(); c->d_saved.release(); c->d_bcol.release();
+    c->h_elogw.release(); c->h_doff.release(); c->h_results.release(); c->h_vrow.release(); c->h_vlast.release();
+    c->d_vrow.release(); c->d_vlast.release(); c->d_queue.release(); c->d_saved.release(); c->d_bcol.release();
     c->d_state.release(); c->d_off.release(); c->d_estart.release(); c->d_blo.release(); c->d_bhi.release(); c->d_dlo.release();
     c->d_order.release(); c->d_graph_status.release(); c->d_elogw.release(); c->d_doff.release(); c->d_jobs.release();
     c->d_graphs.release(); c->d_models.release(); c->d_results.release(); c->d_scores.release(); c->d_ptr32.release();
@@ -276,9 +276,8 @@ static int pack_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unorder
     if ((long long)c->h_state.n + g.n_sites > 0x7fffffffLL || (long long)c->h_estart.n + n_edges > 0x7fffffffLL)
         return fail(PG2_ERR_INVALID, "batch too large: more than 2^31 sites or edges; split the batch");
     int *ps = c->h_state.extend(g.n_sites), *po = c->h_off.extend(g.n_sites + 1), *pe = c->h_estart.extend(n_edges);
-    int *pslot = c->h_slot.extend(g.n_sites);
     float *pw = c->h_elogw.extend(n_edges);
-    if (!ps || !po || !pe || !pw || !pslot) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    if (!ps || !po || !pe || !pw) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
     memcpy(ps, g.state, sizeof(int) * g.n_sites);
     memcpy(po, g.bwd_off, sizeof(int) * (g.n_sites + 1));
     if (n_edges) {
@@ -305,55 +304,85 @@ static int pack_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unorder
     dg.simple = simple;
     dg.zero_w = 1;
     for (int k = 0; k < n_edges; k++) if (pw[k] != 0.0f || (pw[k] == 0.0f && std::signbit(pw[k]))) dg.zero_w = 0;
-    // Saved-row slots for the strip kernel: a DP row p (site p < n_sites-1) that is the source of an edge
-    // p -> s with s - p >= 2 (s a DP row too) must stay addressable until row s is done.  A slot is reused
-    // two rows after its last reader (the skewed sweep reads it one step late on the next lane).
-    std::vector<int> slot_of(g.n_sites, -1);
     dg.n_slots = 0;
-    if (!simple && maxdeg > 0) {
-        std::vector<int> last_use(g.n_sites, -1);
-        for (int s = 1; s < g.n_sites - 1; s++)
-            for (int k = po[s]; k < po[s + 1]; k++) {
-                int p = pe[k];
-                if (p >= 0 && p < s && s - p >= 2 && last_use[p] < s) last_use[p] = s;
-            }
-        std::vector<int> free_slots;
-        std::vector<std::vector<int> > release(g.n_sites + 3);
-        int n_slots = 0;
-        for (int s = 0; s < g.n_sites - 1; s++) {
-            for (size_t r = 0; r < release[s].size(); r++) free_slots.push_back(release[s][r]);
-            release[s].clear();
-            if (last_use[s] > 0) {
-                int slot;
-                if (!free_slots.empty()) { slot = free_slots.back(); free_slots.pop_back(); }
-                else slot = n_slots++;
-                slot_of[s] = slot;
-                release[std::min(last_use[s] + 2, g.n_sites + 2)].push_back(slot);
-            }
-        }
-        dg.n_slots = n_slots;
-    }
-    // rowinfo word per site (pg2_strip_geom.cuh)
-    for (int s = 0; s < g.n_sites; s++) {
-        int st = ps[s] < 0 ? 0 : (ps[s] & ROWINFO_STATE_MASK);
-        int k0 = po[s], k1 = po[s + 1];
-        bool ok = k0 >= 0 && k1 >= k0 && k1 <= n_edges;
-        bool fast = s == 0 ? (ok && k1 == k0) : (ok && k1 - k0 == 1 && pe[k0] == s - 1);
-        bool zw = true;
-        if (ok) for (int k = k0; k < k1; k++) if (pw[k] != 0.0f || std::signbit(pw[k])) zw = false;
-        pslot[s] = st | (fast ? ROWINFO_FAST : 0) | (zw ? ROWINFO_ZERO_W : 0) | ((slot_of[s] + 1) << ROWINFO_SLOT_SHIFT);
-    }
-    // rows the end corner reads: predecessors of the stop site and the last DP row (Y close, :1468-1469)
-    if (g.n_sites >= 2) {
-        int stop = g.n_sites - 1;
-        pslot[stop - 1] |= ROWINFO_ENDPRED;
-        if (po[stop] >= 0 && po[stop + 1] <= n_edges)
-            for (int k = po[stop]; k < po[stop + 1]; k++)
-                if (pe[k] >= 0 && pe[k] < stop) pslot[pe[k]] |= ROWINFO_ENDPRED;
-    }
+    dg.vrow_base = -1;
+    dg.n_vrows = g.n_sites - 1;
+    dg.vlast_base = -1;
+    dg.pad = 0;
     *gid = (int)b->graphs.size();
     b->graphs.push_back(dg);
     seen.emplace(key, *gid);
+    return PG2_OK;
+}
+
+// Row program of a graph used as the strip kernel's ROW graph (pg2_strip_geom.cuh): virtual rows, saved-row
+// slots, and the site -> completing-virtual-row map the traceback needs.  Built once per distinct graph.
+// Returns PG2_ERR_UNSUPPORTED when the graph needs more saved-row slots than the table can name.
+static int build_row_program(pg2_ctx *c, DevGraph &dg) {
+    if (dg.vrow_base >= 0) return PG2_OK;
+    const int n = dg.n_sites, rows = n - 1;
+    const int *ps = c->h_state.p + dg.state_base, *po = c->h_off.p + dg.off_base, *pe = c->h_estart.p + dg.edge_base;
+    const float *pw = c->h_elogw.p + dg.edge_base;
+    // Saved-row slots: a DP row p that is the source of an edge p -> s with s - p >= 2 (s a DP row too) must stay
+    // addressable until row s is done.  A slot is reused two rows after its last reader (the skewed sweep
+    // reads it one step late on the next lane).
+    std::vector<int> last_use(n, -1), slot_of(n, -1);
+    for (int s = 1; s < rows; s++)
+        for (int k = po[s]; k < po[s + 1]; k++) {
+            int p = pe[k];
+            if (p >= 0 && p < s && s - p >= 2 && last_use[p] < s) last_use[p] = s;
+        }
+    std::vector<int> free_slots;
+    std::vector<std::vector<int> > release(n + 3);
+    int n_slots = 0;
+    for (int s = 0; s < rows; s++) {
+        for (size_t r = 0; r < release[s].size(); r++) free_slots.push_back(release[s][r]);
+        if (last_use[s] > 0) {
+            int slot;
+            if (!free_slots.empty()) { slot = free_slots.back(); free_slots.pop_back(); }
+            else slot = n_slots++;
+            slot_of[s] = slot;
+            release[std::min(last_use[s] + 2, n + 2)].push_back(slot);
+        }
+    }
+    if (n_slots > STRIP_MAX_SLOTS) return PG2_ERR_UNSUPPORTED;
+    dg.n_slots = n_slots;
+    // rows the end corner reads: predecessors of the stop site and the last DP row (Y close, :1468-1469)
+    std::vector<char> endpred(n, 0);
+    endpred[rows - 1 >= 0 ? rows - 1 : 0] = 1;
+    for (int k = po[n - 1]; k < po[n]; k++)
+        if (pe[k] >= 0 && pe[k] < n - 1) endpred[pe[k]] = 1;
+    int nv = 0;
+    for (int s = 0; s < rows; s++) nv += std::max(po[s + 1] - po[s], 1);
+    dg.vrow_base = (int)(c->h_vrow.n / 4);
+    dg.vlast_base = (int)c->h_vlast.n;
+    dg.n_vrows = nv;
+    int *vr = c->h_vrow.extend((size_t)nv * 4), *vl = c->h_vlast.extend(n);
+    if (!vr || !vl) return PG2_ERR_NOMEM;
+    int v = 0;
+    for (int s = 0; s < rows; s++) {
+        const int k0 = po[s], k1 = po[s + 1], deg = k1 - k0;
+        const int st = ps[s] < 0 ? 0 : (ps[s] & VR_STATE_MASK);
+        const int tail = (endpred[s] ? VR_ENDPRED : 0) | ((slot_of[s] + 1) << VR_SLOT_SHIFT);
+        if (deg == 0) {
+            // the start site (and any unreachable site): nothing to accumulate.  Site 0 also carries REG so
+            // that it may take the in-place fast row: its sources are the -inf initial strip.
+            int info = st | VR_FIRST | VR_LAST | VR_NOEDGE | VR_ZERO_W | (s == 0 ? VR_REG : 0) | tail;
+            vr[4 * v] = info; vr[4 * v + 1] = -1; vr[4 * v + 2] = s; vr[4 * v + 3] = 0;
+            v++;
+        }
+        for (int k = k0; k < k1; k++) {
+            const int p = pe[k];
+            const bool reg = (p == s - 1);
+            const bool zw = pw[k] == 0.0f && !std::signbit(pw[k]);
+            int info = st | (k == k0 ? VR_FIRST : 0) | (k == k1 - 1 ? VR_LAST | tail : 0) | (reg ? VR_REG : 0) | (zw ? VR_ZERO_W : 0);
+            int src = (reg || p < 0 || p >= n ? 0 : (slot_of[p] < 0 ? 0 : slot_of[p])) | ((k - k0) << 16);
+            vr[4 * v] = info; vr[4 * v + 1] = k; vr[4 * v + 2] = s; vr[4 * v + 3] = src;
+            v++;
+        }
+        vl[s] = v - 1;
+    }
+    vl[n - 1] = v - 1;
     return PG2_OK;
 }
 
@@ -404,7 +433,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     pg2_batch *b = new pg2_batch();
     b->n_jobs = n_jobs;
     b->jobs.resize(n_jobs);
-    c->h_state.clear(); c->h_off.clear(); c->h_estart.clear(); c->h_elogw.clear(); c->h_slot.clear();
+    c->h_state.clear(); c->h_off.clear(); c->h_estart.clear(); c->h_elogw.clear(); c->h_vrow.clear(); c->h_vlast.clear();
     c->h_blo.clear(); c->h_bhi.clear(); c->h_dlo.clear(); c->h_doff.clear();
     std::unordered_map<GraphKey, int, GraphKeyHash> seen;
     seen.reserve((size_t)n_jobs * 2 + 16);
@@ -430,13 +459,19 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         } else {
             J.cells = (long long)J.lx * J.ly;
         }
-        const DevGraph &GL = b->graphs[J.left], &GR = b->graphs[J.right];
+        DevGraph &GL = b->graphs[J.left];
+        const DevGraph &GR = b->graphs[J.right];
         J.kernel = strip_eligible(J.lx, J.ly, J.banded != 0, GL.simple, GR.simple, GL.max_indeg, GR.max_indeg, c->models[j.model].fas) ? 1 : 0;
         if (c->force_wavefront) J.kernel = 0;
+        if (J.kernel == 1) {
+            rc = build_row_program(c, GL);
+            if (rc == PG2_ERR_UNSUPPORTED) J.kernel = 0;  // too many parked rows: the general kernel takes it
+            else if (rc != PG2_OK) { delete b; return fail(rc, "pinned staging allocation failed"); }
+        }
         J.strip_k = J.kernel == 1 ? strip_pick_k(J.ly) : 0;
         J.strip_general = (J.kernel == 1 && !(GL.simple && GL.zero_w)) ? 1 : 0;
         if (J.kernel == 1 && c->models[j.model].fas <= STRIP_SMALL_FAS) J.strip_general |= 2;  // bit 1: shared-table variant
-        J.ptr_cells = J.kernel == 1 ? strip_cells(J.lx, J.ly, J.strip_k) : J.cells;
+        J.ptr_cells = J.kernel == 1 ? strip_cells(GL.n_vrows, J.ly, J.strip_k) : J.cells;
         J.step_base = step_base;
         J.step_cap = j.left.n_sites + j.right.n_sites;
         step_base += J.step_cap;
@@ -492,7 +527,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
 static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     int rc;
 #define ENS(buf, n) if ((rc = (buf).ensure(n)) != PG2_OK) return fail(rc, "device allocation failed (%s)", #buf)
-    ENS(c->d_slot, c->h_slot.n + 1); ENS(c->d_queue, 4);
+    ENS(c->d_vrow, c->h_vrow.n + 4); ENS(c->d_vlast, c->h_vlast.n + 1); ENS(c->d_queue, 4);
     ENS(c->d_state, c->h_state.n + 1); ENS(c->d_off, c->h_off.n + 1); ENS(c->d_estart, c->h_estart.n + 1); ENS(c->d_elogw, c->h_elogw.n + 1);
     ENS(c->d_blo, c->h_blo.n + 1); ENS(c->d_bhi, c->h_bhi.n + 1); ENS(c->d_dlo, c->h_dlo.n + 1); ENS(c->d_doff, c->h_doff.n + 1);
     ENS(c->d_jobs, b->jobs.size() + 1); ENS(c->d_graphs, b->graphs.size() + 1); ENS(c->d_order, b->order.size() + 1);
@@ -503,7 +538,8 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     if ((n) > 0) { CU(cudaMemcpyAsync((dst).p, (src), (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, c->stream)); bytes += (long long)(n) * sizeof(T); }
     H2D(c->d_state, c->h_state.p, c->h_state.n, int);
     H2D(c->d_off, c->h_off.p, c->h_off.n, int);
-    H2D(c->d_slot, c->h_slot.p, c->h_slot.n, int);
+    H2D(c->d_vrow, c->h_vrow.p, c->h_vrow.n, int);
+    H2D(c->d_vlast, c->h_vlast.p, c->h_vlast.n, int);
     H2D(c->d_estart, c->h_estart.p, c->h_estart.n, int);
     H2D(c->d_elogw, c->h_elogw.p, c->h_elogw.n, float);
     H2D(c->d_blo, c->h_blo.p, c->h_blo.n, int);
@@ -592,7 +628,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
         } else {
             int warps = std::min(resident_warps, std::max(g.count, 1));
             launch_strip_fill(g.strip_k, (g.strip_general & 1) != 0, (g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
-                              c->d_estart.p, c->d_elogw.p, c->d_slot.p, c->d_ptr16.p, c->d_results.p, c->d_saved.p,
+                              c->d_estart.p, c->d_elogw.p, reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_ptr16.p, c->d_results.p, c->d_saved.p,
                               (long long)std::max(g.max_slots, 1) * 32 * g.strip_k, c->d_bcol.p, (long long)g.max_lx, c->d_queue.p,
                               warps, c->stream);
             st.jobs_strip += g.count;
@@ -600,7 +636,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
             st.traceback_bytes += g.cells * 2;
         }
         CU(cudaEventRecord(c->ev[3], c->stream));
-        launch_traceback(g.count, ids, c->d_jobs.p, c->d_graphs.p, c->d_off.p, c->d_estart.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p,
+        launch_traceback(g.count, ids, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p, c->d_off.p, c->d_estart.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p,
                          c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_steps.p, c->d_results.p, c->stream);
         CU(cudaEventRecord(c->ev[4], c->stream));
         CU(cudaEventSynchronize(c->ev[4]));

@@ -12,10 +12,13 @@
 // written to a per-warp boundary column (next block's left neighbour, and what the end corner reads).
 // Back-pointers: one uint16 per cell, written step-major so that every step is one coalesced store.
 //
-// Two row bodies.  fast_row: the row has exactly one backward edge, from the row above (every row of a
-// leaf graph, ~90 % of the rows of an ancestor graph) -- scores are updated in place, no staging.
-// general_row: any in-degree / span, sources staged from registers or the saved-row scratch.  The choice
-// is warp-uniform per step (one __any_sync), so a warp never executes both bodies for one step.
+// Row program.  The row graph is flattened on the host into VIRTUAL rows, one backward edge each (d_vrow,
+// pg2_strip_geom.cuh): a site with three incoming edges takes three steps, a plain site one.  Lanes stay in
+// lockstep on virtual rows, so the sweep costs sum(in-degree) + 31 steps instead of sum over steps of the
+// largest in-degree among the 32 rows in flight.  Two step bodies: fast_row (the site has exactly one edge,
+// from the row above: every row of a leaf graph, ~90 % of an ancestor graph) updates the strip in place;
+// general_step accumulates one edge into per-lane accumulators and commits on the site's LAST virtual
+// row.  The choice is warp-uniform per step (one __any_sync).
 //
 // Arithmetic follows the reference candidate by candidate (src/main/viterbi_alignment.cpp:856-971,
 // 1328-1436, 2029-2219): same order, same FP64 association, strict '>' (first candidate wins ties).
@@ -37,7 +40,7 @@ bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int
     if (!r_simple) return false;
     if (l_maxdeg > STRIP_MAX_LEFT_INDEG) return false;
     if (lx < 1 || ly < 1) return false;
-    if (fas > ROWINFO_STATE_MASK) return false;
+    if (fas > VR_STATE_MASK) return false;
     return true;
 }
 
@@ -52,8 +55,10 @@ template <int K> struct LaneState {
 
 struct StripCtx {
     // row graph (left)
-    const int *l_rowinfo, *l_off, *l_estart;
+    const int4 *l_vrow;
+    const int *l_off, *l_estart;
     const float *l_elogw;
+    int nv;                      // virtual rows
     // model
     const float *table;          // global float table (any alphabet)
     const double2 *stab;         // shared {2*lng + ls, lng + ls} table, or nullptr when the alphabet is too big
@@ -157,60 +162,78 @@ __device__ __forceinline__ void fast_row(const StripCtx &c, LaneState<K> &st, in
     st.bX = recvX; st.bY = recvY; st.bM = recvM;
 }
 
-// Any in-degree / span: sources come from the previous-row registers or the saved-row scratch.
-template <int K, bool SMALLTAB>
-__device__ __forceinline__ void general_row(const StripCtx &c, LaneState<K> &st, int lane, int i, int sl, double recvX, double recvY,
-                                         double recvM, unsigned short *out_words) {
-    const double ninf = neg_inf();
-    const int c0 = c.c_block + lane * K;
+// Per-lane accumulators of a site whose edges are spread over several virtual rows.
+template <int K> struct LaneAcc {
     double nX[K], nM[K];
     unsigned pX[K], pM[K];
+};
+
+// candidates of ONE backward edge into the accumulators; (sX,sY,sM)[0] is column c0-1 of the source row,
+// [k+1] column c0+k
+template <int K, bool SMALLTAB>
+__device__ __forceinline__ void accumulate_edge(const StripCtx &c, const LaneState<K> &st, LaneAcc<K> &acc, int sl, int p,
+                                                double wl, unsigned ord, const double *sX, const double *sY, const double *sM) {
+    const double pen = (c.reduced && p == 0) ? 0.0 : c.open;  // get_log_gap_open_penalty (basic_alignment.h:490-513)
 #pragma unroll
-    for (int k = 0; k < K; ++k) { nX[k] = ninf; nM[k] = ninf; pX[k] = NO_MAT; pM[k] = NO_MAT; }
-    const int k0 = c.l_off[i], k1 = c.l_off[i + 1];
-    for (int e = k0; e < k1; ++e) {
-        const int p = c.l_estart[e];
-        const double wl = (double)c.l_elogw[e];
-        const unsigned ord = (unsigned)(e - k0) << 2;
-        const bool from_regs = (p == i - 1);
-        const double4 *row = nullptr;
-        double4 bnd = make_double4(ninf, ninf, ninf, 0.0);
-        if (from_regs) {
-            bnd = make_double4(st.bX, st.bY, st.bM, 0.0);
-        } else {
-            const int slot = (int)((unsigned)c.l_rowinfo[p] >> ROWINFO_SLOT_SHIFT) - 1;
-            row = c.saved + (long long)slot * c.W + lane * K;
+    for (int k = 0; k < K; ++k) {
+        double s = __dadd_rn(sX[k + 1], st.extX[k]);                  // X: ext, double, open (:2116-2211)
+        if (s > acc.nX[k]) { acc.nX[k] = s; acc.pX[k] = X_MAT | ord; }
+        s = __dadd_rn(sY[k + 1], c.open);
+        if (s > acc.nX[k]) { acc.nX[k] = s; acc.pX[k] = Y_MAT | ord; }
+        s = __dadd_rn(__dadd_rn(sM[k + 1], c.lng), pen);
+        if (s > acc.nX[k]) { acc.nX[k] = s; acc.pX[k] = M_MAT | ord; }
+        double mlog, xlog;
+        subst_terms<SMALLTAB>(c, sl, st.colbase[k], mlog, xlog);
+        s = __dadd_rn(__dadd_rn(__dadd_rn(sM[k], mlog), wl), st.wr[k]);  // M: from M, X, Y (:2029-2112)
+        if (s > acc.nM[k]) { acc.nM[k] = s; acc.pM[k] = M_MAT | ord; }
+        s = __dadd_rn(__dadd_rn(__dadd_rn(sX[k], xlog), wl), st.wr[k]);
+        if (s > acc.nM[k]) { acc.nM[k] = s; acc.pM[k] = X_MAT | ord; }
+        s = __dadd_rn(__dadd_rn(__dadd_rn(sY[k], xlog), wl), st.wr[k]);
+        if (s > acc.nM[k]) { acc.nM[k] = s; acc.pM[k] = Y_MAT | ord; }
+    }
+}
+
+// One virtual row of any shape.  `any_saved` (warp-uniform): some lane's edge starts at a parked row this
+// step; when false every source is the lane's own previous-row strip and no staging happens.
+// Returns true when the site was completed (st now holds row `i`, out_words are valid).
+template <int K, bool SMALLTAB>
+__device__ __forceinline__ bool general_step(const StripCtx &c, LaneState<K> &st, LaneAcc<K> &acc, int lane, int4 vr,
+                                             bool any_saved, double recvX, double recvY, double recvM,
+                                             unsigned short *out_words) {
+    const double ninf = neg_inf();
+    const int info = vr.x, i = vr.z;
+    const int sl = info & VR_STATE_MASK;
+    if (info & VR_FIRST) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { acc.nX[k] = ninf; acc.nM[k] = ninf; acc.pX[k] = NO_MAT; acc.pM[k] = NO_MAT; }
+    }
+    if (!(info & VR_NOEDGE)) {
+        const int p = c.l_estart[vr.y];
+        const double wl = (info & VR_ZERO_W) ? 0.0 : (double)c.l_elogw[vr.y];
+        const unsigned ord = ((unsigned)vr.w >> 16) << 2;
+        double sX[K + 1], sY[K + 1], sM[K + 1];
+        sX[0] = st.bX; sY[0] = st.bY; sM[0] = st.bM;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { sX[k + 1] = st.X[k]; sY[k + 1] = st.Y[k]; sM[k + 1] = st.M[k]; }
+        if (any_saved && !(info & VR_REG)) {
+            const int slot = vr.w & 0xffff;
+            const double4 *row = c.saved + (long long)slot * c.W + lane * K;
+            double4 bnd = make_double4(ninf, ninf, ninf, 0.0);
             if (lane > 0) bnd = row[-1];
             else if (!c.first_block) bnd = c.bcol_prev[p];
-        }
-        const double pen = (c.reduced && p == 0) ? 0.0 : c.open;
-        double qX = bnd.x, qY = bnd.y, qM = bnd.z;  // (p, j-1), walking right
+            sX[0] = bnd.x; sY[0] = bnd.y; sM[0] = bnd.z;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double sX, sY, sM;  // (p, j)
-            if (from_regs) { sX = st.X[k]; sY = st.Y[k]; sM = st.M[k]; }
-            else { double4 v = row[k]; sX = v.x; sY = v.y; sM = v.z; }
-            double s = __dadd_rn(sX, st.extX[k]);
-            if (s > nX[k]) { nX[k] = s; pX[k] = X_MAT | ord; }
-            s = __dadd_rn(sY, c.open);
-            if (s > nX[k]) { nX[k] = s; pX[k] = Y_MAT | ord; }
-            s = __dadd_rn(__dadd_rn(sM, c.lng), pen);
-            if (s > nX[k]) { nX[k] = s; pX[k] = M_MAT | ord; }
-            double mlog, xlog;
-            subst_terms<SMALLTAB>(c, sl, st.colbase[k], mlog, xlog);
-            s = __dadd_rn(__dadd_rn(__dadd_rn(qM, mlog), wl), st.wr[k]);
-            if (s > nM[k]) { nM[k] = s; pM[k] = M_MAT | ord; }
-            s = __dadd_rn(__dadd_rn(__dadd_rn(qX, xlog), wl), st.wr[k]);
-            if (s > nM[k]) { nM[k] = s; pM[k] = X_MAT | ord; }
-            s = __dadd_rn(__dadd_rn(__dadd_rn(qY, xlog), wl), st.wr[k]);
-            if (s > nM[k]) { nM[k] = s; pM[k] = Y_MAT | ord; }
-            qX = sX; qY = sY; qM = sM;
+            for (int k = 0; k < K; ++k) { double4 v = row[k]; sX[k + 1] = v.x; sY[k + 1] = v.y; sM[k + 1] = v.z; }
         }
+        accumulate_edge<K, SMALLTAB>(c, st, acc, sl, p, wl, ord, sX, sY, sM);
     }
-    if (c0 == 0) {
-        nM[0] = (i == 0) ? 0.0 : ninf;
-        pM[0] = NO_MAT;
+    if (!(info & VR_LAST)) return false;
+    // column 0 has no M; (0,0) is the start corner (:725-733, :956-969)
+    if (c.c_block + lane * K == 0) {
+        acc.nM[0] = (i == 0) ? 0.0 : ninf;
+        acc.pM[0] = NO_MAT;
     }
+    // Y(i,j) from (i,j-1): ext, double, open -- sequential along the row
     const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : c.ext;
     double lX = recvX, lY = recvY, lM = recvM;
 #pragma unroll
@@ -224,11 +247,12 @@ __device__ __forceinline__ void general_row(const StripCtx &c, LaneState<K> &st,
         if (s > best) { best = s; ptr = X_MAT; }
         s = __dadd_rn(__dadd_rn(lM, c.lng), penY);
         if (s > best) { best = s; ptr = M_MAT; }
-        out_words[k] = (unsigned short)strip_word(pX[k], ptr, pM[k]);
-        lX = nX[k]; lY = best; lM = nM[k];
-        st.X[k] = nX[k]; st.Y[k] = best; st.M[k] = nM[k];
+        out_words[k] = (unsigned short)strip_word(acc.pX[k], ptr, acc.pM[k]);
+        lX = acc.nX[k]; lY = best; lM = acc.nM[k];
+        st.X[k] = acc.nX[k]; st.Y[k] = best; st.M[k] = acc.nM[k];
     }
     st.bX = recvX; st.bY = recvY; st.bM = recvM;
+    return true;
 }
 
 // per-lane constants of one column block
@@ -276,9 +300,10 @@ __device__ __forceinline__ void strip_end_corner(const StripCtx &c, const double
 }
 
 __device__ __forceinline__ void strip_make_ctx(StripCtx &c, const DevJob &J, const DevGraph &GL, const DevGraph &GR, const DevModel &m,
-                                               const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
+                                               const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
                                                int K) {
-    c.l_rowinfo = d_rowinfo + GL.state_base;
+    c.l_vrow = d_vrow + GL.vrow_base;
+    c.nv = GL.n_vrows;
     c.l_off = d_off + GL.off_base;
     c.l_estart = d_estart + GL.edge_base;
     c.l_elogw = d_elogw + GL.edge_base;
@@ -298,19 +323,24 @@ __device__ __forceinline__ void strip_make_ctx(StripCtx &c, const DevJob &J, con
     c.W = 32 * K;
 }
 
-// One step of one lane: pick the row body.  `all_fast` / `any_weights` are warp-uniform.
+// One step of one lane.  `all_fast`, `any_weights`, `any_saved` are warp-uniform.  Returns true when the
+// lane completed a site this step (pointer words valid, st holds the site's row).
 template <int K, bool GENERAL, bool SMALLTAB>
-__device__ __forceinline__ void strip_lane_step(const StripCtx &c, LaneState<K> &st, int lane, int i, int info, bool all_fast,
-                                                bool any_weights, double wl, double rX, double rY, double rM,
-                                                unsigned short *w) {
-    const int sl = info & ROWINFO_STATE_MASK;
+__device__ __forceinline__ bool strip_lane_step(const StripCtx &c, LaneState<K> &st, LaneAcc<K> &acc, int lane, int4 vr,
+                                                bool all_fast, bool any_weights, bool any_saved, double rX, double rY,
+                                                double rM, unsigned short *w) {
     if (!GENERAL || all_fast) {
+        const int i = vr.z, sl = vr.x & VR_STATE_MASK;
         const bool corner = (i == 0) && (c.c_block + lane * K == 0);  // row 0 is a fast row
-        if (any_weights) fast_row<K, true, SMALLTAB>(c, st, i, sl, wl, corner, rX, rY, rM, w);
-        else fast_row<K, false, SMALLTAB>(c, st, i, sl, wl, corner, rX, rY, rM, w);
-    } else {
-        general_row<K, SMALLTAB>(c, st, lane, i, sl, rX, rY, rM, w);
+        if (any_weights) {
+            const double wl = (vr.x & (VR_ZERO_W | VR_NOEDGE)) ? 0.0 : (double)c.l_elogw[vr.y];
+            fast_row<K, true, SMALLTAB>(c, st, i, sl, wl, corner, rX, rY, rM, w);
+        } else {
+            fast_row<K, false, SMALLTAB>(c, st, i, sl, 0.0, corner, rX, rY, rM, w);
+        }
+        return true;
     }
+    return general_step<K, SMALLTAB>(c, st, acc, lane, vr, any_saved, rX, rY, rM, w);
 }
 
 #ifndef PG2_HOST_EMU
@@ -318,10 +348,16 @@ __device__ __forceinline__ void strip_lane_step(const StripCtx &c, LaneState<K> 
 // float model parameters (F2F) inside the step loop whenever registers get tight
 __device__ __forceinline__ void pin(double &v) { asm volatile("" : "+d"(v)); }
 
+#ifndef PG2_STRIP_MINB_SIMPLE
+#define PG2_STRIP_MINB_SIMPLE 4
+#endif
+#ifndef PG2_STRIP_MINB_GENERAL
+#define PG2_STRIP_MINB_GENERAL 4
+#endif
 template <int K, bool GENERAL, bool SMALLTAB>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, GENERAL ? PG2_STRIP_MINB_GENERAL : PG2_STRIP_MINB_SIMPLE)
 strip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
-                  const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
+                  const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
                   unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
                   long long bcol_per_warp, int *queue) {
     __shared__ double2 s_tab[SMALLTAB ? 4 : 1][SMALLTAB ? STRIP_SMALL_FAS * STRIP_SMALL_FAS : 1];
@@ -346,7 +382,7 @@ strip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevG
         const DevGraph GL = graphs[J.left], GR = graphs[J.right];
         const DevModel m = models[J.model];
         StripCtx c;
-        strip_make_ctx(c, J, GL, GR, m, d_off, d_estart, d_elogw, d_rowinfo, K);
+        strip_make_ctx(c, J, GL, GR, m, d_off, d_estart, d_elogw, d_vrow, K);
         pin(c.open); pin(c.ext); pin(c.end_ext); pin(c.lng);
         c.saved = saved;
         c.ptr = ptrs + J.cell_base;
@@ -376,61 +412,63 @@ strip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevG
             c.bcol_prev = (b & 1) ? bcol0 : bcol1;
             c.bcol_cur = (b & 1) ? bcol1 : bcol0;
             LaneState<K> st;
+            LaneAcc<K> acc;
             strip_init_lane<K>(c, st, lane, r_state, r_elogw);
 #pragma unroll
-            for (int k = 0; k < K; ++k) pin(st.extX[k]);
+            for (int k = 0; k < K; ++k) { pin(st.extX[k]); acc.nX[k] = acc.nM[k] = ninf; acc.pX[k] = acc.pM[k] = NO_MAT; }
             pin(st.penY1);
             // the lane that owns the block's last valid column feeds the boundary column: every row when
             // another block follows, else only the rows the end corner reads (predecessors of the stop site)
             const int last_col = min(c.c_block + c.W, c.ly) - 1;
             const int last_lane = (last_col - c.c_block) / K, last_k = (last_col - c.c_block) % K;
-            const int bcol_need = (b + 1 < n_blocks) ? ~0 : ROWINFO_ENDPRED;
+            const int bcol_need = (b + 1 < n_blocks) ? ~0 : VR_ENDPRED;
             // lane 0 of the first block has no left neighbour: adding -inf to whatever the shuffle delivers
             // (its own column) yields the -inf boundary on the FP64 pipe, no selects
             double lane0_mask = (lane == 0 && c.first_block) ? ninf : 0.0;
             pin(lane0_mask);
-            unsigned short *out = c.ptr + ((long long)b * (c.lx + 31) * 32 + lane) * KS;
-            const int n_steps = c.lx + 31;
+            unsigned short *out = c.ptr + ((long long)b * (c.nv + 31) * 32 + lane) * KS;
+            const int n_steps = c.nv + 31;
             for (int t = 0; t < n_steps; ++t) {
                 // hand the previous step's last column to the next lane
                 double rX = __dadd_rn(__shfl_up_sync(0xffffffffu, st.X[K - 1], 1), lane0_mask);
                 double rY = __dadd_rn(__shfl_up_sync(0xffffffffu, st.Y[K - 1], 1), lane0_mask);
                 double rM = __dadd_rn(__shfl_up_sync(0xffffffffu, st.M[K - 1], 1), lane0_mask);
-                const int i = t - lane;
-                const bool active = (i >= 0 && i < c.lx);
-                int info = ROWINFO_FAST | ROWINFO_ZERO_W;
-                double wl = 0.0;
-                if (active) info = c.l_rowinfo[i];
-                bool all_fast = true, any_weights = !c.wr_zero;
+                const int v = t - lane;
+                const bool active = (v >= 0 && v < c.nv);
+                int4 vr = make_int4(VR_FAST | VR_ZERO_W, -1, 0, 0);
+                if (active) vr = __ldg(c.l_vrow + v);
+                bool all_fast = true, any_weights = !c.wr_zero, any_saved = false;
                 if (GENERAL && !left_fast) {
-                    all_fast = !__any_sync(0xffffffffu, !(info & ROWINFO_FAST));
-                    const bool lane_w = !(info & ROWINFO_ZERO_W);
-                    any_weights = __any_sync(0xffffffffu, lane_w) || !c.wr_zero;
-                    if (active && all_fast && lane_w) wl = (double)c.l_elogw[c.l_off[i]];
+                    all_fast = !__any_sync(0xffffffffu, (vr.x & VR_FAST) != VR_FAST);
+                    any_weights = __any_sync(0xffffffffu, !(vr.x & (VR_ZERO_W | VR_NOEDGE))) || !c.wr_zero;
+                    any_saved = __any_sync(0xffffffffu, active && !(vr.x & (VR_REG | VR_NOEDGE)));
                 }
                 if (active) {
-                    if (lane == 0 && !c.first_block) { double4 v = c.bcol_prev[i]; rX = v.x; rY = v.y; rM = v.z; }
+                    if (lane == 0 && !c.first_block) { double4 bv = c.bcol_prev[vr.z]; rX = bv.x; rY = bv.y; rM = bv.z; }
                     unsigned short w[KS];
                     if (KS > K) w[KS - 1] = 0;
-                    strip_lane_step<K, GENERAL, SMALLTAB>(c, st, lane, i, info, all_fast, any_weights, wl, rX, rY, rM, w);
-                    // coalesced pointer store: KS half-words per lane, step-major
-                    unsigned *dst = reinterpret_cast<unsigned *>(out + (long long)t * 32 * KS);
+                    const bool done = strip_lane_step<K, GENERAL, SMALLTAB>(c, st, acc, lane, vr, all_fast, any_weights, any_saved,
+                                                                            rX, rY, rM, w);
+                    if (done) {
+                        // coalesced pointer store: KS half-words per lane, step-major
+                        unsigned *dst = reinterpret_cast<unsigned *>(out + (long long)t * 32 * KS);
 #pragma unroll
-                    for (int h = 0; h < KS / 2; ++h) dst[h] = (unsigned)w[2 * h] | ((unsigned)w[2 * h + 1] << 16);
-                    // park rows that feed long-span edges
-                    if (GENERAL) {
-                        const int slot = (int)((unsigned)info >> ROWINFO_SLOT_SHIFT) - 1;
-                        if (slot >= 0) {
-                            double4 *row = c.saved + (long long)slot * c.W + lane * K;
+                        for (int h = 0; h < KS / 2; ++h) dst[h] = (unsigned)w[2 * h] | ((unsigned)w[2 * h + 1] << 16);
+                        // park rows that feed long-span edges
+                        if (GENERAL) {
+                            const int slot = (int)((unsigned)vr.x >> VR_SLOT_SHIFT) - 1;
+                            if (slot >= 0) {
+                                double4 *row = c.saved + (long long)slot * c.W + lane * K;
 #pragma unroll
-                            for (int k = 0; k < K; ++k) row[k] = make_double4(st.X[k], st.Y[k], st.M[k], 0.0);
+                                for (int k = 0; k < K; ++k) row[k] = make_double4(st.X[k], st.Y[k], st.M[k], 0.0);
+                            }
                         }
-                    }
-                    if (lane == last_lane && (info & bcol_need)) {
-                        double vx = ninf, vy = ninf, vm = ninf;
+                        if (lane == last_lane && (vr.x & bcol_need)) {
+                            double vx = ninf, vy = ninf, vm = ninf;
 #pragma unroll
-                        for (int k = 0; k < K; ++k) if (k == last_k) { vx = st.X[k]; vy = st.Y[k]; vm = st.M[k]; }
-                        c.bcol_cur[i] = make_double4(vx, vy, vm, 0.0);
+                            for (int k = 0; k < K; ++k) if (k == last_k) { vx = st.X[k]; vy = st.Y[k]; vm = st.M[k]; }
+                            c.bcol_cur[vr.z] = make_double4(vx, vy, vm, 0.0);
+                        }
                     }
                 }
                 __syncwarp();
@@ -446,16 +484,16 @@ strip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevG
 }
 #endif
 
-// CPU test emulation of one warp (tests/emu): the same row bodies, lanes run one after the other inside
+// CPU test emulation of one warp (tests/emu): the same step bodies, lanes run one after the other inside
 // a step with the shuffle replaced by a snapshot of the previous step.
 template <int K>
 static void strip_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &GR, const DevModel &m, const int *d_state,
-                              const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
+                              const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
                               unsigned short *ptrs, DevResult *res, double4 *saved, double4 *bcol0, double4 *bcol1) {
 #ifdef PG2_HOST_EMU
     const double ninf = neg_inf();
     StripCtx c;
-    strip_make_ctx(c, J, GL, GR, m, d_off, d_estart, d_elogw, d_rowinfo, K);
+    strip_make_ctx(c, J, GL, GR, m, d_off, d_estart, d_elogw, d_vrow, K);
     c.saved = saved;
     c.ptr = ptrs + J.cell_base;
     std::vector<double2> tab;
@@ -479,51 +517,57 @@ static void strip_emulate_job(const DevJob &J, const DevGraph &GL, const DevGrap
         c.bcol_prev = (b & 1) ? bcol0 : bcol1;
         c.bcol_cur = (b & 1) ? bcol1 : bcol0;
         LaneState<K> st[32];
-        for (int l = 0; l < 32; ++l) strip_init_lane<K>(c, st[l], l, r_state, r_elogw);
+        LaneAcc<K> acc[32];
+        for (int l = 0; l < 32; ++l) {
+            strip_init_lane<K>(c, st[l], l, r_state, r_elogw);
+            for (int k = 0; k < K; ++k) { acc[l].nX[k] = acc[l].nM[k] = ninf; acc[l].pX[k] = acc[l].pM[k] = NO_MAT; }
+        }
         const int last_col = (c.c_block + c.W < c.ly ? c.c_block + c.W : c.ly) - 1;
         const int last_lane = (last_col - c.c_block) / K, last_k = (last_col - c.c_block) % K;
-        for (int t = 0; t < c.lx + 31; ++t) {
+        const int bcol_need = (b + 1 < n_blocks) ? ~0 : VR_ENDPRED;
+        for (int t = 0; t < c.nv + 31; ++t) {
             double sx[32], sy[32], sm[32];
-            int info[32];
-            bool all_fast = true, any_weights = !c.wr_zero;
+            int4 vr[32];
+            bool all_fast = true, any_weights = !c.wr_zero, any_saved = false;
             for (int l = 0; l < 32; ++l) {
                 sx[l] = st[l].X[K - 1]; sy[l] = st[l].Y[K - 1]; sm[l] = st[l].M[K - 1];
-                const int i = t - l;
-                info[l] = (i >= 0 && i < c.lx) ? c.l_rowinfo[i] : (ROWINFO_FAST | ROWINFO_ZERO_W);
+                const int v = t - l;
+                const bool active = v >= 0 && v < c.nv;
+                vr[l] = active ? c.l_vrow[v] : make_int4(VR_FAST | VR_ZERO_W, -1, 0, 0);
                 if (!left_fast) {
-                    if (!(info[l] & ROWINFO_FAST)) all_fast = false;
-                    if (!(info[l] & ROWINFO_ZERO_W)) any_weights = true;
+                    if ((vr[l].x & VR_FAST) != VR_FAST) all_fast = false;
+                    if (!(vr[l].x & (VR_ZERO_W | VR_NOEDGE))) any_weights = true;
+                    if (active && !(vr[l].x & (VR_REG | VR_NOEDGE))) any_saved = true;
                 }
             }
             for (int l = 0; l < 32; ++l) {
-                const int i = t - l;
-                if (i < 0 || i >= c.lx) continue;
+                const int v = t - l;
+                if (v < 0 || v >= c.nv) continue;
                 double rX, rY, rM;
                 if (l == 0) {
                     if (c.first_block) rX = rY = rM = ninf;
-                    else { double4 v = c.bcol_prev[i]; rX = v.x; rY = v.y; rM = v.z; }
+                    else { double4 bv = c.bcol_prev[vr[l].z]; rX = bv.x; rY = bv.y; rM = bv.z; }
                 } else { rX = sx[l - 1]; rY = sy[l - 1]; rM = sm[l - 1]; }
-                double wl = 0.0;
-                if (!left_fast && all_fast && !(info[l] & ROWINFO_ZERO_W)) wl = (double)c.l_elogw[c.l_off[i]];
                 unsigned short w[8];
-                if (smalltab) strip_lane_step<K, true, true>(c, st[l], l, i, info[l], all_fast, any_weights, wl, rX, rY, rM, w);
-                else strip_lane_step<K, true, false>(c, st[l], l, i, info[l], all_fast, any_weights, wl, rX, rY, rM, w);
-                unsigned short *out = c.ptr + (((long long)b * (c.lx + 31) + t) * 32 + l) * KS;
+                bool done;
+                if (smalltab) done = strip_lane_step<K, true, true>(c, st[l], acc[l], l, vr[l], all_fast, any_weights, any_saved, rX, rY, rM, w);
+                else done = strip_lane_step<K, true, false>(c, st[l], acc[l], l, vr[l], all_fast, any_weights, any_saved, rX, rY, rM, w);
+                if (!done) continue;
+                unsigned short *out = c.ptr + (((long long)b * (c.nv + 31) + t) * 32 + l) * KS;
                 for (int k = 0; k < K; ++k) out[k] = w[k];
-                const int slot = (int)((unsigned)info[l] >> ROWINFO_SLOT_SHIFT) - 1;
+                const int slot = (int)((unsigned)vr[l].x >> VR_SLOT_SHIFT) - 1;
                 if (slot >= 0) {
                     double4 *row = c.saved + (long long)slot * c.W + l * K;
                     for (int k = 0; k < K; ++k) row[k] = make_double4(st[l].X[k], st[l].Y[k], st[l].M[k], 0.0);
                 }
-                const int bcol_need = (b + 1 < n_blocks) ? ~0 : ROWINFO_ENDPRED;
-                if (l == last_lane && (info[l] & bcol_need))
-                    c.bcol_cur[i] = make_double4(st[l].X[last_k], st[l].Y[last_k], st[l].M[last_k], 0.0);
+                if (l == last_lane && (vr[l].x & bcol_need))
+                    c.bcol_cur[vr[l].z] = make_double4(st[l].X[last_k], st[l].Y[last_k], st[l].M[last_k], 0.0);
             }
         }
     }
     strip_end_corner(c, ((n_blocks - 1) & 1) ? bcol1 : bcol0, r_elogw, res);
 #else
-    (void)J; (void)GL; (void)GR; (void)m; (void)d_state; (void)d_off; (void)d_estart; (void)d_elogw; (void)d_rowinfo; (void)ptrs;
+    (void)J; (void)GL; (void)GR; (void)m; (void)d_state; (void)d_off; (void)d_estart; (void)d_elogw; (void)d_vrow; (void)ptrs;
     (void)res; (void)saved; (void)bcol0; (void)bcol1;
 #endif
 }
@@ -532,7 +576,7 @@ static void strip_emulate_job(const DevJob &J, const DevGraph &GL, const DevGrap
 int strip_warps_per_sm() { return 16; }
 
 void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
-                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int *d_rowinfo,
+                       const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
                        unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
                        long long bcol_per_warp, int *queue, int n_warps, cudaStream_t stream) {
     if (n_jobs <= 0) return;
@@ -542,7 +586,7 @@ void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const Dev
     const int blocks = (n_warps * 32 + threads - 1) / threads;
 #define PG2_STRIP_LAUNCH(KK, G, S)                                                                                            \
     strip_fill_kernel<KK, G, S><<<blocks, threads, 0, stream>>>(n_jobs, jobs, job_ids, graphs, models, d_state, d_off, d_estart, \
-                                                                d_elogw, d_rowinfo, ptrs, results, saved_all, saved_per_warp,  \
+                                                                d_elogw, d_vrow, ptrs, results, saved_all, saved_per_warp,  \
                                                                 bcol_all, bcol_per_warp, queue)
 #define PG2_STRIP_CASE(KK)                                         \
     case KK:                                                       \
@@ -566,7 +610,7 @@ void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const Dev
         if (res->status != JOB_OK) continue;
         double4 *bcol0 = bcol_all, *bcol1 = bcol_all + bcol_per_warp;
         switch (K) {
-#define PG2_STRIP_CASE(KK) case KK: strip_emulate_job<KK>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_rowinfo, ptrs, res, saved_all, bcol0, bcol1); break;
+#define PG2_STRIP_CASE(KK) case KK: strip_emulate_job<KK>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, ptrs, res, saved_all, bcol0, bcol1); break;
             PG2_STRIP_CASE(2) PG2_STRIP_CASE(3) PG2_STRIP_CASE(4) PG2_STRIP_CASE(5) PG2_STRIP_CASE(6) PG2_STRIP_CASE(8)
 #undef PG2_STRIP_CASE
             default: break;

@@ -7,18 +7,32 @@ namespace pg2 {
 
 constexpr int STRIP_MAX_LEFT_INDEG = 16;
 
-// d_rowinfo[]: one word per site of a graph used as the ROW graph of the strip kernel
-//   bits 0-11  character state (0 for the start/stop sites)
-//   bit  12    fast row: exactly one backward edge, from the site just above (also set for site 0)
-//   bit  13    every backward edge of the site has log weight +0.0
-//   bit  14    the end corner reads this row's last column
-//   bits 16-31 saved-row slot + 1 when the site is the source of a long-span edge, else 0
-constexpr int ROWINFO_STATE_MASK = 0xfff;
-constexpr int ROWINFO_FAST = 1 << 12;
-constexpr int ROWINFO_ZERO_W = 1 << 13;
-constexpr int ROWINFO_ENDPRED = 1 << 14;  // bit 14: the end corner reads this row (predecessor of the stop site, or the last row)
+// d_vrow[]: the row program of a graph used as the ROW graph of the strip kernel.  A DP row with d
+// backward edges becomes d consecutive virtual rows, one edge each, so that a warp whose lanes are on
+// different rows never waits for the lane with the highest in-degree: every lane does exactly one edge per
+// step.  Entry = int4 {info, edge, site, src}:
+//   info bits 0-11  character state of the site (0 for the start site)
+//        bit  12    FIRST virtual row of the site (accumulators start at -inf)
+//        bit  13    LAST virtual row of the site (Y chain, pointers, commit)
+//        bit  14    REG: the edge starts at the site just above (source row is in registers)
+//        bit  15    ZERO_W: the edge's log weight is +0.0
+//        bit  16    ENDPRED: the end corner reads this row's last column (set on the LAST virtual row)
+//        bit  17    NOEDGE: the site has no backward edge (the start site; unreachable sites)
+//        bits 18-31 saved-row slot + 1 when the site is the source of a long-span edge (on the LAST row)
+//   edge  CSR position of the edge (graph-relative), -1 when NOEDGE
+//   site  the DP row
+//   src   bits 0-15 saved-row slot of the edge's start site (when not REG), bits 16-23 edge ordinal in the site
+constexpr int VR_STATE_MASK = 0xfff;
+constexpr int VR_FIRST = 1 << 12;
+constexpr int VR_LAST = 1 << 13;
+constexpr int VR_REG = 1 << 14;
+constexpr int VR_ZERO_W = 1 << 15;
+constexpr int VR_ENDPRED = 1 << 16;
+constexpr int VR_NOEDGE = 1 << 17;
+constexpr int VR_SLOT_SHIFT = 18;
+constexpr int VR_FAST = VR_FIRST | VR_LAST | VR_REG;  // all three: the in-place fast row applies
+constexpr int STRIP_MAX_SLOTS = 16000;
 constexpr int STRIP_SMALL_FAS = 16;       // alphabets up to this size use the shared double2 table (DNA: 15)
-constexpr int ROWINFO_SLOT_SHIFT = 16;
 
 // uint16 cell word: X ptr bits 0-5 (mat | lord<<2), Y ptr bits 6-7 (mat), M ptr bits 8-13 (mat | lord<<2)
 __host__ __device__ inline unsigned strip_word(unsigned px, unsigned py, unsigned pm) {
@@ -41,16 +55,18 @@ __host__ __device__ inline int strip_pick_k(int ly) {
     }
     return best;
 }
-__host__ __device__ inline long long strip_cells(int lx, int ly, int K) {
+// nv = virtual rows of the row graph; v = the virtual row that completes DP row i
+__host__ __device__ inline long long strip_cells(int nv, int ly, int K) {
     int W = 32 * K;
     long long blocks = (ly + W - 1) / W;
-    return blocks * (long long)(lx + 31) * 32 * strip_ks(K);
+    return blocks * (long long)(nv + 31) * 32 * strip_ks(K);
 }
-__host__ __device__ inline long long strip_ptr_index(int lx, int ly, int K, int i, int j) {
+__host__ __device__ inline long long strip_ptr_index(int nv, int ly, int K, int v, int j) {
+    (void)ly;
     int W = 32 * K;
     int b = j / W, jj = j - b * W;
     int l = jj / K, k = jj - l * K;
-    return (((long long)b * (lx + 31) + (i + l)) * 32 + l) * strip_ks(K) + k;
+    return (((long long)b * (nv + 31) + (v + l)) * 32 + l) * strip_ks(K) + k;
 }
 
 // Decodes one pointer of a strip-kernel half-word into the API encoding (mat | lord<<2 | rord<<8).

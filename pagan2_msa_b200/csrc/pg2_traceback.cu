@@ -114,6 +114,8 @@ __global__ void validate_jobs_kernel(int n_jobs, const DevJob *jobs, const DevGr
 // Cell pointer lookup for both fill kernels' layouts.
 struct TraceCtx {
     const DevJob *J;
+    const int *vlast;  // strip layout: per site of the row graph, the virtual row that completed it
+    int nv;
     const int *blo, *bhi, *dlo;
     const long long *doff;
     const unsigned *ptr32;        // wavefront layout: anti-diagonal-major, one word per cell
@@ -136,13 +138,13 @@ __device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int
         out = word_ptr(t.ptr32[J.cell_base + idx], mat);
     } else {
         if (i == 0 && j == 0) { out = NO_MAT; return true; }  // start corner: no predecessor
-        unsigned w = t.ptr16[J.cell_base + strip_ptr_index(J.lx, J.ly, J.strip_k, i, j)];
+        unsigned w = t.ptr16[J.cell_base + strip_ptr_index(t.nv, J.ly, J.strip_k, t.vlast[i], j)];
         out = strip_decode_ptr(w, mat);
     }
     return true;
 }
 
-__device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graphs, const int *d_off,
+__device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                               const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo,
                               const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps,
                               DevResult *results) {
@@ -154,6 +156,8 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
     const int *l_es = d_estart + GL.edge_base, *r_es = d_estart + GR.edge_base;
     TraceCtx tc;
     tc.J = &J;
+    tc.vlast = (J.kernel == 1) ? d_vlast + GL.vlast_base : nullptr;
+    tc.nv = GL.n_vrows;
     tc.blo = J.banded ? d_blo + J.band_base : nullptr;
     tc.bhi = J.banded ? d_bhi + J.band_base : nullptr;
     tc.dlo = J.banded ? d_dlo + J.diag_base : nullptr;
@@ -198,13 +202,14 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
 }
 
 #ifndef PG2_HOST_EMU
-__global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_off,
+__global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast,
+                                 const int *d_off,
                                  const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo,
                                  const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps,
                                  DevResult *results) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
-    traceback_one(job_ids[t], jobs, graphs, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+    traceback_one(job_ids[t], jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
 }
 #endif
 
@@ -238,18 +243,18 @@ void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *j
 #endif
 }
 
-void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_off,
+void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
                       const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps, DevResult *results, cudaStream_t stream) {
     if (n_jobs <= 0) return;
 #ifndef PG2_HOST_EMU
     const int threads = 64;
-    traceback_kernel<<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_off, d_estart, d_blo,
+    traceback_kernel<<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_vlast, d_off, d_estart, d_blo,
                                                                               d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
 #else
     (void)stream;
     for (int t = 0; t < n_jobs; ++t)
-        traceback_one(job_ids[t], jobs, graphs, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+        traceback_one(job_ids[t], jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
 #endif
 }
 

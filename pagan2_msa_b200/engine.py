@@ -49,7 +49,7 @@ _libs = {}
 
 
 def load_library(path=None):
-    path = path or LIB_PATH
+    path = path or os.environ.get("PG2_LIB") or LIB_PATH  # PG2_LIB: an alternative build of the same CUDA library (tuning)
     if path not in _libs:
         if not os.path.exists(path):
             raise Pg2Error(abi.PG2_ERR_NO_DEVICE, "%s not built (run __graft_entry__.build()); no CPU fallback exists" % path)
