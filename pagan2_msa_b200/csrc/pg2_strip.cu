@@ -352,7 +352,7 @@ __device__ __forceinline__ void pin(double &v) { asm volatile("" : "+d"(v)); }
 #define PG2_STRIP_MINB_SIMPLE 4
 #endif
 #ifndef PG2_STRIP_MINB_GENERAL
-#define PG2_STRIP_MINB_GENERAL 4
+#define PG2_STRIP_MINB_GENERAL 3
 #endif
 template <int K, bool GENERAL, bool SMALLTAB>
 __global__ void __launch_bounds__(128, GENERAL ? PG2_STRIP_MINB_GENERAL : PG2_STRIP_MINB_SIMPLE)
