@@ -99,7 +99,8 @@ typedef struct pg2_job {
 /* ---- outputs ------------------------------------------------------------------------------- */
 
 /* Result header of one job.  The traceback itself is returned compactly: n_steps packed back-pointers
- * (uint32 each) in WALK order (end corner first), at steps[step_off .. step_off+n_steps).
+ * (uint16 each: the encoding below needs 14 bits) in WALK order (end corner first), at
+ * steps[step_off .. step_off+n_steps).
  * pg2_expand_path() turns them into the reference's vector<Path_pointer>. */
 typedef struct pg2_result {
     double score;              /* Viterbi log-score == max_end.score (viterbi_alignment.cpp:1558-1566) */
@@ -149,10 +150,10 @@ int pg2_model_release(pg2_ctx *ctx, int32_t handle);
 
 /* Align n_jobs independent graph pairs: fill + end corner + traceback.  Replaces
  * viterbi_alignment.cpp:238-296 and :379-383 for each job.  `steps` receives the packed pointers of all
- * jobs back to back (capacity step_cap uint32; a job needs at most left.n_sites + right.n_sites).
+ * jobs back to back (capacity step_cap uint16; a job needs at most left.n_sites + right.n_sites).
  * Returns PG2_OK when the batch ran; per-job outcomes are in results[i].status. */
 int pg2_align_batch(pg2_ctx *ctx, int32_t n_jobs, const pg2_job *jobs, pg2_result *results,
-                    uint32_t *steps, int64_t step_cap);
+                    uint16_t *steps, int64_t step_cap);
 
 /* The same call split in three, for callers that keep a launch batch resident in HBM (and for
  * measurement: bench.py times pg2_batch_run alone for the device-resident figure):
@@ -164,7 +165,7 @@ int pg2_align_batch(pg2_ctx *ctx, int32_t n_jobs, const pg2_job *jobs, pg2_resul
 typedef struct pg2_batch pg2_batch;
 int pg2_batch_create(pg2_ctx *ctx, int32_t n_jobs, const pg2_job *jobs, pg2_batch **out);
 int pg2_batch_run(pg2_ctx *ctx, pg2_batch *batch);
-int pg2_batch_fetch(pg2_ctx *ctx, pg2_batch *batch, pg2_result *results, uint32_t *steps, int64_t step_cap);
+int pg2_batch_fetch(pg2_ctx *ctx, pg2_batch *batch, pg2_result *results, uint16_t *steps, int64_t step_cap);
 int64_t pg2_batch_step_capacity(const pg2_batch *batch);
 void pg2_batch_destroy(pg2_ctx *ctx, pg2_batch *batch);
 
@@ -176,7 +177,7 @@ void pg2_batch_destroy(pg2_ctx *ctx, pg2_batch *batch);
  * (viterbi_alignment.cpp:1054-1057,1079-1101,1128,1155), in marking order; capacities as out_steps.
  * Pure integer/FP64 host work on data the device produced; it runs no DP. */
 int pg2_expand_path(const pg2_job *job, const pg2_model_desc *model, const pg2_result *result,
-                    const uint32_t *steps, pg2_step *out_steps, int32_t *n_out,
+                    const uint16_t *steps, pg2_step *out_steps, int32_t *n_out,
                     int32_t *used_left, int32_t *n_used_left, int32_t *used_right, int32_t *n_used_right);
 
 /* Engine statistics of the last pg2_align_batch on this ctx (for bench.py): device milliseconds of

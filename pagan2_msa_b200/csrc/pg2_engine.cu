@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -35,7 +36,7 @@ int strip_warps_per_sm();
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
 void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
-                      const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps, DevResult *results, cudaStream_t stream);
+                      const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps, DevResult *results, cudaStream_t stream);
 }  // namespace pg2
 
 using namespace pg2;
@@ -152,7 +153,8 @@ struct pg2_ctx {
     DevBuf<DevModel> d_models;
     DevBuf<DevResult> d_results;
     DevBuf<double4> d_scores;
-    DevBuf<unsigned> d_ptr32, d_steps;
+    DevBuf<unsigned> d_ptr32;
+    DevBuf<unsigned short> d_steps;
     DevBuf<unsigned short> d_ptr16;
     PinVec<DevResult> h_results;
     cudaEvent_t ev[8];
@@ -260,7 +262,9 @@ struct GraphKeyHash {
     }
 };
 
-static int pack_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unordered_map<GraphKey, int, GraphKeyHash> &seen, int *gid) {
+// Phase 1 of packing (serial): de-duplicate by host-array identity and reserve staging space.
+static int reserve_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unordered_map<GraphKey, int, GraphKeyHash> &seen,
+                         std::vector<const pg2_graph *> &sources, int *gid) {
     if (g.n_sites < 2 || !g.state || !g.bwd_off || (g.n_edges > 0 && (!g.edge_start || !g.edge_logw || !g.edge_index)))
         return fail(PG2_ERR_INVALID, "graph with null arrays or fewer than 2 sites");
     GraphKey key = {g.state, g.bwd_off, g.edge_start, g.edge_logw, g.n_sites};
@@ -268,23 +272,38 @@ static int pack_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unorder
     if (it != seen.end()) { *gid = it->second; return PG2_OK; }
     int n_edges = g.bwd_off[g.n_sites];
     if (n_edges < 0 || n_edges != g.n_edges) return fail(PG2_ERR_INVALID, "graph: n_edges does not match bwd_off[n_sites]");
+    if ((long long)c->h_state.n + g.n_sites > 0x7fffffffLL || (long long)c->h_estart.n + n_edges > 0x7fffffffLL)
+        return fail(PG2_ERR_INVALID, "batch too large: more than 2^31 sites or edges; split the batch");
     DevGraph dg;
+    memset(&dg, 0, sizeof dg);
     dg.n_sites = g.n_sites;
     dg.state_base = (int)c->h_state.n;
     dg.off_base = (int)c->h_off.n;
     dg.edge_base = (int)c->h_estart.n;
-    if ((long long)c->h_state.n + g.n_sites > 0x7fffffffLL || (long long)c->h_estart.n + n_edges > 0x7fffffffLL)
-        return fail(PG2_ERR_INVALID, "batch too large: more than 2^31 sites or edges; split the batch");
-    int *ps = c->h_state.extend(g.n_sites), *po = c->h_off.extend(g.n_sites + 1), *pe = c->h_estart.extend(n_edges);
-    float *pw = c->h_elogw.extend(n_edges);
-    if (!ps || !po || !pe || !pw) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    if (!c->h_state.extend(g.n_sites) || !c->h_off.extend(g.n_sites + 1) || !c->h_estart.extend(n_edges) || !c->h_elogw.extend(n_edges))
+        return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    dg.vrow_base = -1;
+    dg.n_vrows = g.n_sites - 1;
+    dg.vlast_base = -1;
+    *gid = (int)b->graphs.size();
+    b->graphs.push_back(dg);
+    sources.push_back(&g);
+    seen.emplace(key, *gid);
+    return PG2_OK;
+}
+
+// Phase 2 of packing (any thread): copy one graph into the staging arrays and summarise its shape
+// (which fill kernel may take it; the device re-validates everything).
+static void copy_graph(pg2_ctx *c, DevGraph &dg, const pg2_graph &g) {
+    const int n_edges = g.n_edges;
+    int *ps = c->h_state.p + dg.state_base, *po = c->h_off.p + dg.off_base, *pe = c->h_estart.p + dg.edge_base;
+    float *pw = c->h_elogw.p + dg.edge_base;
     memcpy(ps, g.state, sizeof(int) * g.n_sites);
     memcpy(po, g.bwd_off, sizeof(int) * (g.n_sites + 1));
     if (n_edges) {
         memcpy(pe, g.edge_start, sizeof(int) * n_edges);
         memcpy(pw, g.edge_logw, sizeof(float) * n_edges);
     }
-    // shape summary used to pick the fill kernel (the device re-validates everything)
     int simple = 1, maxdeg = 0;
     for (int s = 0; s < g.n_sites; s++) {
         int k0 = po[s], k1 = po[s + 1];
@@ -303,16 +322,7 @@ static int pack_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unorder
     dg.max_indeg = maxdeg;
     dg.simple = simple;
     dg.zero_w = 1;
-    for (int k = 0; k < n_edges; k++) if (pw[k] != 0.0f || (pw[k] == 0.0f && std::signbit(pw[k]))) dg.zero_w = 0;
-    dg.n_slots = 0;
-    dg.vrow_base = -1;
-    dg.n_vrows = g.n_sites - 1;
-    dg.vlast_base = -1;
-    dg.pad = 0;
-    *gid = (int)b->graphs.size();
-    b->graphs.push_back(dg);
-    seen.emplace(key, *gid);
-    return PG2_OK;
+    for (int k = 0; k < n_edges; k++) if (pw[k] != 0.0f || std::signbit(pw[k])) { dg.zero_w = 0; break; }
 }
 
 // Row program of a graph used as the strip kernel's ROW graph (pg2_strip_geom.cuh): virtual rows, saved-row
@@ -437,16 +447,51 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     c->h_blo.clear(); c->h_bhi.clear(); c->h_dlo.clear(); c->h_doff.clear();
     std::unordered_map<GraphKey, int, GraphKeyHash> seen;
     seen.reserve((size_t)n_jobs * 2 + 16);
-    long long step_base = 0;
+    std::vector<const pg2_graph *> sources;
+    sources.reserve((size_t)n_jobs + 16);
+    // ---- phase 1 (serial): argument checks, graph de-duplication, staging reservations ----
     for (int t = 0; t < n_jobs; t++) {
         const pg2_job &j = jobs[t];
         DevJob &J = b->jobs[t];
         memset(&J, 0, sizeof J);
         if (j.model < 0 || j.model >= (int)c->models.size() || !c->models[j.model].live) { delete b; return fail(PG2_ERR_INVALID, "job names an unknown model handle"); }
         if ((j.upper == nullptr) != (j.lower == nullptr)) { delete b; return fail(PG2_ERR_INVALID, "job band needs both upper and lower (or neither)"); }
-        int rc = pack_graph(c, b, j.left, seen, &J.left);
-        if (rc == PG2_OK) rc = pack_graph(c, b, j.right, seen, &J.right);
+        int gl = 0, gr = 0;
+        int rc = reserve_graph(c, b, j.left, seen, sources, &gl);
+        if (rc == PG2_OK) rc = reserve_graph(c, b, j.right, seen, sources, &gr);
         if (rc != PG2_OK) { delete b; return rc; }
+        J.left = gl;
+        J.right = gr;
+    }
+    // ---- phase 2 (parallel): copy the distinct graphs into pinned staging, summarise their shape ----
+    {
+        const int ng = (int)b->graphs.size();
+        size_t total_bytes = c->h_state.n * 8 + c->h_estart.n * 8;
+        int nthreads = 1;
+        if (total_bytes > ((size_t)8 << 20)) {
+            unsigned hw = std::thread::hardware_concurrency();
+            nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+            const char *pt = getenv("PG2_PACK_THREADS");
+            if (pt && atoi(pt) > 0) nthreads = atoi(pt);
+        }
+        auto work = [&](int lo, int hi) { for (int gi = lo; gi < hi; gi++) copy_graph(c, b->graphs[gi], *sources[gi]); };
+        if (nthreads <= 1 || ng < 64) {
+            work(0, ng);
+        } else {
+            std::vector<std::thread> pool;
+            for (int w = 0; w < nthreads; w++) {
+                int lo = (int)((long long)ng * w / nthreads), hi = (int)((long long)ng * (w + 1) / nthreads);
+                pool.emplace_back(work, lo, hi);
+            }
+            for (auto &th : pool) th.join();
+        }
+    }
+    // ---- phase 3 (serial): bands, kernel choice, row programs ----
+    long long step_base = 0;
+    for (int t = 0; t < n_jobs; t++) {
+        const pg2_job &j = jobs[t];
+        DevJob &J = b->jobs[t];
+        int rc;
         J.lx = j.left.n_sites - 1;
         J.ly = j.right.n_sites - 1;
         J.model = j.model;
@@ -659,7 +704,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
     return PG2_OK;
 }
 
-extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, uint32_t *steps, int64_t step_cap) {
+extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, uint16_t *steps, int64_t step_cap) {
     if (!c || !b || c->current != b || !b->ran || (b->n_jobs > 0 && (!results || !steps))) return fail(PG2_ERR_INVALID, "pg2_batch_fetch: bad argument or batch not run");
     CU(cudaSetDevice(c->device));
     if (step_cap < b->total_steps) {
@@ -672,14 +717,14 @@ extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, ui
     CU(cudaEventRecord(c->ev[5], c->stream));
     if (b->n_jobs > 0) {
         CU(cudaMemcpyAsync(hr, c->d_results.p, sizeof(DevResult) * b->n_jobs, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(steps, c->d_steps.p, sizeof(unsigned) * (size_t)b->total_steps, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(steps, c->d_steps.p, sizeof(unsigned short) * (size_t)b->total_steps, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaEventRecord(c->ev[6], c->stream));
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]);
     c->stats.d2h_ms = ms;
-    c->stats.d2h_bytes = (long long)sizeof(DevResult) * b->n_jobs + (long long)sizeof(unsigned) * b->total_steps;
+    c->stats.d2h_bytes = (long long)sizeof(DevResult) * b->n_jobs + (long long)sizeof(unsigned short) * b->total_steps;
     for (int t = 0; t < b->n_jobs; t++) {
         const DevJob &J = b->jobs[t];
         pg2_result &r = results[t];
@@ -705,7 +750,7 @@ extern "C" void pg2_batch_destroy(pg2_ctx *c, pg2_batch *b) {
     delete b;
 }
 
-extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint32_t *steps, int64_t step_cap) {
+extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint16_t *steps, int64_t step_cap) {
     pg2_batch *b = nullptr;
     int rc = pg2_batch_create(c, n_jobs, jobs, &b);
     if (rc != PG2_OK) return rc;

@@ -58,7 +58,7 @@ struct Replay {
 
 }  // namespace
 
-extern "C" int pg2_expand_path(const pg2_job *job, const pg2_model_desc *model, const pg2_result *result, const uint32_t *steps,
+extern "C" int pg2_expand_path(const pg2_job *job, const pg2_model_desc *model, const pg2_result *result, const uint16_t *steps,
                                pg2_step *out_steps, int32_t *n_out, int32_t *used_left, int32_t *n_used_left,
                                int32_t *used_right, int32_t *n_used_right) {
     if (!job || !model || !result || !steps || !out_steps || !n_out) return PG2_ERR_INVALID;
@@ -69,7 +69,7 @@ extern "C" int pg2_expand_path(const pg2_job *job, const pg2_model_desc *model, 
     const pg2_graph &L = job->left, &R = job->right;
     const int lx = L.n_sites - 1, ly = R.n_sites - 1;
     const int cap = L.n_sites + R.n_sites;
-    const uint32_t *rec = steps + result->step_off;
+    const uint16_t *rec = steps + result->step_off;
     const int n_rec = result->n_steps;
     if (n_rec < 1) return PG2_ERR_INVALID;
 

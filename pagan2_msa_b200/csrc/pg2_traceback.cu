@@ -146,7 +146,7 @@ __device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int
 
 __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                               const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo,
-                              const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps,
+                              const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps,
                               DevResult *results) {
     const DevJob &J = jobs[jid];
     DevResult *res = results + jid;
@@ -164,7 +164,7 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
     tc.doff = J.banded ? d_doff + J.diag_base : nullptr;
     tc.ptr32 = ptr32;
     tc.ptr16 = ptr16;
-    unsigned *out = steps + J.step_base;
+    unsigned short *out = steps + J.step_base;
     int n = 0;
 
     // end pointer -> last alignment column (viterbi_alignment.cpp:1047-1069)
@@ -175,7 +175,7 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
     else if (vit == X_MAT) { i = l_es[l_off[J.lx] + ((p >> 2) & 63u)]; j = J.ly - 1; }
     else if (vit == Y_MAT) { i = J.lx - 1; j = r_es[r_off[J.ly] + ((p >> 8) & 63u)]; }
     else { res->status = JOB_NO_PATH; return; }
-    out[n++] = p;
+    out[n++] = (unsigned short)p;
 
     int status = JOB_OK;
     // the reference loop ends when (i<1 && j<1) AFTER reading the cell it stands on (:1073-1181)
@@ -183,7 +183,7 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
         unsigned q;
         if (vit == NO_MAT || !fetch_ptr(tc, vit, i, j, q)) { status = JOB_BROKEN_PATH; break; }
         if (n >= J.step_cap) { status = JOB_BROKEN_PATH; break; }
-        out[n++] = q;
+        out[n++] = (unsigned short)q;
         int src = (int)(q & 3u);
         if (vit == M_MAT) {
             int ni = (src == NO_MAT) ? -1 : l_es[l_off[i] + ((q >> 2) & 63u)];
@@ -205,7 +205,7 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
 __global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast,
                                  const int *d_off,
                                  const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo,
-                                 const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps,
+                                 const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps,
                                  DevResult *results) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
@@ -245,7 +245,7 @@ void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *j
 
 void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
-                      const unsigned *ptr32, const unsigned short *ptr16, unsigned *steps, DevResult *results, cudaStream_t stream) {
+                      const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps, DevResult *results, cudaStream_t stream) {
     if (n_jobs <= 0) return;
 #ifndef PG2_HOST_EMU
     const int threads = 64;

@@ -81,7 +81,7 @@ class Batch:
 
     def fetch(self):
         results = np.zeros(max(self.n, 1), dtype=RESULT_DTYPE)
-        steps = np.zeros(max(self.step_capacity, 1), dtype=np.uint32)
+        steps = np.zeros(max(self.step_capacity, 1), dtype=np.uint16)
         self.engine._check(self.engine.lib.pg2_batch_fetch(
             self.engine.ctx, self._h, results.ctypes.data_as(C.POINTER(abi.Result)), steps.ctypes.data, steps.shape[0]))
         return results[: self.n], steps
@@ -132,17 +132,27 @@ class Engine:
     def batch(self, jobs):
         return Batch(self, jobs)
 
-    def prepare(self, jobs):
+    def prepare(self, jobs, pinned=False):
         """Builds the pg2_job array (the caller-side host buffers of the C-ABI) once; the arrays of the
-        FlatJob objects stay owned by `jobs`.  Returns an opaque tuple for align_prepared()."""
+        FlatJob objects stay owned by `jobs`.  pinned=True puts the result / step buffers in page-locked
+        host memory (torch), which lets the device->host copy run at full PCIe rate.
+        Returns an opaque tuple for align_prepared()."""
         n = len(jobs)
         structs = (abi.Job * max(n, 1))()
         cap = 0
         for k, j in enumerate(jobs):
             structs[k] = j.as_struct(self.model_handle(j.model))
             cap += j.left.n_sites + j.right.n_sites
+        if pinned:
+            import torch
+
+            rbuf = torch.zeros(max(n, 1) * RESULT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+            sbuf = torch.zeros(max(cap, 1), dtype=torch.int16, pin_memory=True)
+            results = rbuf.numpy().view(RESULT_DTYPE)
+            steps = sbuf.numpy().view(np.uint16)
+            return (n, structs, results, steps, (jobs, rbuf, sbuf))
         results = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
-        steps = np.zeros(max(cap, 1), dtype=np.uint32)
+        steps = np.zeros(max(cap, 1), dtype=np.uint16)
         return (n, structs, results, steps, jobs)
 
     def align_prepared(self, prep):

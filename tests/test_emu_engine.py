@@ -121,7 +121,7 @@ def test_invalid_arguments(emu_lib):
         import ctypes as C
         arr = (abi.Job * 1)(js)
         res = (abi.Result * 1)()
-        steps = np.zeros(1000, np.uint32)
+        steps = np.zeros(1000, np.uint16)
         rc = eng.lib.pg2_align_batch(eng.ctx, 1, arr, res, steps.ctypes.data, 1000)
         assert rc == abi.PG2_ERR_INVALID
         assert b"model" in eng.lib.pg2_last_error()
