@@ -86,6 +86,13 @@ class Batch:
             self.engine.ctx, self._h, results.ctypes.data_as(C.POINTER(abi.Result)), steps.ctypes.data, steps.shape[0]))
         return results[: self.n], steps
 
+    def device_buffers(self):
+        """pg2_batch_device_buffers -> (address of the 24-byte result records, address of the packed-pointer
+        buffer, its length in uint16) of the last run, for GPU-to-GPU forwarding (shard.py)."""
+        rp, sp, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self.engine._check(self.engine.lib.pg2_batch_device_buffers(self.engine.ctx, self._h, C.byref(rp), C.byref(sp), C.byref(n)))
+        return rp.value or 0, sp.value or 0, n.value
+
     def close(self):
         if self._h:
             self.engine.lib.pg2_batch_destroy(self.engine.ctx, self._h)
@@ -96,6 +103,19 @@ class Batch:
 
     def __exit__(self, *a):
         self.close()
+
+
+def results_from_records(records, step_off, jobs):
+    """RESULT_DTYPE array (what pg2_batch_fetch returns) from gathered shard records (shard.assemble)."""
+    res = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+    res["score"] = records["score"]
+    res["cells"] = [j.cells for j in jobs]
+    res["step_off"] = step_off
+    res["n_steps"] = records["n_steps"]
+    res["status"] = np.where(records["status"] == 5, abi.PG2_JOB_BAD_GRAPH, records["status"])  # JOB_UNSUPPORTED, as pg2_batch_fetch
+    res["end_ptr"] = records["end_ptr"]
+    res["kernel"] = -1
+    return res
 
 
 class Engine:
