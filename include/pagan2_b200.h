@@ -109,7 +109,8 @@ typedef struct pg2_result {
     int32_t n_steps;           /* number of packed pointers (end pointer + one per visited cell) */
     int32_t status;            /* PG2_JOB_* */
     uint32_t end_ptr;          /* packed end-corner pointer (same encoding as steps[]) */
-    int32_t kernel;            /* which fill kernel ran: 0 = wavefront (general), 1 = strip (fast path) */
+    int32_t kernel;            /* which fill kernel ran: 0 = wavefront (general), 1 = strip (warp per alignment),
+                                  2 = lanes (lane per alignment, jobs sharing the left graph) */
 } pg2_result;
 
 /* Packed back-pointer: bits 0-1 source matrix (PG2_*_MAT, 3 = none), bits 2-7 ordinal of the LEFT
@@ -194,6 +195,8 @@ typedef struct pg2_stats {
     double run_ms;             /* validation + all fill + all traceback launches of the last pg2_batch_run */
     int32_t kernel_launches;   /* kernels launched by the last pg2_batch_run */
     int32_t jobs_strip_groups;
+    int32_t jobs_lanes;        /* jobs the lane-per-alignment kernel took (shared row graph) */
+    int32_t reserved;
 } pg2_stats;
 int pg2_get_stats(pg2_ctx *ctx, pg2_stats *out);
 

@@ -111,6 +111,8 @@ class Stats(C.Structure):
         ("run_ms", C.c_double),
         ("kernel_launches", C.c_int32),
         ("jobs_strip_groups", C.c_int32),
+        ("jobs_lanes", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -57,7 +57,7 @@ struct DevJob {
     int model;           // index into the DevModel array
     unsigned flags;
     int banded;
-    short kernel;        // 0 wavefront, 1 strip
+    short kernel;        // 0 wavefront, 1 strip, 2 lanes
     short strip_general; // strip kernel: 1 = left graph needs the general row body, 0 = plain unit-weight chain
     long long band_base; // into d_blo / d_bhi (lx entries)
     long long diag_base; // into d_dlo / d_doff (lx+ly-1 entries)
@@ -66,7 +66,22 @@ struct DevJob {
     long long ptr_cells; // pointer-buffer entries this job occupies in its kernel's layout
     long long step_base; // into the steps buffer
     int step_cap;
-    int strip_k;         // strip kernel: columns per lane
+    int strip_k;         // strip / lane kernel: columns per lane
+    int lane;            // lane kernel: the job's lane in its task (cell_base = the task's pointer region)
+    int task;            // lane kernel: task index
+};
+
+// Lane kernel work item: up to 32 alignments that share the LEFT (row) graph, model and flags; every right
+// graph is a plain chain.  One warp takes one task, one alignment per lane.
+struct LaneTask {
+    int left;            // DevGraph index of the shared row graph
+    int model;
+    unsigned flags;
+    int n_jobs;          // valid lanes (1..32)
+    int max_ly;          // longest DP column count among the lanes
+    int variant;         // bit 0 general row body, bit 1 shared small table, bit 2 right graphs carry weights
+    long long ptr_base;  // into the group's pointer buffer (half-words)
+    int job_ids[32];
 };
 
 struct DevResult {

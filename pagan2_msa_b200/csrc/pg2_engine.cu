@@ -33,6 +33,11 @@ void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const Dev
                        unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
                        long long bcol_per_warp, int *queue, int n_warps, cudaStream_t stream);
 int strip_warps_per_sm();
+void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
+                      const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
+                      const int4 *d_vrow, unsigned short *ptrs, DevResult *results, double *scratch, long long bcol_doubles,
+                      long long warp_doubles, int *queue, int n_warps, cudaStream_t stream);
+int lane_warps_per_sm();
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
 void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
@@ -110,7 +115,9 @@ struct ModelRec {
 };
 
 struct Group {
-    int kernel;        // 0 wavefront, 1 strip
+    int kernel;        // 0 wavefront, 1 strip, 2 lanes
+    int variant = 0;   // lane kernel: template variant shared by the group's tasks
+    int task_first = 0, task_count = 0;  // lane kernel: range in batch->tasks
     int strip_k;       // strip kernel: columns per lane (all jobs of the group share it)
     int strip_general; // strip kernel: general row body needed
     int first, count;  // range in batch->order
@@ -125,6 +132,7 @@ struct pg2_batch {
     std::vector<DevGraph> graphs;
     std::vector<int> order;  // job ids sorted by (kernel, -cells)
     std::vector<Group> groups;
+    std::vector<LaneTask> tasks;  // lane kernel work items, group by group
     long long total_steps = 0;
     long long total_cells = 0;
     long long h2d_bytes = 0;
@@ -140,12 +148,16 @@ struct pg2_ctx {
     bool models_dirty = true;
     size_t scratch_bytes = (size_t)64 << 30;  // pointer/score scratch per launch group (PG2_SCRATCH_MB overrides)
     bool force_wavefront = false;  // PG2_FORCE_WAVEFRONT=1: route every job through the general kernel (tests)
+    bool no_lanes = false;         // PG2_NO_LANES=1: keep shared-target jobs on the warp-per-alignment strip kernel (tests)
+    size_t lane_scratch_bytes = (size_t)8 << 30;  // cap of the lane kernel's per-warp boundary/saved-row scratch
     // staging (pinned) and device arrays of the current batch
     PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_vrow, h_vlast;
     PinVec<float> h_elogw;
     PinVec<long long> h_doff;
     DevBuf<int> d_state, d_off, d_estart, d_blo, d_bhi, d_dlo, d_order, d_graph_status, d_vrow, d_vlast, d_queue;
     DevBuf<double4> d_saved, d_bcol;
+    DevBuf<double> d_lane_scratch;
+    DevBuf<LaneTask> d_tasks;
     DevBuf<float> d_elogw;
     DevBuf<long long> d_doff;
     DevBuf<DevJob> d_jobs;
@@ -186,6 +198,8 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
     for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
     const char *fw = getenv("PG2_FORCE_WAVEFRONT");
     c->force_wavefront = fw && atoi(fw) != 0;
+    const char *nl = getenv("PG2_NO_LANES");
+    c->no_lanes = nl && atoi(nl) != 0;
     const char *mb = getenv("PG2_SCRATCH_MB");
     if (mb && atoll(mb) > 0) c->scratch_bytes = (size_t)atoll(mb) << 20;
     size_t cap = c->prop.totalGlobalMem / 100 * 45;  // leave room for inputs, steps and the caller
@@ -206,7 +220,7 @@ extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
     c->d_state.release(); c->d_off.release(); c->d_estart.release(); c->d_blo.release(); c->d_bhi.release(); c->d_dlo.release();
     c->d_order.release(); c->d_graph_status.release(); c->d_elogw.release(); c->d_doff.release(); c->d_jobs.release();
     c->d_graphs.release(); c->d_models.release(); c->d_results.release(); c->d_scores.release(); c->d_ptr32.release();
-    c->d_steps.release(); c->d_ptr16.release();
+    c->d_steps.release(); c->d_ptr16.release(); c->d_lane_scratch.release(); c->d_tasks.release();
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -525,10 +539,106 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     b->total_steps = step_base;
     b->n_graphs = (int)b->graphs.size();
 
-    // order: strip jobs first, larger jobs first inside a class (tail balance)
-    b->order.resize(n_jobs);
-    for (int t = 0; t < n_jobs; t++) b->order[t] = t;
-    std::stable_sort(b->order.begin(), b->order.end(), [&](int x, int y) {
+    // ---- lane kernel tasks: strip-eligible jobs that share the row graph, model and flags, 32 per warp ----
+    std::vector<int> lane_order;  // job ids, task by task
+    if (!c->no_lanes && !c->force_wavefront) {
+        std::unordered_map<unsigned long long, int> bucket_of;
+        std::vector<std::vector<int> > buckets;
+        for (int t = 0; t < n_jobs; t++) {
+            const DevJob &J = b->jobs[t];
+            if (J.kernel != 1) continue;
+            const DevGraph &GL = b->graphs[J.left];
+            if ((size_t)lane_warp_doubles(J.lx, GL.n_slots, LANE_K) * sizeof(double) > c->lane_scratch_bytes / 64) continue;
+            unsigned long long key = ((unsigned long long)(unsigned)J.left << 32) | ((unsigned long long)(unsigned)J.model << 2) | (J.flags & 3u);
+            auto it = bucket_of.find(key);
+            if (it == bucket_of.end()) { it = bucket_of.emplace(key, (int)buckets.size()).first; buckets.emplace_back(); }
+            buckets[it->second].push_back(t);
+        }
+        for (auto &bk : buckets) {
+            if ((int)bk.size() < LANE_MIN_JOBS) continue;
+            // lanes of one task sweep max_ly columns: put reads of similar length together
+            std::stable_sort(bk.begin(), bk.end(), [&](int x, int y) { return b->jobs[x].ly > b->jobs[y].ly; });
+            for (size_t pos = 0; pos < bk.size(); pos += 32) {
+                const int n = (int)std::min<size_t>(32, bk.size() - pos);
+                if (n < LANE_MIN_JOBS) break;  // a thin remainder stays on the strip kernel
+                const DevJob &J0 = b->jobs[bk[pos]];
+                const DevGraph &GL = b->graphs[J0.left];
+                LaneTask T;
+                memset(&T, 0, sizeof T);
+                T.left = J0.left;
+                T.model = J0.model;
+                T.flags = J0.flags;
+                T.n_jobs = n;
+                T.max_ly = J0.ly;
+                T.variant = ((GL.simple && GL.zero_w) ? 0 : 1) | (c->models[J0.model].fas <= STRIP_SMALL_FAS ? 2 : 0);
+                for (int l = 0; l < n; l++) {
+                    DevJob &J = b->jobs[bk[pos + l]];
+                    T.job_ids[l] = bk[pos + l];
+                    if (!b->graphs[J.right].zero_w) T.variant |= 4;
+                    J.kernel = 2;
+                    J.strip_k = LANE_K;
+                    J.lane = l;
+                    J.task = (int)b->tasks.size();
+                    J.ptr_cells = 0;
+                }
+                b->tasks.push_back(T);
+            }
+        }
+        // tasks of one variant form a launch; costly tasks first (tail balance)
+        std::vector<int> torder(b->tasks.size());
+        for (size_t k = 0; k < torder.size(); k++) torder[k] = (int)k;
+        auto cost = [&](int k) { const LaneTask &T = b->tasks[k]; return lane_cells(b->graphs[T.left].n_vrows, T.max_ly, LANE_K); };
+        std::stable_sort(torder.begin(), torder.end(), [&](int x, int y) {
+            if (b->tasks[x].variant != b->tasks[y].variant) return b->tasks[x].variant < b->tasks[y].variant;
+            return cost(x) > cost(y);
+        });
+        std::vector<LaneTask> sorted;
+        sorted.reserve(torder.size());
+        for (int k : torder) sorted.push_back(b->tasks[k]);
+        b->tasks.swap(sorted);
+        size_t tpos = 0;
+        while (tpos < b->tasks.size()) {
+            Group g;
+            g.kernel = 2;
+            g.variant = b->tasks[tpos].variant;
+            g.strip_k = LANE_K;
+            g.strip_general = 0;
+            g.first = (int)lane_order.size();
+            g.count = 0;
+            g.cells = 0;
+            g.max_diag = 1;
+            g.max_slots = 0;
+            g.max_lx = 1;
+            g.task_first = (int)tpos;
+            g.task_count = 0;
+            while (tpos < b->tasks.size() && b->tasks[tpos].variant == g.variant) {
+                LaneTask &T = b->tasks[tpos];
+                const DevGraph &GL = b->graphs[T.left];
+                const long long need = lane_cells(GL.n_vrows, T.max_ly, LANE_K);
+                if (g.task_count > 0 && (size_t)(g.cells + need) * 2 > c->scratch_bytes) break;
+                T.ptr_base = g.cells;
+                g.cells += need;
+                g.max_slots = std::max(g.max_slots, GL.n_slots);
+                g.max_lx = std::max(g.max_lx, GL.n_sites - 1);
+                for (int l = 0; l < T.n_jobs; l++) {
+                    DevJob &J = b->jobs[T.job_ids[l]];
+                    J.task = (int)tpos;
+                    J.cell_base = T.ptr_base;
+                    lane_order.push_back(T.job_ids[l]);
+                }
+                g.count += T.n_jobs;
+                g.task_count++;
+                tpos++;
+            }
+            b->groups.push_back(g);
+        }
+    }
+
+    // order: lane jobs (task by task), then strip jobs, then wavefront jobs; larger jobs first inside a class
+    // (tail balance)
+    b->order = lane_order;
+    for (int t = 0; t < n_jobs; t++) if (b->jobs[t].kernel != 2) b->order.push_back(t);
+    std::stable_sort(b->order.begin() + lane_order.size(), b->order.end(), [&](int x, int y) {
         const DevJob &A = b->jobs[x], &B = b->jobs[y];
         if (A.kernel != B.kernel) return A.kernel > B.kernel;
         if (A.strip_k != B.strip_k) return A.strip_k < B.strip_k;
@@ -536,7 +646,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         return A.cells > B.cells;
     });
     // groups under the scratch budget: wavefront 36 B/cell (scores + pointer word), strip 2 B/cell
-    size_t pos = 0;
+    size_t pos = lane_order.size();
     while (pos < b->order.size()) {
         Group g;
         g.kernel = b->jobs[b->order[pos]].kernel;
@@ -577,7 +687,7 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     ENS(c->d_blo, c->h_blo.n + 1); ENS(c->d_bhi, c->h_bhi.n + 1); ENS(c->d_dlo, c->h_dlo.n + 1); ENS(c->d_doff, c->h_doff.n + 1);
     ENS(c->d_jobs, b->jobs.size() + 1); ENS(c->d_graphs, b->graphs.size() + 1); ENS(c->d_order, b->order.size() + 1);
     ENS(c->d_graph_status, b->graphs.size() + 1); ENS(c->d_results, b->jobs.size() + 1); ENS(c->d_steps, (size_t)b->total_steps + 1);
-    ENS(c->d_models, c->models.size() + 1);
+    ENS(c->d_models, c->models.size() + 1); ENS(c->d_tasks, b->tasks.size() + 1);
     long long bytes = 0;
 #define H2D(dst, src, n, T)                                                                                 \
     if ((n) > 0) { CU(cudaMemcpyAsync((dst).p, (src), (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, c->stream)); bytes += (long long)(n) * sizeof(T); }
@@ -594,6 +704,7 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     H2D(c->d_jobs, b->jobs.data(), b->jobs.size(), DevJob);
     H2D(c->d_graphs, b->graphs.data(), b->graphs.size(), DevGraph);
     H2D(c->d_order, b->order.data(), b->order.size(), int);
+    H2D(c->d_tasks, b->tasks.data(), b->tasks.size(), LaneTask);
     {
         std::vector<DevModel> dm(c->models.size());
         for (size_t i = 0; i < dm.size(); i++) dm[i] = c->models[i].dev;
@@ -628,7 +739,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
     }
     // scratch for the largest group of each class
     long long max_w = 0, max_s = 0;
-    for (auto &g : b->groups) (g.kernel == 0 ? max_w : max_s) = std::max(g.kernel == 0 ? max_w : max_s, g.cells);
+    for (auto &g : b->groups) (g.kernel == 0 ? max_w : max_s) = std::max(g.kernel == 0 ? max_w : max_s, g.cells);  // strip and lane groups share d_ptr16
     if (max_w > 0) {
         if ((rc = c->d_scores.ensure((size_t)max_w)) != PG2_OK) return fail(rc, "score scratch allocation failed");
         if ((rc = c->d_ptr32.ensure((size_t)max_w)) != PG2_OK) return fail(rc, "pointer buffer allocation failed");
@@ -639,6 +750,17 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
 #else
     const int resident_warps = c->prop.multiProcessorCount * strip_warps_per_sm();
 #endif
+    const int lane_resident = c->prop.multiProcessorCount * lane_warps_per_sm();
+    auto lane_warps = [&](const Group &g) {
+        const size_t per_warp = (size_t)lane_warp_doubles(g.max_lx, g.max_slots, LANE_K) * sizeof(double);
+        size_t fit = std::max<size_t>(c->lane_scratch_bytes / per_warp, 1);
+        return (int)std::min<size_t>(std::min<size_t>(fit, (size_t)lane_resident), (size_t)std::max(g.task_count, 1));
+    };
+    for (auto &g : b->groups)
+        if (g.kernel == 2) {
+            size_t need = (size_t)lane_warp_doubles(g.max_lx, g.max_slots, LANE_K) * lane_warps(g);
+            if ((rc = c->d_lane_scratch.ensure(need)) != PG2_OK) return fail(rc, "lane scratch allocation failed");
+        }
     for (auto &g : b->groups)
         if (g.kernel == 1) {
             int warps = std::min(resident_warps, std::max(g.count, 1));
@@ -653,7 +775,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
                     c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, c->stream);
     st.fill_ms = st.traceback_ms = 0;
     st.fill_launches = st.traceback_launches = 0;
-    st.jobs_wavefront = st.jobs_strip = 0;
+    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = 0;
     st.jobs_strip_groups = 0;
     st.cells = b->total_cells;
     st.traceback_bytes = 0;
@@ -670,6 +792,14 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
                                   c->d_ptr32.p, c->d_results.p, c->stream);
             st.jobs_wavefront += g.count;
             st.traceback_bytes += g.cells * 4;
+        } else if (g.kernel == 2) {
+            launch_lane_fill(g.variant, g.task_count, c->d_tasks.p + g.task_first, c->d_jobs.p, c->d_graphs.p, c->d_models.p, c->d_state.p,
+                             c->d_off.p, c->d_estart.p, c->d_elogw.p, reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_ptr16.p,
+                             c->d_results.p, c->d_lane_scratch.p, lane_bcol_doubles(g.max_lx),
+                             lane_warp_doubles(g.max_lx, g.max_slots, LANE_K), c->d_queue.p, lane_warps(g), c->stream);
+            st.jobs_lanes += g.count;
+            st.jobs_strip_groups++;
+            st.traceback_bytes += g.cells * 2;
         } else {
             int warps = std::min(resident_warps, std::max(g.count, 1));
             launch_strip_fill(g.strip_k, (g.strip_general & 1) != 0, (g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,

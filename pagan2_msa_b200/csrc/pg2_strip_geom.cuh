@@ -69,6 +69,28 @@ __host__ __device__ inline long long strip_ptr_index(int nv, int ly, int K, int 
     return (((long long)b * (nv + 31) + (v + l)) * 32 + l) * strip_ks(K) + k;
 }
 
+// ---- lane kernel (pg2_lanes.cu): 32 alignments that share the row graph, one per lane -----------------
+// Pointer buffer of one task: [strip][virtual row][K/8][lane] uint4, i.e. 8 half-words (8 columns) per lane
+// per 128-bit store, lanes interleaved so that a warp-wide store is one contiguous 512 B segment.
+constexpr int LANE_K = 8;             // columns per lane strip (multiple of 8)
+constexpr int LANE_MIN_JOBS = 16;     // fewer jobs on one row graph than this stay on the strip kernel
+__host__ __device__ inline long long lane_cells(int nv, int max_ly, int K) {  // half-words per task
+    long long strips = (max_ly + K - 1) / K;
+    return strips * (long long)nv * 32 * K;
+}
+__host__ __device__ inline long long lane_ptr_index(int nv, int K, int v, int j, int lane) {
+    int s = j / K, k = j - s * K;
+    return ((((long long)s * nv + v) * (K / 8) + (k >> 3)) * 32 + lane) * 8 + (k & 7);
+}
+
+// per-warp scratch of the lane kernel, in doubles: two boundary-column buffers [row][X,Y,M][lane] and the
+// saved rows [slot][k][X,Y,M][lane]
+__host__ __device__ inline long long lane_bcol_doubles(int max_lx) { return (long long)max_lx * 96; }
+__host__ __device__ inline long long lane_saved_doubles(int n_slots, int K) { return (long long)n_slots * K * 96; }
+__host__ __device__ inline long long lane_warp_doubles(int max_lx, int n_slots, int K) {
+    return 2 * lane_bcol_doubles(max_lx) + lane_saved_doubles(n_slots > 0 ? n_slots : 1, K);
+}
+
 // Decodes one pointer of a strip-kernel half-word into the API encoding (mat | lord<<2 | rord<<8).
 __host__ __device__ inline unsigned strip_decode_ptr(unsigned w, int mat) {
     if (w & 0x4000u) {  // fast row: raw comparison bits, single left edge (ordinal 0)

@@ -138,8 +138,9 @@ __device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int
         out = word_ptr(t.ptr32[J.cell_base + idx], mat);
     } else {
         if (i == 0 && j == 0) { out = NO_MAT; return true; }  // start corner: no predecessor
-        unsigned w = t.ptr16[J.cell_base + strip_ptr_index(t.nv, J.ly, J.strip_k, t.vlast[i], j)];
-        out = strip_decode_ptr(w, mat);
+        const long long idx = J.kernel == 2 ? lane_ptr_index(t.nv, LANE_K, t.vlast[i], j, J.lane)
+                                            : strip_ptr_index(t.nv, J.ly, J.strip_k, t.vlast[i], j);
+        out = strip_decode_ptr(t.ptr16[J.cell_base + idx], mat);
     }
     return true;
 }
@@ -156,7 +157,7 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
     const int *l_es = d_estart + GL.edge_base, *r_es = d_estart + GR.edge_base;
     TraceCtx tc;
     tc.J = &J;
-    tc.vlast = (J.kernel == 1) ? d_vlast + GL.vlast_base : nullptr;
+    tc.vlast = (J.kernel != 0) ? d_vlast + GL.vlast_base : nullptr;
     tc.nv = GL.n_vrows;
     tc.blo = J.banded ? d_blo + J.band_base : nullptr;
     tc.bhi = J.banded ? d_bhi + J.band_base : nullptr;

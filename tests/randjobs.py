@@ -89,3 +89,26 @@ def random_job(rng, kind="general", fas=15):
         up, lo = random_band(rng, left.n_sites - 1, right.n_sites - 1)
         job.upper, job.lower = up, lo
     return job
+
+
+def random_shared_target_jobs(rng, n_jobs, fas=15, plain_left=False, weights=None, nl=None, nr_max=70):
+    """Placement-shaped launch batch: n_jobs reads (plain chains of varying length) against ONE left graph,
+    same model and flags -- what the lane-per-alignment kernel groups into tasks of 32."""
+    ties = rng.random() < 0.4
+    model = random_model(rng, fas, ties)
+    flags = int(rng.integers(0, 4))
+    nl = int(rng.integers(3, 90)) if nl is None else nl
+    if plain_left:
+        left = FlatGraph.chain(rng.integers(0, fas, size=nl).astype(np.int32))
+    else:
+        left = random_graph(rng, nl, fas, tie_weights=ties)
+    if weights is None:
+        weights = rng.random() < 0.3
+    jobs = []
+    for _ in range(n_jobs):
+        nr = int(rng.integers(1, nr_max))
+        right = FlatGraph.chain(rng.integers(0, fas, size=nr).astype(np.int32))
+        if weights and rng.random() < 0.5:
+            right.logw[:] = np.log(rng.uniform(0.2, 1.0, size=right.logw.shape[0]).astype(np.float32))
+        jobs.append(FlatJob(left, right, model, flags))
+    return jobs

@@ -23,12 +23,14 @@ def emu_lib():
     return EMU_LIB
 
 
-def make_engine(lib, force_wavefront):
+def make_engine(lib, force_wavefront, no_lanes=False):
     os.environ["PG2_FORCE_WAVEFRONT"] = "1" if force_wavefront else "0"
+    os.environ["PG2_NO_LANES"] = "1" if no_lanes else "0"
     try:
         return engine.Engine(0, lib)
     finally:
         os.environ.pop("PG2_FORCE_WAVEFRONT", None)
+        os.environ.pop("PG2_NO_LANES", None)
 
 
 @pytest.mark.parametrize("force_wavefront", [True, False])
@@ -41,9 +43,42 @@ def test_golden(emu_lib, golden, name, force_wavefront):
 
 
 def test_strip_kernel_is_chosen_for_placement(emu_lib, golden):
-    with make_engine(emu_lib, False) as eng:
+    with make_engine(emu_lib, False, no_lanes=True) as eng:
         res = enginecheck.check_batch(eng, golden["place_dna"])
         assert (res["kernel"] == 1).all()
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, golden["place_dna"])
+        assert np.isin(res["kernel"], (1, 2)).all()
+
+
+@pytest.mark.parametrize("seed,plain_left,n_jobs", [(61, False, 70), (62, True, 40), (63, False, 33), (64, False, 16), (65, True, 100)])
+def test_lane_kernel_shared_target_vs_oracle(emu_lib, seed, plain_left, n_jobs):
+    """Jobs that share the left graph are grouped 32 per warp, one alignment per lane (pg2_lanes.cu): every
+    variant (plain / general rows, weights on the read edges), ragged read lengths, thin remainders."""
+    rng = np.random.default_rng(seed)
+    jobs = []
+    for _ in range(3):
+        jobs += randjobs.random_shared_target_jobs(rng, n_jobs, plain_left=plain_left)
+    jobs += [randjobs.random_job(rng, "strip") for _ in range(5)]  # singletons stay on the strip kernel
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, jobs)
+        st = eng.stats()
+    assert (res["kernel"][:3 * n_jobs] == 2).sum() >= 3 * (n_jobs // 32) * 32
+    assert (res["kernel"][-5:] == 1).all()
+    assert st["jobs_lanes"] == int((res["kernel"] == 2).sum())
+
+
+def test_lane_kernel_long_reads_and_bad_job(emu_lib):
+    """Reads longer than one strip x many strips, and a rejected job inside a task (its lane idles)."""
+    rng = np.random.default_rng(66)
+    jobs = randjobs.random_shared_target_jobs(rng, 40, nl=60, nr_max=200)
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    jobs[7].right.state[1] = 99
+    jobs[7].expected_status = abi.PG2_JOB_BAD_GRAPH
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 2).sum() == 32
 
 
 @pytest.mark.parametrize("kind,seed", [("general", 21), ("banded", 22), ("strip", 23)])

@@ -45,9 +45,73 @@ def test_golden_wavefront_kernel(eng_wave, golden, name):
     assert (res["kernel"] == 0).all()
 
 
-def test_placement_uses_strip_kernel(eng, golden):
+@pytest.fixture(scope="module")
+def eng_nolanes():
+    os.environ["PG2_NO_LANES"] = "1"
+    try:
+        e = engine.Engine(0)
+    finally:
+        os.environ.pop("PG2_NO_LANES", None)
+    yield e
+    e.close()
+
+
+def test_placement_uses_register_strip_kernels(eng, eng_nolanes, golden):
     res = enginecheck.check_batch(eng, golden["place_dna"])
+    assert np.isin(res["kernel"], (1, 2)).all()
+    res = enginecheck.check_batch(eng_nolanes, golden["place_dna"])
     assert (res["kernel"] == 1).all()
+
+
+@pytest.mark.parametrize("seed,plain_left,n_jobs", [(161, False, 70), (162, True, 40), (163, False, 33), (164, False, 16), (165, True, 100)])
+def test_lane_kernel_shared_target_vs_oracle(eng, seed, plain_left, n_jobs):
+    """Jobs sharing the left graph run one alignment per lane (pg2_lanes.cu): all template variants, ragged read
+    lengths, thin remainders, singletons left to the strip kernel."""
+    rng = np.random.default_rng(seed)
+    jobs = []
+    for _ in range(6):
+        jobs += randjobs.random_shared_target_jobs(rng, n_jobs, plain_left=plain_left)
+    jobs += [randjobs.random_job(rng, "strip") for _ in range(5)]
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"][:6 * n_jobs] == 2).sum() >= 6 * (n_jobs // 32) * 32
+    assert (res["kernel"][-5:] == 1).all()
+
+
+def test_lane_kernel_long_reads_and_bad_job(eng):
+    rng = np.random.default_rng(166)
+    jobs = randjobs.random_shared_target_jobs(rng, 40, nl=60, nr_max=200)
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    jobs[7].right.state[1] = 99
+    jobs[7].expected_status = abi.PG2_JOB_BAD_GRAPH
+    res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 2).sum() == 32
+
+
+def test_lane_and_strip_kernels_agree_bitwise(eng, eng_nolanes, golden):
+    """The same placement batch through the lane kernel and through the strip kernel: identical bits."""
+    model = golden["place_dna"][0].model
+    rng = np.random.default_rng(167)
+    targets = [j.left for j in golden["place_dna"][:4]]
+    reads, assign = [], []
+    for k in range(400):
+        a = int(rng.integers(0, len(targets)))
+        seq = targets[a].state[1:-1]
+        st = int(rng.integers(0, max(1, len(seq) - 150)))
+        r = seq[st:st + int(rng.integers(30, 151))].copy()
+        r = np.where(r < 4, r, 0).astype(np.int32)
+        reads.append(r)
+        assign.append(a)
+    jobs = synth.placement_jobs(targets, reads, assign, model)
+    ra, sa = eng.align(jobs)
+    rb, sb = eng_nolanes.align(jobs)
+    assert (ra["kernel"] == 2).sum() >= 300 and (rb["kernel"] == 1).all()
+    assert (ra["status"] == 0).all()
+    assert (ra["score"].view(np.uint64) == rb["score"].view(np.uint64)).all()
+    for k, job in enumerate(jobs):
+        pa, _, _ = eng.expand(job, ra[k], sa)
+        pb, _, _ = eng_nolanes.expand(job, rb[k], sb)
+        assert pa.tobytes() == pb.tobytes()
 
 
 @pytest.mark.parametrize("kind,seed", [("general", 121), ("banded", 122), ("strip", 123)])
@@ -62,7 +126,7 @@ def test_both_kernels_agree_on_strip_jobs(eng, eng_wave):
     jobs = [randjobs.random_job(rng, "strip") for _ in range(200)]
     ra, sa = eng.align(jobs)
     rb, sb = eng_wave.align(jobs)
-    assert (ra["kernel"] == 1).all() and (rb["kernel"] == 0).all()
+    assert np.isin(ra["kernel"], (1, 2)).all() and (rb["kernel"] == 0).all()
     assert (ra["score"].view(np.uint64) == rb["score"].view(np.uint64)).all()
     for k, job in enumerate(jobs):
         pa, _, _ = eng.expand(job, ra[k], sa)
@@ -105,7 +169,7 @@ def test_placement_config_scale_properties(eng, golden):
         assign.append(a)
     jobs = synth.placement_jobs(targets, reads, assign, model)
     res, steps = eng.align(jobs)
-    assert (res["status"] == 0).all() and (res["kernel"] == 1).all()
+    assert (res["status"] == 0).all() and (res["kernel"] == 2).all()
     res2, steps2 = eng.align(jobs)
     assert res.tobytes() == res2.tobytes() and steps.tobytes() == steps2.tobytes()
     for k in range(0, 4096, 64):
