@@ -35,9 +35,9 @@ void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const Dev
 int strip_warps_per_sm();
 void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
                       const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
-                      const int4 *d_vrow, unsigned short *ptrs, DevResult *results, double *scratch, long long bcol_doubles,
-                      long long warp_doubles, int *queue, int n_warps, cudaStream_t stream);
-int lane_warps_per_sm();
+                      const int4 *d_vrow, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv, int max_lx,
+                      int max_slots, int *queue, int n_ctas, cudaStream_t stream);
+int lane_ctas_per_sm();
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
 void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
@@ -124,6 +124,7 @@ struct Group {
     long long cells;   // pointer-buffer entries of the group
     int max_diag;
     int max_slots, max_lx;  // strip kernel per-warp scratch: saved rows, boundary column
+    int max_nv = 1;         // lane kernel: longest row program
 };
 
 struct pg2_batch {
@@ -149,7 +150,7 @@ struct pg2_ctx {
     size_t scratch_bytes = (size_t)64 << 30;  // pointer/score scratch per launch group (PG2_SCRATCH_MB overrides)
     bool force_wavefront = false;  // PG2_FORCE_WAVEFRONT=1: route every job through the general kernel (tests)
     bool no_lanes = false;         // PG2_NO_LANES=1: keep shared-target jobs on the warp-per-alignment strip kernel (tests)
-    size_t lane_scratch_bytes = (size_t)8 << 30;  // cap of the lane kernel's per-warp boundary/saved-row scratch
+    size_t lane_scratch_bytes = (size_t)8 << 30;  // cap of the lane kernel's per-CTA wrap / end-column / parked-row scratch
     // staging (pinned) and device arrays of the current batch
     PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_vrow, h_vlast;
     PinVec<float> h_elogw;
@@ -548,7 +549,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             const DevJob &J = b->jobs[t];
             if (J.kernel != 1) continue;
             const DevGraph &GL = b->graphs[J.left];
-            if ((size_t)lane_warp_doubles(J.lx, GL.n_slots, LANE_K) * sizeof(double) > c->lane_scratch_bytes / 64) continue;
+            if ((size_t)lane_cta_doubles(GL.n_vrows, J.lx, GL.n_slots) * sizeof(double) > c->lane_scratch_bytes / 16) continue;
             unsigned long long key = ((unsigned long long)(unsigned)J.left << 32) | ((unsigned long long)(unsigned)J.model << 2) | (J.flags & 3u);
             auto it = bucket_of.find(key);
             if (it == bucket_of.end()) { it = bucket_of.emplace(key, (int)buckets.size()).first; buckets.emplace_back(); }
@@ -560,7 +561,6 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             std::stable_sort(bk.begin(), bk.end(), [&](int x, int y) { return b->jobs[x].ly > b->jobs[y].ly; });
             for (size_t pos = 0; pos < bk.size(); pos += 32) {
                 const int n = (int)std::min<size_t>(32, bk.size() - pos);
-                if (n < LANE_MIN_JOBS) break;  // a thin remainder stays on the strip kernel
                 const DevJob &J0 = b->jobs[bk[pos]];
                 const DevGraph &GL = b->graphs[J0.left];
                 LaneTask T;
@@ -620,6 +620,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
                 g.cells += need;
                 g.max_slots = std::max(g.max_slots, GL.n_slots);
                 g.max_lx = std::max(g.max_lx, GL.n_sites - 1);
+                g.max_nv = std::max(g.max_nv, GL.n_vrows);
                 for (int l = 0; l < T.n_jobs; l++) {
                     DevJob &J = b->jobs[T.job_ids[l]];
                     J.task = (int)tpos;
@@ -750,15 +751,15 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
 #else
     const int resident_warps = c->prop.multiProcessorCount * strip_warps_per_sm();
 #endif
-    const int lane_resident = c->prop.multiProcessorCount * lane_warps_per_sm();
-    auto lane_warps = [&](const Group &g) {
-        const size_t per_warp = (size_t)lane_warp_doubles(g.max_lx, g.max_slots, LANE_K) * sizeof(double);
-        size_t fit = std::max<size_t>(c->lane_scratch_bytes / per_warp, 1);
+    const int lane_resident = c->prop.multiProcessorCount * lane_ctas_per_sm();
+    auto lane_ctas = [&](const Group &g) {
+        const size_t per_cta = (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots) * sizeof(double);
+        size_t fit = std::max<size_t>(c->lane_scratch_bytes / per_cta, 1);
         return (int)std::min<size_t>(std::min<size_t>(fit, (size_t)lane_resident), (size_t)std::max(g.task_count, 1));
     };
     for (auto &g : b->groups)
         if (g.kernel == 2) {
-            size_t need = (size_t)lane_warp_doubles(g.max_lx, g.max_slots, LANE_K) * lane_warps(g);
+            size_t need = (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots) * lane_ctas(g);
             if ((rc = c->d_lane_scratch.ensure(need)) != PG2_OK) return fail(rc, "lane scratch allocation failed");
         }
     for (auto &g : b->groups)
@@ -795,8 +796,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
         } else if (g.kernel == 2) {
             launch_lane_fill(g.variant, g.task_count, c->d_tasks.p + g.task_first, c->d_jobs.p, c->d_graphs.p, c->d_models.p, c->d_state.p,
                              c->d_off.p, c->d_estart.p, c->d_elogw.p, reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_ptr16.p,
-                             c->d_results.p, c->d_lane_scratch.p, lane_bcol_doubles(g.max_lx),
-                             lane_warp_doubles(g.max_lx, g.max_slots, LANE_K), c->d_queue.p, lane_warps(g), c->stream);
+                             c->d_results.p, c->d_lane_scratch.p, g.max_nv, g.max_lx, g.max_slots, c->d_queue.p, lane_ctas(g), c->stream);
             st.jobs_lanes += g.count;
             st.jobs_strip_groups++;
             st.traceback_bytes += g.cells * 2;

@@ -1,192 +1,458 @@
-// pg2_lanes.cu -- placement fill kernel: one LANE per alignment, 32 alignments that share the row graph per warp.
+// pg2_lanes.cu -- placement fill kernel: one LANE per alignment, 32 alignments that share the row graph per
+// warp, the column strips of those alignments pipelined over the warps of a CTA.
 //
 // Query placement aligns many reads against the same tree node (reads_aligner.cpp:983-1216; the temporary
 // node puts the tree node LEFT and the read RIGHT, reads_aligner.h:169-184), so a launch batch holds many jobs
-// with the same LEFT graph.  The engine groups them into tasks of 32 (LaneTask, pg2_device.cuh); one warp takes
+// with the same LEFT graph.  The engine groups them into tasks of 32 (LaneTask, pg2_device.cuh); one CTA takes
 // a task and every lane aligns its own read against the shared row graph.
 //
 // Why: all lanes are on the SAME row at the same time, so everything the row graph decides -- in-degree, edge
-// spans, edge weights, which rows must be parked for long-span edges -- is warp-uniform.  A site with one edge
-// from the row above takes the in-place fast body; a multi-edge site loops over its edges; no lane ever waits
-// for another lane's row shape, there is no skew ramp and no shuffle.  (The warp-per-alignment strip kernel,
-// pg2_strip.cu, has 32 different rows in flight and falls back to its general body whenever one of them is not
-// a plain row.)
+// spans, edge weights, which rows must be parked for long-span edges -- is warp-uniform.  A site with one
+// unit-weight edge from the row above (98 % of the sites of a PAGAN ancestor graph) takes the in-place fast
+// body; any other site parks the row above and accumulates its edges one by one.  No lane ever waits for
+// another lane's row shape, there is no skew ramp and no shuffle.
 //
-// Layout.  Each lane sweeps its read in strips of K columns held in registers (pg2_rowmath.cuh), all rows of
-// the row graph per strip.  The strip's last column is written to a per-warp boundary column [row][X,Y,M][lane]
-// (one coalesced 256 B segment per component) and is the next strip's left neighbour; rows that are the source
-// of a long-span edge are parked in a per-warp saved-row scratch [slot][k][X,Y,M][lane].  Back-pointers: one
-// uint16 per cell, 8 columns per 128-bit store, lanes interleaved (pg2_strip_geom.cuh: lane_ptr_index).
+// Layout.  A lane holds a strip of K = 8 columns of its read in registers and sweeps it down the rows.  The
+// strips of a task are dealt round-robin to the W = 4 warps of the CTA, which run as a software pipeline over
+// blocks of B = 8 virtual rows: warp w works on a block of its strip as soon as its predecessor warp has
+// published the same block of the strip to the left.  That boundary column travels through a shared-memory
+// ring [channel][slot][row][X,Y,M][lane], D = 2 blocks deep, guarded by per-warp progress counters (a producer
+// may run up to D blocks ahead of its consumer; nobody waits at a CTA-wide barrier).  Only every fourth strip
+// boundary (warp 3 -> warp 0 of the next round) goes through a global wrap buffer and comes back by cp.async
+// one block ahead.
+// Back-pointers: one uint16 per cell, 8 columns per 128-bit store, lanes interleaved (pg2_strip_geom.cuh).
 //
-// Arithmetic: the shared row bodies of pg2_rowmath.cuh -- candidate by candidate as the reference
-// (src/main/viterbi_alignment.cpp:856-971, 1328-1436, 2029-2219), strict '>' first-wins.
+// Arithmetic: candidate by candidate as the reference (src/main/viterbi_alignment.cpp:856-971, 1328-1436,
+// 2029-2219), same FP64 association, strict '>' (first candidate wins ties).  The term (M + log_non_gap) +
+// log_gap_open, which the reference computes twice per cell (X move out of the cell, :2190-2211, and Y move
+// out of it), is computed once and kept next to M ("Mo").  The reduced terminal penalty (basic_alignment.h:
+// 490-513) only ever meets a finite M at the start corner, so it is planted there.
 #include "pg2_device.cuh"
 #include "pg2_strip_geom.cuh"
-#include "pg2_rowmath.cuh"
 #ifdef PG2_HOST_EMU
 #include <vector>
 #endif
 
+#ifndef PG2_LANE_MINB
+#define PG2_LANE_MINB 3
+#endif
+
 namespace pg2 {
 
-struct LaneScratch {
-    double *bcol0, *bcol1;  // [row][3][32]
-    double *saved;          // [slot][K][3][32]
+// warp-uniform per-task constants
+struct LaneCtx {
+    const int4 *l_vrow;
+    const int *l_off, *l_estart;
+    const float *l_elogw;
+    int nv, lx, n_slots;
+    const float *table;          // global float table (any alphabet)
+    const double2 *stab;         // shared {2*lng + ls, lng + ls} table (alphabets up to STRIP_SMALL_FAS)
+    int fas;
+    double open, ext, end_ext, lng, lng2;
+    bool term, reduced;
 };
 
-// The whole sweep of ONE lane.  Nothing here talks to another lane; warp-uniformity of the control flow comes
-// from the data (the row program and the task are shared by the 32 lanes).
-//   active   the lane holds a valid job (inactive lanes run along on dummy columns and store nothing)
-//   max_ly   the task's column count (strips are swept for all lanes alike)
-template <int K, bool GENERAL, bool SMALLTAB, bool WR>
-__device__ __forceinline__ void lane_sweep(StripCtx c, const int lane, const bool active, const int max_ly, const int *r_state,
-                                           const float *r_elogw, const LaneScratch sc, uint4 *ptr, DevResult *res) {
+// per-lane state of the strip the lane's warp is sweeping
+template <int K> struct LState {
+    double X[K], Y[K], M[K], Mo[K];  // row handled last; Mo = (M + lng) + open
+    double bX, bY, bM;               // left neighbour column (c0-1) of that row
+    double wr[K];                    // log weight of the column edge into site j (WR variants only)
+    int tab[K];                      // SMALLTAB: byte offset of column j's table column; else state_r[j] * fas
+};
+
+// per-lane geometry of the job
+struct LaneGeom {
+    int ly;            // DP columns of this lane's read (1 for an idle lane)
+    int last_strip;    // strip that holds column ly-1
+    int last_k;        // its position in that strip
+    bool active;
+};
+
+// s = max(b, a) with the first-wins rule (b replaces a only when strictly greater); the outcome is OR-ed into w
+// as one bit.  One DSETP + one 64-bit select + one predicated LOP3.
+__device__ __forceinline__ double sel_gt(double b, double a, unsigned &w, unsigned bit) {
+#ifdef PG2_HOST_EMU
+    if (b > a) { w |= bit; return b; }
+    return a;
+#else
+    double t;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %2, %3;\n\tselp.f64 %0, %2, %3, p;\n\t@p or.b32 %1, %1, %4;\n\t}"
+        : "=d"(t), "+r"(w)
+        : "d"(b), "d"(a), "r"(bit));
+    return t;
+#endif
+}
+
+// running maximum of a general row: if (s > best) { best = s; ptr = (ptr & keep) | code; }
+__device__ __forceinline__ void acc_gt(double s, double &best, unsigned &ptr, unsigned keep, unsigned code) {
+#ifdef PG2_HOST_EMU
+    if (s > best) { best = s; ptr = (ptr & keep) | code; }
+#else
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %2, %0;\n\tselp.f64 %0, %2, %0, p;\n\t@p lop3.b32 %1, %1, %3, %4, 0xEA;\n\t}"
+        : "+d"(best), "+r"(ptr)
+        : "d"(s), "r"(keep), "r"(code));
+#endif
+}
+
+// {m_log, x_log} of one cell: 2*log_non_gap + log_score and log_non_gap + log_score (:1363-1367).
+// rowoff / tabk: byte offsets into the shared double2 table (SMALLTAB) or element offsets into the float table.
+template <bool SMALLTAB>
+__device__ __forceinline__ void lane_subst(const LaneCtx &c, int rowoff, int tabk, double &mlog, double &xlog) {
+    if (SMALLTAB) {
+        const double2 v = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(c.stab) + (rowoff + tabk));
+        mlog = v.x;
+        xlog = v.y;
+    } else {
+        const double ls = (double)__ldg(c.table + rowoff + tabk);
+        mlog = __dadd_rn(c.lng2, ls);
+        xlog = __dadd_rn(c.lng, ls);
+    }
+}
+
+// Y(i,j) from (i,j-1) along the strip: ext, double, open (:2116-2211 with the roles of X and Y swapped).  The
+// two chain-independent candidates are folded first; (g > a ? g : a) with g = first-wins(double, open) equals
+// the sequential first-wins over all three.  Outcome bits go to P2 (open beat double) and P1 (that winner beat
+// ext) of the cell's half-word.  Also makes (rX,rY,rM) the row's left neighbour.
+template <int K, unsigned P2, unsigned P1>
+__device__ __forceinline__ void lane_y_chain(const LaneCtx &c, LState<K> &st, double extY, double rX, double rY, double rM,
+                                             unsigned *w) {
+    double lXo = __dadd_rn(rX, c.open);
+    double lMo = __dadd_rn(__dadd_rn(rM, c.lng), c.open);
+    double lY = rY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const unsigned sh = (k & 1) * 16;
+        const double g = sel_gt(lMo, lXo, w[k >> 1], P2 << sh);
+        const double a = __dadd_rn(lY, extY);
+        const double ny = sel_gt(g, a, w[k >> 1], P1 << sh);
+        lXo = __dadd_rn(st.X[k], c.open);
+        lMo = st.Mo[k];
+        lY = ny;
+        st.Y[k] = ny;
+    }
+    st.bX = rX; st.bY = rY; st.bM = rM;
+}
+
+// Fast-row pointer half-word: bit 14 set, bits 0-5 the raw comparison outcomes
+//   bit0/1 X: (double > ext), (open > max of the first two)      candidates in order X, Y, M
+//   bit2/3 Y: (open > double), (that winner > ext)                candidates in order Y, X, M
+//   bit4/5 M: (X > M), (Y > max of the first two)                 candidates in order M, X, Y
+// (lane_decode_ptr, pg2_strip_geom.cuh).  A cell whose candidates are all -inf gets arbitrary bits: it cannot
+// lie on the Viterbi path.
+//
+// Row whose only backward edge comes from the row above: in-place update of the strip.
+//   WL      the edge carries a log weight (wl)           EXTARR  ex[k] holds the X-extension term of column k
+//   CORNER  the row may be row 0 of the first strip      (else every column extends with log_gap_ext)
+template <int K, bool WL, bool WR, bool SMALLTAB, bool EXTARR, bool CORNER>
+__device__ __forceinline__ void lane_fast_row(const LaneCtx &c, LState<K> &st, int sl, double wl, const double *ex, double extY,
+                                              bool corner, double rX, double rY, double rM, unsigned *w) {
+#pragma unroll
+    for (int h = 0; h < K / 2; ++h) w[h] = 0x40004000u;
+    const int rowoff = SMALLTAB ? sl * 16 : sl;
+    // descending k: X(i,j) reads (i-1,j), M(i,j) reads (i-1,j-1); both still hold row i-1
+#pragma unroll
+    for (int k = K - 1; k >= 0; --k) {
+        const unsigned sh = (k & 1) * 16;
+        const double qX = k ? st.X[k - 1] : st.bX, qY = k ? st.Y[k - 1] : st.bY, qM = k ? st.M[k - 1] : st.bM;
+        // X: ext, double, open (:2116-2211)
+        double a = __dadd_rn(st.X[k], EXTARR ? ex[k] : c.ext);
+        double b = __dadd_rn(st.Y[k], c.open);
+        double t = sel_gt(b, a, w[k >> 1], 1u << sh);
+        const double nx = sel_gt(st.Mo[k], t, w[k >> 1], 2u << sh);
+        // M: from M, X, Y (:2029-2112)
+        double mlog, xlog;
+        lane_subst<SMALLTAB>(c, rowoff, st.tab[k], mlog, xlog);
+        a = __dadd_rn(qM, mlog);
+        b = __dadd_rn(qX, xlog);
+        double d = __dadd_rn(qY, xlog);
+        if (WL) { a = __dadd_rn(a, wl); b = __dadd_rn(b, wl); d = __dadd_rn(d, wl); }
+        if (WR) { a = __dadd_rn(a, st.wr[k]); b = __dadd_rn(b, st.wr[k]); d = __dadd_rn(d, st.wr[k]); }
+        t = sel_gt(b, a, w[k >> 1], 16u << sh);
+        const double nm = sel_gt(d, t, w[k >> 1], 32u << sh);
+        st.X[k] = nx;
+        st.M[k] = nm;
+        st.Mo[k] = __dadd_rn(__dadd_rn(nm, c.lng), c.open);
+    }
+    // Column 0 needs no special case for i > 0: its M sources are the -inf boundary, so M(i,0) = -inf falls
+    // out of the arithmetic.  Row 0 has no edges but its sources are the -inf initial strip, so X(0,j) =
+    // M(0,j) = -inf fall out as well; only the start corner M(0,0) = 0 (:725-733) is planted here, with the
+    // open penalty its two gap moves pay (get_log_gap_open_penalty, basic_alignment.h:490-513).
+    if (CORNER && corner) {
+        st.M[0] = 0.0;
+        st.Mo[0] = __dadd_rn(__dadd_rn(0.0, c.lng), c.reduced ? 0.0 : c.open);
+    }
+    lane_y_chain<K, 4u, 8u>(c, st, extY, rX, rY, rM, w);
+}
+
+// A parked row of one warp: [column 0 = c0-1, column k+1 = c0+k][X, Y, M, Mo][lane].
+template <int K>
+__device__ __forceinline__ void lane_park(const LaneCtx &c, const LState<K> &st, double *slot) {
+    slot[0] = st.bX; slot[32] = st.bY; slot[64] = st.bM;
+    slot[96] = __dadd_rn(__dadd_rn(st.bM, c.lng), c.open);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double *p = slot + (k + 1) * 128;
+        p[0] = st.X[k]; p[32] = st.Y[k]; p[64] = st.M[k]; p[96] = st.Mo[k];
+    }
+}
+
+// One virtual row of a site that is not a fast row (several edges, a long-span edge, an edge weight, or no edge
+// at all).  The row above is parked on the site's first virtual row, so st.X / st.M become the accumulators and
+// every edge reads its source row from a slot.  Returns true on the site's last virtual row; the caller then
+// runs lane_commit.
+template <int K, bool WR, bool SMALLTAB>
+__device__ __forceinline__ bool lane_general_vrow(const LaneCtx &c, LState<K> &st, unsigned *pXM, const double *ex, int4 vr,
+                                                  double *slots) {
     const double ninf = neg_inf();
-    const int n_strips = (max_ly + K - 1) / K;
-    const int my_last_strip = (c.ly - 1) / K, my_last_k = (c.ly - 1) % K;
-    constexpr int Q = K / 8;
-
-    for (int s = 0; s < n_strips; ++s) {
-        const int c0 = s * K;
-        const bool first = (s == 0);
-        double *bprev = (s & 1) ? sc.bcol0 : sc.bcol1;
-        double *bcur = (s & 1) ? sc.bcol1 : sc.bcol0;
-        c.c_block = c0;
-        c.first_block = first;
-
-        LaneState<K> st;
-        LaneAcc<K> acc;
+    const int info = vr.x, sl = info & VR_STATE_MASK;
+    const int rowoff = SMALLTAB ? sl * 16 : sl;
+    if (info & VR_FIRST) {
+        lane_park<K>(c, st, slots + (long long)c.n_slots * LANE_SLOT_DOUBLES);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { st.X[k] = ninf; st.M[k] = ninf; pXM[k] = NO_MAT | (NO_MAT << 8); }
+    }
+    if (!(info & VR_NOEDGE)) {
+        const double wl = (info & VR_ZERO_W) ? 0.0 : (double)c.l_elogw[vr.y];  // + 0.0 is exact
+        const unsigned ord = ((unsigned)vr.w >> 16) << 2;
+        const int slot = (info & VR_REG) ? c.n_slots : (vr.w & 0xffff);
+        const double *row = slots + (long long)slot * LANE_SLOT_DOUBLES;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int j = c0 + k;
-            const bool v = active && j < c.ly;
-            st.X[k] = st.Y[k] = st.M[k] = ninf;
-            st.extX[k] = (c.term && (j == 0 || j == c.ly - 1)) ? c.end_ext : c.ext;
-            st.wr[k] = (WR && v && j >= 1) ? (double)r_elogw[j - 1] : 0.0;  // chain edge (j-1 -> j), CSR position j-1
-            st.colbase[k] = (v && j >= 1) ? r_state[j] * c.fas : 0;
-            acc.nX[k] = acc.nM[k] = ninf;
-            acc.pX[k] = acc.pM[k] = NO_MAT;
-        }
-        st.penY1 = (c.reduced && first) ? 0.0 : c.open;  // Y move out of column 0 (basic_alignment.h:494)
-        st.bX = st.bY = st.bM = ninf;
-
-        const bool store_ptr = active && c0 < c.ly;
-        const bool write_bcol = s < my_last_strip;   // a lane past its last strip leaves its end column alone
-        const bool write_end = s == my_last_strip;
-
-        // one-row-ahead prefetch of the row program entry and of the row's left neighbour
-        int4 vr_n = __ldg(c.l_vrow);
-        double nX = ninf, nY = ninf, nM = ninf;
-        if (!first) {
-            const double *b = bprev + (long long)vr_n.z * 96 + lane;
-            nX = b[0]; nY = b[32]; nM = b[64];
-        }
-        for (int v = 0; v < c.nv; ++v) {
-            const int4 vr = vr_n;
-            const double rX = nX, rY = nY, rM = nM;
-            if (v + 1 < c.nv) {
-                vr_n = __ldg(c.l_vrow + v + 1);
-                if (!first) {
-                    const double *b = bprev + (long long)vr_n.z * 96 + lane;
-                    nX = b[0]; nY = b[32]; nM = b[64];
-                }
-            }
-            const int info = vr.x, i = vr.z, sl = info & VR_STATE_MASK;
-            unsigned short w[K];
-            bool done = true;
-            if (!GENERAL || (info & VR_FAST) == VR_FAST) {
-                const bool corner = first && i == 0;
-                if (!GENERAL || (info & (VR_ZERO_W | VR_NOEDGE))) {
-                    fast_row<K, false, WR, SMALLTAB>(c, st, i, sl, 0.0, corner, rX, rY, rM, w);
-                } else {
-                    const double wl = (double)c.l_elogw[vr.y];
-                    fast_row<K, true, WR, SMALLTAB>(c, st, i, sl, wl, corner, rX, rY, rM, w);
-                }
-            } else {
-                if (info & VR_FIRST) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) { acc.nX[k] = ninf; acc.nM[k] = ninf; acc.pX[k] = NO_MAT; acc.pM[k] = NO_MAT; }
-                }
-                if (!(info & VR_NOEDGE)) {
-                    const int p = c.l_estart[vr.y];
-                    const unsigned ord = ((unsigned)vr.w >> 16) << 2;
-                    double sX[K + 1], sY[K + 1], sM[K + 1];
-                    if (info & VR_REG) {
-                        sX[0] = st.bX; sY[0] = st.bY; sM[0] = st.bM;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) { sX[k + 1] = st.X[k]; sY[k + 1] = st.Y[k]; sM[k + 1] = st.M[k]; }
-                    } else {
-                        const int slot = vr.w & 0xffff;
-                        const double *row = sc.saved + (long long)slot * K * 96 + lane;
-                        sX[0] = sY[0] = sM[0] = ninf;
-                        if (!first) {
-                            const double *b = bprev + (long long)p * 96 + lane;
-                            sX[0] = b[0]; sY[0] = b[32]; sM[0] = b[64];
-                        }
-#pragma unroll
-                        for (int k = 0; k < K; ++k) { sX[k + 1] = row[k * 96]; sY[k + 1] = row[k * 96 + 32]; sM[k + 1] = row[k * 96 + 64]; }
-                    }
-                    if (info & VR_ZERO_W) {
-                        accumulate_edge<K, SMALLTAB, false, WR>(c, st, acc, sl, p, 0.0, ord, sX, sY, sM);
-                    } else {
-                        const double wl = (double)c.l_elogw[vr.y];
-                        accumulate_edge<K, SMALLTAB, true, WR>(c, st, acc, sl, p, wl, ord, sX, sY, sM);
-                    }
-                }
-                done = (info & VR_LAST) != 0;
-                if (done) commit_site<K>(c, st, acc, i, first, rX, rY, rM, w);
-            }
-            if (!done) continue;
-
-            if (store_ptr) {
-                uint4 *dst = ptr + (((long long)s * c.nv + v) * Q) * 32 + lane;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    uint4 o;
-                    o.x = (unsigned)w[8 * q + 0] | ((unsigned)w[8 * q + 1] << 16);
-                    o.y = (unsigned)w[8 * q + 2] | ((unsigned)w[8 * q + 3] << 16);
-                    o.z = (unsigned)w[8 * q + 4] | ((unsigned)w[8 * q + 5] << 16);
-                    o.w = (unsigned)w[8 * q + 6] | ((unsigned)w[8 * q + 7] << 16);
-                    dst[q * 32] = o;
-                }
-            }
-            if (GENERAL) {
-                const int slot = (int)((unsigned)info >> VR_SLOT_SHIFT) - 1;
-                if (slot >= 0) {
-                    double *row = sc.saved + (long long)slot * K * 96 + lane;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) { row[k * 96] = st.X[k]; row[k * 96 + 32] = st.Y[k]; row[k * 96 + 64] = st.M[k]; }
-                }
-            }
-            double *b = bcur + (long long)i * 96 + lane;
-            if (write_bcol) {
-                b[0] = st.X[K - 1]; b[32] = st.Y[K - 1]; b[64] = st.M[K - 1];
-            } else if ((info & VR_ENDPRED) && write_end) {
-                // rows the end corner reads: keep the lane's LAST column (ly-1) instead
-                double vx = ninf, vy = ninf, vm = ninf;
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (k == my_last_k) { vx = st.X[k]; vy = st.Y[k]; vm = st.M[k]; }
-                b[0] = vx; b[32] = vy; b[64] = vm;
-            }
+            const double *up = row + (k + 1) * 128, *dg = row + k * 128;
+            // X: ext, double, open (:2116-2211); the open candidate was formed when the source row was made
+            acc_gt(__dadd_rn(up[0], ex[k]), st.X[k], pXM[k], 0xff00u, X_MAT | ord);
+            acc_gt(__dadd_rn(up[32], c.open), st.X[k], pXM[k], 0xff00u, Y_MAT | ord);
+            acc_gt(up[96], st.X[k], pXM[k], 0xff00u, M_MAT | ord);
+            // M: from M, X, Y (:2029-2112), ((score + log) + wl) + wr
+            double mlog, xlog;
+            lane_subst<SMALLTAB>(c, rowoff, st.tab[k], mlog, xlog);
+            double a = __dadd_rn(__dadd_rn(dg[64], mlog), wl);
+            double b = __dadd_rn(__dadd_rn(dg[0], xlog), wl);
+            double d = __dadd_rn(__dadd_rn(dg[32], xlog), wl);
+            if (WR) { a = __dadd_rn(a, st.wr[k]); b = __dadd_rn(b, st.wr[k]); d = __dadd_rn(d, st.wr[k]); }
+            acc_gt(a, st.M[k], pXM[k], 0x00ffu, (M_MAT | ord) << 8);
+            acc_gt(b, st.M[k], pXM[k], 0x00ffu, (X_MAT | ord) << 8);
+            acc_gt(d, st.M[k], pXM[k], 0x00ffu, (Y_MAT | ord) << 8);
         }
     }
-    if (!active) return;
-    // iterate_bwd_edges_for_end_corner (:1440-1552) with a single right edge (ly-1 -> stop)
-    const double *lastcol = ((my_last_strip & 1) ? sc.bcol1 : sc.bcol0) + lane;
+    return (info & VR_LAST) != 0;
+}
+
+// Last virtual row of a general site: the accumulators hold X(i,.) and M(i,.); refresh Mo, run the Y chain and
+// emit general-form half-words: X pointer bits 0-5, raw Y outcome bits 6-7, M pointer bits 8-13, bit 14 clear.
+template <int K>
+__device__ __forceinline__ void lane_commit(const LaneCtx &c, LState<K> &st, const unsigned *pXM, double extY, double rX, double rY,
+                                            double rM, unsigned *w) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.Mo[k] = __dadd_rn(__dadd_rn(st.M[k], c.lng), c.open);
+#pragma unroll
+    for (int h = 0; h < K / 2; ++h) w[h] = pXM[2 * h] | (pXM[2 * h + 1] << 16);
+    lane_y_chain<K, 64u, 128u>(c, st, extY, rX, rY, rM, w);
+}
+
+// per-lane constants of one strip
+template <int K, bool WR, bool SMALLTAB>
+__device__ __forceinline__ void lane_strip_init(const LaneCtx &c, LState<K> &st, const LaneGeom &g, int c0, const int *r_state,
+                                                const float *r_elogw) {
+    const double ninf = neg_inf();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = c0 + k;
+        const bool v = g.active && j < g.ly;
+        st.X[k] = st.Y[k] = st.M[k] = st.Mo[k] = ninf;
+        st.wr[k] = (WR && v && j >= 1) ? (double)r_elogw[j - 1] : 0.0;  // chain edge (j-1 -> j), CSR position j-1
+        const int sr = (v && j >= 1) ? r_state[j] : 0;
+        st.tab[k] = SMALLTAB ? sr * c.fas * 16 : sr * c.fas;
+    }
+    st.bX = st.bY = st.bM = ninf;
+}
+
+// warp-wide OR of a per-lane condition (the CPU test emulation runs one lane at a time: a lane for which the
+// condition is false computes the same values on either side of the branch it selects)
+__device__ __forceinline__ bool lane_any(bool x) {
+#ifdef PG2_HOST_EMU
+    return x;
+#else
+    return __any_sync(0xffffffffu, x);
+#endif
+}
+
+// X-extension term of the K columns of strip s (viterbi_alignment.cpp:864-868): log_gap_end_ext on the first and
+// the last DP column when terminal gaps are cheap, log_gap_ext elsewhere
+template <int K>
+__device__ __forceinline__ void lane_ext_terms(const LaneCtx &c, const LaneGeom &g, int s, double *ex) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = s * K + k;
+        ex[k] = (c.term && (j == 0 || j == g.ly - 1)) ? c.end_ext : c.ext;
+    }
+}
+
+// A pipeline block whose LANE_B virtual rows are all plain interior rows (one unit-weight edge from the row
+// above, not row 0, not read by the end corner, never parked): the hot loop, nothing but the row body, the
+// boundary hand-over and the pointer store.
+template <int K, bool SMALLTAB, bool WR, bool EXTARR>
+__device__ __forceinline__ void lane_fast_block(const LaneCtx &c, LState<K> &st, const double *ex, int v0, bool first, bool store_ptr,
+                                                const double *ring_in, double *out, uint4 *dst) {
+    const double ninf = neg_inf();
+    constexpr int Q = K / 8;
+    int info_n = __ldg(&c.l_vrow[v0].x);
+    for (int r = 0; r < LANE_B; ++r) {
+        const int sl = info_n & VR_STATE_MASK;
+        if (r + 1 < LANE_B) info_n = __ldg(&c.l_vrow[v0 + r + 1].x);
+        double rX = ninf, rY = ninf, rM = ninf;
+        if (!first) { rX = ring_in[r * 96]; rY = ring_in[r * 96 + 32]; rM = ring_in[r * 96 + 64]; }
+        unsigned w[K / 2];
+        lane_fast_row<K, false, WR, SMALLTAB, EXTARR, false>(c, st, sl, 0.0, ex, c.ext, false, rX, rY, rM, w);
+        if (store_ptr) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                uint4 o;
+                o.x = w[4 * q]; o.y = w[4 * q + 1]; o.z = w[4 * q + 2]; o.w = w[4 * q + 3];
+                dst[(r * Q + q) * 32] = o;
+            }
+        }
+        if (out) {
+            double *b = out + r * 96;
+            b[0] = st.X[K - 1]; b[32] = st.Y[K - 1]; b[64] = st.M[K - 1];
+        }
+    }
+}
+
+// One pipeline block of one lane: virtual rows [v0, v1) of strip `s`.
+//   ring_in   left neighbour column of these rows, [row - v0][X,Y,M][lane] (already offset by the lane); unused
+//             for the first strip (-inf boundary)
+//   ring_out  where this strip's last column goes for the next strip, same shape; wrap_out (global, indexed by
+//             virtual row) instead when the next strip belongs to the next round; both null for the last strip
+template <int K, bool GENERAL, bool SMALLTAB, bool WR>
+__device__ __forceinline__ void lane_block(const LaneCtx &c, LState<K> &st, const LaneGeom &g, int s, int v0, int v1,
+                                           const double *ring_in, double *ring_out, double *wrap_out, double *slots, double *endcol,
+                                           uint4 *ptr) {
+    const double ninf = neg_inf();
+    const bool first = (s == 0);
+    const bool store_ptr = g.active && s * K < g.ly;
+    const bool is_last = g.active && s == g.last_strip;
+    constexpr int Q = K / 8;
+    // warp-uniform: is this a block of plain interior rows?
+    if (v1 - v0 == LANE_B) {
+        int all = ~0, any = 0;
+#pragma unroll
+        for (int r = 0; r < LANE_B; ++r) {
+            const int info = __ldg(&c.l_vrow[v0 + r].x);
+            all &= info;
+            any |= info;
+        }
+        const int need = VR_FAST | VR_ZERO_W;
+        const int none = VR_ENDPRED | VR_NOEDGE | (int)(~0u << VR_SLOT_SHIFT);
+        if ((all & need) == need && !(any & none)) {
+            double *out = wrap_out ? wrap_out + (long long)v0 * 96 : ring_out;
+            uint4 *dst = ptr + ((long long)s * c.nv + v0) * Q * 32;
+            if (lane_any(first || is_last)) {
+                double ex[K];
+                lane_ext_terms<K>(c, g, s, ex);
+                lane_fast_block<K, SMALLTAB, WR, true>(c, st, ex, v0, first, store_ptr, ring_in, out, dst);
+            } else {
+                lane_fast_block<K, SMALLTAB, WR, false>(c, st, nullptr, v0, first, store_ptr, ring_in, out, dst);
+            }
+            return;
+        }
+    }
+    // mixed block: row by row
+    double ex[K];
+    unsigned pXM[K];  // general rows: X pointer | M pointer << 8 (mat | edge ordinal << 2)
+    lane_ext_terms<K>(c, g, s, ex);
+    int4 vr_n = __ldg(c.l_vrow + v0);
+    // a site whose virtual rows straddle the block boundary keeps its pointer accumulators in the warp's scratch
+    unsigned *pxm_save = reinterpret_cast<unsigned *>(slots + (long long)(c.n_slots + 1) * LANE_SLOT_DOUBLES);
+#pragma unroll
+    for (int k = 0; k < K; ++k) pXM[k] = 0;
+    if (GENERAL && !(vr_n.x & VR_FIRST)) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) pXM[k] = pxm_save[k * 64];
+    }
+    bool open_site = false;
+    for (int v = v0; v < v1; ++v) {
+        const int4 vr = vr_n;
+        if (v + 1 < v1) vr_n = __ldg(c.l_vrow + v + 1);
+        const int info = vr.x, i = vr.z;
+        const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : c.ext;
+        unsigned w[K / 2];
+        // one edge from the row above (or row 0): in place; with the edge's log weight when it has one
+        const bool fast = (info & VR_FAST) == VR_FAST;
+        const bool weighted = !(info & (VR_ZERO_W | VR_NOEDGE));
+        if (GENERAL && !fast) {
+            open_site = !lane_general_vrow<K, WR, SMALLTAB>(c, st, pXM, ex, vr, slots);
+            if (open_site) continue;
+        }
+        double rX = ninf, rY = ninf, rM = ninf;
+        if (!first) {
+            const double *b = ring_in + (v - v0) * 96;
+            rX = b[0]; rY = b[32]; rM = b[64];
+        }
+        if (!GENERAL || fast) {
+            if (GENERAL && weighted)
+                lane_fast_row<K, true, WR, SMALLTAB, true, false>(c, st, info & VR_STATE_MASK, (double)c.l_elogw[vr.y], ex, extY, false,
+                                                                   rX, rY, rM, w);
+            else
+                lane_fast_row<K, false, WR, SMALLTAB, true, true>(c, st, info & VR_STATE_MASK, 0.0, ex, extY, first && i == 0, rX, rY,
+                                                                   rM, w);
+        } else {
+            lane_commit<K>(c, st, pXM, extY, rX, rY, rM, w);
+        }
+
+        if (store_ptr) {
+            uint4 *dst = ptr + ((long long)s * c.nv + v) * Q * 32;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                uint4 o;
+                o.x = w[4 * q]; o.y = w[4 * q + 1]; o.z = w[4 * q + 2]; o.w = w[4 * q + 3];
+                dst[q * 32] = o;
+            }
+        }
+        if (wrap_out) {
+            double *b = wrap_out + (long long)v * 96;
+            b[0] = st.X[K - 1]; b[32] = st.Y[K - 1]; b[64] = st.M[K - 1];
+        } else if (ring_out) {
+            double *b = ring_out + (v - v0) * 96;
+            b[0] = st.X[K - 1]; b[32] = st.Y[K - 1]; b[64] = st.M[K - 1];
+        }
+        if (GENERAL) {
+            const int slot = (int)((unsigned)info >> VR_SLOT_SHIFT) - 1;
+            if (slot >= 0) lane_park<K>(c, st, slots + (long long)slot * LANE_SLOT_DOUBLES);
+        }
+        if ((info & VR_ENDPRED) && is_last) {
+            // rows the end corner reads: the lane's LAST column (ly-1)
+            double vx = ninf, vy = ninf, vm = ninf;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (k == g.last_k) { vx = st.X[k]; vy = st.Y[k]; vm = st.M[k]; }
+            double *b = endcol + (long long)i * 96;
+            b[0] = vx; b[32] = vy; b[64] = vm;
+        }
+    }
+    if (GENERAL && open_site) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) pxm_save[k * 64] = pXM[k];
+    }
+}
+
+// iterate_bwd_edges_for_end_corner (:1440-1552) with a single right edge (ly-1 -> stop)
+__device__ __forceinline__ void lane_end_corner(const LaneCtx &c, const LaneGeom &g, const double *endcol, const float *r_elogw,
+                                                DevResult *res) {
+    const double ninf = neg_inf();
     double best = ninf;
     unsigned bptr = NO_MAT;
     const int kl0 = c.l_off[c.lx], kl1 = c.l_off[c.lx + 1];
-    const double wr = (double)r_elogw[c.ly - 1];  // edge (ly-1 -> ly)
+    const double wr = (double)r_elogw[g.ly - 1];  // edge (ly-1 -> ly)
     for (int kl = kl0; kl < kl1; ++kl) {
-        const double *v = lastcol + (long long)c.l_estart[kl] * 96;
-        double sc_ = __dadd_rn(__dadd_rn(__dadd_rn(v[64], c.lng), (double)c.l_elogw[kl]), wr);
-        if (sc_ > best) { best = sc_; bptr = pack_ptr(M_MAT, kl - kl0, 0); }
-        sc_ = v[0];  // score_gap_close: + 0
-        if (sc_ > best) { best = sc_; bptr = pack_ptr(X_MAT, kl - kl0, 0); }
+        const double *v = endcol + (long long)c.l_estart[kl] * 96;
+        double s = __dadd_rn(__dadd_rn(__dadd_rn(v[64], c.lng), (double)c.l_elogw[kl]), wr);
+        if (s > best) { best = s; bptr = pack_ptr(M_MAT, kl - kl0, 0); }
+        s = v[0];  // score_gap_close: + 0
+        if (s > best) { best = s; bptr = pack_ptr(X_MAT, kl - kl0, 0); }
         if (kl == kl0) {
-            sc_ = lastcol[(long long)(c.lx - 1) * 96 + 32];
-            if (sc_ > best) { best = sc_; bptr = pack_ptr(Y_MAT, 0, 0); }
+            s = endcol[(long long)(c.lx - 1) * 96 + 32];
+            if (s > best) { best = s; bptr = pack_ptr(Y_MAT, 0, 0); }
         }
     }
     res->score = best;
@@ -194,13 +460,15 @@ __device__ __forceinline__ void lane_sweep(StripCtx c, const int lane, const boo
     res->status = (best == ninf) ? JOB_NO_PATH : JOB_OK;
 }
 
-__device__ __forceinline__ void lane_make_ctx(StripCtx &c, const LaneTask &T, int ly, const DevGraph &GL, const DevModel &m,
-                                              const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow, int K) {
+__device__ __forceinline__ void lane_make_ctx(LaneCtx &c, const LaneTask &T, const DevGraph &GL, const DevModel &m, const int *d_off,
+                                              const int *d_estart, const float *d_elogw, const int4 *d_vrow) {
     c.l_vrow = d_vrow + GL.vrow_base;
     c.nv = GL.n_vrows;
     c.l_off = d_off + GL.off_base;
     c.l_estart = d_estart + GL.edge_base;
     c.l_elogw = d_elogw + GL.edge_base;
+    c.lx = GL.n_sites - 1;
+    c.n_slots = GL.n_slots;
     c.table = m.table;
     c.stab = nullptr;
     c.fas = m.fas;
@@ -211,89 +479,176 @@ __device__ __forceinline__ void lane_make_ctx(StripCtx &c, const LaneTask &T, in
     c.lng2 = (double)__fmul_rn(2.0f, m.lng);
     c.term = !(T.flags & FLAG_NO_TERMINAL_EDGES);
     c.reduced = (T.flags & FLAG_REDUCED) != 0;
-    c.wr_zero = !(T.variant & 4);
-    c.lx = GL.n_sites - 1;
-    c.ly = ly;
-    c.W = K;
-    c.saved = nullptr;
-    c.bcol_prev = c.bcol_cur = nullptr;
-    c.ptr = nullptr;
-    c.c_block = 0;
-    c.first_block = true;
+}
+
+__device__ __forceinline__ void lane_make_geom(LaneGeom &g, bool active, int ly) {
+    g.active = active;
+    g.ly = active ? ly : 1;
+    g.last_strip = (g.ly - 1) / LANE_K;
+    g.last_k = (g.ly - 1) % LANE_K;
+}
+
+// Pipeline schedule of one task: warp w handles strips w, w + W, ...; its work items are numbered u = 0, 1, ...;
+// item u is block b = u % period of round r = u / period, i.e. of strip r * W + w (items with b >= n_blocks are
+// empty: the period is padded so that warp 0 never prefetches a wrap row of the round in progress).
+//   warp w > 0 may start item u when warp w-1 has published item u (same block, strip to the left);
+//   warp w < W-1 may write ring slot u % D when warp w+1 has published item u - D;
+//   warp 0 may prefetch the wrap rows of item u (round >= 1) when warp W-1 has published item u - period.
+struct LaneSched {
+    int n_strips, rounds, n_blocks, period, items;
+};
+__device__ __forceinline__ LaneSched lane_schedule(int nv, int max_ly) {
+    LaneSched s;
+    s.n_strips = (max_ly + LANE_K - 1) / LANE_K;
+    s.rounds = (s.n_strips + LANE_W - 1) / LANE_W;
+    s.n_blocks = (nv + LANE_B - 1) / LANE_B;
+    s.period = s.n_blocks > LANE_W + 1 ? s.n_blocks : LANE_W + 1;
+    s.items = s.rounds * s.period;
+    return s;
+}
+
+// shared-memory ring: channels 0 .. W-2 (warp c -> warp c+1) are LANE_D blocks deep, channel W-1 (the wrap
+// prefetch of warp 0) two blocks; one block = [LANE_B rows][X,Y,M][32 lanes] doubles
+constexpr int LANE_BLOCK_DOUBLES = LANE_B * 96;
+constexpr int LANE_RING_DOUBLES = ((LANE_W - 1) * LANE_D + 2) * LANE_BLOCK_DOUBLES;
+__device__ __forceinline__ int lane_ring_offset(int channel, int u) {
+    return channel < LANE_W - 1 ? (channel * LANE_D + u % LANE_D) * LANE_BLOCK_DOUBLES
+                                : ((LANE_W - 1) * LANE_D + (u & 1)) * LANE_BLOCK_DOUBLES;
 }
 
 #ifndef PG2_HOST_EMU
-#ifndef PG2_LANE_MINB
-#define PG2_LANE_MINB 3
+// spin until *p >= target (a per-warp progress counter in shared memory, published with lane_publish)
+__device__ __forceinline__ void lane_wait(const volatile int *p, int target) {
+    if (target <= 0) return;
+#ifdef PG2_LANE_SLEEP
+    while (*p < target) __nanosleep(PG2_LANE_SLEEP);
+#else
+    while (*p < target) {}
 #endif
+    __threadfence_block();
+}
+__device__ __forceinline__ void lane_publish(volatile int *p, int value, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *p = value;
+}
+
 template <int K, bool GENERAL, bool SMALLTAB, bool WR>
-__global__ void __launch_bounds__(128, PG2_LANE_MINB)
+__global__ void __launch_bounds__(LANE_W * 32, PG2_LANE_MINB)
 lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs, const DevModel *models,
                  const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
-                 unsigned short *ptrs, DevResult *results, double *scratch, long long bcol_doubles, long long warp_doubles,
-                 int *queue) {
-    __shared__ double2 s_tab[SMALLTAB ? 4 : 1][SMALLTAB ? STRIP_SMALL_FAS * STRIP_SMALL_FAS : 1];
+                 unsigned short *ptrs, DevResult *results, double *scratch, long long wrap_doubles, long long endcol_doubles,
+                 long long slot_doubles, int *queue) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    double2 *s_tab = reinterpret_cast<double2 *>(ring + LANE_RING_DOUBLES);
+    __shared__ int s_task;
+    __shared__ int s_progress[LANE_W];
     const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    LaneScratch sc;
-    sc.bcol0 = scratch + (long long)warp_global * warp_doubles;
-    sc.bcol1 = sc.bcol0 + bcol_doubles;
-    sc.saved = sc.bcol1 + bcol_doubles;
+    const int w = threadIdx.x >> 5;
+    double *wrap = scratch + (long long)blockIdx.x * (wrap_doubles + endcol_doubles + LANE_W * slot_doubles);
+    double *endcol = wrap + wrap_doubles;
+    double *slots = endcol + endcol_doubles + (long long)w * slot_doubles + lane;
+    volatile int *progress = s_progress;
     int tab_model = -1;
 
     for (;;) {
-        int q = 0;
-        if (lane == 0) q = atomicAdd(queue, 1);
-        q = __shfl_sync(0xffffffffu, q, 0);
+        __syncthreads();  // the previous task's end corners are done with endcol; s_task / s_progress may be rewritten
+        if (threadIdx.x == 0) s_task = atomicAdd(queue, 1);
+        if (threadIdx.x < LANE_W) s_progress[threadIdx.x] = 0;
+        __syncthreads();
+        const int q = s_task;
         if (q >= n_tasks) break;
         const LaneTask &T = tasks[q];
         const bool valid = lane < T.n_jobs;
         const int jid = T.job_ids[valid ? lane : 0];
         const DevJob &J = jobs[jid];
         DevResult *res = results + jid;
-        const bool active = valid && res->status == JOB_OK;
-        if (!__any_sync(0xffffffffu, active)) continue;
+        LaneGeom g;
+        lane_make_geom(g, valid && res->status == JOB_OK, J.ly);
         const DevGraph GL = graphs[T.left], GR = graphs[J.right];
         const DevModel m = models[T.model];
-        StripCtx c;
-        lane_make_ctx(c, T, active ? J.ly : 1, GL, m, d_off, d_estart, d_elogw, d_vrow, K);
+        LaneCtx c;
+        lane_make_ctx(c, T, GL, m, d_off, d_estart, d_elogw, d_vrow);
+        // keep the doubles in registers: ptxas otherwise re-derives them from the float model parameters
+        // (F2F) inside the row loop whenever registers get tight
+        asm volatile("" : "+d"(c.open), "+d"(c.ext), "+d"(c.lng));
         if (SMALLTAB) {
-            if (tab_model != T.model) {
-                __syncwarp();
-                for (int e = lane; e < m.fas * m.fas; e += 32) {
-                    double ls = (double)m.table[e];
-                    s_tab[wib][e] = make_double2(__dadd_rn(c.lng2, ls), __dadd_rn(c.lng, ls));
+            if (tab_model != T.model) {  // block-uniform
+                for (int e = threadIdx.x; e < m.fas * m.fas; e += blockDim.x) {
+                    const double ls = (double)m.table[e];
+                    s_tab[e] = make_double2(__dadd_rn(c.lng2, ls), __dadd_rn(c.lng, ls));
                 }
-                __syncwarp();
                 tab_model = T.model;
+                __syncthreads();
             }
-            c.stab = s_tab[wib];
+            c.stab = s_tab;
         }
-        lane_sweep<K, GENERAL, SMALLTAB, WR>(c, lane, active, T.max_ly, d_state + GR.state_base, d_elogw + GR.edge_base, sc,
-                                            reinterpret_cast<uint4 *>(ptrs + T.ptr_base), res);
-        __syncwarp();
+        const int *r_state = d_state + GR.state_base;
+        const float *r_elogw = d_elogw + GR.edge_base;
+        uint4 *ptr = reinterpret_cast<uint4 *>(ptrs + T.ptr_base) + lane;
+        const LaneSched sch = lane_schedule(c.nv, T.max_ly);
+        LState<K> st;
+        lane_strip_init<K, WR, SMALLTAB>(c, st, g, 0, r_state, r_elogw);
+
+        for (int u = 0; u < sch.items; ++u) {
+            const int r = u / sch.period, b = u - r * sch.period, s = r * LANE_W + w;
+            if (w == 0) {
+                // start bringing the NEXT item's wrap rows (written by warp W-1 one round earlier) into the ring;
+                // the copy lands while this item is being computed
+                const int u1 = u + 1, r1 = u1 / sch.period, b1 = u1 - r1 * sch.period;
+                if (r1 >= 1 && r1 < sch.rounds && b1 < sch.n_blocks) {
+                    lane_wait(progress + LANE_W - 1, u1 - sch.period + 1);
+                    const int v0 = b1 * LANE_B, v1 = min(v0 + LANE_B, c.nv);
+                    double *dst = ring + lane_ring_offset(LANE_W - 1, u1) + lane;
+                    const double *src = wrap + (long long)v0 * 96 + lane;
+                    for (int e = 0; e < (v1 - v0) * 3; ++e) {
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e * 32);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + e * 32) : "memory");
+                    }
+                }
+            }
+            if (s < sch.n_strips && b < sch.n_blocks) {
+                const bool has_next = s + 1 < sch.n_strips;
+                if (w > 0) lane_wait(progress + w - 1, u + 1);                                 // input block published
+                if (has_next && w < LANE_W - 1) lane_wait(progress + w + 1, u - LANE_D + 1);   // output slot drained
+                if (b == 0) lane_strip_init<K, WR, SMALLTAB>(c, st, g, s * K, r_state, r_elogw);
+                const int v0 = b * LANE_B, v1 = min(v0 + LANE_B, c.nv);
+                const double *ring_in = ring + lane_ring_offset((w + LANE_W - 1) % LANE_W, u) + lane;
+                double *ring_out = (has_next && w != LANE_W - 1) ? ring + lane_ring_offset(w, u) + lane : nullptr;
+                double *wrap_out = (has_next && w == LANE_W - 1) ? wrap + lane : nullptr;
+                lane_block<K, GENERAL, SMALLTAB, WR>(c, st, g, s, v0, v1, ring_in, ring_out, wrap_out, slots, endcol + lane, ptr);
+            }
+            if (w == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+            lane_publish(progress + w, u + 1, lane);
+        }
+        __syncthreads();
+        if (w == 0 && g.active) lane_end_corner(c, g, endcol + lane, r_elogw, res);
     }
 }
 #endif
 
-int lane_warps_per_sm() { return 4 * 3; }
+int lane_ctas_per_sm() { return PG2_LANE_MINB; }
 
-// Launches one group of lane tasks that share the kernel variant.  `scratch`: n_warps * warp_doubles doubles.
+// Launches one group of lane tasks that share the kernel variant.  `scratch`: n_ctas * lane_cta_doubles doubles.
 void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
                       const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
-                      const int4 *d_vrow, unsigned short *ptrs, DevResult *results, double *scratch, long long bcol_doubles,
-                      long long warp_doubles, int *queue, int n_warps, cudaStream_t stream) {
+                      const int4 *d_vrow, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv, int max_lx,
+                      int max_slots, int *queue, int n_ctas, cudaStream_t stream) {
     if (n_tasks <= 0) return;
     constexpr int K = LANE_K;
+    const long long wrap_doubles = (long long)max_nv * 96, endcol_doubles = (long long)max_lx * 96;
+    const long long slot_doubles = (long long)(max_slots + 2) * LANE_SLOT_DOUBLES;
 #ifndef PG2_HOST_EMU
     cudaMemsetAsync(queue, 0, sizeof(int), stream);
-    const int threads = 128;
-    const int blocks = (n_warps * 32 + threads - 1) / threads;
-#define PG2_LANE_LAUNCH(G, S, W)                                                                                              \
-    lane_fill_kernel<K, G, S, W><<<blocks, threads, 0, stream>>>(n_tasks, tasks, jobs, graphs, models, d_state, d_off, d_estart, \
-                                                                 d_elogw, d_vrow, ptrs, results, scratch, bcol_doubles,       \
-                                                                 warp_doubles, queue)
+    const int smem = LANE_RING_DOUBLES * (int)sizeof(double) + ((variant & 2) ? STRIP_SMALL_FAS * STRIP_SMALL_FAS * (int)sizeof(double2) : 0);
+#define PG2_LANE_LAUNCH(G, S, W)                                                                                                  \
+    do {                                                                                                                          \
+        cudaFuncSetAttribute(lane_fill_kernel<K, G, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                    \
+        lane_fill_kernel<K, G, S, W><<<n_ctas, LANE_W * 32, smem, stream>>>(n_tasks, tasks, jobs, graphs, models, d_state, d_off, \
+                                                                            d_estart, d_elogw, d_vrow, ptrs, results, scratch,    \
+                                                                            wrap_doubles, endcol_doubles, slot_doubles, queue);   \
+    } while (0)
     switch (variant & 7) {
         case 0: PG2_LANE_LAUNCH(false, false, false); break;
         case 1: PG2_LANE_LAUNCH(true, false, false); break;
@@ -306,52 +661,88 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
     }
 #undef PG2_LANE_LAUNCH
 #else
-    // CPU test emulation: lanes are independent, so each runs its whole sweep in turn
-    (void)queue; (void)n_warps; (void)stream;
-    LaneScratch sc;
-    sc.bcol0 = scratch;
-    sc.bcol1 = sc.bcol0 + bcol_doubles;
-    sc.saved = sc.bcol1 + bcol_doubles;
-    (void)warp_doubles;
+    // CPU test emulation of ONE CTA: the same items and block bodies; warp w runs item t - w at step t, warps and
+    // lanes one after the other -- one of the interleavings the progress counters admit (a producer's ring slot
+    // is read one step after it was written and rewritten LANE_D steps later).
+    (void)queue; (void)n_ctas; (void)stream;
+    double *wrap = scratch, *endcol = wrap + wrap_doubles, *slots0 = endcol + endcol_doubles;
+    std::vector<double> ring((size_t)LANE_RING_DOUBLES);
     for (int q = 0; q < n_tasks; ++q) {
         const LaneTask &T = tasks[q];
         const DevGraph GL = graphs[T.left];
         const DevModel m = models[T.model];
+        LaneCtx c;
+        lane_make_ctx(c, T, GL, m, d_off, d_estart, d_elogw, d_vrow);
         std::vector<double2> tab;
+        if (variant & 2) {
+            tab.resize((size_t)m.fas * m.fas);
+            for (int e = 0; e < m.fas * m.fas; ++e) {
+                const double ls = (double)m.table[e];
+                tab[e] = make_double2(c.lng2 + ls, c.lng + ls);
+            }
+            c.stab = tab.data();
+        }
+        const LaneSched sch = lane_schedule(c.nv, T.max_ly);
+        std::vector<LState<K> > st((size_t)LANE_W * 32);
+        LaneGeom geom[32];
+        const int *r_state[32];
+        const float *r_elogw[32];
+        DevResult *res[32];
         for (int lane = 0; lane < 32; ++lane) {
             const bool valid = lane < T.n_jobs;
             const int jid = T.job_ids[valid ? lane : 0];
             const DevJob &J = jobs[jid];
-            DevResult *res = results + jid;
-            const bool active = valid && res->status == JOB_OK;
-            if (!active) continue;  // an inactive lane stores nothing anybody reads
+            res[lane] = results + jid;
+            lane_make_geom(geom[lane], valid && res[lane]->status == JOB_OK, J.ly);
             const DevGraph GR = graphs[J.right];
-            StripCtx c;
-            lane_make_ctx(c, T, J.ly, GL, m, d_off, d_estart, d_elogw, d_vrow, K);
-            if (variant & 2) {
-                if (tab.empty()) {
-                    tab.resize((size_t)m.fas * m.fas);
-                    for (int e = 0; e < m.fas * m.fas; ++e) {
-                        double ls = (double)m.table[e];
-                        tab[e] = make_double2(c.lng2 + ls, c.lng + ls);
+            r_state[lane] = d_state + GR.state_base;
+            r_elogw[lane] = d_elogw + GR.edge_base;
+        }
+        for (int t = 0; t < sch.items + LANE_W - 1; ++t) {
+            for (int w = 0; w < LANE_W; ++w) {
+                const int u = t - w;
+                if (u < 0 || u >= sch.items) continue;
+                const int r = u / sch.period, b = u - r * sch.period, s = r * LANE_W + w;
+                if (s < sch.n_strips && b < sch.n_blocks) {
+                    const int v0 = b * LANE_B, v1 = v0 + LANE_B < c.nv ? v0 + LANE_B : c.nv;
+                    const bool has_next = s + 1 < sch.n_strips;
+                    for (int lane = 0; lane < 32; ++lane) {
+                        LState<K> &S = st[(size_t)w * 32 + lane];
+#define PG2_LANE_EMU(G, SM, WRV)                                                                                      \
+    do {                                                                                                               \
+        if (b == 0) lane_strip_init<K, WRV, SM>(c, S, geom[lane], s * K, r_state[lane], r_elogw[lane]);                \
+        lane_block<K, G, SM, WRV>(c, S, geom[lane], s, v0, v1,                                                         \
+                                  ring.data() + lane_ring_offset((w + LANE_W - 1) % LANE_W, u) + lane,                 \
+                                  (has_next && w != LANE_W - 1) ? ring.data() + lane_ring_offset(w, u) + lane : nullptr, \
+                                  (has_next && w == LANE_W - 1) ? wrap + lane : nullptr,                               \
+                                  slots0 + (long long)w * slot_doubles + lane, endcol + lane,                          \
+                                  reinterpret_cast<uint4 *>(ptrs + T.ptr_base) + lane);                                \
+    } while (0)
+                        switch (variant & 7) {
+                            case 0: PG2_LANE_EMU(false, false, false); break;
+                            case 1: PG2_LANE_EMU(true, false, false); break;
+                            case 2: PG2_LANE_EMU(false, true, false); break;
+                            case 3: PG2_LANE_EMU(true, true, false); break;
+                            case 4: PG2_LANE_EMU(false, false, true); break;
+                            case 5: PG2_LANE_EMU(true, false, true); break;
+                            case 6: PG2_LANE_EMU(false, true, true); break;
+                            case 7: PG2_LANE_EMU(true, true, true); break;
+                        }
+#undef PG2_LANE_EMU
                     }
                 }
-                c.stab = tab.data();
-            }
-            uint4 *ptr = reinterpret_cast<uint4 *>(ptrs + T.ptr_base);
-            const int *rs = d_state + GR.state_base;
-            const float *rw = d_elogw + GR.edge_base;
-            switch (variant & 7) {
-                case 0: lane_sweep<K, false, false, false>(c, lane, true, T.max_ly, rs, rw, sc, ptr, res); break;
-                case 1: lane_sweep<K, true, false, false>(c, lane, true, T.max_ly, rs, rw, sc, ptr, res); break;
-                case 2: lane_sweep<K, false, true, false>(c, lane, true, T.max_ly, rs, rw, sc, ptr, res); break;
-                case 3: lane_sweep<K, true, true, false>(c, lane, true, T.max_ly, rs, rw, sc, ptr, res); break;
-                case 4: lane_sweep<K, false, false, true>(c, lane, true, T.max_ly, rs, rw, sc, ptr, res); break;
-                case 5: lane_sweep<K, true, false, true>(c, lane, true, T.max_ly, rs, rw, sc, ptr, res); break;
-                case 6: lane_sweep<K, false, true, true>(c, lane, true, T.max_ly, rs, rw, sc, ptr, res); break;
-                case 7: lane_sweep<K, true, true, true>(c, lane, true, T.max_ly, rs, rw, sc, ptr, res); break;
+                if (w == 0) {
+                    const int u1 = u + 1, r1 = u1 / sch.period, b1 = u1 - r1 * sch.period;
+                    if (r1 >= 1 && r1 < sch.rounds && b1 < sch.n_blocks) {
+                        const int v0 = b1 * LANE_B, v1 = v0 + LANE_B < c.nv ? v0 + LANE_B : c.nv;
+                        memcpy(ring.data() + lane_ring_offset(LANE_W - 1, u1), wrap + (long long)v0 * 96,
+                               sizeof(double) * (size_t)(v1 - v0) * 96);
+                    }
+                }
             }
         }
+        for (int lane = 0; lane < 32; ++lane)
+            if (geom[lane].active) lane_end_corner(c, geom[lane], endcol + lane, r_elogw[lane], res[lane]);
     }
 #endif
 }

@@ -73,7 +73,17 @@ __host__ __device__ inline long long strip_ptr_index(int nv, int ly, int K, int 
 // Pointer buffer of one task: [strip][virtual row][K/8][lane] uint4, i.e. 8 half-words (8 columns) per lane
 // per 128-bit store, lanes interleaved so that a warp-wide store is one contiguous 512 B segment.
 constexpr int LANE_K = 8;             // columns per lane strip (multiple of 8)
+constexpr int LANE_W = 4;             // warps per CTA = strips of one task in flight
+#ifndef PG2_LANE_B
+#define PG2_LANE_B 8
+#endif
+#ifndef PG2_LANE_D
+#define PG2_LANE_D 2
+#endif
+constexpr int LANE_B = PG2_LANE_B;    // virtual rows per pipeline block
+constexpr int LANE_D = PG2_LANE_D;    // blocks a warp may run ahead of the warp that consumes its boundary column
 constexpr int LANE_MIN_JOBS = 16;     // fewer jobs on one row graph than this stay on the strip kernel
+constexpr int LANE_SLOT_DOUBLES = (LANE_K + 1) * 4 * 32;  // one parked row of one warp: [K+1 columns][X,Y,M,Mo][lane]
 __host__ __device__ inline long long lane_cells(int nv, int max_ly, int K) {  // half-words per task
     long long strips = (max_ly + K - 1) / K;
     return strips * (long long)nv * 32 * K;
@@ -82,13 +92,12 @@ __host__ __device__ inline long long lane_ptr_index(int nv, int K, int v, int j,
     int s = j / K, k = j - s * K;
     return ((((long long)s * nv + v) * (K / 8) + (k >> 3)) * 32 + lane) * 8 + (k & 7);
 }
-
-// per-warp scratch of the lane kernel, in doubles: two boundary-column buffers [row][X,Y,M][lane] and the
-// saved rows [slot][k][X,Y,M][lane]
-__host__ __device__ inline long long lane_bcol_doubles(int max_lx) { return (long long)max_lx * 96; }
-__host__ __device__ inline long long lane_saved_doubles(int n_slots, int K) { return (long long)n_slots * K * 96; }
-__host__ __device__ inline long long lane_warp_doubles(int max_lx, int n_slots, int K) {
-    return 2 * lane_bcol_doubles(max_lx) + lane_saved_doubles(n_slots > 0 ? n_slots : 1, K);
+// per-CTA global scratch of the lane kernel, in doubles: the wrap column [virtual row][X,Y,M][lane] (strip
+// boundary handed from the CTA's last warp to its first), the end column [row][X,Y,M][lane] (what the end
+// corner reads) and per warp n_slots + 2 parked rows (the saved rows, the row above a general site, and the
+// pointer accumulators of a site that straddles two pipeline blocks).
+__host__ __device__ inline long long lane_cta_doubles(int max_nv, int max_lx, int n_slots) {
+    return (long long)max_nv * 96 + (long long)max_lx * 96 + (long long)LANE_W * (n_slots + 2) * LANE_SLOT_DOUBLES;
 }
 
 // Decodes one pointer of a strip-kernel half-word into the API encoding (mat | lord<<2 | rord<<8).
@@ -103,6 +112,14 @@ __host__ __device__ inline unsigned strip_decode_ptr(unsigned w, int mat) {
     if (mat == X_MAT) return w & 0x3fu;
     if (mat == Y_MAT) return (w >> 6) & 3u;
     return (w >> 8) & 0x3fu;
+}
+
+// Lane-kernel half-words: fast rows as above; general rows carry the X pointer in bits 0-5, the raw outcome bits
+// of the Y chain in bits 6 (open beat double) and 7 (that winner beat ext), the M pointer in bits 8-13.
+__host__ __device__ inline unsigned lane_decode_ptr(unsigned w, int mat) {
+    if ((w & 0x4000u) || mat != Y_MAT) return strip_decode_ptr(w, mat);
+    unsigned p2 = (w >> 6) & 1u, p1 = (w >> 7) & 1u;
+    return p1 ? (p2 ? M_MAT : X_MAT) : Y_MAT;
 }
 
 }  // namespace pg2

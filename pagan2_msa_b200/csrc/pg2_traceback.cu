@@ -140,7 +140,8 @@ __device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int
         if (i == 0 && j == 0) { out = NO_MAT; return true; }  // start corner: no predecessor
         const long long idx = J.kernel == 2 ? lane_ptr_index(t.nv, LANE_K, t.vlast[i], j, J.lane)
                                             : strip_ptr_index(t.nv, J.ly, J.strip_k, t.vlast[i], j);
-        out = strip_decode_ptr(t.ptr16[J.cell_base + idx], mat);
+        const unsigned w = t.ptr16[J.cell_base + idx];
+        out = J.kernel == 2 ? lane_decode_ptr(w, mat) : strip_decode_ptr(w, mat);
     }
     return true;
 }

@@ -64,9 +64,23 @@ def test_lane_kernel_shared_target_vs_oracle(emu_lib, seed, plain_left, n_jobs):
     with make_engine(emu_lib, False) as eng:
         res = enginecheck.check_batch(eng, jobs)
         st = eng.stats()
-    assert (res["kernel"][:3 * n_jobs] == 2).sum() >= 3 * (n_jobs // 32) * 32
+    assert (res["kernel"][:3 * n_jobs] == 2).all()
     assert (res["kernel"][-5:] == 1).all()
     assert st["jobs_lanes"] == int((res["kernel"] == 2).sum())
+
+
+@pytest.mark.parametrize("seed", [71, 72, 73, 74])
+def test_lane_kernel_schedule_shapes(emu_lib, seed):
+    """Pipeline schedule edge cases: row programs shorter than the pipeline depth, one strip only, many
+    rounds (reads of several hundred columns), reads of one site."""
+    rng = np.random.default_rng(seed)
+    jobs = []
+    for nl, nr_max in ((1, 4), (2, 9), (5, 40), (30, 9), (33, 300), (150, 120), (9, 70)):
+        jobs += randjobs.random_shared_target_jobs(rng, 20, nl=nl, nr_max=nr_max)
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 2).all()
 
 
 def test_lane_kernel_long_reads_and_bad_job(emu_lib):
@@ -78,7 +92,7 @@ def test_lane_kernel_long_reads_and_bad_job(emu_lib):
     jobs[7].expected_status = abi.PG2_JOB_BAD_GRAPH
     with make_engine(emu_lib, False) as eng:
         res = enginecheck.check_batch(eng, jobs)
-    assert (res["kernel"] == 2).sum() == 32
+    assert (res["kernel"] == 2).all()
 
 
 @pytest.mark.parametrize("kind,seed", [("general", 21), ("banded", 22), ("strip", 23)])

@@ -74,7 +74,7 @@ def test_lane_kernel_shared_target_vs_oracle(eng, seed, plain_left, n_jobs):
     jobs += [randjobs.random_job(rng, "strip") for _ in range(5)]
     jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
     res = enginecheck.check_batch(eng, jobs)
-    assert (res["kernel"][:6 * n_jobs] == 2).sum() >= 6 * (n_jobs // 32) * 32
+    assert (res["kernel"][:6 * n_jobs] == 2).all()
     assert (res["kernel"][-5:] == 1).all()
 
 
@@ -85,7 +85,7 @@ def test_lane_kernel_long_reads_and_bad_job(eng):
     jobs[7].right.state[1] = 99
     jobs[7].expected_status = abi.PG2_JOB_BAD_GRAPH
     res = enginecheck.check_batch(eng, jobs)
-    assert (res["kernel"] == 2).sum() == 32
+    assert (res["kernel"] == 2).all()
 
 
 def test_lane_and_strip_kernels_agree_bitwise(eng, eng_nolanes, golden):
@@ -105,7 +105,7 @@ def test_lane_and_strip_kernels_agree_bitwise(eng, eng_nolanes, golden):
     jobs = synth.placement_jobs(targets, reads, assign, model)
     ra, sa = eng.align(jobs)
     rb, sb = eng_nolanes.align(jobs)
-    assert (ra["kernel"] == 2).sum() >= 300 and (rb["kernel"] == 1).all()
+    assert (ra["kernel"] == 2).all() and (rb["kernel"] == 1).all()
     assert (ra["status"] == 0).all()
     assert (ra["score"].view(np.uint64) == rb["score"].view(np.uint64)).all()
     for k, job in enumerate(jobs):
