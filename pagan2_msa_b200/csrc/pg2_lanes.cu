@@ -32,6 +32,9 @@
 #ifdef PG2_HOST_EMU
 #include <vector>
 #endif
+#ifdef PG2_LANE_TIMING
+#include <cstdio>
+#endif
 
 #ifndef PG2_LANE_MINB
 #define PG2_LANE_MINB 3
@@ -140,12 +143,12 @@ __device__ __forceinline__ void lane_y_chain(const LaneCtx &c, LState<K> &st, do
 // (lane_decode_ptr, pg2_strip_geom.cuh).  A cell whose candidates are all -inf gets arbitrary bits: it cannot
 // lie on the Viterbi path.
 //
-// Row whose only backward edge comes from the row above: in-place update of the strip.
+// Row whose only backward edge comes from the row above: in-place update of X and M of the strip (the Y chain
+// follows, lane_y_chain).
 //   WL      the edge carries a log weight (wl)           EXTARR  ex[k] holds the X-extension term of column k
-//   CORNER  the row may be row 0 of the first strip      (else every column extends with log_gap_ext)
-template <int K, bool WL, bool WR, bool SMALLTAB, bool EXTARR, bool CORNER>
-__device__ __forceinline__ void lane_fast_row(const LaneCtx &c, LState<K> &st, int sl, double wl, const double *ex, double extY,
-                                              bool corner, double rX, double rY, double rM, unsigned *w) {
+//                                                        (else every column extends with log_gap_ext)
+template <int K, bool WL, bool WR, bool SMALLTAB, bool EXTARR>
+__device__ __forceinline__ void lane_xm_row(const LaneCtx &c, LState<K> &st, int sl, double wl, const double *ex, unsigned *w) {
 #pragma unroll
     for (int h = 0; h < K / 2; ++h) w[h] = 0x40004000u;
     const int rowoff = SMALLTAB ? sl * 16 : sl;
@@ -175,13 +178,7 @@ __device__ __forceinline__ void lane_fast_row(const LaneCtx &c, LState<K> &st, i
     }
     // Column 0 needs no special case for i > 0: its M sources are the -inf boundary, so M(i,0) = -inf falls
     // out of the arithmetic.  Row 0 has no edges but its sources are the -inf initial strip, so X(0,j) =
-    // M(0,j) = -inf fall out as well; only the start corner M(0,0) = 0 (:725-733) is planted here, with the
-    // open penalty its two gap moves pay (get_log_gap_open_penalty, basic_alignment.h:490-513).
-    if (CORNER && corner) {
-        st.M[0] = 0.0;
-        st.Mo[0] = __dadd_rn(__dadd_rn(0.0, c.lng), c.reduced ? 0.0 : c.open);
-    }
-    lane_y_chain<K, 4u, 8u>(c, st, extY, rX, rY, rM, w);
+    // M(0,j) = -inf fall out as well; the start corner is planted by the caller (lane_slow_row).
 }
 
 // A parked row of one warp: [column 0 = c0-1, column k+1 = c0+k][X, Y, M, Mo][lane].
@@ -196,58 +193,59 @@ __device__ __forceinline__ void lane_park(const LaneCtx &c, const LState<K> &st,
     }
 }
 
-// One virtual row of a site that is not a fast row (several edges, a long-span edge, an edge weight, or no edge
-// at all).  The row above is parked on the site's first virtual row, so st.X / st.M become the accumulators and
-// every edge reads its source row from a slot.  Returns true on the site's last virtual row; the caller then
-// runs lane_commit.
+// Pointer accumulators of a site whose backward edges are visited one virtual row at a time (several edges, a
+// long-span edge, or no edge at all): X pointer (mat | ordinal << 2) << 4 | M pointer, mat in bits 0-1 and
+// ordinal in bits 10-13 -- the layout of the general-form half-word (lane_decode_ptr).
+template <int K> struct LAcc {
+    unsigned pXM[K];
+};
+constexpr unsigned LANE_PX_KEEP = ~0x3f0u, LANE_PM_KEEP = ~0x3c03u;
+__device__ __forceinline__ unsigned lane_px(unsigned mat, unsigned ord) { return (mat | (ord << 2)) << 4; }
+__device__ __forceinline__ unsigned lane_pm(unsigned mat, unsigned ord) { return mat | (ord << 10); }
+
+// One edge of such a site.  The row above is parked on the site's first virtual row (slot n_slots of the warp's
+// scratch), so st.X / st.M become the score accumulators and every edge reads its source row from a slot: one
+// copy of the code, no extra registers in flight.  Returns true on the site's last virtual row.
 template <int K, bool WR, bool SMALLTAB>
-__device__ __forceinline__ bool lane_general_vrow(const LaneCtx &c, LState<K> &st, unsigned *pXM, const double *ex, int4 vr,
-                                                  double *slots) {
+__device__ __forceinline__ bool lane_general_vrow(const LaneCtx &c, LState<K> &st, LAcc<K> &acc, const double *ex, int4 vr, double *slots) {
     const double ninf = neg_inf();
     const int info = vr.x, sl = info & VR_STATE_MASK;
     const int rowoff = SMALLTAB ? sl * 16 : sl;
     if (info & VR_FIRST) {
         lane_park<K>(c, st, slots + (long long)c.n_slots * LANE_SLOT_DOUBLES);
 #pragma unroll
-        for (int k = 0; k < K; ++k) { st.X[k] = ninf; st.M[k] = ninf; pXM[k] = NO_MAT | (NO_MAT << 8); }
+        for (int k = 0; k < K; ++k) { st.X[k] = ninf; st.M[k] = ninf; acc.pXM[k] = lane_px(NO_MAT, 0) | lane_pm(NO_MAT, 0); }
     }
     if (!(info & VR_NOEDGE)) {
         const double wl = (info & VR_ZERO_W) ? 0.0 : (double)c.l_elogw[vr.y];  // + 0.0 is exact
-        const unsigned ord = ((unsigned)vr.w >> 16) << 2;
+        const unsigned ord = (unsigned)vr.w >> 16;
         const int slot = (info & VR_REG) ? c.n_slots : (vr.w & 0xffff);
         const double *row = slots + (long long)slot * LANE_SLOT_DOUBLES;
+        // source row: column c0-1 in [0], column c0+k in [k+1]; all loads in flight at once (one L2 round trip)
+        double sX[K + 1], sY[K + 1], sM[K], sMo[K];
+#pragma unroll
+        for (int k = 0; k <= K; ++k) { sX[k] = row[k * 128]; sY[k] = row[k * 128 + 32]; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) { sM[k] = row[k * 128 + 64]; sMo[k] = row[(k + 1) * 128 + 96]; }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double *up = row + (k + 1) * 128, *dg = row + k * 128;
             // X: ext, double, open (:2116-2211); the open candidate was formed when the source row was made
-            acc_gt(__dadd_rn(up[0], ex[k]), st.X[k], pXM[k], 0xff00u, X_MAT | ord);
-            acc_gt(__dadd_rn(up[32], c.open), st.X[k], pXM[k], 0xff00u, Y_MAT | ord);
-            acc_gt(up[96], st.X[k], pXM[k], 0xff00u, M_MAT | ord);
+            acc_gt(__dadd_rn(sX[k + 1], ex[k]), st.X[k], acc.pXM[k], LANE_PX_KEEP, lane_px(X_MAT, ord));
+            acc_gt(__dadd_rn(sY[k + 1], c.open), st.X[k], acc.pXM[k], LANE_PX_KEEP, lane_px(Y_MAT, ord));
+            acc_gt(sMo[k], st.X[k], acc.pXM[k], LANE_PX_KEEP, lane_px(M_MAT, ord));
             // M: from M, X, Y (:2029-2112), ((score + log) + wl) + wr
             double mlog, xlog;
             lane_subst<SMALLTAB>(c, rowoff, st.tab[k], mlog, xlog);
-            double a = __dadd_rn(__dadd_rn(dg[64], mlog), wl);
-            double b = __dadd_rn(__dadd_rn(dg[0], xlog), wl);
-            double d = __dadd_rn(__dadd_rn(dg[32], xlog), wl);
+            double a = __dadd_rn(__dadd_rn(sM[k], mlog), wl);
+            double b = __dadd_rn(__dadd_rn(sX[k], xlog), wl);
+            double d = __dadd_rn(__dadd_rn(sY[k], xlog), wl);
             if (WR) { a = __dadd_rn(a, st.wr[k]); b = __dadd_rn(b, st.wr[k]); d = __dadd_rn(d, st.wr[k]); }
-            acc_gt(a, st.M[k], pXM[k], 0x00ffu, (M_MAT | ord) << 8);
-            acc_gt(b, st.M[k], pXM[k], 0x00ffu, (X_MAT | ord) << 8);
-            acc_gt(d, st.M[k], pXM[k], 0x00ffu, (Y_MAT | ord) << 8);
+            acc_gt(a, st.M[k], acc.pXM[k], LANE_PM_KEEP, lane_pm(M_MAT, ord));
+            acc_gt(b, st.M[k], acc.pXM[k], LANE_PM_KEEP, lane_pm(X_MAT, ord));
+            acc_gt(d, st.M[k], acc.pXM[k], LANE_PM_KEEP, lane_pm(Y_MAT, ord));
         }
     }
     return (info & VR_LAST) != 0;
-}
-
-// Last virtual row of a general site: the accumulators hold X(i,.) and M(i,.); refresh Mo, run the Y chain and
-// emit general-form half-words: X pointer bits 0-5, raw Y outcome bits 6-7, M pointer bits 8-13, bit 14 clear.
-template <int K>
-__device__ __forceinline__ void lane_commit(const LaneCtx &c, LState<K> &st, const unsigned *pXM, double extY, double rX, double rY,
-                                            double rM, unsigned *w) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) st.Mo[k] = __dadd_rn(__dadd_rn(st.M[k], c.lng), c.open);
-#pragma unroll
-    for (int h = 0; h < K / 2; ++h) w[h] = pXM[2 * h] | (pXM[2 * h + 1] << 16);
-    lane_y_chain<K, 64u, 128u>(c, st, extY, rX, rY, rM, w);
 }
 
 // per-lane constants of one strip
@@ -288,22 +286,23 @@ __device__ __forceinline__ void lane_ext_terms(const LaneCtx &c, const LaneGeom 
     }
 }
 
-// A pipeline block whose LANE_B virtual rows are all plain interior rows (one unit-weight edge from the row
-// above, not row 0, not read by the end corner, never parked): the hot loop, nothing but the row body, the
-// boundary hand-over and the pointer store.
-template <int K, bool SMALLTAB, bool WR, bool EXTARR>
-__device__ __forceinline__ void lane_fast_block(const LaneCtx &c, LState<K> &st, const double *ex, int v0, bool first, bool store_ptr,
-                                                const double *ring_in, double *out, uint4 *dst) {
+// A run of n plain interior rows starting at virtual row v (one unit-weight edge from the row above, not row 0,
+// not read by the end corner, never parked): the hot loop, nothing but the row body, the boundary hand-over and
+// the pointer store.  ex[k]: X-extension term of column k; ring_in / out / dst point at the run's first row.
+template <int K, bool SMALLTAB, bool WR>
+__device__ __forceinline__ void lane_fast_run(const LaneCtx &c, LState<K> &st, const double *ex, int v, int n, bool first, bool store_ptr,
+                                              const double *ring_in, double *out, uint4 *dst) {
     const double ninf = neg_inf();
     constexpr int Q = K / 8;
-    int info_n = __ldg(&c.l_vrow[v0].x);
-    for (int r = 0; r < LANE_B; ++r) {
+    int info_n = __ldg(&c.l_vrow[v].x);
+    for (int r = 0; r < n; ++r) {
         const int sl = info_n & VR_STATE_MASK;
-        if (r + 1 < LANE_B) info_n = __ldg(&c.l_vrow[v0 + r + 1].x);
+        if (r + 1 < n) info_n = __ldg(&c.l_vrow[v + r + 1].x);
         double rX = ninf, rY = ninf, rM = ninf;
         if (!first) { rX = ring_in[r * 96]; rY = ring_in[r * 96 + 32]; rM = ring_in[r * 96 + 64]; }
         unsigned w[K / 2];
-        lane_fast_row<K, false, WR, SMALLTAB, EXTARR, false>(c, st, sl, 0.0, ex, c.ext, false, rX, rY, rM, w);
+        lane_xm_row<K, false, WR, SMALLTAB, true>(c, st, sl, 0.0, ex, w);
+        lane_y_chain<K, 4u, 8u>(c, st, c.ext, rX, rY, rM, w);
         if (store_ptr) {
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -319,7 +318,68 @@ __device__ __forceinline__ void lane_fast_block(const LaneCtx &c, LState<K> &st,
     }
 }
 
-// One pipeline block of one lane: virtual rows [v0, v1) of strip `s`.
+// One virtual row of any other kind -- a row of the first strip or of a strip that holds a last column, row 0, a
+// row the end corner reads, a row that is parked for long-span edges, a weighted edge, one edge of a multi-edge
+// site: the generic body.  Returns true while a multi-edge site stays open.
+template <int K, bool GENERAL, bool SMALLTAB, bool WR>
+__device__ __forceinline__ bool lane_slow_row(const LaneCtx &c, LState<K> &st, LAcc<K> &acc, const double *ex, const LaneGeom &g, int s, int v, bool first,
+                                              bool store_ptr, bool is_last, const double *ring_in, double *out, uint4 *dst, double *slots,
+                                              double *endcol) {
+    const double ninf = neg_inf();
+    constexpr int Q = K / 8;
+    const int4 vr = __ldg(c.l_vrow + v);
+    const int info = vr.x, i = vr.z;
+    const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : c.ext;
+    unsigned w[K / 2];
+    if (GENERAL && (info & VR_FAST) != VR_FAST) {
+        // one edge of a general site; after its last virtual row the accumulators are row i of the strip
+        if (!lane_general_vrow<K, WR, SMALLTAB>(c, st, acc, ex, vr, slots)) return true;
+#pragma unroll
+        for (int k = 0; k < K; ++k) st.Mo[k] = __dadd_rn(__dadd_rn(st.M[k], c.lng), c.open);
+#pragma unroll
+        for (int h = 0; h < K / 2; ++h) w[h] = acc.pXM[2 * h] | (acc.pXM[2 * h + 1] << 16);
+    } else {
+        // one edge from the row above (or row 0): in place, adding the edge's log weight (+ 0.0 is exact)
+        const double wl = (!GENERAL || (info & (VR_ZERO_W | VR_NOEDGE))) ? 0.0 : (double)c.l_elogw[vr.y];
+        lane_xm_row<K, GENERAL, WR, SMALLTAB, true>(c, st, info & VR_STATE_MASK, wl, ex, w);
+        if (first && i == 0) {
+            // the start corner M(0,0) = 0 (:725-733), with the open penalty its two gap moves pay
+            // (get_log_gap_open_penalty, basic_alignment.h:490-513)
+            st.M[0] = 0.0;
+            st.Mo[0] = __dadd_rn(__dadd_rn(0.0, c.lng), c.reduced ? 0.0 : c.open);
+        }
+    }
+    double rX = ninf, rY = ninf, rM = ninf;
+    if (!first) { rX = ring_in[0]; rY = ring_in[32]; rM = ring_in[64]; }
+    lane_y_chain<K, 4u, 8u>(c, st, extY, rX, rY, rM, w);
+    if (store_ptr) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            uint4 o;
+            o.x = w[4 * q]; o.y = w[4 * q + 1]; o.z = w[4 * q + 2]; o.w = w[4 * q + 3];
+            dst[q * 32] = o;
+        }
+    }
+    if (out) { out[0] = st.X[K - 1]; out[32] = st.Y[K - 1]; out[64] = st.M[K - 1]; }
+    if (GENERAL) {
+        const int slot = (int)((unsigned)info >> VR_SLOT_SHIFT) - 1;
+        if (slot >= 0) lane_park<K>(c, st, slots + (long long)slot * LANE_SLOT_DOUBLES);
+    }
+    if ((info & VR_ENDPRED) && is_last) {
+        // rows the end corner reads: the lane's LAST column (ly-1)
+        double vx = ninf, vy = ninf, vm = ninf;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (k == g.last_k) { vx = st.X[k]; vy = st.Y[k]; vm = st.M[k]; }
+        double *b = endcol + (long long)i * 96;
+        b[0] = vx; b[32] = vy; b[64] = vm;
+    }
+    return false;
+}
+
+// One pipeline block of one lane: virtual rows [v0, v1) of strip `s`, as runs of plain rows and single other rows.
+// Code size matters here: the SM's instruction cache holds about 2000 instructions, so there is exactly one copy
+// of the hot loop and one generic body for every other kind of row.
 //   ring_in   left neighbour column of these rows, [row - v0][X,Y,M][lane] (already offset by the lane); unused
 //             for the first strip (-inf boundary)
 //   ring_out  where this strip's last column goes for the next strip, same shape; wrap_out (global, indexed by
@@ -328,111 +388,54 @@ template <int K, bool GENERAL, bool SMALLTAB, bool WR>
 __device__ __forceinline__ void lane_block(const LaneCtx &c, LState<K> &st, const LaneGeom &g, int s, int v0, int v1,
                                            const double *ring_in, double *ring_out, double *wrap_out, double *slots, double *endcol,
                                            uint4 *ptr) {
-    const double ninf = neg_inf();
     const bool first = (s == 0);
     const bool store_ptr = g.active && s * K < g.ly;
     const bool is_last = g.active && s == g.last_strip;
     constexpr int Q = K / 8;
-    // warp-uniform: is this a block of plain interior rows?
-    if (v1 - v0 == LANE_B) {
-        int all = ~0, any = 0;
+    // warp-uniform: which rows of the block are plain interior rows?
+    unsigned plain = 0;
+    int info0 = 0;
 #pragma unroll
-        for (int r = 0; r < LANE_B; ++r) {
+    for (int r = 0; r < LANE_B; ++r) {
+        if (v0 + r < v1) {
             const int info = __ldg(&c.l_vrow[v0 + r].x);
-            all &= info;
-            any |= info;
-        }
-        const int need = VR_FAST | VR_ZERO_W;
-        const int none = VR_ENDPRED | VR_NOEDGE | (int)(~0u << VR_SLOT_SHIFT);
-        if ((all & need) == need && !(any & none)) {
-            double *out = wrap_out ? wrap_out + (long long)v0 * 96 : ring_out;
-            uint4 *dst = ptr + ((long long)s * c.nv + v0) * Q * 32;
-            if (lane_any(first || is_last)) {
-                double ex[K];
-                lane_ext_terms<K>(c, g, s, ex);
-                lane_fast_block<K, SMALLTAB, WR, true>(c, st, ex, v0, first, store_ptr, ring_in, out, dst);
-            } else {
-                lane_fast_block<K, SMALLTAB, WR, false>(c, st, nullptr, v0, first, store_ptr, ring_in, out, dst);
-            }
-            return;
+            if (r == 0) info0 = info;
+            const int need = VR_FAST | VR_ZERO_W;
+            const int none = VR_ENDPRED | VR_NOEDGE | (int)(~0u << VR_SLOT_SHIFT);
+            if ((info & need) == need && !(info & none)) plain |= 1u << r;
         }
     }
-    // mixed block: row by row
     double ex[K];
-    unsigned pXM[K];  // general rows: X pointer | M pointer << 8 (mat | edge ordinal << 2)
     lane_ext_terms<K>(c, g, s, ex);
-    int4 vr_n = __ldg(c.l_vrow + v0);
+    double *out = wrap_out ? wrap_out + (long long)v0 * 96 : ring_out;
+    uint4 *dst = ptr + ((long long)s * c.nv + v0) * Q * 32;
     // a site whose virtual rows straddle the block boundary keeps its pointer accumulators in the warp's scratch
-    unsigned *pxm_save = reinterpret_cast<unsigned *>(slots + (long long)(c.n_slots + 1) * LANE_SLOT_DOUBLES);
+    LAcc<K> acc;
+    unsigned *acc_area = reinterpret_cast<unsigned *>(slots + (long long)(c.n_slots + 1) * LANE_SLOT_DOUBLES);
 #pragma unroll
-    for (int k = 0; k < K; ++k) pXM[k] = 0;
-    if (GENERAL && !(vr_n.x & VR_FIRST)) {
+    for (int k = 0; k < K; ++k) acc.pXM[k] = 0;
+    if (GENERAL && v0 < v1 && !(info0 & VR_FIRST)) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) pXM[k] = pxm_save[k * 64];
+        for (int k = 0; k < K; ++k) acc.pXM[k] = acc_area[k * 64];
     }
     bool open_site = false;
-    for (int v = v0; v < v1; ++v) {
-        const int4 vr = vr_n;
-        if (v + 1 < v1) vr_n = __ldg(c.l_vrow + v + 1);
-        const int info = vr.x, i = vr.z;
-        const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : c.ext;
-        unsigned w[K / 2];
-        // one edge from the row above (or row 0): in place; with the edge's log weight when it has one
-        const bool fast = (info & VR_FAST) == VR_FAST;
-        const bool weighted = !(info & (VR_ZERO_W | VR_NOEDGE));
-        if (GENERAL && !fast) {
-            open_site = !lane_general_vrow<K, WR, SMALLTAB>(c, st, pXM, ex, vr, slots);
-            if (open_site) continue;
-        }
-        double rX = ninf, rY = ninf, rM = ninf;
-        if (!first) {
-            const double *b = ring_in + (v - v0) * 96;
-            rX = b[0]; rY = b[32]; rM = b[64];
-        }
-        if (!GENERAL || fast) {
-            if (GENERAL && weighted)
-                lane_fast_row<K, true, WR, SMALLTAB, true, false>(c, st, info & VR_STATE_MASK, (double)c.l_elogw[vr.y], ex, extY, false,
-                                                                   rX, rY, rM, w);
-            else
-                lane_fast_row<K, false, WR, SMALLTAB, true, true>(c, st, info & VR_STATE_MASK, 0.0, ex, extY, first && i == 0, rX, rY,
-                                                                   rM, w);
+    int r = 0;
+    const int n = v1 - v0;
+    while (r < n) {
+        const int run = __ffs((int)~(plain >> r)) - 1;  // plain rows from r on
+        if (run > 0) {
+            lane_fast_run<K, SMALLTAB, WR>(c, st, ex, v0 + r, run, first, store_ptr, ring_in + r * 96, out ? out + r * 96 : nullptr,
+                                           dst + r * Q * 32);
+            r += run;
         } else {
-            lane_commit<K>(c, st, pXM, extY, rX, rY, rM, w);
-        }
-
-        if (store_ptr) {
-            uint4 *dst = ptr + ((long long)s * c.nv + v) * Q * 32;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                uint4 o;
-                o.x = w[4 * q]; o.y = w[4 * q + 1]; o.z = w[4 * q + 2]; o.w = w[4 * q + 3];
-                dst[q * 32] = o;
-            }
-        }
-        if (wrap_out) {
-            double *b = wrap_out + (long long)v * 96;
-            b[0] = st.X[K - 1]; b[32] = st.Y[K - 1]; b[64] = st.M[K - 1];
-        } else if (ring_out) {
-            double *b = ring_out + (v - v0) * 96;
-            b[0] = st.X[K - 1]; b[32] = st.Y[K - 1]; b[64] = st.M[K - 1];
-        }
-        if (GENERAL) {
-            const int slot = (int)((unsigned)info >> VR_SLOT_SHIFT) - 1;
-            if (slot >= 0) lane_park<K>(c, st, slots + (long long)slot * LANE_SLOT_DOUBLES);
-        }
-        if ((info & VR_ENDPRED) && is_last) {
-            // rows the end corner reads: the lane's LAST column (ly-1)
-            double vx = ninf, vy = ninf, vm = ninf;
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                if (k == g.last_k) { vx = st.X[k]; vy = st.Y[k]; vm = st.M[k]; }
-            double *b = endcol + (long long)i * 96;
-            b[0] = vx; b[32] = vy; b[64] = vm;
+            open_site = lane_slow_row<K, GENERAL, SMALLTAB, WR>(c, st, acc, ex, g, s, v0 + r, first, store_ptr, is_last, ring_in + r * 96,
+                                                                out ? out + r * 96 : nullptr, dst + r * Q * 32, slots, endcol);
+            r += 1;
         }
     }
     if (GENERAL && open_site) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) pxm_save[k * 64] = pXM[k];
+        for (int k = 0; k < K; ++k) acc_area[k * 64] = acc.pXM[k];
     }
 }
 
@@ -517,20 +520,35 @@ __device__ __forceinline__ int lane_ring_offset(int channel, int u) {
 }
 
 #ifndef PG2_HOST_EMU
-// spin until *p >= target (a per-warp progress counter in shared memory, published with lane_publish)
-__device__ __forceinline__ void lane_wait(const volatile int *p, int target) {
+// Progress counters (shared memory, one per pipeline stage).  A stage publishes "item u done" with a release
+// store after its lanes have synchronised; a waiting stage polls with acquire loads.  CTA scope is all that
+// is needed: producer and consumer run on the same SM.
+__device__ __forceinline__ void lane_wait(const int *p, int target) {
     if (target <= 0) return;
-#ifdef PG2_LANE_SLEEP
-    while (*p < target) __nanosleep(PG2_LANE_SLEEP);
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    int v;
+    for (;;) {
+#if defined(PG2_LANE_FENCE_NONE)
+        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
 #else
-    while (*p < target) {}
+        asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
 #endif
-    __threadfence_block();
+        if (v >= target) break;
+#ifdef PG2_LANE_SLEEP
+        __nanosleep(PG2_LANE_SLEEP);
+#endif
+    }
 }
-__device__ __forceinline__ void lane_publish(volatile int *p, int value, int lane) {
-    __threadfence_block();
+__device__ __forceinline__ void lane_publish(int *p, int value, int lane) {
     __syncwarp();
-    if (lane == 0) *p = value;
+    if (lane == 0) {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+#if defined(PG2_LANE_FENCE_NONE)
+        asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(value) : "memory");
+#else
+        asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(value) : "memory");
+#endif
+    }
 }
 
 template <int K, bool GENERAL, bool SMALLTAB, bool WR>
@@ -545,11 +563,18 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
     __shared__ int s_task;
     __shared__ int s_progress[LANE_W];
     const int lane = threadIdx.x & 31;
+    // pipeline stage of this warp.  Hardware warp k of every CTA lives on SM sub-partition k % 4; rotating the
+    // stages by the CTA index puts one warp of each stage on every sub-partition (stage 0 carries the wrap
+    // prefetch, the last stage idles in a short last round), so the sub-partitions stay evenly loaded.
+#ifdef PG2_LANE_NOROT
     const int w = threadIdx.x >> 5;
+#else
+    const int w = ((threadIdx.x >> 5) + blockIdx.x) % LANE_W;
+#endif
     double *wrap = scratch + (long long)blockIdx.x * (wrap_doubles + endcol_doubles + LANE_W * slot_doubles);
     double *endcol = wrap + wrap_doubles;
     double *slots = endcol + endcol_doubles + (long long)w * slot_doubles + lane;
-    volatile int *progress = s_progress;
+    int *progress = s_progress;
     int tab_model = -1;
 
     for (;;) {
@@ -591,6 +616,14 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
         LState<K> st;
         lane_strip_init<K, WR, SMALLTAB>(c, st, g, 0, r_state, r_elogw);
 
+#ifdef PG2_LANE_TIMING
+        long long t_in = 0, t_out = 0, t_blk = 0, t_pre = 0, t_all = clock64();
+#define PG2_T0 const long long tt0_ = clock64()
+#define PG2_T1(acc) acc += clock64() - tt0_
+#else
+#define PG2_T0
+#define PG2_T1(acc)
+#endif
         for (int u = 0; u < sch.items; ++u) {
             const int r = u / sch.period, b = u - r * sch.period, s = r * LANE_W + w;
             if (w == 0) {
@@ -610,18 +643,23 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
             }
             if (s < sch.n_strips && b < sch.n_blocks) {
                 const bool has_next = s + 1 < sch.n_strips;
-                if (w > 0) lane_wait(progress + w - 1, u + 1);                                 // input block published
-                if (has_next && w < LANE_W - 1) lane_wait(progress + w + 1, u - LANE_D + 1);   // output slot drained
+                { PG2_T0; if (w > 0) lane_wait(progress + w - 1, u + 1); PG2_T1(t_in); }        // input block published
+                { PG2_T0; if (has_next && w < LANE_W - 1) lane_wait(progress + w + 1, u - LANE_D + 1); PG2_T1(t_out); }  // output slot drained
                 if (b == 0) lane_strip_init<K, WR, SMALLTAB>(c, st, g, s * K, r_state, r_elogw);
                 const int v0 = b * LANE_B, v1 = min(v0 + LANE_B, c.nv);
                 const double *ring_in = ring + lane_ring_offset((w + LANE_W - 1) % LANE_W, u) + lane;
                 double *ring_out = (has_next && w != LANE_W - 1) ? ring + lane_ring_offset(w, u) + lane : nullptr;
                 double *wrap_out = (has_next && w == LANE_W - 1) ? wrap + lane : nullptr;
-                lane_block<K, GENERAL, SMALLTAB, WR>(c, st, g, s, v0, v1, ring_in, ring_out, wrap_out, slots, endcol + lane, ptr);
+                { PG2_T0; lane_block<K, GENERAL, SMALLTAB, WR>(c, st, g, s, v0, v1, ring_in, ring_out, wrap_out, slots, endcol + lane, ptr); PG2_T1(t_blk); }
             }
-            if (w == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+            { PG2_T0; if (w == 0) asm volatile("cp.async.wait_all;" ::: "memory"); PG2_T1(t_pre); }
             lane_publish(progress + w, u + 1, lane);
         }
+#ifdef PG2_LANE_TIMING
+        if (lane == 0 && (blockIdx.x % 97) == 5 && q < 2000)
+            printf("task %d cta %d stage %d: total %lld in_wait %lld out_wait %lld block %lld cpwait %lld items %d\n", q, blockIdx.x, w,
+                   clock64() - t_all, t_in, t_out, t_blk, t_pre, sch.items);
+#endif
         __syncthreads();
         if (w == 0 && g.active) lane_end_corner(c, g, endcol + lane, r_elogw, res);
     }

@@ -94,8 +94,8 @@ __host__ __device__ inline long long lane_ptr_index(int nv, int K, int v, int j,
 }
 // per-CTA global scratch of the lane kernel, in doubles: the wrap column [virtual row][X,Y,M][lane] (strip
 // boundary handed from the CTA's last warp to its first), the end column [row][X,Y,M][lane] (what the end
-// corner reads) and per warp n_slots + 2 parked rows (the saved rows, the row above a general site, and the
-// pointer accumulators of a site that straddles two pipeline blocks).
+// corner reads) and per warp n_slots + 2 parked rows (rows that start long-span edges, the row above an open
+// general site, and the pointer accumulators of a site that straddles two pipeline blocks).
 __host__ __device__ inline long long lane_cta_doubles(int max_nv, int max_lx, int n_slots) {
     return (long long)max_nv * 96 + (long long)max_lx * 96 + (long long)LANE_W * (n_slots + 2) * LANE_SLOT_DOUBLES;
 }
@@ -114,12 +114,13 @@ __host__ __device__ inline unsigned strip_decode_ptr(unsigned w, int mat) {
     return (w >> 8) & 0x3fu;
 }
 
-// Lane-kernel half-words: fast rows as above; general rows carry the X pointer in bits 0-5, the raw outcome bits
-// of the Y chain in bits 6 (open beat double) and 7 (that winner beat ext), the M pointer in bits 8-13.
+// Lane-kernel half-words: fast rows as above (bit 14 set).  General rows (bit 14 clear) keep the raw outcome bits
+// of the Y chain where fast rows have them (bits 2-3), the X pointer (mat | ordinal << 2) in bits 4-9, and the M
+// pointer split: source matrix in bits 0-1, edge ordinal in bits 10-13.
 __host__ __device__ inline unsigned lane_decode_ptr(unsigned w, int mat) {
-    if ((w & 0x4000u) || mat != Y_MAT) return strip_decode_ptr(w, mat);
-    unsigned p2 = (w >> 6) & 1u, p1 = (w >> 7) & 1u;
-    return p1 ? (p2 ? M_MAT : X_MAT) : Y_MAT;
+    if ((w & 0x4000u) || mat == Y_MAT) return strip_decode_ptr(w | 0x4000u, mat);
+    if (mat == X_MAT) return (w >> 4) & 0x3fu;
+    return (w & 3u) | (((w >> 10) & 0xfu) << 2);
 }
 
 }  // namespace pg2

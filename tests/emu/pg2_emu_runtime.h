@@ -29,6 +29,7 @@ struct int4 { int x, y, z, w; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
 
 static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 template <class T> static inline T __ldcg(const T *p) { return *p; }
