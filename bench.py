@@ -32,7 +32,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from pagan2_msa_b200 import abi, jobio, synth  # noqa: E402
 
 TARGETS = os.path.join(ROOT, "tests", "golden", "bench_targets.pjob.gz")
-FP64_INSTR_PER_CELL = 22  # 13 DADD + 9 DSETP per in-degree-1 unit-weight cell
+FP64_INSTR_PER_CELL = 22  # 13 DADD + 9 DSETP per in-degree-1 unit-weight cell (the reference's own count)
+FP64_INSTR_EXECUTED = 15.4  # what the lane kernel's hot loop issues per cell: 9 DADD + 6 DSETP (+ 3 DADD per 8-cell row), from SASS
 PTR_BYTES_PER_CELL = 2    # packed back-pointers streamed to HBM
 
 
@@ -335,6 +336,7 @@ def main():
         launch_ms = ms_fill / max(stats["fill_launches"], 1)
         achieved_gbs = per_launch_cells * PTR_BYTES_PER_CELL / (launch_ms * 1e-3) * 1e-9
         fp64_achieved = cells * FP64_INSTR_PER_CELL / 32.0 / (ms_fill * 1e-3) * 1e-9
+        fp64_executed = cells * FP64_INSTR_EXECUTED / 32.0 / (ms_fill * 1e-3) * 1e-9
         line = {
             "metric": "graph_dp_gcups", "value": total_cells / (ms_dev * 1e-3) * 1e-9, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
@@ -351,15 +353,19 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_kind,
-                         "kernel": "strip_fill_kernel", "algorithmic_bytes_per_cell": PTR_BYTES_PER_CELL,
+                         "kernel": "lane_fill_kernel" if stats["jobs_lanes"] >= stats["jobs_strip"] else "strip_fill_kernel",
+                         "algorithmic_bytes_per_cell": PTR_BYTES_PER_CELL,
                          "launch_ms": launch_ms,
                          "dp_issue": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "1e9 FP64-pipe warp-instr/s",
                                       "frac": fp64_achieved / fp64_peak if fp64_peak else None,
                                       "instr_per_cell": FP64_INSTR_PER_CELL,
+                                      "executed": {"achieved": fp64_executed, "frac": fp64_executed / fp64_peak if fp64_peak else None,
+                                                   "instr_per_cell": FP64_INSTR_EXECUTED,
+                                                   "note": "FP64-pipe instructions the kernel really issues (common terms shared)"},
                                       "peak_source": "pg2_measure_fp64_issue (DADD loop, this run)",
                                       "candidate_update_peak": cand.value}},
             "fill_ms_per_step": ms_fill, "traceback_ms_per_step": tb_ms / args.steps, "wall_ms_per_step": ms_wall,
-            "jobs_ok": ok, "jobs": len(jobs), "kernels": {"strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"]},
+            "jobs_ok": ok, "jobs": len(jobs), "kernels": {"lanes": stats["jobs_lanes"], "strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"]},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(jobs)

@@ -125,6 +125,8 @@ struct Group {
     int max_diag;
     int max_slots, max_lx;  // strip kernel per-warp scratch: saved rows, boundary column
     int max_nv = 1;         // lane kernel: longest row program
+    int phase = 0;          // groups of one phase keep their pointer buffers side by side and share one traceback launch
+    long long ptr_off = 0;  // offset of the group's region in its pointer buffer (d_ptr16 or d_ptr32 / d_scores)
 };
 
 struct pg2_batch {
@@ -675,6 +677,30 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         }
         b->groups.push_back(g);
     }
+    // phases: consecutive groups whose pointer (and score) buffers fit the scratch budget together run their fills
+    // back to back and share ONE traceback launch (the walk is latency bound: one launch for many jobs)
+    {
+        int phase = 0;
+        size_t bytes = 0;
+        long long off16 = 0, off32 = 0;
+        for (auto &g : b->groups) {
+            const size_t need = (size_t)g.cells * (g.kernel == 0 ? 36 : 2);
+            if (bytes > 0 && bytes + need > c->scratch_bytes) { phase++; bytes = 0; off16 = off32 = 0; }
+            g.phase = phase;
+            g.ptr_off = g.kernel == 0 ? off32 : off16;
+            (g.kernel == 0 ? off32 : off16) += g.cells;
+            bytes += need;
+            if (g.kernel == 2) {
+                for (int t = g.task_first; t < g.task_first + g.task_count; t++) {
+                    LaneTask &T = b->tasks[t];
+                    T.ptr_base += g.ptr_off;
+                    for (int l = 0; l < T.n_jobs; l++) b->jobs[T.job_ids[l]].cell_base = T.ptr_base;
+                }
+            } else {
+                for (int k = g.first; k < g.first + g.count; k++) b->jobs[b->order[k]].cell_base += g.ptr_off;
+            }
+        }
+    }
     c->current = b;
     *out = b;
     return PG2_OK;
@@ -738,9 +764,9 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
         st.h2d_ms = ms;
         st.h2d_bytes = b->h2d_bytes;
     }
-    // scratch for the largest group of each class
+    // scratch for the largest phase of each buffer class (strip and lane groups share d_ptr16)
     long long max_w = 0, max_s = 0;
-    for (auto &g : b->groups) (g.kernel == 0 ? max_w : max_s) = std::max(g.kernel == 0 ? max_w : max_s, g.cells);  // strip and lane groups share d_ptr16
+    for (auto &g : b->groups) (g.kernel == 0 ? max_w : max_s) = std::max(g.kernel == 0 ? max_w : max_s, g.ptr_off + g.cells);
     if (max_w > 0) {
         if ((rc = c->d_scores.ensure((size_t)max_w)) != PG2_OK) return fail(rc, "score scratch allocation failed");
         if ((rc = c->d_ptr32.ensure((size_t)max_w)) != PG2_OK) return fail(rc, "pointer buffer allocation failed");
@@ -780,39 +806,50 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
     st.jobs_strip_groups = 0;
     st.cells = b->total_cells;
     st.traceback_bytes = 0;
-    // events: per group fill start/stop + traceback stop are accumulated after a final sync to keep the
-    // stream free of host round trips; with many groups we sync per group (bounded by scratch anyway)
-    for (auto &g : b->groups) {
-        const int *ids = c->d_order.p + g.first;
+    // one phase = fills of its groups back to back, then one traceback launch over all its jobs; the events are
+    // read after the phase (host round trip per phase, bounded by the scratch budget)
+    for (size_t gi = 0; gi < b->groups.size();) {
+        size_t ge = gi;
+        while (ge < b->groups.size() && b->groups[ge].phase == b->groups[gi].phase) ge++;
         CU(cudaEventRecord(c->ev[2], c->stream));
-        if (g.kernel == 0) {
-            int threads = g.max_diag <= 32 ? 32 : g.max_diag <= 64 ? 64 : g.max_diag <= 128 ? 128 : g.max_diag <= 256 ? 256
-                          : g.max_diag <= 512 ? 512 : 1024;
-            launch_wavefront_fill(g.count, threads, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
-                                  c->d_estart.p, c->d_elogw.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_scores.p,
-                                  c->d_ptr32.p, c->d_results.p, c->stream);
-            st.jobs_wavefront += g.count;
-            st.traceback_bytes += g.cells * 4;
-        } else if (g.kernel == 2) {
-            launch_lane_fill(g.variant, g.task_count, c->d_tasks.p + g.task_first, c->d_jobs.p, c->d_graphs.p, c->d_models.p, c->d_state.p,
-                             c->d_off.p, c->d_estart.p, c->d_elogw.p, reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_ptr16.p,
-                             c->d_results.p, c->d_lane_scratch.p, g.max_nv, g.max_lx, g.max_slots, c->d_queue.p, lane_ctas(g), c->stream);
-            st.jobs_lanes += g.count;
-            st.jobs_strip_groups++;
-            st.traceback_bytes += g.cells * 2;
-        } else {
-            int warps = std::min(resident_warps, std::max(g.count, 1));
-            launch_strip_fill(g.strip_k, (g.strip_general & 1) != 0, (g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
-                              c->d_estart.p, c->d_elogw.p, reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_ptr16.p, c->d_results.p, c->d_saved.p,
-                              (long long)std::max(g.max_slots, 1) * 32 * g.strip_k, c->d_bcol.p, (long long)g.max_lx, c->d_queue.p,
-                              warps, c->stream);
-            st.jobs_strip += g.count;
-            st.jobs_strip_groups++;
-            st.traceback_bytes += g.cells * 2;
+        int phase_jobs = 0;
+        for (size_t k = gi; k < ge; k++) {
+            const Group &g = b->groups[k];
+            const int *ids = c->d_order.p + g.first;
+            phase_jobs += g.count;
+            if (g.kernel == 0) {
+                int threads = g.max_diag <= 32 ? 32 : g.max_diag <= 64 ? 64 : g.max_diag <= 128 ? 128 : g.max_diag <= 256 ? 256
+                              : g.max_diag <= 512 ? 512 : 1024;
+                launch_wavefront_fill(g.count, threads, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
+                                      c->d_estart.p, c->d_elogw.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_scores.p,
+                                      c->d_ptr32.p, c->d_results.p, c->stream);
+                st.jobs_wavefront += g.count;
+                st.traceback_bytes += g.cells * 4;
+            } else if (g.kernel == 2) {
+                launch_lane_fill(g.variant, g.task_count, c->d_tasks.p + g.task_first, c->d_jobs.p, c->d_graphs.p, c->d_models.p,
+                                 c->d_state.p, c->d_off.p, c->d_estart.p, c->d_elogw.p, reinterpret_cast<const int4 *>(c->d_vrow.p),
+                                 c->d_ptr16.p, c->d_results.p, c->d_lane_scratch.p, g.max_nv, g.max_lx, g.max_slots, c->d_queue.p,
+                                 lane_ctas(g), c->stream);
+                st.jobs_lanes += g.count;
+                st.jobs_strip_groups++;
+                st.traceback_bytes += g.cells * 2;
+            } else {
+                int warps = std::min(resident_warps, std::max(g.count, 1));
+                launch_strip_fill(g.strip_k, (g.strip_general & 1) != 0, (g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p,
+                                  c->d_models.p, c->d_state.p, c->d_off.p, c->d_estart.p, c->d_elogw.p,
+                                  reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_ptr16.p, c->d_results.p, c->d_saved.p,
+                                  (long long)std::max(g.max_slots, 1) * 32 * g.strip_k, c->d_bcol.p, (long long)g.max_lx, c->d_queue.p,
+                                  warps, c->stream);
+                st.jobs_strip += g.count;
+                st.jobs_strip_groups++;
+                st.traceback_bytes += g.cells * 2;
+            }
+            st.fill_launches++;
         }
         CU(cudaEventRecord(c->ev[3], c->stream));
-        launch_traceback(g.count, ids, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p, c->d_off.p, c->d_estart.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p,
-                         c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_steps.p, c->d_results.p, c->stream);
+        launch_traceback(phase_jobs, c->d_order.p + b->groups[gi].first, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p, c->d_off.p, c->d_estart.p,
+                         c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_steps.p, c->d_results.p,
+                         c->stream);
         CU(cudaEventRecord(c->ev[4], c->stream));
         CU(cudaEventSynchronize(c->ev[4]));
         CU(cudaGetLastError());
@@ -821,8 +858,8 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
         cudaEventElapsedTime(&t, c->ev[3], c->ev[4]);
         st.fill_ms += f;
         st.traceback_ms += t;
-        st.fill_launches++;
         st.traceback_launches++;
+        gi = ge;
     }
     {
         float ms = 0;
