@@ -1,0 +1,55 @@
+// dropin_interposer.cpp -- turns the UNMODIFIED reference objects into `pagan2_b200`: GNU ld --wrap redirects every call
+// of ppa::Viterbi_alignment::align (src/main/viterbi_alignment.cpp:187) to ppa_b200::align_on_device.  This is the
+// binding a maintainer would otherwise make by editing align() itself (INTEGRATION.md shows that edit); the link-time
+// form needs no change to the reference tree and is what tests/test_dropin_e2e.py runs against `pagan2_ref`.
+//
+// Also here: the two translation units of the reference that cannot be built in this image (Exonerate wrapper:
+// boost::regex + an external binary; version check: libcurl) as empty stubs.  Neither touches the alignment path.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "viterbi_alignment_b200.h"
+#include "utils/check_version.h"
+#include "utils/exonerate_queries.h"
+
+using namespace std;
+using namespace ppa;
+
+Exonerate_queries::Exonerate_queries() {}
+bool Exonerate_queries::test_executable() { return false; }
+void Exonerate_queries::local_alignment(map<string, string> *, Fasta_entry *, map<string, hit> *, bool, bool) {}
+void Exonerate_queries::local_alignment(Node *, Fasta_entry *, std::multimap<std::string, std::string> *, std::map<std::string, hit> *, bool,
+                                        bool, bool) {}
+void Exonerate_queries::preselect_targets(map<string, string> *, vector<Fasta_entry> *, map<string, string> *,
+                                          map<string, multimap<string, hit> > *, bool) {}
+void Exonerate_queries::local_pairwise_alignment(string *, string *, vector<Substring_hit> *, int *) {}
+Check_version::Check_version(float) {}
+
+#define ALIGN_SYM _ZN3ppa17Viterbi_alignment5alignEPNS_8SequenceES2_PNS_10Evol_modelEffb
+#define CAT2(a, b) a##b
+#define CAT(a, b) CAT2(a, b)
+
+extern "C" void CAT(__wrap_, ALIGN_SYM)(Viterbi_alignment *self, Sequence *left, Sequence *right, Evol_model *model, float lbl, float rbl,
+                                       bool is_reads) {
+    ppa_b200::align_on_device(self, left, right, model, lbl, rbl, is_reads);
+}
+
+namespace {
+struct Stats_at_exit {
+    ~Stats_at_exit() {
+        const char *p = getenv("PAGAN2_B200_STATS");
+        if (p && *p) {
+            ppa_b200::Totals t = ppa_b200::totals();
+            FILE *f = fopen(p, "w");
+            if (f) {
+                fprintf(f, "{\"jobs\": %lld, \"cells\": %lld, \"batches\": %lld, \"fill_ms\": %.6f, \"traceback_ms\": %.6f}\n", t.jobs, t.cells,
+                        t.batches, t.fill_ms, t.traceback_ms);
+                fclose(f);
+            }
+        }
+    }
+} g_stats_at_exit;
+}  // namespace

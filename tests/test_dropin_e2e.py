@@ -1,0 +1,120 @@
+"""End-to-end drop-in check: the reference command-line program with Viterbi_alignment::align bound to the engine
+(pagan2_msa_b200/host, link-time interposer) must write byte-identical output files to the unmodified reference binary
+(oracle/_ref/pagan2_ref) on the same seeded inputs -- progressive DNA, anchored, pileup + homopolymer, codon and
+query placement runs.
+
+CPU variant: the host mirror linked against the test emulation of the engine (tests/_emu/pagan2_b200_emu) -- checks
+the host mirror (graph packing, path expansion, used-edge marks, build_ancestral_sequence hand-over).
+GPU variant (-m gpu): the real binary pagan2_msa_b200/_dropin/pagan2_b200 over libpagan2_b200.so.
+Both binaries are prebuilt in the build container (they need /root/reference) and travel to the GPU box."""
+import filecmp
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from pagan2_msa_b200 import abi, synth
+
+REF = os.path.join(abi.REPO_ROOT, "oracle", "_ref", "pagan2_ref")
+DROPIN = os.path.join(abi.REPO_ROOT, "pagan2_msa_b200", "_dropin", "pagan2_b200")
+DROPIN_EMU = os.path.join(abi.REPO_ROOT, "tests", "_emu", "pagan2_b200_emu")
+
+
+def build_binaries():
+    if os.path.isdir("/root/reference/src"):
+        oracle_lib.build_ref()
+        subprocess.check_call(["make", "-s", "-C", os.path.join(abi.REPO_ROOT, "pagan2_msa_b200", "csrc")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(abi.REPO_ROOT, "pagan2_msa_b200", "host")])
+        subprocess.check_call(["make", "-s", "-C", os.path.join(abi.REPO_ROOT, "tests", "emu"), "../_emu/pagan2_b200_emu"])
+
+
+def scenario_progressive(tmp, rng):
+    tree, seqs = synth.balanced_tree(3, synth.random_dna(250, rng), rng)
+    synth.write_fasta(os.path.join(tmp, "s.fas"), seqs)
+    open(os.path.join(tmp, "t.nwk"), "w").write(tree + "\n")
+    return [["-s", "s.fas", "-t", "t.nwk", "-o", "out", "--no-anchors", "--silent"]]
+
+
+def scenario_anchored(tmp, rng):
+    tree, seqs = synth.balanced_tree(2, synth.random_dna(1500, rng), rng, sub=0.02, indel=0.003)
+    synth.write_fasta(os.path.join(tmp, "s.fas"), seqs)
+    open(os.path.join(tmp, "t.nwk"), "w").write(tree + "\n")
+    return [["-s", "s.fas", "-t", "t.nwk", "-o", "out", "--use-prefix-anchors", "--anchors-offset", "15", "--silent"]]
+
+
+def scenario_pileup(tmp, rng):
+    t = list(synth.random_dna(300, rng))
+    for i in range(1, len(t)):
+        if rng.random() < 0.35:
+            t[i] = t[i - 1]
+    reads = synth.reads_454("".join(t), 10, 120, rng)
+    synth.write_fasta(os.path.join(tmp, "r.fas"), reads)
+    return [["--pileup-alignment", "--homopolymer", "--queryfile", "r.fas", "-o", "out", "--no-anchors", "--silent"]]
+
+
+def scenario_codons(tmp, rng):
+    tree, seqs = synth.balanced_codon_tree(2, synth.random_codons(40, rng), rng)
+    synth.write_fasta(os.path.join(tmp, "s.fas"), seqs)
+    open(os.path.join(tmp, "t.nwk"), "w").write(tree + "\n")
+    return [["-s", "s.fas", "-t", "t.nwk", "-o", "out", "--codons", "--no-anchors", "--silent"]]
+
+
+def scenario_placement(tmp, rng):
+    tree, seqs = synth.balanced_tree(3, synth.random_dna(250, rng), rng)
+    synth.write_fasta(os.path.join(tmp, "s.fas"), seqs)
+    open(os.path.join(tmp, "t.nwk"), "w").write(tree + "\n")
+    reads = synth.sample_reads(seqs, 8, 90, rng)
+    synth.write_fasta(os.path.join(tmp, "r.fas"), reads)
+    return [["-s", "s.fas", "-t", "t.nwk", "-o", "ref", "--no-anchors", "--silent"],
+            ["--ref-seqfile", "ref.fas", "--ref-treefile", "t.nwk", "--queryfile", "r.fas", "-o", "out", "--no-anchors",
+             "--test-every-node", "--no-preselection", "--silent"]]
+
+
+SCENARIOS = {"progressive": (scenario_progressive, 11), "anchored": (scenario_anchored, 12), "pileup": (scenario_pileup, 13),
+             "codons": (scenario_codons, 14), "placement": (scenario_placement, 15)}
+
+
+def run_program(binary, name):
+    fn, seed = SCENARIOS[name]
+    tmp = tempfile.mkdtemp(prefix="pg2_e2e_")
+    rng = np.random.default_rng(seed)
+    env = dict(os.environ)
+    stats = os.path.join(tmp, "b200_stats.json")
+    env["PAGAN2_B200_STATS"] = stats
+    for args in fn(tmp, rng):
+        subprocess.run([binary] + args, cwd=tmp, env=env, check=True, timeout=1800, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    outs = sorted(f for f in os.listdir(tmp) if f.startswith("out") or f.startswith("ref."))
+    return tmp, outs, stats
+
+
+def compare(binary, name):
+    ref_dir, ref_outs, _ = run_program(REF, name)
+    new_dir, new_outs, stats = run_program(binary, name)
+    assert ref_outs == new_outs and len(ref_outs) >= 1, (ref_outs, new_outs)
+    for f in ref_outs:
+        assert filecmp.cmp(os.path.join(ref_dir, f), os.path.join(new_dir, f), shallow=False), "%s differs (%s)" % (f, name)
+    import json
+
+    with open(stats) as fh:
+        st = json.load(fh)
+    assert st["jobs"] >= 1 and st["cells"] > 0  # the alignments really went through the engine
+    return st
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_dropin_matches_reference_cpu_emulation(name):
+    build_binaries()
+    if not (os.path.exists(REF) and os.path.exists(DROPIN_EMU)):
+        pytest.skip("reference binaries are built in the container that has /root/reference")
+    compare(DROPIN_EMU, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_dropin_matches_reference_on_b200(name):
+    assert os.path.exists(REF) and os.path.exists(DROPIN), "prebuilt binaries missing: run __graft_entry__.build() where /root/reference exists"
+    compare(DROPIN, name)
