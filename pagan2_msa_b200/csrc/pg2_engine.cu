@@ -790,7 +790,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
         }
     for (auto &g : b->groups)
         if (g.kernel == 1) {
-            int warps = std::min(resident_warps, std::max(g.count, 1));
+            int warps = (std::min(resident_warps, std::max(g.count, 1)) + 3) & ~3;  // whole CTAs of 4 warps: every launched warp owns scratch
             size_t saved = (size_t)std::max(g.max_slots, 1) * 32 * g.strip_k * warps;
             size_t bcol = (size_t)g.max_lx * 2 * warps;
             if ((rc = c->d_saved.ensure(saved)) != PG2_OK) return fail(rc, "saved-row scratch allocation failed");
@@ -834,7 +834,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
                 st.jobs_strip_groups++;
                 st.traceback_bytes += g.cells * 2;
             } else {
-                int warps = std::min(resident_warps, std::max(g.count, 1));
+                int warps = (std::min(resident_warps, std::max(g.count, 1)) + 3) & ~3;  // whole CTAs of 4 warps: every launched warp owns scratch
                 launch_strip_fill(g.strip_k, (g.strip_general & 1) != 0, (g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p,
                                   c->d_models.p, c->d_state.p, c->d_off.p, c->d_estart.p, c->d_elogw.p,
                                   reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_ptr16.p, c->d_results.p, c->d_saved.p,

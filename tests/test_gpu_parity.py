@@ -198,3 +198,12 @@ def test_progressive_config_scale_vs_oracle(eng):
     jobs = [enginecheck.expect_from_oracle(job), enginecheck.expect_from_oracle(banded)]
     res = enginecheck.check_batch(eng, jobs)
     assert res["kernel"][0] == 1 and res["kernel"][1] == 0
+
+
+def test_single_job_batches_on_a_fresh_engine(golden):
+    """A batch of ONE strip-kernel job on a fresh context: the launch rounds up to a whole CTA, and every warp of
+    it must own scratch (the drop-in binary aligns one job per call)."""
+    for k in (0, 7, 13):
+        with engine.Engine(0) as e:
+            enginecheck.check_batch(e, [golden["place_dna"][k]])
+            enginecheck.check_batch(e, [golden["pileup_hp"][min(k, len(golden["pileup_hp"]) - 1)]])
