@@ -45,6 +45,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def measured_traffic(n_reads, fill_launches):
+    """DRAM bytes per fill launch from the committed ncu capture (profiles/), valid for the workload it was taken on."""
+    p = os.path.join(ROOT, "profiles", "r1_lanes_v6_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    if t.get("reads_per_gpu") != n_reads or len(t["launches"]) != fill_launches:
+        return None
+    return sum(l["dram_bytes_read"] + l["dram_bytes_write"] for l in t["launches"]) / len(t["launches"])
+
+
 def build_workload(n_reads, seed, rank=0):
     """Returns (jobs, info).  Deterministic in (n_reads, seed, rank)."""
     tjobs = jobio.load_jobs(TARGETS)
@@ -352,7 +364,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_kind,
+                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": measured_traffic(args.reads, stats["fill_launches"]),
+                         "traffic_note": "DRAM read+write bytes per fill launch, ncu capture profiles/r1_lanes_v6_ncu_summary.csv; "
+                                         "algorithmic bytes per launch = %d" % int(per_launch_cells * PTR_BYTES_PER_CELL),
+                         "peak_source": peaks_kind,
                          "kernel": "lane_fill_kernel" if stats["jobs_lanes"] >= stats["jobs_strip"] else "strip_fill_kernel",
                          "algorithmic_bytes_per_cell": PTR_BYTES_PER_CELL,
                          "launch_ms": launch_ms,
