@@ -42,7 +42,7 @@ struct DevGraph {
     int vrow_base;   // into d_vrow (int4 units); -1 until the graph is used as a strip row graph
     int n_vrows;     // virtual rows: one per (DP row, backward edge), edgeless rows count once
     int vlast_base;  // into d_vlast: per site, the virtual row that completes it
-    int pad;
+    int vplain_base; // into d_vlast: per block of LANE_B virtual rows, bit r set when row r is a plain interior row
 };
 
 struct DevModel {

@@ -35,8 +35,8 @@ void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const Dev
 int strip_warps_per_sm();
 void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
                       const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
-                      const int4 *d_vrow, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv, int max_lx,
-                      int max_slots, int *queue, int n_ctas, cudaStream_t stream);
+                      const int4 *d_vrow, const int *d_vlast, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv,
+                      int max_lx, int max_slots, int *queue, int n_ctas, cudaStream_t stream);
 int lane_ctas_per_sm();
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
 void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
@@ -302,6 +302,7 @@ static int reserve_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unor
     dg.vrow_base = -1;
     dg.n_vrows = g.n_sites - 1;
     dg.vlast_base = -1;
+    dg.vplain_base = -1;
     *gid = (int)b->graphs.size();
     b->graphs.push_back(dg);
     sources.push_back(&g);
@@ -410,6 +411,23 @@ static int build_row_program(pg2_ctx *c, DevGraph &dg) {
         vl[s] = v - 1;
     }
     vl[n - 1] = v - 1;
+    // lane kernel: which virtual rows of each pipeline block are plain interior rows (one unit-weight edge from the
+    // row above, not row 0, not read by the end corner, never parked) -- they run in the hot loop
+    const int n_blocks = (nv + LANE_B - 1) / LANE_B;
+    dg.vplain_base = (int)c->h_vlast.n;
+    int *vp = c->h_vlast.extend(n_blocks);
+    if (!vp) return PG2_ERR_NOMEM;
+    vr = c->h_vrow.p + (size_t)dg.vrow_base * 4;  // extend() may have moved nothing here, but stay safe
+    for (int b = 0; b < n_blocks; b++) {
+        unsigned m = 0;
+        for (int r = 0; r < LANE_B && b * LANE_B + r < nv; r++) {
+            const int info = vr[4 * (b * LANE_B + r)];
+            const int need = VR_FAST | VR_ZERO_W;
+            const int none = VR_ENDPRED | VR_NOEDGE | (int)(~0u << VR_SLOT_SHIFT);
+            if ((info & need) == need && !(info & none)) m |= 1u << r;
+        }
+        vp[b] = (int)m;
+    }
     return PG2_OK;
 }
 
@@ -828,7 +846,7 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
             } else if (g.kernel == 2) {
                 launch_lane_fill(g.variant, g.task_count, c->d_tasks.p + g.task_first, c->d_jobs.p, c->d_graphs.p, c->d_models.p,
                                  c->d_state.p, c->d_off.p, c->d_estart.p, c->d_elogw.p, reinterpret_cast<const int4 *>(c->d_vrow.p),
-                                 c->d_ptr16.p, c->d_results.p, c->d_lane_scratch.p, g.max_nv, g.max_lx, g.max_slots, c->d_queue.p,
+                                 c->d_vlast.p, c->d_ptr16.p, c->d_results.p, c->d_lane_scratch.p, g.max_nv, g.max_lx, g.max_slots, c->d_queue.p,
                                  lane_ctas(g), c->stream);
                 st.jobs_lanes += g.count;
                 st.jobs_strip_groups++;

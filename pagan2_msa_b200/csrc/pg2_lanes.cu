@@ -45,6 +45,7 @@ namespace pg2 {
 // warp-uniform per-task constants
 struct LaneCtx {
     const int4 *l_vrow;
+    const int *l_vplain;         // per pipeline block: bit r set when virtual row r of the block is a plain interior row
     const int *l_off, *l_estart;
     const float *l_elogw;
     int nv, lx, n_slots;
@@ -384,29 +385,24 @@ __device__ __forceinline__ bool lane_slow_row(const LaneCtx &c, LState<K> &st, L
 //             for the first strip (-inf boundary)
 //   ring_out  where this strip's last column goes for the next strip, same shape; wrap_out (global, indexed by
 //             virtual row) instead when the next strip belongs to the next round; both null for the last strip
+//   plain     bit r set: virtual row v0 + r is a plain interior row (the host builds the masks, build_row_program)
 template <int K, bool GENERAL, bool SMALLTAB, bool WR>
-__device__ __forceinline__ void lane_block(const LaneCtx &c, LState<K> &st, const LaneGeom &g, int s, int v0, int v1,
+__device__ __forceinline__ void lane_block(const LaneCtx &c, LState<K> &st, const LaneGeom &g, int s, int v0, int v1, unsigned plain,
                                            const double *ring_in, double *ring_out, double *wrap_out, double *slots, double *endcol,
                                            uint4 *ptr) {
     const bool first = (s == 0);
     const bool store_ptr = g.active && s * K < g.ly;
     const bool is_last = g.active && s == g.last_strip;
     constexpr int Q = K / 8;
-    // warp-uniform: which rows of the block are plain interior rows?
-    unsigned plain = 0;
-    int info0 = 0;
-#pragma unroll
-    for (int r = 0; r < LANE_B; ++r) {
-        if (v0 + r < v1) {
-            const int info = __ldg(&c.l_vrow[v0 + r].x);
-            if (r == 0) info0 = info;
-            const int need = VR_FAST | VR_ZERO_W;
-            const int none = VR_ENDPRED | VR_NOEDGE | (int)(~0u << VR_SLOT_SHIFT);
-            if ((info & need) == need && !(info & none)) plain |= 1u << r;
-        }
-    }
+    // only the first strip and a strip that holds some lane's last column have columns with their own
+    // X-extension term (warp-uniform test)
     double ex[K];
-    lane_ext_terms<K>(c, g, s, ex);
+    if (lane_any(first || is_last)) {
+        lane_ext_terms<K>(c, g, s, ex);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) ex[k] = c.ext;
+    }
     double *out = wrap_out ? wrap_out + (long long)v0 * 96 : ring_out;
     uint4 *dst = ptr + ((long long)s * c.nv + v0) * Q * 32;
     // a site whose virtual rows straddle the block boundary keeps its pointer accumulators in the warp's scratch
@@ -414,7 +410,7 @@ __device__ __forceinline__ void lane_block(const LaneCtx &c, LState<K> &st, cons
     unsigned *acc_area = reinterpret_cast<unsigned *>(slots + (long long)(c.n_slots + 1) * LANE_SLOT_DOUBLES);
 #pragma unroll
     for (int k = 0; k < K; ++k) acc.pXM[k] = 0;
-    if (GENERAL && v0 < v1 && !(info0 & VR_FIRST)) {
+    if (GENERAL && !(plain & 1u) && !(__ldg(&c.l_vrow[v0].x) & VR_FIRST)) {
 #pragma unroll
         for (int k = 0; k < K; ++k) acc.pXM[k] = acc_area[k * 64];
     }
@@ -464,8 +460,9 @@ __device__ __forceinline__ void lane_end_corner(const LaneCtx &c, const LaneGeom
 }
 
 __device__ __forceinline__ void lane_make_ctx(LaneCtx &c, const LaneTask &T, const DevGraph &GL, const DevModel &m, const int *d_off,
-                                              const int *d_estart, const float *d_elogw, const int4 *d_vrow) {
+                                              const int *d_estart, const float *d_elogw, const int4 *d_vrow, const int *d_vlast) {
     c.l_vrow = d_vrow + GL.vrow_base;
+    c.l_vplain = d_vlast + GL.vplain_base;
     c.nv = GL.n_vrows;
     c.l_off = d_off + GL.off_base;
     c.l_estart = d_estart + GL.edge_base;
@@ -554,7 +551,7 @@ __device__ __forceinline__ void lane_publish(int *p, int value, int lane) {
 template <int K, bool GENERAL, bool SMALLTAB, bool WR>
 __global__ void __launch_bounds__(LANE_W * 32, PG2_LANE_MINB)
 lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs, const DevModel *models,
-                 const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
+                 const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow, const int *d_vlast,
                  unsigned short *ptrs, DevResult *results, double *scratch, long long wrap_doubles, long long endcol_doubles,
                  long long slot_doubles, int *queue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -594,7 +591,7 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
         const DevGraph GL = graphs[T.left], GR = graphs[J.right];
         const DevModel m = models[T.model];
         LaneCtx c;
-        lane_make_ctx(c, T, GL, m, d_off, d_estart, d_elogw, d_vrow);
+        lane_make_ctx(c, T, GL, m, d_off, d_estart, d_elogw, d_vrow, d_vlast);
         // keep the doubles in registers: ptxas otherwise re-derives them from the float model parameters
         // (F2F) inside the row loop whenever registers get tight
         asm volatile("" : "+d"(c.open), "+d"(c.ext), "+d"(c.lng));
@@ -624,8 +621,14 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
 #define PG2_T0
 #define PG2_T1(acc)
 #endif
+        int plain_n = __ldg(c.l_vplain);  // the next item's row mask, fetched one item ahead
         for (int u = 0; u < sch.items; ++u) {
             const int r = u / sch.period, b = u - r * sch.period, s = r * LANE_W + w;
+            const unsigned plain = (unsigned)plain_n;
+            {
+                const int b1 = (b + 1 == sch.period) ? 0 : b + 1;
+                if (b1 < sch.n_blocks) plain_n = __ldg(c.l_vplain + b1);
+            }
             if (w == 0) {
                 // start bringing the NEXT item's wrap rows (written by warp W-1 one round earlier) into the ring;
                 // the copy lands while this item is being computed
@@ -650,7 +653,7 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
                 const double *ring_in = ring + lane_ring_offset((w + LANE_W - 1) % LANE_W, u) + lane;
                 double *ring_out = (has_next && w != LANE_W - 1) ? ring + lane_ring_offset(w, u) + lane : nullptr;
                 double *wrap_out = (has_next && w == LANE_W - 1) ? wrap + lane : nullptr;
-                { PG2_T0; lane_block<K, GENERAL, SMALLTAB, WR>(c, st, g, s, v0, v1, ring_in, ring_out, wrap_out, slots, endcol + lane, ptr); PG2_T1(t_blk); }
+                { PG2_T0; lane_block<K, GENERAL, SMALLTAB, WR>(c, st, g, s, v0, v1, plain, ring_in, ring_out, wrap_out, slots, endcol + lane, ptr); PG2_T1(t_blk); }
             }
             { PG2_T0; if (w == 0) asm volatile("cp.async.wait_all;" ::: "memory"); PG2_T1(t_pre); }
             lane_publish(progress + w, u + 1, lane);
@@ -671,8 +674,8 @@ int lane_ctas_per_sm() { return PG2_LANE_MINB; }
 // Launches one group of lane tasks that share the kernel variant.  `scratch`: n_ctas * lane_cta_doubles doubles.
 void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
                       const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
-                      const int4 *d_vrow, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv, int max_lx,
-                      int max_slots, int *queue, int n_ctas, cudaStream_t stream) {
+                      const int4 *d_vrow, const int *d_vlast, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv,
+                      int max_lx, int max_slots, int *queue, int n_ctas, cudaStream_t stream) {
     if (n_tasks <= 0) return;
     constexpr int K = LANE_K;
     const long long wrap_doubles = (long long)max_nv * 96, endcol_doubles = (long long)max_lx * 96;
@@ -684,7 +687,8 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
     do {                                                                                                                          \
         cudaFuncSetAttribute(lane_fill_kernel<K, G, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                    \
         lane_fill_kernel<K, G, S, W><<<n_ctas, LANE_W * 32, smem, stream>>>(n_tasks, tasks, jobs, graphs, models, d_state, d_off, \
-                                                                            d_estart, d_elogw, d_vrow, ptrs, results, scratch,    \
+                                                                            d_estart, d_elogw, d_vrow, d_vlast, ptrs, results,    \
+                                                                            scratch,                                              \
                                                                             wrap_doubles, endcol_doubles, slot_doubles, queue);   \
     } while (0)
     switch (variant & 7) {
@@ -710,7 +714,7 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
         const DevGraph GL = graphs[T.left];
         const DevModel m = models[T.model];
         LaneCtx c;
-        lane_make_ctx(c, T, GL, m, d_off, d_estart, d_elogw, d_vrow);
+        lane_make_ctx(c, T, GL, m, d_off, d_estart, d_elogw, d_vrow, d_vlast);
         std::vector<double2> tab;
         if (variant & 2) {
             tab.resize((size_t)m.fas * m.fas);
@@ -749,7 +753,7 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
 #define PG2_LANE_EMU(G, SM, WRV)                                                                                      \
     do {                                                                                                               \
         if (b == 0) lane_strip_init<K, WRV, SM>(c, S, geom[lane], s * K, r_state[lane], r_elogw[lane]);                \
-        lane_block<K, G, SM, WRV>(c, S, geom[lane], s, v0, v1,                                                         \
+        lane_block<K, G, SM, WRV>(c, S, geom[lane], s, v0, v1, (unsigned)c.l_vplain[b],                                                    \
                                   ring.data() + lane_ring_offset((w + LANE_W - 1) % LANE_W, u) + lane,                 \
                                   (has_next && w != LANE_W - 1) ? ring.data() + lane_ring_offset(w, u) + lane : nullptr, \
                                   (has_next && w == LANE_W - 1) ? wrap + lane : nullptr,                               \
