@@ -394,6 +394,10 @@ __device__ __forceinline__ void lane_block(const LaneCtx &c, LState<K> &st, cons
     const bool store_ptr = g.active && s * K < g.ly;
     const bool is_last = g.active && s == g.last_strip;
     constexpr int Q = K / 8;
+#ifndef PG2_HOST_EMU
+    // the next block's row program (one 128-byte line) on its way to L1 while this block computes
+    if (v1 < c.nv) asm volatile("prefetch.global.L1 [%0];" ::"l"(c.l_vrow + v1));
+#endif
     // only the first strip and a strip that holds some lane's last column have columns with their own
     // X-extension term (warp-uniform test)
     double ex[K];
