@@ -171,15 +171,23 @@ def cpu_baseline_sample(jobs, budget_s=12.0):
             "sample": "first %d jobs of the workload (%d cells) in %.1f s, 1 thread" % (n, cells, dt)}
 
 
+_REF_JOBS = None
+
+
+def _ref_init(n_reads, seed):
+    """Pool initializer of the reference arm: every host process builds the (bounded) workload once, outside the clock."""
+    global _REF_JOBS
+    _REF_JOBS, _ = build_workload(n_reads, seed)
+
+
 def _ref_worker(args):
     """One host process of the reference arm: aligns its share of jobs with the reference library."""
-    lo, hi, n_reads, seed = args
+    lo, hi = args
     import oracle_lib
 
-    jobs, _ = build_workload(n_reads, seed)
     use_ref = oracle_lib.ref_available()
     cells = 0
-    for j in jobs[lo:hi]:
+    for j in _REF_JOBS[lo:hi]:
         if use_ref:
             oracle_lib.ref_align_flat(j)
         else:
@@ -199,13 +207,13 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    per_core = 2
+    per_core = 6
     n = cores * per_core
-    jobs, info = build_workload(n, args.seed)
     use_ref = oracle_lib.ref_available()
-    bounds = [(k * per_core, (k + 1) * per_core, n, args.seed) for k in range(cores)]
+    bounds = [(k * per_core, (k + 1) * per_core) for k in range(cores)]
     times, cells_step = [], 0
-    with mp.get_context("fork").Pool(cores) as pool:
+    with mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(n, args.seed)) as pool:
+        pool.map(_ref_worker, [(0, 0)] * cores)  # every worker up and initialised before the clock starts
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             cells_step = sum(pool.map(_ref_worker, bounds))
@@ -224,10 +232,22 @@ def run_reference_arm(args):
                          "sample": "%d alignments per step over %d processes (fork), model build excluded" % (n, cores)},
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout (libraries -- NCCL's version banner, make -- get stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -384,7 +404,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(jobs)
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if dist is not None:
         dist.barrier()
