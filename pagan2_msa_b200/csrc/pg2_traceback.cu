@@ -122,8 +122,11 @@ struct TraceCtx {
     const unsigned short *ptr16;  // strip layout: row-major [i][j], one half-word per cell
 };
 
-__device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int j, unsigned &out) {
+// `chain_left`: set when the cell was filled by an in-place fast row of a register-strip kernel, i.e. its only left
+// edge is (i-1 -> i): the walk then needs no CSR lookup for the left graph.
+__device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int j, unsigned &out, bool &chain_left) {
     const DevJob &J = *t.J;
+    chain_left = false;
     if (i < 0 || j < 0 || i >= J.lx || j >= J.ly) return false;
     if (J.kernel == 0) {
         long long idx;
@@ -141,6 +144,7 @@ __device__ __forceinline__ bool fetch_ptr(const TraceCtx &t, int mat, int i, int
         const long long idx = J.kernel == 2 ? lane_ptr_index(t.nv, LANE_K, t.vlast[i], j, J.lane)
                                             : strip_ptr_index(t.nv, J.ly, J.strip_k, t.vlast[i], j);
         const unsigned w = t.ptr16[J.cell_base + idx];
+        chain_left = (w & 0x4000u) != 0;
         out = J.kernel == 2 ? lane_decode_ptr(w, mat) : strip_decode_ptr(w, mat);
     }
     return true;
@@ -150,7 +154,7 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
                               const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo,
                               const long long *d_doff, const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps,
                               DevResult *results) {
-    const DevJob &J = jobs[jid];
+    const DevJob J = jobs[jid];  // by value: the walk's stores must not force a reload of the job record per step
     DevResult *res = results + jid;
     if (res->status != JOB_OK) return;
     const DevGraph GL = graphs[J.left], GR = graphs[J.right];
@@ -181,20 +185,23 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
 
     int status = JOB_OK;
     // the reference loop ends when (i<1 && j<1) AFTER reading the cell it stands on (:1073-1181)
+    // register-strip kernels only take jobs whose right graph is a plain chain: column j is entered from j-1
+    const bool chain_right = J.kernel != 0;
     for (;;) {
         unsigned q;
-        if (vit == NO_MAT || !fetch_ptr(tc, vit, i, j, q)) { status = JOB_BROKEN_PATH; break; }
+        bool chain_left;
+        if (vit == NO_MAT || !fetch_ptr(tc, vit, i, j, q, chain_left)) { status = JOB_BROKEN_PATH; break; }
         if (n >= J.step_cap) { status = JOB_BROKEN_PATH; break; }
         out[n++] = (unsigned short)q;
         int src = (int)(q & 3u);
         if (vit == M_MAT) {
-            int ni = (src == NO_MAT) ? -1 : l_es[l_off[i] + ((q >> 2) & 63u)];
-            int nj = (src == NO_MAT) ? -1 : r_es[r_off[j] + ((q >> 8) & 63u)];
+            int ni = (src == NO_MAT) ? -1 : (chain_left ? i - 1 : l_es[l_off[i] + ((q >> 2) & 63u)]);
+            int nj = (src == NO_MAT) ? -1 : (chain_right ? j - 1 : r_es[r_off[j] + ((q >> 8) & 63u)]);
             i = ni; j = nj;
         } else if (vit == X_MAT) {
-            i = (src == NO_MAT) ? -1 : l_es[l_off[i] + ((q >> 2) & 63u)];
+            i = (src == NO_MAT) ? -1 : (chain_left ? i - 1 : l_es[l_off[i] + ((q >> 2) & 63u)]);
         } else {
-            j = (src == NO_MAT) ? -1 : r_es[r_off[j] + ((q >> 8) & 63u)];
+            j = (src == NO_MAT) ? -1 : (chain_right ? j - 1 : r_es[r_off[j] + ((q >> 8) & 63u)]);
         }
         vit = src;
         if (i < 1 && j < 1) break;
