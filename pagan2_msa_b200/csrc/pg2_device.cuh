@@ -43,6 +43,8 @@ struct DevGraph {
     int n_vrows;     // virtual rows: one per (DP row, backward edge), edgeless rows count once
     int vlast_base;  // into d_vlast: per site, the virtual row that completes it
     int vplain_base; // into d_vlast: per block of LANE_B virtual rows, bit r set when row r is a plain interior row
+    int implicit;    // 1: plain chain with unit weights whose CSR (d_off / d_estart / d_elogw) is generated on the device
+    int pad[3];
 };
 
 struct DevModel {

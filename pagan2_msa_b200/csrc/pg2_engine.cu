@@ -10,7 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <functional>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -21,6 +23,7 @@
 #include "pg2_strip_geom.cuh"
 
 namespace pg2 {
+void launch_expand_implicit(int n_graphs, const DevGraph *graphs, int *d_off, int *d_estart, float *d_elogw, cudaStream_t stream);
 void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
                      const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
                      DevResult *results, cudaStream_t stream);
@@ -139,7 +142,7 @@ struct pg2_batch {
     long long total_steps = 0;
     long long total_cells = 0;
     long long h2d_bytes = 0;
-    size_t n_state = 0, n_off = 0, n_edge = 0, n_band = 0, n_diag = 0;
+    size_t n_off_total = 0, n_edge_total = 0;  // device sizes of d_off / d_estart (staged explicit graphs + implicit chains)
     bool uploaded = false, ran = false;
 };
 
@@ -175,6 +178,8 @@ struct pg2_ctx {
     cudaEvent_t ev[8];
     pg2_stats stats;
     pg2_batch *current = nullptr;
+    pg2_ctx *sibling = nullptr;    // second set of staging / device buffers + stream for pipelined pg2_align_batch calls
+    bool borrowed_models = false;  // a sibling shares the primary's model tables and must not free them
 };
 
 extern "C" int pg2_abi_version(void) { return PG2_ABI_VERSION; }
@@ -214,9 +219,11 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
 
 extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
     if (!c) return;
+    if (c->sibling) { pg2_ctx_destroy(c->sibling); c->sibling = nullptr; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto &m : c->models) if (m.live && m.d_table) cudaFree(m.d_table);
+    if (!c->borrowed_models)
+        for (auto &m : c->models) if (m.live && m.d_table) cudaFree(m.d_table);
     c->h_state.release(); c->h_off.release(); c->h_estart.release(); c->h_blo.release(); c->h_bhi.release(); c->h_dlo.release();
     c->h_elogw.release(); c->h_doff.release(); c->h_results.release(); c->h_vrow.release(); c->h_vlast.release();
     c->d_vrow.release(); c->d_vlast.release(); c->d_queue.release(); c->d_saved.release(); c->d_bcol.release();
@@ -272,33 +279,45 @@ struct GraphKey {
     int n;
     bool operator==(const GraphKey &o) const { return a == o.a && b == o.b && c == o.c && d == o.d && n == o.n; }
 };
-struct GraphKeyHash {
-    size_t operator()(const GraphKey &k) const {
-        size_t h = (size_t)k.a * 1000003u ^ (size_t)k.b * 10007u ^ (size_t)k.c * 31u ^ (size_t)k.d ^ (size_t)k.n;
-        return h;
+// Identity table of the graphs of one batch: open addressing on the `state` pointer, sized once (a batch names at
+// most 2 graphs per job), 16-byte slots so that the table of a 100 000-job batch stays cache resident; a hit is
+// confirmed against the full key of the graph it names.
+struct GraphTable {
+    struct Slot { const void *a; long long gid; };
+    std::vector<Slot> slots;
+    size_t mask = 0;
+    explicit GraphTable(size_t max_items) {
+        size_t cap = 64;
+        while (cap < max_items * 2 + 16) cap <<= 1;
+        Slot empty = {nullptr, -1};
+        slots.assign(cap, empty);
+        mask = cap - 1;
+    }
+    // returns the slot of `k` (gid >= 0) or the empty slot where it belongs (gid < 0)
+    Slot &find(const GraphKey &k, const std::vector<const pg2_graph *> &sources) {
+        size_t i = ((((size_t)k.a >> 4) * 0x9E3779B97F4A7C15ull) >> 20) & mask;
+        for (;;) {
+            Slot &s = slots[i];
+            if (s.gid < 0) return s;
+            if (s.a == k.a) {
+                const pg2_graph &g = *sources[(size_t)s.gid];
+                if (g.bwd_off == k.b && g.edge_start == k.c && g.edge_logw == k.d && g.n_sites == k.n) return s;
+            }
+            i = (i + 1) & mask;
+        }
     }
 };
 
-// Phase 1 of packing (serial): de-duplicate by host-array identity and reserve staging space.
-static int reserve_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unordered_map<GraphKey, int, GraphKeyHash> &seen,
-                         std::vector<const pg2_graph *> &sources, int *gid) {
-    if (g.n_sites < 2 || !g.state || !g.bwd_off || (g.n_edges > 0 && (!g.edge_start || !g.edge_logw || !g.edge_index)))
+// Packing step 1 (serial): de-duplicate by host-array identity.  Touches the job records only, never the arrays.
+static int intern_graph(pg2_batch *b, const pg2_graph &g, GraphTable &seen, std::vector<const pg2_graph *> &sources, int *gid) {
+    if (g.n_sites < 2 || g.n_edges < 0 || !g.state || !g.bwd_off || (g.n_edges > 0 && (!g.edge_start || !g.edge_logw || !g.edge_index)))
         return fail(PG2_ERR_INVALID, "graph with null arrays or fewer than 2 sites");
     GraphKey key = {g.state, g.bwd_off, g.edge_start, g.edge_logw, g.n_sites};
-    auto it = seen.find(key);
-    if (it != seen.end()) { *gid = it->second; return PG2_OK; }
-    int n_edges = g.bwd_off[g.n_sites];
-    if (n_edges < 0 || n_edges != g.n_edges) return fail(PG2_ERR_INVALID, "graph: n_edges does not match bwd_off[n_sites]");
-    if ((long long)c->h_state.n + g.n_sites > 0x7fffffffLL || (long long)c->h_estart.n + n_edges > 0x7fffffffLL)
-        return fail(PG2_ERR_INVALID, "batch too large: more than 2^31 sites or edges; split the batch");
+    GraphTable::Slot &slot = seen.find(key, sources);
+    if (slot.gid >= 0) { *gid = slot.gid; return PG2_OK; }
     DevGraph dg;
     memset(&dg, 0, sizeof dg);
     dg.n_sites = g.n_sites;
-    dg.state_base = (int)c->h_state.n;
-    dg.off_base = (int)c->h_off.n;
-    dg.edge_base = (int)c->h_estart.n;
-    if (!c->h_state.extend(g.n_sites) || !c->h_off.extend(g.n_sites + 1) || !c->h_estart.extend(n_edges) || !c->h_elogw.extend(n_edges))
-        return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
     dg.vrow_base = -1;
     dg.n_vrows = g.n_sites - 1;
     dg.vlast_base = -1;
@@ -306,41 +325,75 @@ static int reserve_graph(pg2_ctx *c, pg2_batch *b, const pg2_graph &g, std::unor
     *gid = (int)b->graphs.size();
     b->graphs.push_back(dg);
     sources.push_back(&g);
-    seen.emplace(key, *gid);
+    slot.a = key.a;
+    slot.gid = *gid;
     return PG2_OK;
 }
 
-// Phase 2 of packing (any thread): copy one graph into the staging arrays and summarise its shape
-// (which fill kernel may take it; the device re-validates everything).
-static void copy_graph(pg2_ctx *c, DevGraph &dg, const pg2_graph &g) {
+// Packing step 2 (any thread): one pass over a distinct graph's arrays -- shape summary (which fill kernel may take
+// it; the device re-validates everything) and whether the graph is an IMPLICIT chain: site s entered by the one edge
+// (s-1 -> s) with log weight +0.0, i.e. a plain leaf or read.  Only the states of an implicit chain are staged and
+// uploaded; its CSR is generated on the device (expand_implicit_kernel).  max_indeg = -1 flags malformed offsets,
+// -2 an n_edges that does not match bwd_off[n_sites].
+static void classify_graph(DevGraph &dg, const pg2_graph &g) {
     const int n_edges = g.n_edges;
-    int *ps = c->h_state.p + dg.state_base, *po = c->h_off.p + dg.off_base, *pe = c->h_estart.p + dg.edge_base;
-    float *pw = c->h_elogw.p + dg.edge_base;
-    memcpy(ps, g.state, sizeof(int) * g.n_sites);
-    memcpy(po, g.bwd_off, sizeof(int) * (g.n_sites + 1));
-    if (n_edges) {
-        memcpy(pe, g.edge_start, sizeof(int) * n_edges);
-        memcpy(pw, g.edge_logw, sizeof(float) * n_edges);
-    }
+    const int *po = g.bwd_off, *pe = g.edge_start;
+    const float *pw = g.edge_logw;
+    if (po[g.n_sites] != n_edges) { dg.max_indeg = -2; return; }
     int simple = 1, maxdeg = 0;
     for (int s = 0; s < g.n_sites; s++) {
         int k0 = po[s], k1 = po[s + 1];
-        if (k1 < k0 || k1 > n_edges || k0 < 0) { simple = 0; maxdeg = 1 << 30; break; }  // malformed: device flags it
+        if (k1 < k0 || k1 > n_edges || k0 < 0) { simple = 0; maxdeg = -1; break; }  // malformed: the device flags it
         int deg = k1 - k0;
         if (deg > maxdeg) maxdeg = deg;
         if (s > 0 && (deg != 1 || pe[k0] != s - 1)) simple = 0;
         if (s == 0 && deg != 0) simple = 0;
     }
-    if (maxdeg == (1 << 30)) {
-        // keep offsets in range so that no kernel reads out of bounds: collapse to an edgeless graph, flagged bad
-        for (int s = 0; s <= g.n_sites; s++) po[s] = 0;
-        po[0] = 1;  // off[0] != 0 => validation marks JOB_BAD_GRAPH
-        maxdeg = 0;
-    }
     dg.max_indeg = maxdeg;
     dg.simple = simple;
     dg.zero_w = 1;
-    for (int k = 0; k < n_edges; k++) if (pw[k] != 0.0f || std::signbit(pw[k])) { dg.zero_w = 0; break; }
+    if (maxdeg >= 0)
+        for (int k = 0; k < n_edges; k++) if (pw[k] != 0.0f || std::signbit(pw[k])) { dg.zero_w = 0; break; }
+    dg.implicit = (simple && dg.zero_w && n_edges == g.n_sites - 1) ? 1 : 0;
+}
+
+// Packing step 4 (any thread): copy one graph into the staging arrays.
+static void copy_graph(pg2_ctx *c, DevGraph &dg, const pg2_graph &g) {
+    memcpy(c->h_state.p + dg.state_base, g.state, sizeof(int) * g.n_sites);
+    if (dg.implicit) return;
+    const int n_edges = g.n_edges;
+    int *po = c->h_off.p + dg.off_base, *pe = c->h_estart.p + dg.edge_base;
+    float *pw = c->h_elogw.p + dg.edge_base;
+    if (dg.max_indeg < 0) {
+        // malformed offsets: keep them in range so that no kernel reads out of bounds -- an edgeless graph, flagged bad
+        for (int s = 0; s <= g.n_sites; s++) po[s] = 0;
+        po[0] = 1;  // off[0] != 0 => validation marks JOB_BAD_GRAPH
+        dg.max_indeg = 0;
+    } else {
+        memcpy(po, g.bwd_off, sizeof(int) * (g.n_sites + 1));
+    }
+    if (n_edges) {
+        memcpy(pe, g.edge_start, sizeof(int) * n_edges);
+        memcpy(pw, g.edge_logw, sizeof(float) * n_edges);
+    }
+}
+
+// CSR of a staged graph as the host sees it: the staged arrays, or the implied chain of an implicit graph
+struct HostCsr {
+    const int *po, *pe;
+    const float *pw;
+    bool implicit;
+    int off(int s) const { return implicit ? (s > 0 ? s - 1 : 0) : po[s]; }
+    int start(int k) const { return implicit ? k : pe[k]; }
+    float logw(int k) const { return implicit ? 0.0f : pw[k]; }
+};
+static HostCsr host_csr(pg2_ctx *c, const DevGraph &dg) {
+    HostCsr h;
+    h.implicit = dg.implicit != 0;
+    h.po = h.implicit ? nullptr : c->h_off.p + dg.off_base;
+    h.pe = h.implicit ? nullptr : c->h_estart.p + dg.edge_base;
+    h.pw = h.implicit ? nullptr : c->h_elogw.p + dg.edge_base;
+    return h;
 }
 
 // Row program of a graph used as the strip kernel's ROW graph (pg2_strip_geom.cuh): virtual rows, saved-row
@@ -349,15 +402,15 @@ static void copy_graph(pg2_ctx *c, DevGraph &dg, const pg2_graph &g) {
 static int build_row_program(pg2_ctx *c, DevGraph &dg) {
     if (dg.vrow_base >= 0) return PG2_OK;
     const int n = dg.n_sites, rows = n - 1;
-    const int *ps = c->h_state.p + dg.state_base, *po = c->h_off.p + dg.off_base, *pe = c->h_estart.p + dg.edge_base;
-    const float *pw = c->h_elogw.p + dg.edge_base;
+    const int *ps = c->h_state.p + dg.state_base;
+    const HostCsr csr = host_csr(c, dg);
     // Saved-row slots: a DP row p that is the source of an edge p -> s with s - p >= 2 (s a DP row too) must stay
     // addressable until row s is done.  A slot is reused two rows after its last reader (the skewed sweep
     // reads it one step late on the next lane).
     std::vector<int> last_use(n, -1), slot_of(n, -1);
     for (int s = 1; s < rows; s++)
-        for (int k = po[s]; k < po[s + 1]; k++) {
-            int p = pe[k];
+        for (int k = csr.off(s); k < csr.off(s + 1); k++) {
+            int p = csr.start(k);
             if (p >= 0 && p < s && s - p >= 2 && last_use[p] < s) last_use[p] = s;
         }
     std::vector<int> free_slots;
@@ -378,10 +431,10 @@ static int build_row_program(pg2_ctx *c, DevGraph &dg) {
     // rows the end corner reads: predecessors of the stop site and the last DP row (Y close, :1468-1469)
     std::vector<char> endpred(n, 0);
     endpred[rows - 1 >= 0 ? rows - 1 : 0] = 1;
-    for (int k = po[n - 1]; k < po[n]; k++)
-        if (pe[k] >= 0 && pe[k] < n - 1) endpred[pe[k]] = 1;
+    for (int k = csr.off(n - 1); k < csr.off(n); k++)
+        if (csr.start(k) >= 0 && csr.start(k) < n - 1) endpred[csr.start(k)] = 1;
     int nv = 0;
-    for (int s = 0; s < rows; s++) nv += std::max(po[s + 1] - po[s], 1);
+    for (int s = 0; s < rows; s++) nv += std::max(csr.off(s + 1) - csr.off(s), 1);
     dg.vrow_base = (int)(c->h_vrow.n / 4);
     dg.vlast_base = (int)c->h_vlast.n;
     dg.n_vrows = nv;
@@ -389,7 +442,7 @@ static int build_row_program(pg2_ctx *c, DevGraph &dg) {
     if (!vr || !vl) return PG2_ERR_NOMEM;
     int v = 0;
     for (int s = 0; s < rows; s++) {
-        const int k0 = po[s], k1 = po[s + 1], deg = k1 - k0;
+        const int k0 = csr.off(s), k1 = csr.off(s + 1), deg = k1 - k0;
         const int st = ps[s] < 0 ? 0 : (ps[s] & VR_STATE_MASK);
         const int tail = (endpred[s] ? VR_ENDPRED : 0) | ((slot_of[s] + 1) << VR_SLOT_SHIFT);
         if (deg == 0) {
@@ -400,9 +453,9 @@ static int build_row_program(pg2_ctx *c, DevGraph &dg) {
             v++;
         }
         for (int k = k0; k < k1; k++) {
-            const int p = pe[k];
+            const int p = csr.start(k);
             const bool reg = (p == s - 1);
-            const bool zw = pw[k] == 0.0f && !std::signbit(pw[k]);
+            const bool zw = csr.logw(k) == 0.0f && !std::signbit(csr.logw(k));
             int info = st | (k == k0 ? VR_FIRST : 0) | (k == k1 - 1 ? VR_LAST | tail : 0) | (reg ? VR_REG : 0) | (zw ? VR_ZERO_W : 0);
             int src = (reg || p < 0 || p >= n ? 0 : (slot_of[p] < 0 ? 0 : slot_of[p])) | ((k - k0) << 16);
             vr[4 * v] = info; vr[4 * v + 1] = k; vr[4 * v + 2] = s; vr[4 * v + 3] = src;
@@ -470,8 +523,22 @@ static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t 
     return PG2_OK;
 }
 
+// PG2_TIMING=1: wall time of the host packing steps on stderr (tuning aid)
+struct PackTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    PackTimer() : on(getenv("PG2_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "pg2 pack: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_batch **out) {
     if (!c || !out || n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail(PG2_ERR_INVALID, "pg2_batch_create: bad argument");
+    PackTimer timer;
     *out = nullptr;
     CU(cudaSetDevice(c->device));
     if (c->current) return fail(PG2_ERR_INVALID, "pg2_batch_create: another batch is live on this ctx (destroy it first)");
@@ -480,11 +547,11 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     b->jobs.resize(n_jobs);
     c->h_state.clear(); c->h_off.clear(); c->h_estart.clear(); c->h_elogw.clear(); c->h_vrow.clear(); c->h_vlast.clear();
     c->h_blo.clear(); c->h_bhi.clear(); c->h_dlo.clear(); c->h_doff.clear();
-    std::unordered_map<GraphKey, int, GraphKeyHash> seen;
-    seen.reserve((size_t)n_jobs * 2 + 16);
+    GraphTable seen((size_t)n_jobs * 2);
+    b->graphs.reserve((size_t)n_jobs + 16);
     std::vector<const pg2_graph *> sources;
     sources.reserve((size_t)n_jobs + 16);
-    // ---- phase 1 (serial): argument checks, graph de-duplication, staging reservations ----
+    // ---- step 1 (serial): argument checks, graph de-duplication; reads the job records only ----
     for (int t = 0; t < n_jobs; t++) {
         const pg2_job &j = jobs[t];
         DevJob &J = b->jobs[t];
@@ -492,37 +559,73 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         if (j.model < 0 || j.model >= (int)c->models.size() || !c->models[j.model].live) { delete b; return fail(PG2_ERR_INVALID, "job names an unknown model handle"); }
         if ((j.upper == nullptr) != (j.lower == nullptr)) { delete b; return fail(PG2_ERR_INVALID, "job band needs both upper and lower (or neither)"); }
         int gl = 0, gr = 0;
-        int rc = reserve_graph(c, b, j.left, seen, sources, &gl);
-        if (rc == PG2_OK) rc = reserve_graph(c, b, j.right, seen, sources, &gr);
+        int rc = intern_graph(b, j.left, seen, sources, &gl);
+        if (rc == PG2_OK) rc = intern_graph(b, j.right, seen, sources, &gr);
         if (rc != PG2_OK) { delete b; return rc; }
         J.left = gl;
         J.right = gr;
     }
-    // ---- phase 2 (parallel): copy the distinct graphs into pinned staging, summarise their shape ----
+    timer.lap("1 dedup");
+    const int ng = (int)b->graphs.size();
+    int nthreads = 1;
     {
-        const int ng = (int)b->graphs.size();
-        size_t total_bytes = c->h_state.n * 8 + c->h_estart.n * 8;
-        int nthreads = 1;
-        if (total_bytes > ((size_t)8 << 20)) {
+        size_t sites = 0;
+        for (int gi = 0; gi < ng; gi++) sites += (size_t)b->graphs[gi].n_sites;
+        if (sites * 16 > ((size_t)8 << 20) && ng >= 64) {
             unsigned hw = std::thread::hardware_concurrency();
-            nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+            nthreads = (int)std::min<unsigned>(hw ? hw : 4, 16);
             const char *pt = getenv("PG2_PACK_THREADS");
             if (pt && atoi(pt) > 0) nthreads = atoi(pt);
         }
-        auto work = [&](int lo, int hi) { for (int gi = lo; gi < hi; gi++) copy_graph(c, b->graphs[gi], *sources[gi]); };
-        if (nthreads <= 1 || ng < 64) {
-            work(0, ng);
-        } else {
-            std::vector<std::thread> pool;
-            for (int w = 0; w < nthreads; w++) {
-                int lo = (int)((long long)ng * w / nthreads), hi = (int)((long long)ng * (w + 1) / nthreads);
-                pool.emplace_back(work, lo, hi);
-            }
-            for (auto &th : pool) th.join();
+    }
+    auto parallel_over_graphs = [&](const std::function<void(int)> &fn) {
+        if (nthreads <= 1) { for (int gi = 0; gi < ng; gi++) fn(gi); return; }
+        std::vector<std::thread> pool;
+        for (int w = 0; w < nthreads; w++) {
+            int lo = (int)((long long)ng * w / nthreads), hi = (int)((long long)ng * (w + 1) / nthreads);
+            pool.emplace_back([&fn, lo, hi]() { for (int gi = lo; gi < hi; gi++) fn(gi); });
+        }
+        for (auto &th : pool) th.join();
+    };
+    // ---- step 2 (parallel): one pass over every distinct graph: shape, implicit chains ----
+    parallel_over_graphs([&](int gi) { classify_graph(b->graphs[gi], *sources[gi]); });
+    timer.lap("2 classify graphs");
+    // ---- step 3 (serial): bases.  Explicit graphs come first in d_off / d_estart / d_elogw (staged and uploaded),
+    //      implicit chains behind them (generated on the device) ----
+    {
+        long long n_state = 0, e_off = 0, e_edge = 0, i_off = 0, i_edge = 0;
+        for (int gi = 0; gi < ng; gi++) {
+            DevGraph &dg = b->graphs[gi];
+            if (dg.max_indeg == -2) { delete b; return fail(PG2_ERR_INVALID, "graph: n_edges does not match bwd_off[n_sites]"); }
+            const pg2_graph &g = *sources[gi];
+            dg.state_base = (int)n_state;
+            n_state += g.n_sites;
+            if (dg.implicit) { dg.off_base = (int)i_off; dg.edge_base = (int)i_edge; i_off += g.n_sites + 1; i_edge += g.n_edges; }
+            else { dg.off_base = (int)e_off; dg.edge_base = (int)e_edge; e_off += g.n_sites + 1; e_edge += g.n_edges; }
+        }
+        if (n_state > 0x7fffffffLL || e_off + i_off > 0x7fffffffLL || e_edge + i_edge > 0x7fffffffLL) {
+            delete b;
+            return fail(PG2_ERR_INVALID, "batch too large: more than 2^31 sites or edges; split the batch");
+        }
+        for (int gi = 0; gi < ng; gi++) {
+            DevGraph &dg = b->graphs[gi];
+            if (dg.implicit) { dg.off_base += (int)e_off; dg.edge_base += (int)e_edge; }
+        }
+        b->n_off_total = (size_t)(e_off + i_off);
+        b->n_edge_total = (size_t)(e_edge + i_edge);
+        auto grow = [](auto &v, size_t k) { return k == 0 || v.extend(k) != nullptr; };  // extend(0) of an empty vector is null
+        if (!grow(c->h_state, (size_t)n_state) || !grow(c->h_off, (size_t)e_off) || !grow(c->h_estart, (size_t)e_edge) ||
+            !grow(c->h_elogw, (size_t)e_edge)) {
+            delete b;
+            return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
         }
     }
+    // ---- step 4 (parallel): copy the distinct graphs into pinned staging ----
+    parallel_over_graphs([&](int gi) { copy_graph(c, b->graphs[gi], *sources[gi]); });
+    timer.lap("3-4 bases, copy graphs");
     // ---- phase 3 (serial): bands, kernel choice, row programs ----
     long long step_base = 0;
+    int pick_ly = -1, pick_k = 0;  // strip_pick_k of the last read length seen (reads of a batch mostly share it)
     for (int t = 0; t < n_jobs; t++) {
         const pg2_job &j = jobs[t];
         DevJob &J = b->jobs[t];
@@ -548,7 +651,8 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             if (rc == PG2_ERR_UNSUPPORTED) J.kernel = 0;  // too many parked rows: the general kernel takes it
             else if (rc != PG2_OK) { delete b; return fail(rc, "pinned staging allocation failed"); }
         }
-        J.strip_k = J.kernel == 1 ? strip_pick_k(J.ly) : 0;
+        if (J.kernel == 1 && J.ly != pick_ly) { pick_ly = J.ly; pick_k = strip_pick_k(J.ly); }
+        J.strip_k = J.kernel == 1 ? pick_k : 0;
         J.strip_general = (J.kernel == 1 && !(GL.simple && GL.zero_w)) ? 1 : 0;
         if (J.kernel == 1 && c->models[j.model].fas <= STRIP_SMALL_FAS) J.strip_general |= 2;  // bit 1: shared-table variant
         J.ptr_cells = J.kernel == 1 ? strip_cells(GL.n_vrows, J.ly, J.strip_k) : J.cells;
@@ -560,25 +664,35 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     b->total_steps = step_base;
     b->n_graphs = (int)b->graphs.size();
 
+    timer.lap("5 bands, kernels, row programs");
     // ---- lane kernel tasks: strip-eligible jobs that share the row graph, model and flags, 32 per warp ----
     std::vector<int> lane_order;  // job ids, task by task
     if (!c->no_lanes && !c->force_wavefront) {
-        std::unordered_map<unsigned long long, int> bucket_of;
+        // buckets by (left graph, model, flags); a left graph almost always comes with one (model, flags) pair, so the
+        // lookup is a short list per graph instead of a hash table
+        struct BucketRef { int model; unsigned flags; int bucket; };
+        std::vector<std::vector<BucketRef> > by_graph(b->graphs.size());
         std::vector<std::vector<int> > buckets;
         for (int t = 0; t < n_jobs; t++) {
             const DevJob &J = b->jobs[t];
             if (J.kernel != 1) continue;
             const DevGraph &GL = b->graphs[J.left];
             if ((size_t)lane_cta_doubles(GL.n_vrows, J.lx, GL.n_slots) * sizeof(double) > c->lane_scratch_bytes / 16) continue;
-            unsigned long long key = ((unsigned long long)(unsigned)J.left << 32) | ((unsigned long long)(unsigned)J.model << 2) | (J.flags & 3u);
-            auto it = bucket_of.find(key);
-            if (it == bucket_of.end()) { it = bucket_of.emplace(key, (int)buckets.size()).first; buckets.emplace_back(); }
-            buckets[it->second].push_back(t);
+            std::vector<BucketRef> &refs = by_graph[J.left];
+            int bi = -1;
+            for (const BucketRef &r : refs) if (r.model == J.model && r.flags == (J.flags & 3u)) { bi = r.bucket; break; }
+            if (bi < 0) {
+                bi = (int)buckets.size();
+                refs.push_back({J.model, J.flags & 3u, bi});
+                buckets.emplace_back();
+            }
+            buckets[bi].push_back(t);
         }
         for (auto &bk : buckets) {
             if ((int)bk.size() < LANE_MIN_JOBS) continue;
             // lanes of one task sweep max_ly columns: put reads of similar length together
-            std::stable_sort(bk.begin(), bk.end(), [&](int x, int y) { return b->jobs[x].ly > b->jobs[y].ly; });
+            auto longer = [&](int x, int y) { return b->jobs[x].ly > b->jobs[y].ly; };
+            if (!std::is_sorted(bk.begin(), bk.end(), longer)) std::stable_sort(bk.begin(), bk.end(), longer);
             for (size_t pos = 0; pos < bk.size(); pos += 32) {
                 const int n = (int)std::min<size_t>(32, bk.size() - pos);
                 const DevJob &J0 = b->jobs[bk[pos]];
@@ -655,6 +769,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         }
     }
 
+    timer.lap("6 lane tasks");
     // order: lane jobs (task by task), then strip jobs, then wavefront jobs; larger jobs first inside a class
     // (tail balance)
     b->order = lane_order;
@@ -719,6 +834,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             }
         }
     }
+    timer.lap("7 order, groups, phases");
     c->current = b;
     *out = b;
     return PG2_OK;
@@ -728,7 +844,7 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     int rc;
 #define ENS(buf, n) if ((rc = (buf).ensure(n)) != PG2_OK) return fail(rc, "device allocation failed (%s)", #buf)
     ENS(c->d_vrow, c->h_vrow.n + 4); ENS(c->d_vlast, c->h_vlast.n + 1); ENS(c->d_queue, 4);
-    ENS(c->d_state, c->h_state.n + 1); ENS(c->d_off, c->h_off.n + 1); ENS(c->d_estart, c->h_estart.n + 1); ENS(c->d_elogw, c->h_elogw.n + 1);
+    ENS(c->d_state, c->h_state.n + 1); ENS(c->d_off, b->n_off_total + 1); ENS(c->d_estart, b->n_edge_total + 1); ENS(c->d_elogw, b->n_edge_total + 1);
     ENS(c->d_blo, c->h_blo.n + 1); ENS(c->d_bhi, c->h_bhi.n + 1); ENS(c->d_dlo, c->h_dlo.n + 1); ENS(c->d_doff, c->h_doff.n + 1);
     ENS(c->d_jobs, b->jobs.size() + 1); ENS(c->d_graphs, b->graphs.size() + 1); ENS(c->d_order, b->order.size() + 1);
     ENS(c->d_graph_status, b->graphs.size() + 1); ENS(c->d_results, b->jobs.size() + 1); ENS(c->d_steps, (size_t)b->total_steps + 1);
@@ -759,6 +875,8 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
         }
         c->models_dirty = false;
     }
+    // the CSR of implicit chains (plain leaves and reads) is generated where it is used
+    launch_expand_implicit((int)b->graphs.size(), c->d_graphs.p, c->d_off.p, c->d_estart.p, c->d_elogw.p, c->stream);
     b->h2d_bytes = bytes;
     b->uploaded = true;
     return PG2_OK;
@@ -767,7 +885,8 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
 }
 
 // Upload (if needed) and enqueue validation + every group's fill and traceback on the ctx stream.
-extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
+// async: enqueue only -- no host round trips, no per-phase timings; batch_wait() completes the run
+static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
     if (!c || !b || c->current != b) return fail(PG2_ERR_INVALID, "pg2_batch_run: bad batch");
     CU(cudaSetDevice(c->device));
     int rc;
@@ -776,10 +895,13 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
         CU(cudaEventRecord(c->ev[0], c->stream));
         if ((rc = upload_batch(c, b)) != PG2_OK) return rc;
         CU(cudaEventRecord(c->ev[1], c->stream));
-        CU(cudaEventSynchronize(c->ev[1]));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-        st.h2d_ms = ms;
+        st.h2d_ms = 0;
+        if (!async) {
+            CU(cudaEventSynchronize(c->ev[1]));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+            st.h2d_ms = ms;
+        }
         st.h2d_bytes = b->h2d_bytes;
     }
     // scratch for the largest phase of each buffer class (strip and lane groups share d_ptr16)
@@ -869,25 +991,30 @@ extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) {
                          c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_steps.p, c->d_results.p,
                          c->stream);
         CU(cudaEventRecord(c->ev[4], c->stream));
-        CU(cudaEventSynchronize(c->ev[4]));
-        CU(cudaGetLastError());
-        float f = 0, t = 0;
-        cudaEventElapsedTime(&f, c->ev[2], c->ev[3]);
-        cudaEventElapsedTime(&t, c->ev[3], c->ev[4]);
-        st.fill_ms += f;
-        st.traceback_ms += t;
+        if (!async) {
+            CU(cudaEventSynchronize(c->ev[4]));
+            CU(cudaGetLastError());
+            float f = 0, t = 0;
+            cudaEventElapsedTime(&f, c->ev[2], c->ev[3]);
+            cudaEventElapsedTime(&t, c->ev[3], c->ev[4]);
+            st.fill_ms += f;
+            st.traceback_ms += t;
+        }
         st.traceback_launches++;
         gi = ge;
     }
-    {
+    st.kernel_launches = 3 + st.fill_launches + st.traceback_launches + st.jobs_strip_groups;
+    st.run_ms = 0;
+    if (!async && !b->groups.empty()) {
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev[7], c->ev[4]);
-        st.run_ms = b->groups.empty() ? 0.0 : ms;
-        st.kernel_launches = 2 + st.fill_launches + st.traceback_launches + st.jobs_strip_groups;
+        st.run_ms = ms;
     }
     b->ran = true;
     return PG2_OK;
 }
+
+extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) { return batch_run_impl(c, b, false); }
 
 extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, uint16_t *steps, int64_t step_cap) {
     if (!c || !b || c->current != b || !b->ran || (b->n_jobs > 0 && (!results || !steps))) return fail(PG2_ERR_INVALID, "pg2_batch_fetch: bad argument or batch not run");
@@ -935,13 +1062,146 @@ extern "C" void pg2_batch_destroy(pg2_ctx *c, pg2_batch *b) {
     delete b;
 }
 
-extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint16_t *steps, int64_t step_cap) {
+// One launch batch from host buffers to host buffers.  Large batches are cut into chunks that alternate between the
+// ctx and its sibling (a second set of staging / device buffers and a second stream): the host packs chunk k+1 while
+// the device computes chunk k, and the results of chunk k come back while chunk k+1 computes.  Jobs that share the
+// left graph stay in one chunk, so the lane kernel keeps full tasks.
+static int align_batch_single(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint16_t *steps, int64_t step_cap) {
     pg2_batch *b = nullptr;
+    PackTimer timer;
     int rc = pg2_batch_create(c, n_jobs, jobs, &b);
     if (rc != PG2_OK) return rc;
+    timer.lap("= create");
     rc = pg2_batch_run(c, b);
+    timer.lap("= run (upload + kernels)");
     if (rc == PG2_OK) rc = pg2_batch_fetch(c, b, results, steps, step_cap);
+    timer.lap("= fetch");
     pg2_batch_destroy(c, b);
+    return rc;
+}
+
+static int ensure_sibling(pg2_ctx *c) {
+    if (!c->sibling) {
+        pg2_ctx *s = nullptr;
+        int rc = pg2_ctx_create(c->device, &s);
+        if (rc != PG2_OK) return rc;
+        s->borrowed_models = true;
+        s->scratch_bytes = c->scratch_bytes / 2;
+        s->force_wavefront = c->force_wavefront;
+        s->no_lanes = c->no_lanes;
+        c->sibling = s;
+    }
+    c->sibling->models = c->models;  // same device tables
+    c->sibling->models_dirty = true;
+    return PG2_OK;
+}
+
+extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint16_t *steps, int64_t step_cap) {
+    if (!c || n_jobs < 0 || (n_jobs > 0 && (!jobs || !results || !steps))) return fail(PG2_ERR_INVALID, "pg2_align_batch: bad argument");
+    const char *np = getenv("PG2_NO_PIPELINE");
+    const char *mj = getenv("PG2_PIPELINE_MIN_JOBS");  // tests force the pipelined path on small batches
+    const int min_jobs = (mj && atoi(mj) > 0) ? atoi(mj) : 8192;
+    if (n_jobs < min_jobs || (np && atoi(np) != 0)) return align_batch_single(c, n_jobs, jobs, results, steps, step_cap);
+    PackTimer timer;
+    // group the jobs by left graph (first-appearance order), then cut into chunks of about equal cell counts
+    std::vector<int> perm(n_jobs);
+    std::vector<long long> cells_prefix((size_t)n_jobs + 1, 0);
+    {
+        std::unordered_map<const void *, int> group_of;
+        group_of.reserve(4096);
+        std::vector<int> gid(n_jobs), count;
+        for (int t = 0; t < n_jobs; t++) {
+            auto it = group_of.find(jobs[t].left.state);
+            if (it == group_of.end()) { it = group_of.emplace(jobs[t].left.state, (int)count.size()).first; count.push_back(0); }
+            gid[t] = it->second;
+            count[it->second]++;
+        }
+        std::vector<int> start(count.size() + 1, 0);
+        for (size_t g = 0; g < count.size(); g++) start[g + 1] = start[g] + count[g];
+        for (int t = 0; t < n_jobs; t++) perm[start[gid[t]]++] = t;
+        for (int k = 0; k < n_jobs; k++) {
+            const pg2_job &j = jobs[perm[k]];
+            cells_prefix[k + 1] = cells_prefix[k] + (long long)std::max(j.left.n_sites, 1) * std::max(j.right.n_sites, 1);
+        }
+    }
+    const long long total = cells_prefix[n_jobs];
+    int n_chunks = (int)std::min<long long>(8, std::max<long long>(2, total / 4000000000LL));
+    const char *nc = getenv("PG2_PIPELINE_CHUNKS");
+    if (nc && atoi(nc) > 0) n_chunks = atoi(nc);
+    std::vector<int> cut(1, 0);
+    for (int k = 1; k < n_chunks; k++) {
+        const long long want = total * k / n_chunks;
+        int pos = (int)(std::lower_bound(cells_prefix.begin(), cells_prefix.end(), want) - cells_prefix.begin());
+        // prefer a boundary between two left graphs; inside a big group cut at a multiple of 32 jobs
+        int lo = pos;
+        while (lo > cut.back() && jobs[perm[lo]].left.state == jobs[perm[lo - 1]].left.state && pos - lo < 4096) lo--;
+        if (lo > cut.back() && jobs[perm[lo]].left.state != jobs[perm[lo - 1]].left.state) pos = lo;
+        else pos = cut.back() + ((pos - cut.back()) & ~31);
+        if (pos > cut.back() && pos < n_jobs) cut.push_back(pos);
+    }
+    cut.push_back(n_jobs);
+    int rc = ensure_sibling(c);
+    if (rc != PG2_OK) return rc;
+    timer.lap("= group + chunk");
+
+    struct InFlight { pg2_ctx *ctx = nullptr; pg2_batch *batch = nullptr; int lo = 0, hi = 0; long long step_base = 0; };
+    InFlight slot[2];
+    std::vector<pg2_job> chunk_jobs;
+    std::vector<pg2_result> chunk_res;
+    long long step_base = 0, h2d = 0, d2h = 0;
+    pg2_stats agg;
+    memset(&agg, 0, sizeof agg);
+    auto finish = [&](InFlight &f) -> int {
+        if (!f.batch) return PG2_OK;
+        const int n = f.hi - f.lo;
+        chunk_res.resize((size_t)n);
+        int r = pg2_batch_fetch(f.ctx, f.batch, chunk_res.data(), steps + f.step_base, step_cap - f.step_base);
+        if (r == PG2_OK) {
+            for (int k = 0; k < n; k++) {
+                pg2_result &o = results[perm[f.lo + k]];
+                o = chunk_res[(size_t)k];
+                o.step_off += f.step_base;
+            }
+            const pg2_stats &st = f.ctx->stats;
+            agg.h2d_bytes += st.h2d_bytes; agg.d2h_bytes += st.d2h_bytes; agg.cells += st.cells; agg.traceback_bytes += st.traceback_bytes;
+            agg.fill_launches += st.fill_launches; agg.traceback_launches += st.traceback_launches; agg.kernel_launches += st.kernel_launches;
+            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes;
+            agg.jobs_strip_groups += st.jobs_strip_groups; agg.d2h_ms += st.d2h_ms;
+        }
+        pg2_batch_destroy(f.ctx, f.batch);
+        f.batch = nullptr;
+        return r;
+    };
+    rc = PG2_OK;
+    for (size_t k = 0; k + 1 < cut.size() && rc == PG2_OK; k++) {
+        InFlight &f = slot[k & 1];
+        rc = finish(f);  // the chunk that used this slot two rounds ago
+        if (rc != PG2_OK) break;
+        f.ctx = (k & 1) ? c->sibling : c;
+        f.lo = cut[k];
+        f.hi = cut[k + 1];
+        f.step_base = step_base;
+        chunk_jobs.resize((size_t)(f.hi - f.lo));
+        long long cap = 0;
+        for (int i = f.lo; i < f.hi; i++) {
+            chunk_jobs[(size_t)(i - f.lo)] = jobs[perm[i]];
+            cap += jobs[perm[i]].left.n_sites + jobs[perm[i]].right.n_sites;
+        }
+        if (step_base + cap > step_cap) { rc = fail(PG2_ERR_CAPACITY, "step buffer too small"); break; }
+        step_base += cap;
+        rc = pg2_batch_create(f.ctx, f.hi - f.lo, chunk_jobs.data(), &f.batch);
+        if (rc == PG2_OK) rc = batch_run_impl(f.ctx, f.batch, true);
+        if (rc != PG2_OK && f.batch) { pg2_batch_destroy(f.ctx, f.batch); f.batch = nullptr; }
+    }
+    for (int s2 = 0; s2 < 2; s2++) {
+        // oldest first: slot parity of the next chunk index tells which slot is older
+        InFlight &f = slot[((cut.size() - 1) + s2) & 1];
+        int r = finish(f);
+        if (rc == PG2_OK) rc = r;
+    }
+    (void)h2d; (void)d2h;
+    if (rc == PG2_OK) c->stats = agg;
+    timer.lap("= pipelined chunks");
     return rc;
 }
 

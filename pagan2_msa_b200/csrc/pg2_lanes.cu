@@ -39,6 +39,14 @@
 #ifndef PG2_LANE_MINB
 #define PG2_LANE_MINB 3
 #endif
+// rows of the hot loop per iteration (tuning: -DPG2_LANE_UNROLL=2)
+#define PG2_PRAGMA_(x) _Pragma(#x)
+#define PG2_PRAGMA(x) PG2_PRAGMA_(x)
+#ifdef PG2_LANE_UNROLL
+#define PG2_LANE_ROW_UNROLL PG2_PRAGMA(unroll PG2_LANE_UNROLL)
+#else
+#define PG2_LANE_ROW_UNROLL
+#endif
 
 namespace pg2 {
 
@@ -296,6 +304,7 @@ __device__ __forceinline__ void lane_fast_run(const LaneCtx &c, LState<K> &st, c
     const double ninf = neg_inf();
     constexpr int Q = K / 8;
     int info_n = __ldg(&c.l_vrow[v].x);
+    PG2_LANE_ROW_UNROLL
     for (int r = 0; r < n; ++r) {
         const int sl = info_n & VR_STATE_MASK;
         if (r + 1 < n) info_n = __ldg(&c.l_vrow[v + r + 1].x);

@@ -222,6 +222,32 @@ __global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *j
 }
 #endif
 
+// CSR of an implicit chain: site s >= 1 is entered by the one edge (s-1 -> s) with log weight +0.0
+__device__ __forceinline__ void expand_chain(const DevGraph &G, int *d_off, int *d_estart, float *d_elogw, int lane, int nlanes) {
+    int *off = d_off + G.off_base, *es = d_estart + G.edge_base;
+    float *ew = d_elogw + G.edge_base;
+    for (int s = lane; s <= G.n_sites; s += nlanes) off[s] = s > 0 ? s - 1 : 0;
+    for (int k = lane; k < G.n_sites - 1; k += nlanes) { es[k] = k; ew[k] = 0.0f; }
+}
+#ifndef PG2_HOST_EMU
+__global__ void expand_implicit_kernel(int n_graphs, const DevGraph *graphs, int *d_off, int *d_estart, float *d_elogw) {
+    int g = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+    if (g >= n_graphs || !graphs[g].implicit) return;
+    expand_chain(graphs[g], d_off, d_estart, d_elogw, threadIdx.x & 31, 32);
+}
+#endif
+void launch_expand_implicit(int n_graphs, const DevGraph *graphs, int *d_off, int *d_estart, float *d_elogw, cudaStream_t stream) {
+    if (n_graphs <= 0) return;
+#ifndef PG2_HOST_EMU
+    const int warps = 8;
+    expand_implicit_kernel<<<(n_graphs + warps - 1) / warps, warps * 32, 0, stream>>>(n_graphs, graphs, d_off, d_estart, d_elogw);
+#else
+    (void)stream;
+    for (int g = 0; g < n_graphs; ++g)
+        if (graphs[g].implicit) expand_chain(graphs[g], d_off, d_estart, d_elogw, 0, 1);
+#endif
+}
+
 void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
                      const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
                      DevResult *results, cudaStream_t stream) {

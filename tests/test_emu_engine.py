@@ -174,3 +174,29 @@ def test_invalid_arguments(emu_lib):
         rc = eng.lib.pg2_align_batch(eng.ctx, 1, arr, res, steps.ctypes.data, 1000)
         assert rc == abi.PG2_ERR_INVALID
         assert b"model" in eng.lib.pg2_last_error()
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 5])
+def test_pipelined_align_batch_matches_single_shot(emu_lib, chunks):
+    """pg2_align_batch cuts large batches into chunks that alternate between two contexts (host packing of chunk
+    k+1 overlaps the device work of chunk k).  Same results, same packed paths per job, any chunk count; jobs that
+    share a left graph stay together."""
+    rng = np.random.default_rng(80 + chunks)
+    jobs = []
+    for _ in range(4):
+        jobs += randjobs.random_shared_target_jobs(rng, 37)
+    jobs += [randjobs.random_job(rng, kind) for kind in ("strip", "general", "banded") for _ in range(6)]
+    rng.shuffle(jobs)
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    os.environ["PG2_PIPELINE_MIN_JOBS"] = "8"
+    os.environ["PG2_PIPELINE_CHUNKS"] = str(chunks)
+    try:
+        with make_engine(emu_lib, False) as eng:
+            res = enginecheck.check_batch(eng, jobs)
+            assert (res["kernel"] == 2).sum() >= 4 * 32
+            assert eng.stats()["jobs_lanes"] + eng.stats()["jobs_strip"] + eng.stats()["jobs_wavefront"] == len(jobs)
+            # twice on the same engine: the sibling context and its buffers are reused
+            enginecheck.check_batch(eng, jobs[::-1])
+    finally:
+        os.environ.pop("PG2_PIPELINE_MIN_JOBS", None)
+        os.environ.pop("PG2_PIPELINE_CHUNKS", None)

@@ -207,3 +207,23 @@ def test_single_job_batches_on_a_fresh_engine(golden):
         with engine.Engine(0) as e:
             enginecheck.check_batch(e, [golden["place_dna"][k]])
             enginecheck.check_batch(e, [golden["pileup_hp"][min(k, len(golden["pileup_hp"]) - 1)]])
+
+
+def test_pipelined_align_batch_on_device(eng):
+    """The chunked, double-buffered pg2_align_batch path (two contexts, two streams) against the oracle."""
+    rng = np.random.default_rng(181)
+    jobs = []
+    for _ in range(6):
+        jobs += randjobs.random_shared_target_jobs(rng, 70)
+    jobs += [randjobs.random_job(rng, kind) for kind in ("strip", "general", "banded") for _ in range(10)]
+    rng.shuffle(jobs)
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    os.environ["PG2_PIPELINE_MIN_JOBS"] = "8"
+    os.environ["PG2_PIPELINE_CHUNKS"] = "4"
+    try:
+        res = enginecheck.check_batch(eng, jobs)
+        assert (res["kernel"] == 2).sum() >= 6 * 64
+        enginecheck.check_batch(eng, jobs[::-1])
+    finally:
+        os.environ.pop("PG2_PIPELINE_MIN_JOBS", None)
+        os.environ.pop("PG2_PIPELINE_CHUNKS", None)
