@@ -143,8 +143,10 @@ struct pg2_batch {
     long long total_cells = 0;
     long long h2d_bytes = 0;
     size_t n_off_total = 0, n_edge_total = 0;  // device sizes of d_off / d_estart (staged explicit graphs + implicit chains)
-    bool uploaded = false, ran = false;
+    bool uploaded = false, ran = false, fetch_enqueued = false;
 };
+
+constexpr int PIPE_SLOTS = 4;  // chunks of one pg2_align_batch call in flight at once (packing / H2D / kernels / D2H overlap)
 
 struct pg2_ctx {
     int device = 0;
@@ -178,7 +180,7 @@ struct pg2_ctx {
     cudaEvent_t ev[8];
     pg2_stats stats;
     pg2_batch *current = nullptr;
-    pg2_ctx *sibling = nullptr;    // second set of staging / device buffers + stream for pipelined pg2_align_batch calls
+    pg2_ctx *sibling[PIPE_SLOTS - 1] = {};  // further sets of staging / device buffers + streams for pipelined pg2_align_batch calls
     bool borrowed_models = false;  // a sibling shares the primary's model tables and must not free them
 };
 
@@ -219,7 +221,7 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
 
 extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
     if (!c) return;
-    if (c->sibling) { pg2_ctx_destroy(c->sibling); c->sibling = nullptr; }
+    for (auto &sib : c->sibling) if (sib) { pg2_ctx_destroy(sib); sib = nullptr; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (!c->borrowed_models)
@@ -688,6 +690,19 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             }
             buckets[bi].push_back(t);
         }
+        // one launch instead of two when a batch mixes plain-chain and general row graphs: the general variant runs
+        // plain rows through the same hot loop, and one task queue has one tail
+        bool lane_merge = false;
+        {
+            bool any_plain = false, any_general = false;
+            for (auto &bk : buckets) {
+                if ((int)bk.size() < LANE_MIN_JOBS) continue;
+                const DevGraph &GL = b->graphs[b->jobs[bk[0]].left];
+                ((GL.simple && GL.zero_w) ? any_plain : any_general) = true;
+            }
+            const char *lm = getenv("PG2_LANE_MERGE");
+            lane_merge = any_plain && any_general && !(lm && atoi(lm) == 0);
+        }
         for (auto &bk : buckets) {
             if ((int)bk.size() < LANE_MIN_JOBS) continue;
             // lanes of one task sweep max_ly columns: put reads of similar length together
@@ -704,7 +719,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
                 T.flags = J0.flags;
                 T.n_jobs = n;
                 T.max_ly = J0.ly;
-                T.variant = ((GL.simple && GL.zero_w) ? 0 : 1) | (c->models[J0.model].fas <= STRIP_SMALL_FAS ? 2 : 0);
+                T.variant = ((GL.simple && GL.zero_w && !lane_merge) ? 0 : 1) | (c->models[J0.model].fas <= STRIP_SMALL_FAS ? 2 : 0);
                 for (int l = 0; l < n; l++) {
                     DevJob &J = b->jobs[bk[pos + l]];
                     T.job_ids[l] = bk[pos + l];
@@ -1016,13 +1031,12 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
 
 extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) { return batch_run_impl(c, b, false); }
 
-extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, uint16_t *steps, int64_t step_cap) {
-    if (!c || !b || c->current != b || !b->ran || (b->n_jobs > 0 && (!results || !steps))) return fail(PG2_ERR_INVALID, "pg2_batch_fetch: bad argument or batch not run");
+// Results come back in two steps: fetch_enqueue puts the device->host copies of the result records (into the ctx's
+// pinned staging) and of the packed paths (straight into the caller's buffer) on the ctx stream behind the kernels;
+// fetch_complete waits for them and fills the caller's pg2_result records.
+static int fetch_enqueue(pg2_ctx *c, pg2_batch *b, uint16_t *steps, int64_t step_cap) {
     CU(cudaSetDevice(c->device));
-    if (step_cap < b->total_steps) {
-        for (int t = 0; t < b->n_jobs; t++) results[t].n_steps = b->jobs[t].step_cap;
-        return fail(PG2_ERR_CAPACITY, "step buffer too small");
-    }
+    if (step_cap < b->total_steps) return fail(PG2_ERR_CAPACITY, "step buffer too small");
     c->h_results.clear();
     DevResult *hr = c->h_results.extend((size_t)b->n_jobs + 1);
     if (!hr) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
@@ -1032,7 +1046,15 @@ extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, ui
         CU(cudaMemcpyAsync(steps, c->d_steps.p, sizeof(unsigned short) * (size_t)b->total_steps, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaEventRecord(c->ev[6], c->stream));
+    b->fetch_enqueued = true;
+    return PG2_OK;
+}
+
+static int fetch_complete(pg2_ctx *c, pg2_batch *b, pg2_result *results) {
+    CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    const DevResult *hr = c->h_results.p;
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]);
     c->stats.d2h_ms = ms;
@@ -1052,6 +1074,17 @@ extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, ui
     return PG2_OK;
 }
 
+extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, uint16_t *steps, int64_t step_cap) {
+    if (!c || !b || c->current != b || !b->ran || (b->n_jobs > 0 && (!results || !steps))) return fail(PG2_ERR_INVALID, "pg2_batch_fetch: bad argument or batch not run");
+    if (step_cap < b->total_steps) {
+        for (int t = 0; t < b->n_jobs; t++) results[t].n_steps = b->jobs[t].step_cap;
+        return fail(PG2_ERR_CAPACITY, "step buffer too small");
+    }
+    int rc = fetch_enqueue(c, b, steps, step_cap);
+    if (rc != PG2_OK) return rc;
+    return fetch_complete(c, b, results);
+}
+
 extern "C" void pg2_batch_destroy(pg2_ctx *c, pg2_batch *b) {
     if (!b) return;
     if (c) {
@@ -1062,10 +1095,11 @@ extern "C" void pg2_batch_destroy(pg2_ctx *c, pg2_batch *b) {
     delete b;
 }
 
-// One launch batch from host buffers to host buffers.  Large batches are cut into chunks that alternate between the
-// ctx and its sibling (a second set of staging / device buffers and a second stream): the host packs chunk k+1 while
-// the device computes chunk k, and the results of chunk k come back while chunk k+1 computes.  Jobs that share the
-// left graph stay in one chunk, so the lane kernel keeps full tasks.
+// One launch batch from host buffers to host buffers.  Large batches are cut into chunks that rotate over the ctx
+// and its siblings (further sets of staging / device buffers, each with its own stream): the host packs chunk k+1
+// while the device computes chunk k, the kernels of consecutive chunks overlap on the device (the tail of one
+// launch is filled by the next), and results stream back while later chunks compute.  Jobs that share the left
+// graph stay in one chunk, so the lane kernel keeps full tasks.
 static int align_batch_single(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint16_t *steps, int64_t step_cap) {
     pg2_batch *b = nullptr;
     PackTimer timer;
@@ -1080,20 +1114,34 @@ static int align_batch_single(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, p
     return rc;
 }
 
-static int ensure_sibling(pg2_ctx *c) {
-    if (!c->sibling) {
-        pg2_ctx *s = nullptr;
-        int rc = pg2_ctx_create(c->device, &s);
-        if (rc != PG2_OK) return rc;
-        s->borrowed_models = true;
-        s->scratch_bytes = c->scratch_bytes / 2;
-        s->force_wavefront = c->force_wavefront;
-        s->no_lanes = c->no_lanes;
-        c->sibling = s;
+static int ensure_siblings(pg2_ctx *c, int n_slots) {
+    for (int k = 0; k + 1 < n_slots; k++) {
+        if (!c->sibling[k]) {
+            pg2_ctx *s = nullptr;
+            int rc = pg2_ctx_create(c->device, &s);
+            if (rc != PG2_OK) return rc;
+            s->borrowed_models = true;
+            s->scratch_bytes = c->scratch_bytes / PIPE_SLOTS;
+            s->force_wavefront = c->force_wavefront;
+            s->no_lanes = c->no_lanes;
+            c->sibling[k] = s;
+        }
+        c->sibling[k]->models = c->models;  // same device tables
+        c->sibling[k]->models_dirty = true;
     }
-    c->sibling->models = c->models;  // same device tables
-    c->sibling->models_dirty = true;
     return PG2_OK;
+}
+
+// page-locked host memory takes asynchronous device->host copies; a copy into pageable memory would block the caller
+static bool host_pointer_is_pinned(const void *p) {
+#ifdef PG2_HOST_EMU
+    (void)p;
+    return true;
+#else
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+#endif
 }
 
 extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint16_t *steps, int64_t step_cap) {
@@ -1125,7 +1173,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         }
     }
     const long long total = cells_prefix[n_jobs];
-    int n_chunks = (int)std::min<long long>(8, std::max<long long>(2, total / 4000000000LL));
+    int n_chunks = (int)std::min<long long>(8, std::max<long long>(2, total / 3000000000LL));
     const char *nc = getenv("PG2_PIPELINE_CHUNKS");
     if (nc && atoi(nc) > 0) n_chunks = atoi(nc);
     std::vector<int> cut(1, 0);
@@ -1140,22 +1188,31 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         if (pos > cut.back() && pos < n_jobs) cut.push_back(pos);
     }
     cut.push_back(n_jobs);
-    int rc = ensure_sibling(c);
+    int n_slots = PIPE_SLOTS;
+    const char *ns = getenv("PG2_PIPELINE_SLOTS");
+    if (ns && atoi(ns) >= 1 && atoi(ns) <= PIPE_SLOTS) n_slots = atoi(ns);
+    n_slots = std::min<int>(n_slots, (int)cut.size() - 1);
+    int rc = ensure_siblings(c, n_slots);
     if (rc != PG2_OK) return rc;
+    const bool async_d2h = host_pointer_is_pinned(steps);
     timer.lap("= group + chunk");
 
+    // Chunk k runs on slot k % n_slots: pack, upload, kernels and (into pinned caller memory) the copy back are all
+    // enqueued without waiting; the host only waits for a chunk when its slot is needed again or at the end.
     struct InFlight { pg2_ctx *ctx = nullptr; pg2_batch *batch = nullptr; int lo = 0, hi = 0; long long step_base = 0; };
-    InFlight slot[2];
+    InFlight slot[PIPE_SLOTS];
     std::vector<pg2_job> chunk_jobs;
     std::vector<pg2_result> chunk_res;
-    long long step_base = 0, h2d = 0, d2h = 0;
+    long long step_base = 0;
     pg2_stats agg;
     memset(&agg, 0, sizeof agg);
     auto finish = [&](InFlight &f) -> int {
         if (!f.batch) return PG2_OK;
         const int n = f.hi - f.lo;
         chunk_res.resize((size_t)n);
-        int r = pg2_batch_fetch(f.ctx, f.batch, chunk_res.data(), steps + f.step_base, step_cap - f.step_base);
+        int r = PG2_OK;
+        if (!f.batch->fetch_enqueued) r = fetch_enqueue(f.ctx, f.batch, steps + f.step_base, step_cap - f.step_base);
+        if (r == PG2_OK) r = fetch_complete(f.ctx, f.batch, chunk_res.data());
         if (r == PG2_OK) {
             for (int k = 0; k < n; k++) {
                 pg2_result &o = results[perm[f.lo + k]];
@@ -1173,11 +1230,13 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         return r;
     };
     rc = PG2_OK;
-    for (size_t k = 0; k + 1 < cut.size() && rc == PG2_OK; k++) {
-        InFlight &f = slot[k & 1];
-        rc = finish(f);  // the chunk that used this slot two rounds ago
+    const size_t n_cut = cut.size() - 1;
+    for (size_t k = 0; k < n_cut && rc == PG2_OK; k++) {
+        InFlight &f = slot[k % (size_t)n_slots];
+        rc = finish(f);  // the chunk that used this slot n_slots rounds ago
         if (rc != PG2_OK) break;
-        f.ctx = (k & 1) ? c->sibling : c;
+        const size_t si = k % (size_t)n_slots;
+        f.ctx = si == 0 ? c : c->sibling[si - 1];
         f.lo = cut[k];
         f.hi = cut[k + 1];
         f.step_base = step_base;
@@ -1191,15 +1250,15 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         step_base += cap;
         rc = pg2_batch_create(f.ctx, f.hi - f.lo, chunk_jobs.data(), &f.batch);
         if (rc == PG2_OK) rc = batch_run_impl(f.ctx, f.batch, true);
+        if (rc == PG2_OK && async_d2h) rc = fetch_enqueue(f.ctx, f.batch, steps + f.step_base, step_cap - f.step_base);
         if (rc != PG2_OK && f.batch) { pg2_batch_destroy(f.ctx, f.batch); f.batch = nullptr; }
     }
-    for (int s2 = 0; s2 < 2; s2++) {
-        // oldest first: slot parity of the next chunk index tells which slot is older
-        InFlight &f = slot[((cut.size() - 1) + s2) & 1];
+    for (size_t k = 0; k < (size_t)n_slots; k++) {
+        // oldest first
+        InFlight &f = slot[(n_cut + k) % (size_t)n_slots];
         int r = finish(f);
         if (rc == PG2_OK) rc = r;
     }
-    (void)h2d; (void)d2h;
     if (rc == PG2_OK) c->stats = agg;
     timer.lap("= pipelined chunks");
     return rc;
