@@ -45,16 +45,26 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def measured_traffic(n_reads, fill_launches):
-    """DRAM bytes per fill launch from the committed ncu capture (profiles/), valid for the workload it was taken on."""
-    p = os.path.join(ROOT, "profiles", "r1_lanes_v6_traffic.json")
+TRAFFIC_PROFILE = "r1_lanes_v8_traffic.json"  # tools/ncu_summary.py output of the committed ncu capture
+
+
+def measured_profile(n_reads, fill_launches):
+    """Per-launch figures of the committed ncu capture (profiles/), valid for the workload it was taken on:
+    (DRAM read+write bytes per fill launch, dispatch-port busy % of the fill launches weighted by time)."""
+    p = os.path.join(ROOT, "profiles", TRAFFIC_PROFILE)
     if not os.path.exists(p):
-        return None
+        return None, None
     with open(p) as f:
         t = json.load(f)
     if t.get("reads_per_gpu") != n_reads or len(t["launches"]) != fill_launches:
-        return None
-    return sum(l["dram_bytes_read"] + l["dram_bytes_write"] for l in t["launches"]) / len(t["launches"])
+        return None, None
+    ls = t["launches"]
+    traffic = sum(l["dram_bytes_read"] + l["dram_bytes_write"] for l in ls) / len(ls)
+    tt = sum(l["time_ms_under_ncu"] for l in ls)
+    busy = None
+    if all(l.get("dispatch_busy_pct") is not None for l in ls) and tt > 0:
+        busy = sum(l["dispatch_busy_pct"] * l["time_ms_under_ncu"] for l in ls) / tt
+    return traffic, busy
 
 
 def build_workload(n_reads, seed, rank=0):
@@ -268,6 +278,8 @@ def main():
     from pagan2_msa_b200 import engine
 
     rank, world, local, dist = dist_setup(args.gpus)
+    # the host packing threads of all ranks share this box's cores
+    os.environ.setdefault("PG2_PACK_THREADS", str(max(1, min(16, len(os.sched_getaffinity(0)) // max(world, 1)))))
     if rank == 0:
         __graft_entry__.build()
     if dist is not None:
@@ -363,6 +375,9 @@ def main():
     if rank == 0:
         dadd, cand = C.c_double(), C.c_double()
         eng.lib.pg2_measure_fp64_issue(local, C.byref(dadd), C.byref(cand))
+        mix, mix_mhz = (C.c_double * 3)(), C.c_double()
+        eng.lib.pg2_measure_dispatch_mix(local, mix, C.byref(mix_mhz))
+        traffic, dispatch_busy = measured_profile(args.reads, stats["fill_launches"])
         fp64_peak = dadd.value  # 1e9 FP64-pipe warp-instructions / s, chip-wide
         per_launch_cells = cells / max(stats["fill_launches"], 1)
         launch_ms = ms_fill / max(stats["fill_launches"], 1)
@@ -384,8 +399,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": measured_traffic(args.reads, stats["fill_launches"]),
-                         "traffic_note": "DRAM read+write bytes per fill launch, ncu capture profiles/r1_lanes_v6_ncu_summary.csv; "
+                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic,
+                         "traffic_note": "DRAM read+write bytes per fill launch, ncu capture profiles/" + TRAFFIC_PROFILE + "; "
                                          "algorithmic bytes per launch = %d" % int(per_launch_cells * PTR_BYTES_PER_CELL),
                          "peak_source": peaks_kind,
                          "kernel": "lane_fill_kernel" if stats["jobs_lanes"] >= stats["jobs_strip"] else "strip_fill_kernel",
@@ -398,7 +413,15 @@ def main():
                                                    "instr_per_cell": FP64_INSTR_EXECUTED,
                                                    "note": "FP64-pipe instructions the kernel really issues (common terms shared)"},
                                       "peak_source": "pg2_measure_fp64_issue (DADD loop, this run)",
-                                      "candidate_update_peak": cand.value}},
+                                      "candidate_update_peak": cand.value,
+                                      "dispatch": {"cycles_8dadd_16fadd_both": [mix[0], mix[1], mix[2]],
+                                                   "fp64_dispatch_cycles": (mix[2] - mix[1]) / 8.0 if mix[2] else None,
+                                                   "busy_frac_ncu": dispatch_busy / 100.0 if dispatch_busy else None,
+                                                   "note": "an FP64 instruction holds the sub-partition's dispatch port for "
+                                                           "fp64_dispatch_cycles cycles (measured in this run: 8 DADD + 16 FADD per "
+                                                           "iteration cost cycles[2], not max); busy_frac_ncu = (issue_active + "
+                                                           "fp64_pipe_active/2) of the fill launches in the committed ncu capture, "
+                                                           "the fraction of dispatch cycles the kernel uses"}}},
             "fill_ms_per_step": ms_fill, "traceback_ms_per_step": tb_ms / args.steps, "wall_ms_per_step": ms_wall,
             "jobs_ok": ok, "jobs": len(jobs), "kernels": {"lanes": stats["jobs_lanes"], "strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"]},
         }

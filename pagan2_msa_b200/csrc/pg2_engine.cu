@@ -1151,18 +1151,29 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
     const int min_jobs = (mj && atoi(mj) > 0) ? atoi(mj) : 8192;
     if (n_jobs < min_jobs || (np && atoi(np) != 0)) return align_batch_single(c, n_jobs, jobs, results, steps, step_cap);
     PackTimer timer;
-    // group the jobs by left graph (first-appearance order), then cut into chunks of about equal cell counts
+    // group the jobs by left graph (first-appearance order), then cut into chunks by cell count
     std::vector<int> perm(n_jobs);
     std::vector<long long> cells_prefix((size_t)n_jobs + 1, 0);
     {
-        std::unordered_map<const void *, int> group_of;
-        group_of.reserve(4096);
+        // open-addressing table on the left graph's `state` pointer -> group id
+        size_t cap = 1024;
+        while (cap < (size_t)n_jobs * 2) cap <<= 1;
+        struct Slot { const void *key; int gid; };
+        std::vector<Slot> table(cap, Slot{nullptr, -1});
         std::vector<int> gid(n_jobs), count;
+        const void *last_key = nullptr;
+        int last_gid = -1;
         for (int t = 0; t < n_jobs; t++) {
-            auto it = group_of.find(jobs[t].left.state);
-            if (it == group_of.end()) { it = group_of.emplace(jobs[t].left.state, (int)count.size()).first; count.push_back(0); }
-            gid[t] = it->second;
-            count[it->second]++;
+            const void *key = jobs[t].left.state;
+            if (key != last_key) {
+                size_t i = ((((size_t)key >> 4) * 0x9E3779B97F4A7C15ull) >> 24) & (cap - 1);
+                while (table[i].gid >= 0 && table[i].key != key) i = (i + 1) & (cap - 1);
+                if (table[i].gid < 0) { table[i].key = key; table[i].gid = (int)count.size(); count.push_back(0); }
+                last_key = key;
+                last_gid = table[i].gid;
+            }
+            gid[t] = last_gid;
+            count[last_gid]++;
         }
         std::vector<int> start(count.size() + 1, 0);
         for (size_t g = 0; g < count.size(); g++) start[g + 1] = start[g] + count[g];
@@ -1173,16 +1184,29 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         }
     }
     const long long total = cells_prefix[n_jobs];
-    int n_chunks = (int)std::min<long long>(8, std::max<long long>(2, total / 3000000000LL));
+    int n_chunks = (int)std::min<long long>(8, std::max<long long>(2, total / 2500000000LL));
     const char *nc = getenv("PG2_PIPELINE_CHUNKS");
     if (nc && atoi(nc) > 0) n_chunks = atoi(nc);
+    // chunk weights: a small first chunk puts the device to work early, a small last chunk keeps the copy back of
+    // the final results short; the chunks in between amortise the per-chunk packing and launches
+    std::vector<double> weight((size_t)n_chunks, 3.0);
+    if (n_chunks >= 4) { weight[0] = 1.0; weight[1] = 2.0; weight[(size_t)n_chunks - 1] = 2.0; }
+    if (const char *pw = getenv("PG2_PIPELINE_WEIGHTS")) {  // tuning: comma-separated relative chunk sizes
+        std::vector<double> w;
+        for (const char *q = pw; *q;) { char *e; double v = strtod(q, &e); if (e == q) break; if (v > 0) w.push_back(v); q = *e ? e + 1 : e; }
+        if (w.size() >= 2) { weight = w; n_chunks = (int)w.size(); }
+    }
+    double wsum = 0;
+    for (double w : weight) wsum += w;
     std::vector<int> cut(1, 0);
+    double wacc = 0;
     for (int k = 1; k < n_chunks; k++) {
-        const long long want = total * k / n_chunks;
+        wacc += weight[(size_t)k - 1];
+        const long long want = (long long)((double)total * (wacc / wsum));
         int pos = (int)(std::lower_bound(cells_prefix.begin(), cells_prefix.end(), want) - cells_prefix.begin());
         // prefer a boundary between two left graphs; inside a big group cut at a multiple of 32 jobs
         int lo = pos;
-        while (lo > cut.back() && jobs[perm[lo]].left.state == jobs[perm[lo - 1]].left.state && pos - lo < 4096) lo--;
+        while (lo > cut.back() && jobs[perm[lo]].left.state == jobs[perm[lo - 1]].left.state && pos - lo < 1024) lo--;
         if (lo > cut.back() && jobs[perm[lo]].left.state != jobs[perm[lo - 1]].left.state) pos = lo;
         else pos = cut.back() + ((pos - cut.back()) & ~31);
         if (pos > cut.back() && pos < n_jobs) cut.push_back(pos);

@@ -44,6 +44,31 @@ __global__ void __launch_bounds__(256) candidate_kernel(double *out, double inc,
     for (int k = 0; k < CHAINS; ++k) { s += best[k]; p ^= ptr[k]; }
     if (s == 12345.678 || p == 0xdeadbeefu) out[0] = s;
 }
+
+// Dispatch model: NF independent FADDs and ND independent DADDs per thread and iteration.  If an FP64
+// instruction holds the sub-partition's dispatch port for two cycles, the mix costs NF + 2*ND cycles per warp and
+// iteration; if FP32 work could issue in the shadow of the FP64 pipe it would cost max(NF + ND, 2*ND).
+template <int NF, int ND>
+__global__ void __launch_bounds__(256) mix_kernel(double *out, double dinc, float finc, int iters) {
+    double a[ND > 0 ? ND : 1];
+    float f[NF > 0 ? NF : 1];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) a[k] = (double)(threadIdx.x + k);
+#pragma unroll
+    for (int k = 0; k < NF; ++k) f[k] = (float)(threadIdx.x + 2 * k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) a[k] = __dadd_rn(a[k], dinc);
+#pragma unroll
+        for (int k = 0; k < NF; ++k) f[k] = __fadd_rn(f[k], finc);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) s += a[k];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) s += (double)f[k];
+    if (s == 12345.678) out[0] = s;
+}
 #endif
 }  // namespace pg2
 
@@ -86,6 +111,53 @@ extern "C" int pg2_measure_fp64_issue(int device, double *dadd_gips, double *can
     if (cudaGetLastError() != cudaSuccess) return PG2_ERR_CUDA;
     *dadd_gips = best_d * 1e-9;
     *cand_gips = best_c * 1e-9;
+    return PG2_OK;
+#endif
+}
+
+// Cycles per warp and iteration on one SM sub-partition (8 resident warps each) for three loops: 8 DADD, 16 FADD,
+// and 8 DADD + 16 FADD.  cycles[2] close to cycles[0] + cycles[1] (16 + 16 = 32) means an FP64 instruction costs two
+// dispatch cycles in which nothing else issues: the fill kernels' bound is then (instructions + FP64 instructions)
+// dispatch cycles, which is what bench.py reports as roofline.dp_issue.dispatch.
+extern "C" int pg2_measure_dispatch_mix(int device, double *cycles, double *sm_clock_mhz) {
+#ifdef PG2_HOST_EMU
+    (void)device; (void)cycles; (void)sm_clock_mhz;
+    return PG2_ERR_NO_DEVICE;
+#else
+    if (!cycles || !sm_clock_mhz) return PG2_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return PG2_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PG2_ERR_CUDA;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    *sm_clock_mhz = khz * 1e-3;
+    double *out = nullptr;
+    if (cudaMalloc((void **)&out, 64) != cudaSuccess) return PG2_ERR_NOMEM;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int threads = 256, blocks = prop.multiProcessorCount * 4, iters = 1 << 15;  // 32 warps per SM = 8 per sub-partition
+    for (int which = 0; which < 3; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            float ms = 0;
+            cudaEventRecord(e0);
+            if (which == 0) pg2::mix_kernel<0, 8><<<blocks, threads>>>(out, 1.0000001, 1.0001f, iters);
+            else if (which == 1) pg2::mix_kernel<16, 0><<<blocks, threads>>>(out, 1.0000001, 1.0001f, iters);
+            else pg2::mix_kernel<16, 8><<<blocks, threads>>>(out, 1.0000001, 1.0001f, iters);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep && ms < best) best = ms;
+        }
+        // warps per sub-partition = blocks * 8 / (SMs * 4) = 8; cycles per warp-iteration of ONE warp's share of the port
+        const double total_cycles = best * 1e-3 * khz * 1e3;
+        cycles[which] = total_cycles / iters / 8.0;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return PG2_ERR_CUDA;
     return PG2_OK;
 #endif
 }

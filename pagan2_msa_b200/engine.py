@@ -42,6 +42,7 @@ def _bind(lib):
     lib.pg2_batch_device_buffers.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
     lib.pg2_stream_synchronize.argtypes = [vp]
     lib.pg2_measure_fp64_issue.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.pg2_measure_dispatch_mix.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return lib
 
 
