@@ -50,7 +50,8 @@ TRAFFIC_PROFILE = "r1_lanes_v8_traffic.json"  # tools/ncu_summary.py output of t
 
 def measured_profile(n_reads, fill_launches):
     """Per-launch figures of the committed ncu capture (profiles/), valid for the workload it was taken on:
-    (DRAM read+write bytes per fill launch, dispatch-port busy % of the fill launches weighted by time)."""
+    (DRAM read+write bytes per fill launch, {issue-slot, FP64-pipe, ALU-pipe busy % and warp-instructions} of the fill
+    launches, weighted by time)."""
     p = os.path.join(ROOT, "profiles", TRAFFIC_PROFILE)
     if not os.path.exists(p):
         return None, None
@@ -62,8 +63,10 @@ def measured_profile(n_reads, fill_launches):
     traffic = sum(l["dram_bytes_read"] + l["dram_bytes_write"] for l in ls) / len(ls)
     tt = sum(l["time_ms_under_ncu"] for l in ls)
     busy = None
-    if all(l.get("dispatch_busy_pct") is not None for l in ls) and tt > 0:
-        busy = sum(l["dispatch_busy_pct"] * l["time_ms_under_ncu"] for l in ls) / tt
+    if all(l.get("issue_active_pct") is not None for l in ls) and tt > 0:
+        busy = {k: sum(l[k] * l["time_ms_under_ncu"] for l in ls) / tt
+                for k in ("issue_active_pct", "fp64_pipe_active_pct", "alu_pipe_active_pct") if all(l.get(k) is not None for l in ls)}
+        busy["warp_instructions"] = sum(l["warp_instructions"] for l in ls)
     return traffic, busy
 
 
@@ -414,14 +417,16 @@ def main():
                                                    "note": "FP64-pipe instructions the kernel really issues (common terms shared)"},
                                       "peak_source": "pg2_measure_fp64_issue (DADD loop, this run)",
                                       "candidate_update_peak": cand.value,
-                                      "dispatch": {"cycles_8dadd_16fadd_both": [mix[0], mix[1], mix[2]],
-                                                   "fp64_dispatch_cycles": (mix[2] - mix[1]) / 8.0 if mix[2] else None,
-                                                   "busy_frac_ncu": dispatch_busy / 100.0 if dispatch_busy else None,
-                                                   "note": "an FP64 instruction holds the sub-partition's dispatch port for "
-                                                           "fp64_dispatch_cycles cycles (measured in this run: 8 DADD + 16 FADD per "
-                                                           "iteration cost cycles[2], not max); busy_frac_ncu = (issue_active + "
-                                                           "fp64_pipe_active/2) of the fill launches in the committed ncu capture, "
-                                                           "the fraction of dispatch cycles the kernel uses"}}},
+                                      "issue_slots": {
+                                          "cycles_8dadd_16fadd_both": [mix[0], mix[1], mix[2]],
+                                          "busy_frac_ncu": dispatch_busy["issue_active_pct"] / 100.0 if dispatch_busy else None,
+                                          "fp64_pipe_frac_ncu": dispatch_busy["fp64_pipe_active_pct"] / 100.0 if dispatch_busy else None,
+                                          "alu_pipe_frac_ncu": dispatch_busy.get("alu_pipe_active_pct", 0.0) / 100.0 if dispatch_busy else None,
+                                          "warp_instr_per_32_cells_ncu": dispatch_busy["warp_instructions"] / (cells / 32.0) if dispatch_busy else None,
+                                          "note": "8 DADD + 16 FADD per loop iteration cost cycles[2] ~ 24 issue cycles, not "
+                                                  "cycles[0] + cycles[1]: FP64 instructions (2 pipe cycles each) overlap other issue, so "
+                                                  "the fill kernel's bound is the issue port (1 warp-instruction / cycle / sub-partition); "
+                                                  "busy_frac_ncu = smsp__issue_active of the fill launches in the committed ncu capture"}}},
             "fill_ms_per_step": ms_fill, "traceback_ms_per_step": tb_ms / args.steps, "wall_ms_per_step": ms_wall,
             "jobs_ok": ok, "jobs": len(jobs), "kernels": {"lanes": stats["jobs_lanes"], "strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"]},
         }

@@ -212,9 +212,10 @@ int pg2_stream_synchronize(pg2_ctx *ctx);
  * candidate update.  Runs two small kernels for a few milliseconds. */
 int pg2_measure_fp64_issue(int device, double *dadd_gips, double *cand_gips);
 
-/* Dispatch-port model behind that roofline: cycles per warp and loop iteration on one SM sub-partition for
- * cycles[0] 8 independent DADDs, cycles[1] 16 independent FADDs, cycles[2] both together.  cycles[2] ~= cycles[0] +
- * cycles[1] shows that an FP64 instruction holds the dispatch port for two cycles (nothing issues in its shadow).
+/* Issue-port check behind that roofline: cycles per warp and loop iteration on one SM sub-partition for
+ * cycles[0] 8 independent DADDs, cycles[1] 16 independent FADDs, cycles[2] both together.  cycles[2] ~= 24 (the
+ * instruction count) rather than cycles[0] + cycles[1] shows that FP64 instructions (2 pipe cycles each) overlap other
+ * issue: a kernel with fewer than half FP64 instructions is bound by the issue port, one warp-instruction per cycle.
  * sm_clock_mhz: the clock the cycle counts were derived with. */
 int pg2_measure_dispatch_mix(int device, double cycles[3], double *sm_clock_mhz);
 

@@ -45,9 +45,10 @@ __global__ void __launch_bounds__(256) candidate_kernel(double *out, double inc,
     if (s == 12345.678 || p == 0xdeadbeefu) out[0] = s;
 }
 
-// Dispatch model: NF independent FADDs and ND independent DADDs per thread and iteration.  If an FP64
-// instruction holds the sub-partition's dispatch port for two cycles, the mix costs NF + 2*ND cycles per warp and
-// iteration; if FP32 work could issue in the shadow of the FP64 pipe it would cost max(NF + ND, 2*ND).
+// Issue-port check: NF independent FADDs and ND independent DADDs per thread and iteration.  If an FP64 instruction
+// held the sub-partition's dispatch port for its two pipe cycles, the mix would cost NF + 2*ND cycles per warp and
+// iteration; if other work issues in the shadow of the FP64 pipe it costs max(NF + ND, 2*ND).  Measured on B200:
+// 16.1 / 16.5 / 25.6 cycles for (0,8) / (16,0) / (16,8), i.e. the second.
 template <int NF, int ND>
 __global__ void __launch_bounds__(256) mix_kernel(double *out, double dinc, float finc, int iters) {
     double a[ND > 0 ? ND : 1];
@@ -116,9 +117,7 @@ extern "C" int pg2_measure_fp64_issue(int device, double *dadd_gips, double *can
 }
 
 // Cycles per warp and iteration on one SM sub-partition (8 resident warps each) for three loops: 8 DADD, 16 FADD,
-// and 8 DADD + 16 FADD.  cycles[2] close to cycles[0] + cycles[1] (16 + 16 = 32) means an FP64 instruction costs two
-// dispatch cycles in which nothing else issues: the fill kernels' bound is then (instructions + FP64 instructions)
-// dispatch cycles, which is what bench.py reports as roofline.dp_issue.dispatch.
+// and 8 DADD + 16 FADD (see mix_kernel).
 extern "C" int pg2_measure_dispatch_mix(int device, double *cycles, double *sm_clock_mhz) {
 #ifdef PG2_HOST_EMU
     (void)device; (void)cycles; (void)sm_clock_mhz;

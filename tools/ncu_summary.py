@@ -57,10 +57,10 @@ def main():
         launches.append({
             "kernel": short, "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
             "time_ms_under_ncu": val("gpu__time_duration.sum"), "warp_instructions": val("smsp__inst_executed.sum"),
+            # the kernel's bound is the issue port (one warp-instruction per cycle and sub-partition): the FP64 pipe
+            # (2 cycles per instruction) and the ALU pipe run in its shadow (pg2_measure_dispatch_mix)
             "issue_active_pct": issue, "fp64_pipe_active_pct": fp64,
-            # an FP64 instruction holds the dispatch port for two cycles (pg2_measure_dispatch_mix): the port is busy
-            # issue_active + fp64_instr = issue_active + fp64_pipe_active / 2 of the cycles
-            "dispatch_busy_pct": None if issue is None or fp64 is None else issue + fp64 / 2.0,
+            "alu_pipe_active_pct": val("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
         })
         table.append([short] + [r[col[m]] if m in col else "" for m in KEEP])
     out = {"source": "ncu --set full --clock-control none (%s, %d reads); tools/ncu_summary.py" % (args.command, args.reads),
