@@ -71,6 +71,8 @@ struct DevJob {
     int strip_k;         // strip / lane kernel: columns per lane
     int lane;            // lane kernel: the job's lane in its task (cell_base = the task's pointer region)
     int task;            // lane kernel: task index
+    int max_diag;        // banded jobs: cells on the longest in-band anti-diagonal
+    int pad;
 };
 
 // Lane kernel work item: up to 32 alignments that share the LEFT (row) graph, model and flags; every right
@@ -104,6 +106,8 @@ __host__ __device__ inline unsigned pack_ptr(int mat, int lord, int rord) {
 __host__ __device__ inline unsigned cell_word(unsigned px, unsigned py, unsigned pm) {
     return (px & 0xffu) | ((py & 0xffu) << 8) | ((pm & 0x3fffu) << 16);
 }
+// bits 30 / 31 of a cell word: left site i / right site j has exactly one backward edge, from the site before it
+constexpr unsigned WORD_PLAIN_LEFT = 1u << 30, WORD_PLAIN_RIGHT = 1u << 31;
 __host__ __device__ inline unsigned word_ptr(unsigned w, int mat) {
     if (mat == X_MAT) return w & 0xffu;                                    // mat | lord<<2
     if (mat == Y_MAT) { unsigned y = (w >> 8) & 0xffu; return (y & 3u) | ((y >> 2) << 8); }

@@ -30,7 +30,7 @@ void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *j
 void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                            const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                            const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores,
-                           unsigned *ptrs, DevResult *results, cudaStream_t stream);
+                           unsigned *ptrs, DevResult *results, int max_diag, cudaStream_t stream);
 void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
                        const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
                        unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
@@ -42,7 +42,7 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
                       int max_lx, int max_slots, int *queue, int n_ctas, cudaStream_t stream);
 int lane_ctas_per_sm();
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
-void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
+void launch_traceback(int n_jobs, int n_wave, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
                       const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps, DevResult *results, cudaStream_t stream);
 }  // namespace pg2
@@ -503,6 +503,7 @@ static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t 
     }
     if (blo[0] > 0) ok = false;
     long long cells = 0;
+    int max_diag = 1;
     if (ok) {
         // rows on diagonal s: blo[i]+i <= s <= bhi[i]+i, both strictly increasing in i
         int first = 0, last = -1;
@@ -511,7 +512,10 @@ static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t 
             while (first < lx && bhi[first] + first < s) ++first;
             dlo[s] = first;
             doff[s] = cells;
-            if (last >= first) cells += last - first + 1;
+            if (last >= first) {
+                cells += last - first + 1;
+                max_diag = std::max(max_diag, last - first + 1);
+            }
         }
         dlo[nd] = 0;
         doff[nd] = cells;
@@ -522,6 +526,7 @@ static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t 
         cells = 1;
     }
     J.cells = cells;
+    J.max_diag = max_diag;
     return PG2_OK;
 }
 
@@ -817,7 +822,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             if (g.count > 0 && (size_t)(g.cells + padded) * per_cell > c->scratch_bytes) break;
             J.cell_base = g.cells;
             g.cells += padded;
-            g.max_diag = std::max(g.max_diag, std::min(J.lx, J.ly));
+            g.max_diag = std::max(g.max_diag, J.banded ? J.max_diag : std::min(J.lx, J.ly));
             g.max_slots = std::max(g.max_slots, b->graphs[J.left].n_slots);
             g.max_lx = std::max(g.max_lx, J.lx);
             g.count++;
@@ -967,17 +972,18 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
         size_t ge = gi;
         while (ge < b->groups.size() && b->groups[ge].phase == b->groups[gi].phase) ge++;
         CU(cudaEventRecord(c->ev[2], c->stream));
-        int phase_jobs = 0;
+        int phase_jobs = 0, phase_wave_jobs = 0;
         for (size_t k = gi; k < ge; k++) {
             const Group &g = b->groups[k];
             const int *ids = c->d_order.p + g.first;
             phase_jobs += g.count;
+            if (g.kernel == 0) phase_wave_jobs += g.count;
             if (g.kernel == 0) {
                 int threads = g.max_diag <= 32 ? 32 : g.max_diag <= 64 ? 64 : g.max_diag <= 128 ? 128 : g.max_diag <= 256 ? 256
                               : g.max_diag <= 512 ? 512 : 1024;
                 launch_wavefront_fill(g.count, threads, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
                                       c->d_estart.p, c->d_elogw.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_scores.p,
-                                      c->d_ptr32.p, c->d_results.p, c->stream);
+                                      c->d_ptr32.p, c->d_results.p, g.max_diag, c->stream);
                 st.jobs_wavefront += g.count;
                 st.traceback_bytes += g.cells * 4;
             } else if (g.kernel == 2) {
@@ -1002,7 +1008,7 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
             st.fill_launches++;
         }
         CU(cudaEventRecord(c->ev[3], c->stream));
-        launch_traceback(phase_jobs, c->d_order.p + b->groups[gi].first, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p, c->d_off.p, c->d_estart.p,
+        launch_traceback(phase_jobs, phase_wave_jobs, c->d_order.p + b->groups[gi].first, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p, c->d_off.p, c->d_estart.p,
                          c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_steps.p, c->d_results.p,
                          c->stream);
         CU(cudaEventRecord(c->ev[4], c->stream));

@@ -210,7 +210,133 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
     res->status = status;
 }
 
+// ---- wavefront-layout jobs: one warp per path, the pointer words around the walk fetched a window at a time ----
+// The walk is a chain of dependent loads; with one thread per path every step costs two L2/HBM round trips (band
+// geometry, then the pointer word) -- 0.5 s for the 400 000 steps of a 200 kb anchored alignment.  Here the warp
+// loads the words of diagonals s0-31..s0, rows i0-31..i0 (32 coalesced loads in flight at once) into shared memory
+// and lane 0 walks inside the window: at least 16 steps per round trip.
+constexpr int TW = 32;
+struct TraceWin {
+    unsigned w[TW * TW];   // [diagonal s0-d][row i0-r]
+    long long base[TW];    // pointer-buffer offset of row lo[d] on diagonal s0-d
+    int lo[TW], hi[TW];    // in-band rows of diagonal s0-d (hi < lo: none)
+    int s0, i0;
+};
+
+__device__ __forceinline__ void win_geometry(const DevJob &J, const TraceCtx &t, TraceWin &W, int d) {
+    const int s = W.s0 - d;
+    if (s < 0) { W.lo[d] = 0; W.hi[d] = -1; W.base[d] = 0; return; }
+    if (J.banded) {
+        const long long b = t.doff[s];
+        W.lo[d] = t.dlo[s];
+        W.hi[d] = W.lo[d] + (int)(t.doff[s + 1] - b) - 1;
+        W.base[d] = b;
+    } else {
+        W.lo[d] = diag_lo(s, J.ly);
+        W.hi[d] = diag_hi(s, J.lx);
+        W.base[d] = diag_cum(s, J.lx, J.ly);
+    }
+}
+__device__ __forceinline__ void win_load(const DevJob &J, const TraceCtx &t, TraceWin &W, int d, int r) {
+    const int i = W.i0 - r;
+    unsigned v = 0;
+    if (i >= W.lo[d] && i <= W.hi[d]) v = t.ptr32[J.cell_base + W.base[d] + (i - W.lo[d])];
+    W.w[d * TW + r] = v;
+}
+
+// walk state of one path (held by lane 0)
+struct TraceState {
+    int i, j, vit, n, status;
+    bool done;
+};
+
+__device__ __forceinline__ void trace_wave_begin(const DevJob &J, DevResult *res, const int *l_off, const int *r_off, const int *l_es,
+                                                 const int *r_es, unsigned short *out, TraceState &st) {
+    // end pointer -> last alignment column (viterbi_alignment.cpp:1047-1069)
+    const unsigned p = res->end_ptr;
+    st.vit = (int)(p & 3u);
+    st.n = 0;
+    st.status = JOB_OK;
+    st.done = false;
+    st.i = st.j = 0;
+    if (st.vit == M_MAT) { st.i = l_es[l_off[J.lx] + ((p >> 2) & 63u)]; st.j = r_es[r_off[J.ly] + ((p >> 8) & 63u)]; }
+    else if (st.vit == X_MAT) { st.i = l_es[l_off[J.lx] + ((p >> 2) & 63u)]; st.j = J.ly - 1; }
+    else if (st.vit == Y_MAT) { st.i = J.lx - 1; st.j = r_es[r_off[J.ly] + ((p >> 8) & 63u)]; }
+    else { st.status = JOB_NO_PATH; st.done = true; return; }
+    out[st.n++] = (unsigned short)p;
+}
+
+// walks while the cells are inside the window; returns with st.done set, or at a cell outside the window
+__device__ __forceinline__ void trace_wave_walk(const DevJob &J, const TraceWin &W, const int *l_off, const int *r_off, const int *l_es,
+                                                const int *r_es, unsigned short *out, TraceState &st) {
+    for (;;) {
+        const int i = st.i, j = st.j;
+        if (st.vit == NO_MAT || i < 0 || j < 0 || i >= J.lx || j >= J.ly) { st.status = JOB_BROKEN_PATH; st.done = true; return; }
+        const int d = W.s0 - (i + j), r = W.i0 - i;
+        if (d < 0 || d >= TW || r < 0 || r >= TW) return;  // next window
+        if (i < W.lo[d] || i > W.hi[d]) { st.status = JOB_BROKEN_PATH; st.done = true; return; }  // outside the band
+        if (st.n >= J.step_cap) { st.status = JOB_BROKEN_PATH; st.done = true; return; }
+        const unsigned w = W.w[d * TW + r];
+        const unsigned q = word_ptr(w, st.vit);
+        out[st.n++] = (unsigned short)q;
+        const int src = (int)(q & 3u);
+        // the reference loop ends when (i<1 && j<1) AFTER reading the cell it stands on (:1073-1181)
+        if (st.vit == M_MAT || st.vit == X_MAT)
+            st.i = (src == NO_MAT) ? -1 : ((w & WORD_PLAIN_LEFT) ? i - 1 : l_es[l_off[i] + ((q >> 2) & 63u)]);
+        if (st.vit == M_MAT || st.vit == Y_MAT)
+            st.j = (src == NO_MAT) ? -1 : ((w & WORD_PLAIN_RIGHT) ? j - 1 : r_es[r_off[j] + ((q >> 8) & 63u)]);
+        st.vit = src;
+        if (st.i < 1 && st.j < 1) { st.done = true; return; }
+    }
+}
+
 #ifndef PG2_HOST_EMU
+__global__ void __launch_bounds__(128) traceback_wave_kernel(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs,
+                                                             const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi,
+                                                             const int *d_dlo, const long long *d_doff, const unsigned *ptr32,
+                                                             unsigned short *steps, DevResult *results) {
+    __shared__ TraceWin wins[4];
+    const int lane = threadIdx.x & 31, t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= n_jobs) return;
+    const int jid = job_ids[t];
+    const DevJob J = jobs[jid];
+    DevResult *res = results + jid;
+    if (J.kernel != 0 || res->status != JOB_OK) return;  // warp-uniform
+    TraceWin &W = wins[threadIdx.x >> 5];
+    const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+    const int *l_off = d_off + GL.off_base, *r_off = d_off + GR.off_base;
+    const int *l_es = d_estart + GL.edge_base, *r_es = d_estart + GR.edge_base;
+    TraceCtx tc;
+    tc.J = &J; tc.vlast = nullptr; tc.nv = 0;
+    tc.blo = nullptr; tc.bhi = nullptr;
+    tc.dlo = J.banded ? d_dlo + J.diag_base : nullptr;
+    tc.doff = J.banded ? d_doff + J.diag_base : nullptr;
+    tc.ptr32 = ptr32; tc.ptr16 = nullptr;
+    unsigned short *out = steps + J.step_base;
+    TraceState st;
+    st.i = st.j = 0; st.vit = NO_MAT; st.n = 0; st.status = JOB_OK; st.done = false;
+    if (lane == 0) trace_wave_begin(J, res, l_off, r_off, l_es, r_es, out, st);
+    for (;;) {
+        const int done = __shfl_sync(0xffffffffu, (int)st.done, 0);
+        if (done) break;
+        const int bi = __shfl_sync(0xffffffffu, st.i, 0), bj = __shfl_sync(0xffffffffu, st.j, 0);
+        if (bi < 0 || bj < 0 || bi >= J.lx || bj >= J.ly) {  // the walk left the matrix: lane 0 reports it
+            if (lane == 0) { st.status = JOB_BROKEN_PATH; st.done = true; }
+            continue;
+        }
+        if (lane == 0) { W.s0 = bi + bj; W.i0 = bi; }
+        __syncwarp();
+        win_geometry(J, tc, W, lane);
+        __syncwarp();
+#pragma unroll 8
+        for (int d = 0; d < TW; ++d) win_load(J, tc, W, d, lane);
+        __syncwarp();
+        if (lane == 0) trace_wave_walk(J, W, l_off, r_off, l_es, r_es, out, st);
+        __syncwarp();
+    }
+    if (lane == 0) { res->n_steps = st.n; res->status = st.status; }
+}
+
 __global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast,
                                  const int *d_off,
                                  const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo,
@@ -218,6 +344,7 @@ __global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *j
                                  DevResult *results) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
+    if (jobs[job_ids[t]].kernel == 0) return;  // wavefront-layout jobs: traceback_wave_kernel
     traceback_one(job_ids[t], jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
 }
 #endif
@@ -278,18 +405,55 @@ void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *j
 #endif
 }
 
-void launch_traceback(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
+// n_wave: how many of the jobs were filled by the wavefront kernel (they get the warp-per-path walk)
+void launch_traceback(int n_jobs, int n_wave, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
                       const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps, DevResult *results, cudaStream_t stream) {
     if (n_jobs <= 0) return;
 #ifndef PG2_HOST_EMU
     const int threads = 64;
-    traceback_kernel<<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_vlast, d_off, d_estart, d_blo,
-                                                                              d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+    if (n_wave < n_jobs)
+        traceback_kernel<<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_vlast, d_off, d_estart, d_blo,
+                                                                                  d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+    if (n_wave > 0)
+        traceback_wave_kernel<<<(n_jobs + 3) / 4, 128, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff,
+                                                                   ptr32, steps, results);
 #else
-    (void)stream;
-    for (int t = 0; t < n_jobs; ++t)
-        traceback_one(job_ids[t], jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+    (void)stream; (void)n_wave;
+    for (int t = 0; t < n_jobs; ++t) {
+        const int jid = job_ids[t];
+        const DevJob J = jobs[jid];
+        if (J.kernel != 0) {
+            traceback_one(jid, jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+            continue;
+        }
+        // the warp-per-path walk, lanes one after the other
+        DevResult *res = results + jid;
+        if (res->status != JOB_OK) continue;
+        const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+        const int *l_off = d_off + GL.off_base, *r_off = d_off + GR.off_base;
+        const int *l_es = d_estart + GL.edge_base, *r_es = d_estart + GR.edge_base;
+        TraceCtx tc;
+        tc.J = &J; tc.vlast = nullptr; tc.nv = 0;
+        tc.blo = nullptr; tc.bhi = nullptr;
+        tc.dlo = J.banded ? d_dlo + J.diag_base : nullptr;
+        tc.doff = J.banded ? d_doff + J.diag_base : nullptr;
+        tc.ptr32 = ptr32; tc.ptr16 = nullptr;
+        unsigned short *out = steps + J.step_base;
+        TraceState st;
+        TraceWin W;
+        trace_wave_begin(J, res, l_off, r_off, l_es, r_es, out, st);
+        while (!st.done) {
+            if (st.i < 0 || st.j < 0 || st.i >= J.lx || st.j >= J.ly) { st.status = JOB_BROKEN_PATH; break; }
+            W.s0 = st.i + st.j; W.i0 = st.i;
+            for (int lane = 0; lane < TW; ++lane) win_geometry(J, tc, W, lane);
+            for (int d = 0; d < TW; ++d)
+                for (int lane = 0; lane < TW; ++lane) win_load(J, tc, W, d, lane);
+            trace_wave_walk(J, W, l_off, r_off, l_es, r_es, out, st);
+        }
+        res->n_steps = st.n;
+        res->status = st.status;
+    }
 #endif
 }
 

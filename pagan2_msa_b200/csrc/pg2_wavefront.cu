@@ -1,20 +1,38 @@
 // pg2_wavefront.cu -- general fill kernel: one CTA per alignment, anti-diagonal wavefront.
 //
-// Handles every job shape (arbitrary in-degree and edge spans on both graphs, anchor bands).  Scores
-// live in an anti-diagonal-major double4 scratch in HBM/L2 so that the common predecessors (i-1,j),
-// (i-1,j-1), (i,j-1) of consecutive threads sit in consecutive cells (coalesced), and long-span
-// predecessors are still addressable.  One packed 32-bit word of back-pointers per cell is streamed out
-// for the traceback kernel.
+// Handles every job shape (arbitrary in-degree and edge spans on both graphs, anchor bands).  The scores of
+// the two previous anti-diagonals live in a shared-memory ring: the predecessors (i-1,j), (i,j-1), (i-1,j-1) --
+// every predecessor of a plain site, 97 % of the sites of a PAGAN ancestor -- cost one shared-memory read, so a
+// diagonal step is a barrier plus L1-resident CSR lookups instead of three chains of L2 round trips.  All
+// scores also go to an anti-diagonal-major double4 scratch in HBM/L2 for long-span edges (skipped when both
+// graphs are plain chains: nothing then reads further back than two diagonals).  One packed 32-bit word of
+// back-pointers per cell is streamed out for the traceback kernel.
 //
 // Restates compute_fwd_scores / iterate_bwd_edges_for_gap / iterate_bwd_edges_for_match /
 // iterate_bwd_edges_for_end_corner (reference src/main/viterbi_alignment.cpp:856-971, 1328-1552,
 // 2029-2255).  Candidate order and FP64 association follow the reference exactly; ties keep the first
 // candidate (strict '>', basic_alignment.h:449-462).
 #include "pg2_device.cuh"
+#ifdef PG2_HOST_EMU
+#include <vector>
+#endif
 
 namespace pg2 {
 
+constexpr int WAVE_RING_MAX = 2816;  // longest diagonal the shared-memory ring takes: 9 doubles per cell, 198 KB
+
+// scores of diagonals s, s-1, s-2 in shared memory: buf[slot][X,Y,M][cap]
+struct WaveRing {
+    double *buf;         // nullptr: the diagonals of this job do not fit; every read goes to the global scratch
+    int cap;             // cells per diagonal the ring holds
+    int s;               // diagonal being computed; cells on s-1 and s-2 are served from the ring
+    int slot0, slot1, slot2;
+    int lo0, lo1, hi1, lo2, hi2;  // first row of diagonal s; row ranges of diagonals s-1 and s-2
+    bool global_scores;  // false: both graphs are plain chains, the global scratch is never read
+};
+
 struct WaveCtx {
+    WaveRing ring;
     const DevJob *job;
     const int *l_state, *l_off, *l_estart;
     const float *l_elogw;
@@ -35,6 +53,19 @@ __device__ __forceinline__ long long cell_index(const WaveCtx &c, int p, int q) 
 
 // Tunnel_slice::at (utils/tunnel_matrix.h:85-98): -inf outside the band
 __device__ __forceinline__ double4 load_cell(const WaveCtx &c, int p, int q) {
+    if (c.ring.buf) {
+        // rows lo..hi of a diagonal are exactly its in-band cells (the band is monotone)
+        const int ds = c.ring.s - (p + q);
+        if (ds == 1 || ds == 2) {
+            const int lo = ds == 1 ? c.ring.lo1 : c.ring.lo2, hi = ds == 1 ? c.ring.hi1 : c.ring.hi2;
+            if (p < lo || p > hi) {
+                double ninf = neg_inf();
+                return make_double4(ninf, ninf, ninf, 0.0);
+            }
+            const double *b = c.ring.buf + (ds == 1 ? c.ring.slot1 : c.ring.slot2) * 3 * c.ring.cap + (p - lo);
+            return make_double4(b[0], b[c.ring.cap], b[2 * c.ring.cap], 0.0);
+        }
+    }
     if (c.banded && (q < c.blo[p] || q > c.bhi[p])) {
         double ninf = neg_inf();
         return make_double4(ninf, ninf, ninf, 0.0);
@@ -156,6 +187,29 @@ __device__ __forceinline__ void make_wave_ctx(WaveCtx &c, const DevJob &J, const
     c.dlo = c.banded ? d_dlo + J.diag_base : nullptr;
     c.doff = c.banded ? d_doff + J.diag_base : nullptr;
     c.scores = scores + J.cell_base;
+    c.ring.buf = nullptr;
+    c.ring.cap = 0;
+    c.ring.global_scores = true;
+}
+
+// the ring holds this job's diagonals: serve near reads from it; plain chains on both sides never read the scratch
+__device__ __forceinline__ void wave_use_ring(WaveCtx &c, double *buf, int cap, const DevGraph &GL, const DevGraph &GR) {
+    c.ring.buf = buf;
+    c.ring.cap = cap;
+    c.ring.global_scores = !(GL.simple && GR.simple);
+    c.ring.lo1 = 0; c.ring.hi1 = 0;   // diagonal 0 is the start corner
+    c.ring.lo2 = 0; c.ring.hi2 = -1;  // there is no diagonal -1
+}
+__device__ __forceinline__ void wave_ring_begin(WaveCtx &c, int s, int ilo) {
+    c.ring.s = s;
+    c.ring.slot0 = s % 3;
+    c.ring.slot1 = (s + 2) % 3;
+    c.ring.slot2 = (s + 1) % 3;
+    c.ring.lo0 = ilo;
+}
+__device__ __forceinline__ void wave_ring_end(WaveCtx &c, int ilo, int ihi) {
+    c.ring.lo2 = c.ring.lo1; c.ring.hi2 = c.ring.hi1;
+    c.ring.lo1 = ilo; c.ring.hi1 = ihi;
 }
 
 // initialise_array_corner (:725-733)
@@ -164,6 +218,7 @@ __device__ __forceinline__ void wave_init(const WaveCtx &c, unsigned *P) {
     double2 *s0 = reinterpret_cast<double2 *>(c.scores);
     s0[0] = make_double2(ninf, ninf);
     s0[1] = make_double2(0.0, 0.0);
+    if (c.ring.buf) { c.ring.buf[0] = ninf; c.ring.buf[c.ring.cap] = ninf; c.ring.buf[2 * c.ring.cap] = 0.0; }  // slot 0 = diagonal 0
     P[0] = cell_word(NO_MAT, NO_MAT, NO_MAT);
 }
 
@@ -195,18 +250,29 @@ __device__ __forceinline__ void wave_cell(const WaveCtx &c, const DevModel &m, u
         double x_log = __dadd_rn((double)m.lng, ls);
         match_pairs(c, c.l_off[i], c.l_off[i + 1], c.r_off[j], c.r_off[j + 1], m_log, x_log, x_log, false, sm, pm);
     }
-    double2 *dst = reinterpret_cast<double2 *>(c.scores + idx);
-    dst[0] = make_double2(sx, sy);
-    dst[1] = make_double2(sm, 0.0);
-    // gap_cell returns (mat | ord<<2) for both X and Y, which is the in-word form
-    P[idx] = cell_word(px, py, pm);
+    if (c.ring.buf) {
+        double *b = c.ring.buf + c.ring.slot0 * 3 * c.ring.cap + (i - c.ring.lo0);
+        b[0] = sx; b[c.ring.cap] = sy; b[2 * c.ring.cap] = sm;
+    }
+    if (c.ring.global_scores) {
+        double2 *dst = reinterpret_cast<double2 *>(c.scores + idx);
+        dst[0] = make_double2(sx, sy);
+        dst[1] = make_double2(sm, 0.0);
+    }
+    // gap_cell returns (mat | ord<<2) for both X and Y, which is the in-word form.  Bits 30 / 31: the only backward
+    // edge of left site i / right site j comes from the site before it -- the walk then needs no CSR lookup.
+    unsigned plain = 0;
+    if (i > 0) { const int k0 = c.l_off[i]; if (c.l_off[i + 1] - k0 == 1 && c.l_estart[k0] == i - 1) plain |= WORD_PLAIN_LEFT; }
+    if (j > 0) { const int k0 = c.r_off[j]; if (c.r_off[j + 1] - k0 == 1 && c.r_estart[k0] == j - 1) plain |= WORD_PLAIN_RIGHT; }
+    P[idx] = cell_word(px, py, pm) | plain;
 }
 
 #ifndef PG2_HOST_EMU
 __global__ void __launch_bounds__(1024, 1)
 wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models, const int *d_state,
                       const int *d_off, const int *d_estart, const float *d_elogw, const int *d_blo, const int *d_bhi,
-                      const int *d_dlo, const long long *d_doff, double4 *scores, unsigned *ptrs, DevResult *results) {
+                      const int *d_dlo, const long long *d_doff, double4 *scores, unsigned *ptrs, DevResult *results, int ring_cap) {
+    extern __shared__ __align__(16) double wave_smem[];
     const int jid = job_ids[blockIdx.x];
     const DevJob &J = jobs[jid];
     DevResult *res = results + jid;
@@ -215,6 +281,7 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
     const DevModel m = models[J.model];
     WaveCtx c;
     make_wave_ctx(c, J, GL, GR, d_state, d_off, d_estart, d_elogw, d_blo, d_bhi, d_dlo, d_doff, scores);
+    if (ring_cap > 0) wave_use_ring(c, wave_smem, ring_cap, GL, GR);
     unsigned *P = ptrs + J.cell_base;
     const unsigned flags = J.flags;
     const float lng2 = __fmul_rn(2.0f, m.lng);  // 2*model->log_non_gap() stays float (:1364)
@@ -227,10 +294,13 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
         int ilo, ihi;
         long long base;
         diag_geometry(c, s, ilo, ihi, base);
+        wave_ring_begin(c, s, ilo);
         for (int i = ilo + (int)threadIdx.x; i <= ihi; i += (int)blockDim.x)
             wave_cell(c, m, flags, lng2, i, s - i, base + (i - ilo), P);
-        __syncthreads();
+        __syncthreads();  // diagonal s is complete; the ring slot of diagonal s-2 may be overwritten
+        wave_ring_end(c, ilo, ihi);
     }
+    wave_ring_begin(c, n_diag, 0);  // the end corner reads cells of the last two diagonals from the ring
     if (threadIdx.x == 0) end_corner(c, m, res);
 }
 #endif
@@ -238,11 +308,15 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
 void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                            const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                            const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores,
-                           unsigned *ptrs, DevResult *results, cudaStream_t stream) {
+                           unsigned *ptrs, DevResult *results, int max_diag, cudaStream_t stream) {
     if (n_jobs <= 0) return;
+    // ring of three diagonals x {X,Y,M} in shared memory when the group's longest diagonal fits
+    const int ring_cap = max_diag <= WAVE_RING_MAX ? (max_diag > 0 ? max_diag : 1) : 0;
 #ifndef PG2_HOST_EMU
-    wavefront_fill_kernel<<<n_jobs, threads, 0, stream>>>(jobs, job_ids, graphs, models, d_state, d_off, d_estart, d_elogw, d_blo,
-                                                          d_bhi, d_dlo, d_doff, scores, ptrs, results);
+    const int smem = ring_cap * 9 * (int)sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(wavefront_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    wavefront_fill_kernel<<<n_jobs, threads, smem, stream>>>(jobs, job_ids, graphs, models, d_state, d_off, d_estart, d_elogw, d_blo,
+                                                             d_bhi, d_dlo, d_doff, scores, ptrs, results, ring_cap);
 #else
     // CPU test emulation: anti-diagonals in order, cells of one diagonal in any order
     (void)threads; (void)stream;
@@ -255,15 +329,21 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
         const DevModel m = models[J.model];
         WaveCtx c;
         make_wave_ctx(c, J, GL, GR, d_state, d_off, d_estart, d_elogw, d_blo, d_bhi, d_dlo, d_doff, scores);
+        std::vector<double> ring((size_t)ring_cap * 9 + 1);
+        if (ring_cap > 0) wave_use_ring(c, ring.data(), ring_cap, GL, GR);
         unsigned *P = ptrs + J.cell_base;
         const float lng2 = __fmul_rn(2.0f, m.lng);
         wave_init(c, P);
-        for (int s = 1; s < c.lx + c.ly - 1; ++s) {
+        const int n_diag = c.lx + c.ly - 1;
+        for (int s = 1; s < n_diag; ++s) {
             int ilo, ihi;
             long long base;
             diag_geometry(c, s, ilo, ihi, base);
+            wave_ring_begin(c, s, ilo);
             for (int i = ihi; i >= ilo; --i) wave_cell(c, m, J.flags, lng2, i, s - i, base + (i - ilo), P);
+            wave_ring_end(c, ilo, ihi);
         }
+        wave_ring_begin(c, n_diag, 0);
         end_corner(c, m, res);
     }
 #endif

@@ -82,10 +82,14 @@ def random_job(rng, kind="general", fas=15):
             right.logw[:] = np.log(rng.uniform(0.2, 1.0, size=right.logw.shape[0]).astype(np.float32))
         return FlatJob(left, right, model, flags)
     nl, nr = int(rng.integers(1, 70)), int(rng.integers(1, 70))
-    left = random_graph(rng, nl, fas, tie_weights=ties)
-    right = random_graph(rng, nr, fas, tie_weights=ties)
+    if kind == "banded_chain":  # plain chains on both sides inside a band (anchored leaf x leaf): no score scratch reads
+        left = FlatGraph.chain(rng.integers(0, fas, size=nl).astype(np.int32))
+        right = FlatGraph.chain(rng.integers(0, fas, size=nr).astype(np.int32))
+    else:
+        left = random_graph(rng, nl, fas, tie_weights=ties)
+        right = random_graph(rng, nr, fas, tie_weights=ties)
     job = FlatJob(left, right, model, flags)
-    if kind == "banded":
+    if kind in ("banded", "banded_chain"):
         up, lo = random_band(rng, left.n_sites - 1, right.n_sites - 1)
         job.upper, job.lower = up, lo
     return job

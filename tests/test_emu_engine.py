@@ -95,7 +95,7 @@ def test_lane_kernel_long_reads_and_bad_job(emu_lib):
     assert (res["kernel"] == 2).all()
 
 
-@pytest.mark.parametrize("kind,seed", [("general", 21), ("banded", 22), ("strip", 23)])
+@pytest.mark.parametrize("kind,seed", [("general", 21), ("banded", 22), ("strip", 23), ("banded_chain", 24)])
 def test_random_jobs_vs_oracle(emu_lib, kind, seed):
     rng = np.random.default_rng(seed)
     jobs = [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for _ in range(60)]

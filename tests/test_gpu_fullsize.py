@@ -112,3 +112,14 @@ def test_config1_progressive_1kb_wave(eng, golden):
     wave2 = [abi.FlatJob(anc[2 * k], anc[2 * k + 1], model, 2) for k in range(3)]
     res = enginecheck.check_batch(eng, [enginecheck.expect_from_oracle(j) for j in wave2])
     assert (res["kernel"] == 0).all()
+
+
+def test_wavefront_diagonals_longer_than_the_ring(eng, golden):
+    """A general x general job whose anti-diagonals (3000 cells) exceed the wavefront kernel's shared-memory ring
+    (WAVE_RING_MAX = 2816): every score read goes to the global scratch, the original path."""
+    rng = np.random.default_rng(2816)
+    model = golden["prog_dna"][0].model
+    left = randjobs.random_graph(rng, 3000, 4, p_extra=0.05, max_span=8)
+    right = randjobs.random_graph(rng, 3000, 4, p_extra=0.05, max_span=8)
+    res = enginecheck.check_batch(eng, [enginecheck.expect_from_oracle(abi.FlatJob(left, right, model, 2))])
+    assert res["kernel"][0] == 0 and res["status"][0] == 0

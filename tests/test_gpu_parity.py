@@ -114,7 +114,7 @@ def test_lane_and_strip_kernels_agree_bitwise(eng, eng_nolanes, golden):
         assert pa.tobytes() == pb.tobytes()
 
 
-@pytest.mark.parametrize("kind,seed", [("general", 121), ("banded", 122), ("strip", 123)])
+@pytest.mark.parametrize("kind,seed", [("general", 121), ("banded", 122), ("strip", 123), ("banded_chain", 124)])
 def test_random_jobs_vs_oracle(eng, kind, seed):
     rng = np.random.default_rng(seed)
     jobs = [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for _ in range(300)]
