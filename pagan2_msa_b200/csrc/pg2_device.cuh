@@ -44,7 +44,9 @@ struct DevGraph {
     int vlast_base;  // into d_vlast: per site, the virtual row that completes it
     int vplain_base; // into d_vlast: per block of LANE_B virtual rows, bit r set when row r is a plain interior row
     int implicit;    // 1: plain chain with unit weights whose CSR (d_off / d_estart / d_elogw) is generated on the device
-    int pad[3];
+    int np_base;     // into d_vlast: sorted list of the DP sites that are NOT plain (site 0, and every site whose backward
+    int n_np;        //   edges are not exactly one edge from the site before it); -1 until a wavefront job uses the graph
+    int npmask_base; // into d_vlast: bit s & 31 of word s >> 5 set when DP site s is plain
 };
 
 struct DevModel {

@@ -29,8 +29,8 @@ void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *j
                      DevResult *results, cudaStream_t stream);
 void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                            const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
-                           const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores,
-                           unsigned *ptrs, DevResult *results, int max_diag, cudaStream_t stream);
+                           const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, const int *d_vlast,
+                           double4 *scores, unsigned *ptrs, DevResult *results, int max_diag, cudaStream_t stream);
 void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
                        const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
                        unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
@@ -321,6 +321,7 @@ static int intern_graph(pg2_batch *b, const pg2_graph &g, GraphTable &seen, std:
     memset(&dg, 0, sizeof dg);
     dg.n_sites = g.n_sites;
     dg.vrow_base = -1;
+    dg.np_base = -1;
     dg.n_vrows = g.n_sites - 1;
     dg.vlast_base = -1;
     dg.vplain_base = -1;
@@ -530,6 +531,32 @@ static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t 
     return PG2_OK;
 }
 
+// Sites of a graph the wavefront kernel cannot take through its plain-cell body (pg2_wavefront.cu): the start site and
+// every site whose backward edges are not exactly one edge from the site before it.  Sorted list + plain-site bitmap.
+static int build_nonplain(pg2_ctx *c, DevGraph &dg) {
+    if (dg.np_base >= 0) return PG2_OK;
+    const int rows = dg.n_sites - 1;  // DP sites 0 .. n_sites-2
+    const HostCsr csr = host_csr(c, dg);
+    std::vector<int> np;
+    std::vector<unsigned> mask((size_t)(rows + 31) / 32 + 1, 0u);
+    np.push_back(0);
+    for (int s = 1; s < rows; s++) {
+        const int k0 = csr.off(s), k1 = csr.off(s + 1);
+        if (k1 - k0 == 1 && csr.start(k0) == s - 1) mask[(size_t)s >> 5] |= 1u << (s & 31);
+        else np.push_back(s);
+    }
+    dg.np_base = (int)c->h_vlast.n;
+    dg.n_np = (int)np.size();
+    int *dst = c->h_vlast.extend(np.size());
+    if (!dst) return PG2_ERR_NOMEM;
+    memcpy(dst, np.data(), np.size() * sizeof(int));
+    dg.npmask_base = (int)c->h_vlast.n;
+    int *md = c->h_vlast.extend(mask.size());
+    if (!md) return PG2_ERR_NOMEM;
+    memcpy(md, mask.data(), mask.size() * sizeof(unsigned));
+    return PG2_OK;
+}
+
 // PG2_TIMING=1: wall time of the host packing steps on stderr (tuning aid)
 struct PackTimer {
     bool on;
@@ -657,6 +684,11 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             rc = build_row_program(c, GL);
             if (rc == PG2_ERR_UNSUPPORTED) J.kernel = 0;  // too many parked rows: the general kernel takes it
             else if (rc != PG2_OK) { delete b; return fail(rc, "pinned staging allocation failed"); }
+        }
+        if (J.kernel == 0) {
+            rc = build_nonplain(c, GL);
+            if (rc == PG2_OK) rc = build_nonplain(c, b->graphs[J.right]);
+            if (rc != PG2_OK) { delete b; return fail(rc, "pinned staging allocation failed"); }
         }
         if (J.kernel == 1 && J.ly != pick_ly) { pick_ly = J.ly; pick_k = strip_pick_k(J.ly); }
         J.strip_k = J.kernel == 1 ? pick_k : 0;
@@ -982,8 +1014,8 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                 int threads = g.max_diag <= 32 ? 32 : g.max_diag <= 64 ? 64 : g.max_diag <= 128 ? 128 : g.max_diag <= 256 ? 256
                               : g.max_diag <= 512 ? 512 : 1024;
                 launch_wavefront_fill(g.count, threads, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
-                                      c->d_estart.p, c->d_elogw.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_scores.p,
-                                      c->d_ptr32.p, c->d_results.p, g.max_diag, c->stream);
+                                      c->d_estart.p, c->d_elogw.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_vlast.p,
+                                      c->d_scores.p, c->d_ptr32.p, c->d_results.p, g.max_diag, c->stream);
                 st.jobs_wavefront += g.count;
                 st.traceback_bytes += g.cells * 4;
             } else if (g.kernel == 2) {

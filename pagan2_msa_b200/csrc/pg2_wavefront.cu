@@ -33,6 +33,12 @@ struct WaveRing {
 
 struct WaveCtx {
     WaveRing ring;
+    // two-pass diagonals (ring only): sorted non-plain sites and plain-site bitmaps of both graphs, cursors at the
+    // first listed site inside the current diagonal's row / column range
+    const int *np_l, *np_r;
+    const unsigned *mask_l, *mask_r;
+    int n_np_l, n_np_r, cur_l, cur_r;
+    bool two_pass;
     const DevJob *job;
     const int *l_state, *l_off, *l_estart;
     const float *l_elogw;
@@ -190,10 +196,20 @@ __device__ __forceinline__ void make_wave_ctx(WaveCtx &c, const DevJob &J, const
     c.ring.buf = nullptr;
     c.ring.cap = 0;
     c.ring.global_scores = true;
+    c.two_pass = false;
 }
 
 // the ring holds this job's diagonals: serve near reads from it; plain chains on both sides never read the scratch
-__device__ __forceinline__ void wave_use_ring(WaveCtx &c, double *buf, int cap, const DevGraph &GL, const DevGraph &GR) {
+__device__ __forceinline__ void wave_use_ring(WaveCtx &c, double *buf, int cap, const DevGraph &GL, const DevGraph &GR,
+                                              const int *d_vlast) {
+    if (GL.np_base >= 0 && GR.np_base >= 0) {
+        c.two_pass = true;
+        c.np_l = d_vlast + GL.np_base; c.n_np_l = GL.n_np;
+        c.np_r = d_vlast + GR.np_base; c.n_np_r = GR.n_np;
+        c.mask_l = reinterpret_cast<const unsigned *>(d_vlast + GL.npmask_base);
+        c.mask_r = reinterpret_cast<const unsigned *>(d_vlast + GR.npmask_base);
+        c.cur_l = c.cur_r = 0;
+    }
     c.ring.buf = buf;
     c.ring.cap = cap;
     c.ring.global_scores = !(GL.simple && GR.simple);
@@ -267,11 +283,104 @@ __device__ __forceinline__ void wave_cell(const WaveCtx &c, const DevModel &m, u
     P[idx] = cell_word(px, py, pm) | plain;
 }
 
+// a cell of the two previous diagonals (ds = 1 or 2) from the ring; rows outside the diagonal's range are outside the band
+__device__ __forceinline__ void ring_near(const WaveCtx &c, int ds, int p, double &x, double &y, double &m) {
+    const int lo = ds == 1 ? c.ring.lo1 : c.ring.lo2, hi = ds == 1 ? c.ring.hi1 : c.ring.hi2;
+    if (p < lo || p > hi) { x = y = m = neg_inf(); return; }
+    const double *b = c.ring.buf + (ds == 1 ? c.ring.slot1 : c.ring.slot2) * 3 * c.ring.cap + (p - lo);
+    x = b[0]; y = b[c.ring.cap]; m = b[2 * c.ring.cap];
+}
+
+__device__ __forceinline__ bool site_plain(const unsigned *mask, int s) { return (mask[s >> 5] >> (s & 31)) & 1u; }
+
+// compute_fwd_scores for a cell whose left site i and right site j are both plain (one backward edge each, from i-1 and
+// j-1; i, j >= 1): the same candidates in the same order as gap_cell / match_pairs with single-trip loops, all three
+// source cells from the ring.
+__device__ __forceinline__ void wave_cell_plain(const WaveCtx &c, const DevModel &m, unsigned flags, float lng2, int i, int j, long long idx,
+                                                unsigned *P) {
+    const bool term = !(flags & FLAG_NO_TERMINAL_EDGES);
+    const bool reduced = (flags & FLAG_REDUCED) != 0;
+    const double ninf = neg_inf();
+    const double open = (double)m.open, lng = (double)m.lng;
+    double ux, uy, um, lx_, ly_, lm, dx, dy, dm;
+    ring_near(c, 1, i - 1, ux, uy, um);  // (i-1, j)
+    ring_near(c, 1, i, lx_, ly_, lm);    // (i, j-1)
+    ring_near(c, 2, i - 1, dx, dy, dm);  // (i-1, j-1)
+    const double wl = (double)c.l_elogw[c.l_off[i]], wr = (double)c.r_elogw[c.r_off[j]];
+    const double ls = (double)__ldg(m.table + (size_t)c.l_state[i] + (size_t)c.r_state[j] * (size_t)m.fas);
+    // X: ext, double, open from (i-1, j)   (gap_cell<true>)
+    double sx = ninf, s;
+    unsigned px = NO_MAT;
+    s = __dadd_rn(ux, (double)((term && j == c.ly - 1) ? m.end_ext : m.ext));
+    if (s > sx) { sx = s; px = X_MAT; }
+    s = __dadd_rn(__dadd_rn(uy, 0.0), open);
+    if (s > sx) { sx = s; px = Y_MAT; }
+    s = __dadd_rn(__dadd_rn(um, lng), (reduced && i == 1) ? 0.0 : open);
+    if (s > sx) { sx = s; px = M_MAT; }
+    // Y: ext, double, open from (i, j-1)   (gap_cell<false>)
+    double sy = ninf;
+    unsigned py = NO_MAT;
+    s = __dadd_rn(ly_, (double)((term && i == c.lx - 1) ? m.end_ext : m.ext));
+    if (s > sy) { sy = s; py = Y_MAT; }
+    s = __dadd_rn(__dadd_rn(lx_, 0.0), open);
+    if (s > sy) { sy = s; py = X_MAT; }
+    s = __dadd_rn(__dadd_rn(lm, lng), (reduced && j == 1) ? 0.0 : open);
+    if (s > sy) { sy = s; py = M_MAT; }
+    // M: from M, X, Y of (i-1, j-1)   (match_pairs)
+    const double m_log = __dadd_rn((double)lng2, ls), x_log = __dadd_rn(lng, ls);
+    double sm = ninf;
+    unsigned pm = NO_MAT;
+    s = __dadd_rn(__dadd_rn(__dadd_rn(dm, m_log), wl), wr);
+    if (s > sm) { sm = s; pm = M_MAT; }
+    s = __dadd_rn(__dadd_rn(__dadd_rn(dx, x_log), wl), wr);
+    if (s > sm) { sm = s; pm = X_MAT; }
+    s = __dadd_rn(__dadd_rn(__dadd_rn(dy, x_log), wl), wr);
+    if (s > sm) { sm = s; pm = Y_MAT; }
+    double *b = c.ring.buf + c.ring.slot0 * 3 * c.ring.cap + (i - c.ring.lo0);
+    b[0] = sx; b[c.ring.cap] = sy; b[2 * c.ring.cap] = sm;
+    if (c.ring.global_scores) {
+        double2 *dst = reinterpret_cast<double2 *>(c.scores + idx);
+        dst[0] = make_double2(sx, sy);
+        dst[1] = make_double2(sm, 0.0);
+    }
+    P[idx] = cell_word(px, py, pm) | WORD_PLAIN_LEFT | WORD_PLAIN_RIGHT;
+}
+
+// One anti-diagonal, the share of thread `tid` of `nthreads`.  With the ring: first every cell whose two sites are
+// plain (one lean body, no CSR walk, no divergence), then the cells of the listed non-plain rows and columns that
+// cross this diagonal through the general body -- a few per cent of the cells, gathered into the first threads
+// instead of dragging every warp through the edge loops.  Cells of one diagonal are independent.
+__device__ __forceinline__ void wave_diagonal(WaveCtx &c, const DevModel &m, unsigned flags, float lng2, int s, int ilo, int ihi, long long base,
+                                              unsigned *P, int tid, int nthreads) {
+    if (!c.two_pass) {
+        for (int i = ilo + tid; i <= ihi; i += nthreads) wave_cell(c, m, flags, lng2, i, s - i, base + (i - ilo), P);
+        return;
+    }
+    for (int i = ilo + tid; i <= ihi; i += nthreads)
+        if (site_plain(c.mask_l, i) && site_plain(c.mask_r, s - i)) wave_cell_plain(c, m, flags, lng2, i, s - i, base + (i - ilo), P);
+    // listed rows inside [ilo, ihi] and listed columns inside [s - ihi, s - ilo]; both ranges only move forward
+    const int jlo = s - ihi, jhi = s - ilo;
+    while (c.cur_l < c.n_np_l && c.np_l[c.cur_l] < ilo) ++c.cur_l;
+    while (c.cur_r < c.n_np_r && c.np_r[c.cur_r] < jlo) ++c.cur_r;
+    for (int e = c.cur_l + tid; e < c.n_np_l; e += nthreads) {
+        const int i = c.np_l[e];
+        if (i > ihi) break;
+        wave_cell(c, m, flags, lng2, i, s - i, base + (i - ilo), P);
+    }
+    for (int e = c.cur_r + tid; e < c.n_np_r; e += nthreads) {
+        const int j = c.np_r[e];
+        if (j > jhi) break;
+        const int i = s - j;
+        if (site_plain(c.mask_l, i)) wave_cell(c, m, flags, lng2, i, j, base + (i - ilo), P);  // else: done with its row above
+    }
+}
+
 #ifndef PG2_HOST_EMU
 __global__ void __launch_bounds__(1024, 1)
 wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models, const int *d_state,
                       const int *d_off, const int *d_estart, const float *d_elogw, const int *d_blo, const int *d_bhi,
-                      const int *d_dlo, const long long *d_doff, double4 *scores, unsigned *ptrs, DevResult *results, int ring_cap) {
+                      const int *d_dlo, const long long *d_doff, const int *d_vlast, double4 *scores, unsigned *ptrs, DevResult *results,
+                      int ring_cap) {
     extern __shared__ __align__(16) double wave_smem[];
     const int jid = job_ids[blockIdx.x];
     const DevJob &J = jobs[jid];
@@ -281,7 +390,7 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
     const DevModel m = models[J.model];
     WaveCtx c;
     make_wave_ctx(c, J, GL, GR, d_state, d_off, d_estart, d_elogw, d_blo, d_bhi, d_dlo, d_doff, scores);
-    if (ring_cap > 0) wave_use_ring(c, wave_smem, ring_cap, GL, GR);
+    if (ring_cap > 0) wave_use_ring(c, wave_smem, ring_cap, GL, GR, d_vlast);
     unsigned *P = ptrs + J.cell_base;
     const unsigned flags = J.flags;
     const float lng2 = __fmul_rn(2.0f, m.lng);  // 2*model->log_non_gap() stays float (:1364)
@@ -295,8 +404,7 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
         long long base;
         diag_geometry(c, s, ilo, ihi, base);
         wave_ring_begin(c, s, ilo);
-        for (int i = ilo + (int)threadIdx.x; i <= ihi; i += (int)blockDim.x)
-            wave_cell(c, m, flags, lng2, i, s - i, base + (i - ilo), P);
+        wave_diagonal(c, m, flags, lng2, s, ilo, ihi, base, P, (int)threadIdx.x, (int)blockDim.x);
         __syncthreads();  // diagonal s is complete; the ring slot of diagonal s-2 may be overwritten
         wave_ring_end(c, ilo, ihi);
     }
@@ -307,8 +415,8 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
 
 void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                            const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
-                           const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, double4 *scores,
-                           unsigned *ptrs, DevResult *results, int max_diag, cudaStream_t stream) {
+                           const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, const int *d_vlast,
+                           double4 *scores, unsigned *ptrs, DevResult *results, int max_diag, cudaStream_t stream) {
     if (n_jobs <= 0) return;
     // ring of three diagonals x {X,Y,M} in shared memory when the group's longest diagonal fits
     const int ring_cap = max_diag <= WAVE_RING_MAX ? (max_diag > 0 ? max_diag : 1) : 0;
@@ -316,7 +424,7 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
     const int smem = ring_cap * 9 * (int)sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(wavefront_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     wavefront_fill_kernel<<<n_jobs, threads, smem, stream>>>(jobs, job_ids, graphs, models, d_state, d_off, d_estart, d_elogw, d_blo,
-                                                             d_bhi, d_dlo, d_doff, scores, ptrs, results, ring_cap);
+                                                             d_bhi, d_dlo, d_doff, d_vlast, scores, ptrs, results, ring_cap);
 #else
     // CPU test emulation: anti-diagonals in order, cells of one diagonal in any order
     (void)threads; (void)stream;
@@ -330,7 +438,7 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
         WaveCtx c;
         make_wave_ctx(c, J, GL, GR, d_state, d_off, d_estart, d_elogw, d_blo, d_bhi, d_dlo, d_doff, scores);
         std::vector<double> ring((size_t)ring_cap * 9 + 1);
-        if (ring_cap > 0) wave_use_ring(c, ring.data(), ring_cap, GL, GR);
+        if (ring_cap > 0) wave_use_ring(c, ring.data(), ring_cap, GL, GR, d_vlast);
         unsigned *P = ptrs + J.cell_base;
         const float lng2 = __fmul_rn(2.0f, m.lng);
         wave_init(c, P);
@@ -340,7 +448,8 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
             long long base;
             diag_geometry(c, s, ilo, ihi, base);
             wave_ring_begin(c, s, ilo);
-            for (int i = ihi; i >= ilo; --i) wave_cell(c, m, J.flags, lng2, i, s - i, base + (i - ilo), P);
+            // a handful of emulated threads, last first: the shares of a diagonal are independent of each other
+            for (int tid = 4; tid >= 0; --tid) wave_diagonal(c, m, J.flags, lng2, s, ilo, ihi, base, P, tid, 5);
             wave_ring_end(c, ilo, ihi);
         }
         wave_ring_begin(c, n_diag, 0);
