@@ -213,13 +213,14 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
 // ---- wavefront-layout jobs: one warp per path, the pointer words around the walk fetched a window at a time ----
 // The walk is a chain of dependent loads; with one thread per path every step costs two L2/HBM round trips (band
 // geometry, then the pointer word) -- 0.5 s for the 400 000 steps of a 200 kb anchored alignment.  Here the warp
-// loads the words of diagonals s0-31..s0, rows i0-31..i0 (32 coalesced loads in flight at once) into shared memory
+// loads the words of diagonals s0-63..s0, rows i0-31..i0 (64 coalesced loads, 16 in flight at once) into shared memory
 // and lane 0 walks inside the window: at least 16 steps per round trip.
-constexpr int TW = 32;
+constexpr int TW = 32;   // rows per window (one per lane)
+constexpr int TWD = 64;  // diagonals per window: a run of 32 match steps goes up 32 rows and 64 diagonals
 struct TraceWin {
-    unsigned w[TW * TW];   // [diagonal s0-d][row i0-r]
-    long long base[TW];    // pointer-buffer offset of row lo[d] on diagonal s0-d
-    int lo[TW], hi[TW];    // in-band rows of diagonal s0-d (hi < lo: none)
+    unsigned w[TWD * TW];  // [diagonal s0-d][row i0-r]
+    long long base[TWD];   // pointer-buffer offset of row lo[d] on diagonal s0-d
+    int lo[TWD], hi[TWD];  // in-band rows of diagonal s0-d (hi < lo: none)
     int s0, i0;
 };
 
@@ -273,7 +274,7 @@ __device__ __forceinline__ void trace_wave_walk(const DevJob &J, const TraceWin 
         const int i = st.i, j = st.j;
         if (st.vit == NO_MAT || i < 0 || j < 0 || i >= J.lx || j >= J.ly) { st.status = JOB_BROKEN_PATH; st.done = true; return; }
         const int d = W.s0 - (i + j), r = W.i0 - i;
-        if (d < 0 || d >= TW || r < 0 || r >= TW) return;  // next window
+        if (d < 0 || d >= TWD || r < 0 || r >= TW) return;  // next window
         if (i < W.lo[d] || i > W.hi[d]) { st.status = JOB_BROKEN_PATH; st.done = true; return; }  // outside the band
         if (st.n >= J.step_cap) { st.status = JOB_BROKEN_PATH; st.done = true; return; }
         const unsigned w = W.w[d * TW + r];
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(128) traceback_wave_kernel(int n_jobs, const i
                                                              const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi,
                                                              const int *d_dlo, const long long *d_doff, const unsigned *ptr32,
                                                              unsigned short *steps, DevResult *results) {
-    __shared__ TraceWin wins[4];
+    __shared__ TraceWin wins[4];  // 4 x 9.2 KB
     const int lane = threadIdx.x & 31, t = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= n_jobs) return;
     const int jid = job_ids[t];
@@ -327,9 +328,10 @@ __global__ void __launch_bounds__(128) traceback_wave_kernel(int n_jobs, const i
         if (lane == 0) { W.s0 = bi + bj; W.i0 = bi; }
         __syncwarp();
         win_geometry(J, tc, W, lane);
+        win_geometry(J, tc, W, lane + 32);
         __syncwarp();
-#pragma unroll 8
-        for (int d = 0; d < TW; ++d) win_load(J, tc, W, d, lane);
+#pragma unroll 16
+        for (int d = 0; d < TWD; ++d) win_load(J, tc, W, d, lane);
         __syncwarp();
         if (lane == 0) trace_wave_walk(J, W, l_off, r_off, l_es, r_es, out, st);
         __syncwarp();
@@ -446,8 +448,8 @@ void launch_traceback(int n_jobs, int n_wave, const int *job_ids, const DevJob *
         while (!st.done) {
             if (st.i < 0 || st.j < 0 || st.i >= J.lx || st.j >= J.ly) { st.status = JOB_BROKEN_PATH; break; }
             W.s0 = st.i + st.j; W.i0 = st.i;
-            for (int lane = 0; lane < TW; ++lane) win_geometry(J, tc, W, lane);
-            for (int d = 0; d < TW; ++d)
+            for (int d = 0; d < TWD; ++d) win_geometry(J, tc, W, d);
+            for (int d = 0; d < TWD; ++d)
                 for (int lane = 0; lane < TW; ++lane) win_load(J, tc, W, d, lane);
             trace_wave_walk(J, W, l_off, r_off, l_es, r_es, out, st);
         }

@@ -202,7 +202,9 @@ __device__ __forceinline__ void make_wave_ctx(WaveCtx &c, const DevJob &J, const
 // the ring holds this job's diagonals: serve near reads from it; plain chains on both sides never read the scratch
 __device__ __forceinline__ void wave_use_ring(WaveCtx &c, double *buf, int cap, const DevGraph &GL, const DevGraph &GR,
                                               const int *d_vlast) {
-    if (GL.np_base >= 0 && GR.np_base >= 0) {
+    // two passes pay when the listed sites are a handful (plain leaves inside an anchor band): the general body's
+    // latency is then off the diagonal's critical path; with a few per cent of listed sites the single pass is faster
+    if (GL.np_base >= 0 && GR.np_base >= 0 && GL.n_np + GR.n_np <= 2 + (GL.n_sites + GR.n_sites) / 400) {
         c.two_pass = true;
         c.np_l = d_vlast + GL.np_base; c.n_np_l = GL.n_np;
         c.np_r = d_vlast + GR.np_base; c.n_np_r = GR.n_np;
