@@ -149,6 +149,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local, world):
+    """One process per GPU, run on the cores next to that GPU: pinned staging buffers and the packing threads then sit
+    on the GPU's own NUMA node (H2D / D2H do not cross the socket link).  Returns the cores this rank may use."""
+    mine = sorted(os.sched_getaffinity(0))
+    if world <= 1:
+        return mine
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cores = sorted(set(near) & set(mine))
+        if len(cores) >= 2:
+            os.sched_setaffinity(0, cores)
+            return cores
+    except Exception:
+        pass
+    return mine
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,7 +304,9 @@ def main():
 
     rank, world, local, dist = dist_setup(args.gpus)
     # the host packing threads of all ranks share this box's cores
-    os.environ.setdefault("PG2_PACK_THREADS", str(max(1, min(16, len(os.sched_getaffinity(0)) // max(world, 1)))))
+    n_cores_box = len(os.sched_getaffinity(0))
+    near_cores = bind_to_gpu_numa_node(local, world)
+    os.environ.setdefault("PG2_PACK_THREADS", str(max(1, min(16, n_cores_box // max(world, 1)))))
     if rank == 0:
         __graft_entry__.build()
     if dist is not None:
@@ -361,6 +385,8 @@ def main():
         h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
     barrier()
 
+    print("rank %d: e2e %.1f ms/step, device %.1f ms/step, %d near cores" % (
+        rank, sum(e2e_t) / args.steps * 1e3, dev_ms / args.steps, len(near_cores)), file=sys.stderr, flush=True)
     cells = info["cells_per_step"]
     local_vals = np.array([dev_ms / args.steps, fill_ms / args.steps, sum(e2e_t) / args.steps * 1e3, wall_dev / args.steps * 1e3],
                           dtype=np.float64)
@@ -396,7 +422,9 @@ def main():
                        "reads_per_gpu": args.reads, "targets": info["n_targets"], "cells_per_step_per_gpu": cells,
                        "l2_policy": "inputs+outputs per step (%.1f GB of back-pointers) exceed L2" % (stats["traceback_bytes"] * 1e-9),
                        "parallelism": "independent alignments sharded by index range, %d rank(s); results + packed paths "
-                                      "gathered to rank 0 over NCCL every step (%.2f ms/step on rank 0)" % (world, gather_ms / args.steps)},
+                                      "gathered to rank 0 over NCCL every step (%.2f ms/step on rank 0)" % (world, gather_ms / args.steps),
+                       "host": "%d cores, %d packing threads per rank, rank bound to the %d cores next to its GPU" % (
+                           n_cores_box, int(os.environ["PG2_PACK_THREADS"]), len(near_cores))},
             "e2e": {"value": total_cells / (ms_e2e * 1e-3) * 1e-9, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
