@@ -187,22 +187,34 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
     // the reference loop ends when (i<1 && j<1) AFTER reading the cell it stands on (:1073-1181)
     // register-strip kernels only take jobs whose right graph is a plain chain: column j is entered from j-1
     const bool chain_right = J.kernel != 0;
+    // lane layout: the virtual row of site i travels with the walk (a plain row sits one virtual row below its only
+    // source), so plain rows cost one load per step -- the half-word itself.  With 100 000 paths in flight the walk is
+    // bound by the rate of 32-byte sectors (one per step), not by latency: a look-ahead window that fetched the next 8
+    // rows and diagonal cells at once doubled the sector count and the time (2.1 -> 4.3 ms).
+    int v = -1;  // vlast[i], or -1: not known
     for (;;) {
         unsigned q;
         bool chain_left;
-        if (vit == NO_MAT || !fetch_ptr(tc, vit, i, j, q, chain_left)) { status = JOB_BROKEN_PATH; break; }
+        if (J.kernel == 2) {
+            if (vit == NO_MAT || i < 0 || j < 0 || i >= J.lx || j >= J.ly) { status = JOB_BROKEN_PATH; break; }
+            if (i == 0 && j == 0) { q = NO_MAT; chain_left = false; }  // start corner: no predecessor
+            else {
+                if (v < 0) v = tc.vlast[i];
+                const unsigned w = tc.ptr16[J.cell_base + lane_ptr_index(tc.nv, LANE_K, v, j, J.lane)];
+                chain_left = (w & 0x4000u) != 0;
+                q = lane_decode_ptr(w, vit);
+            }
+        } else if (vit == NO_MAT || !fetch_ptr(tc, vit, i, j, q, chain_left)) { status = JOB_BROKEN_PATH; break; }
         if (n >= J.step_cap) { status = JOB_BROKEN_PATH; break; }
         out[n++] = (unsigned short)q;
         int src = (int)(q & 3u);
-        if (vit == M_MAT) {
-            int ni = (src == NO_MAT) ? -1 : (chain_left ? i - 1 : l_es[l_off[i] + ((q >> 2) & 63u)]);
-            int nj = (src == NO_MAT) ? -1 : (chain_right ? j - 1 : r_es[r_off[j] + ((q >> 8) & 63u)]);
-            i = ni; j = nj;
-        } else if (vit == X_MAT) {
-            i = (src == NO_MAT) ? -1 : (chain_left ? i - 1 : l_es[l_off[i] + ((q >> 2) & 63u)]);
-        } else {
-            j = (src == NO_MAT) ? -1 : (chain_right ? j - 1 : r_es[r_off[j] + ((q >> 8) & 63u)]);
+        if (vit == M_MAT || vit == X_MAT) {
+            if (src == NO_MAT) i = -1;
+            else if (chain_left) { i -= 1; if (v >= 0) v -= 1; }
+            else { i = l_es[l_off[i] + ((q >> 2) & 63u)]; v = -1; }
         }
+        if (vit == M_MAT || vit == Y_MAT)
+            j = (src == NO_MAT) ? -1 : (chain_right ? j - 1 : r_es[r_off[j] + ((q >> 8) & 63u)]);
         vit = src;
         if (i < 1 && j < 1) break;
     }

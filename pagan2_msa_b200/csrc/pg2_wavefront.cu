@@ -39,6 +39,7 @@ struct WaveCtx {
     const unsigned *mask_l, *mask_r;
     int n_np_l, n_np_r, cur_l, cur_r;
     bool two_pass;
+    bool chain_job;  // both graphs are plain chains and a diagonal never has more cells than the CTA has threads
     const DevJob *job;
     const int *l_state, *l_off, *l_estart;
     const float *l_elogw;
@@ -197,6 +198,7 @@ __device__ __forceinline__ void make_wave_ctx(WaveCtx &c, const DevJob &J, const
     c.ring.cap = 0;
     c.ring.global_scores = true;
     c.two_pass = false;
+    c.chain_job = false;
 }
 
 // the ring holds this job's diagonals: serve near reads from it; plain chains on both sides never read the scratch
@@ -298,8 +300,8 @@ __device__ __forceinline__ bool site_plain(const unsigned *mask, int s) { return
 // compute_fwd_scores for a cell whose left site i and right site j are both plain (one backward edge each, from i-1 and
 // j-1; i, j >= 1): the same candidates in the same order as gap_cell / match_pairs with single-trip loops, all three
 // source cells from the ring.
-__device__ __forceinline__ void wave_cell_plain(const WaveCtx &c, const DevModel &m, unsigned flags, float lng2, int i, int j, long long idx,
-                                                unsigned *P) {
+__device__ __forceinline__ void wave_cell_plain_core(const WaveCtx &c, const DevModel &m, unsigned flags, float lng2, int i, int j, long long idx,
+                                                     unsigned *P, int sl, int sr, double wl, double wr) {
     const bool term = !(flags & FLAG_NO_TERMINAL_EDGES);
     const bool reduced = (flags & FLAG_REDUCED) != 0;
     const double ninf = neg_inf();
@@ -308,8 +310,7 @@ __device__ __forceinline__ void wave_cell_plain(const WaveCtx &c, const DevModel
     ring_near(c, 1, i - 1, ux, uy, um);  // (i-1, j)
     ring_near(c, 1, i, lx_, ly_, lm);    // (i, j-1)
     ring_near(c, 2, i - 1, dx, dy, dm);  // (i-1, j-1)
-    const double wl = (double)c.l_elogw[c.l_off[i]], wr = (double)c.r_elogw[c.r_off[j]];
-    const double ls = (double)__ldg(m.table + (size_t)c.l_state[i] + (size_t)c.r_state[j] * (size_t)m.fas);
+    const double ls = (double)__ldg(m.table + (size_t)sl + (size_t)sr * (size_t)m.fas);
     // X: ext, double, open from (i-1, j)   (gap_cell<true>)
     double sx = ninf, s;
     unsigned px = NO_MAT;
@@ -346,6 +347,38 @@ __device__ __forceinline__ void wave_cell_plain(const WaveCtx &c, const DevModel
         dst[1] = make_double2(sm, 0.0);
     }
     P[idx] = cell_word(px, py, pm) | WORD_PLAIN_LEFT | WORD_PLAIN_RIGHT;
+}
+__device__ __forceinline__ void wave_cell_plain(const WaveCtx &c, const DevModel &m, unsigned flags, float lng2, int i, int j, long long idx,
+                                                unsigned *P) {
+    wave_cell_plain_core(c, m, flags, lng2, i, j, idx, P, c.l_state[i], c.r_state[j], (double)c.l_elogw[c.l_off[i]],
+                         (double)c.r_elogw[c.r_off[j]]);
+}
+
+// Chain x chain jobs (anchored leaf x leaf, 400 000 short diagonals): a thread keeps the cell with the same offset on
+// every diagonal, so from one diagonal to the next exactly one of its row / column moves on by one site.  The state and
+// edge weight of the current and of the NEXT row and column stay in registers; the load for the site after that is issued
+// a diagonal ahead, so no global load sits on the diagonal's critical path (nor does the band geometry, see the kernel).
+struct ChainTrack {
+    int i, j;  // the row / column the fields below describe (-2: nothing loaded)
+    int sl, sl_n, sr, sr_n;
+    double wl, wl_n, wr, wr_n;
+};
+__device__ __forceinline__ void chain_site(const int *state, const float *elogw, int n, int s, int &st, double &w) {
+    const int q = s < 1 ? 1 : (s > n - 1 ? n - 1 : s);  // a plain chain: site q >= 1 is entered by edge q-1
+    st = state[q];
+    w = (double)elogw[q - 1];
+}
+__device__ __forceinline__ void wave_chain_cell(const WaveCtx &c, const DevModel &m, unsigned flags, float lng2, int s, int ilo, int ihi,
+                                                long long base, unsigned *P, int tid, ChainTrack &t) {
+    const int i = ilo + tid, j = s - i;
+    if (i == t.i + 1) { t.sl = t.sl_n; t.wl = t.wl_n; chain_site(c.l_state, c.l_elogw, c.lx, i + 1, t.sl_n, t.wl_n); }
+    else if (i != t.i) { chain_site(c.l_state, c.l_elogw, c.lx, i, t.sl, t.wl); chain_site(c.l_state, c.l_elogw, c.lx, i + 1, t.sl_n, t.wl_n); }
+    if (j == t.j + 1) { t.sr = t.sr_n; t.wr = t.wr_n; chain_site(c.r_state, c.r_elogw, c.ly, j + 1, t.sr_n, t.wr_n); }
+    else if (j != t.j) { chain_site(c.r_state, c.r_elogw, c.ly, j, t.sr, t.wr); chain_site(c.r_state, c.r_elogw, c.ly, j + 1, t.sr_n, t.wr_n); }
+    t.i = i; t.j = j;
+    if (i > ihi) return;
+    if (i >= 1 && j >= 1) wave_cell_plain_core(c, m, flags, lng2, i, j, base + tid, P, t.sl, t.sr, t.wl, t.wr);
+    else wave_cell(c, m, flags, lng2, i, j, base + tid, P);  // first row / column: the general body
 }
 
 // One anti-diagonal, the share of thread `tid` of `nthreads`.  With the ring: first every cell whose two sites are
@@ -401,6 +434,23 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
     __syncthreads();
 
     const int n_diag = c.lx + c.ly - 1;
+    if (ring_cap > 0 && GL.simple && GR.simple && ring_cap <= (int)blockDim.x) {
+        // chain x chain: per-thread site tracking, band geometry fetched one diagonal ahead
+        c.chain_job = true;
+        ChainTrack track;
+        track.i = track.j = -2;
+        int ilo, ihi, ilo_n = 0, ihi_n = 0;
+        long long base, base_n = 0;
+        diag_geometry(c, 1, ilo, ihi, base);
+        for (int s = 1; s < n_diag; ++s) {
+            if (s + 1 < n_diag) diag_geometry(c, s + 1, ilo_n, ihi_n, base_n);  // lands while this diagonal computes
+            wave_ring_begin(c, s, ilo);
+            wave_chain_cell(c, m, flags, lng2, s, ilo, ihi, base, P, (int)threadIdx.x, track);
+            __syncthreads();
+            wave_ring_end(c, ilo, ihi);
+            ilo = ilo_n; ihi = ihi_n; base = base_n;
+        }
+    } else
     for (int s = 1; s < n_diag; ++s) {
         int ilo, ihi;
         long long base;
@@ -445,6 +495,22 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
         const float lng2 = __fmul_rn(2.0f, m.lng);
         wave_init(c, P);
         const int n_diag = c.lx + c.ly - 1;
+        // the kernel's thread count for this group: a power of two >= max_diag (pg2_engine.cu)
+        int emu_threads = 32;
+        while (emu_threads < max_diag && emu_threads < 1024) emu_threads *= 2;
+        if (ring_cap > 0 && GL.simple && GR.simple && ring_cap <= emu_threads) {
+            c.chain_job = true;
+            std::vector<ChainTrack> track((size_t)emu_threads);
+            for (auto &t : track) t.i = t.j = -2;
+            for (int s = 1; s < n_diag; ++s) {
+                int ilo, ihi;
+                long long base;
+                diag_geometry(c, s, ilo, ihi, base);
+                wave_ring_begin(c, s, ilo);
+                for (int tid = emu_threads - 1; tid >= 0; --tid) wave_chain_cell(c, m, J.flags, lng2, s, ilo, ihi, base, P, tid, track[(size_t)tid]);
+                wave_ring_end(c, ilo, ihi);
+            }
+        } else
         for (int s = 1; s < n_diag; ++s) {
             int ilo, ihi;
             long long base;
