@@ -443,7 +443,15 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
         long long base, base_n = 0;
         diag_geometry(c, 1, ilo, ihi, base);
         for (int s = 1; s < n_diag; ++s) {
-            if (s + 1 < n_diag) diag_geometry(c, s + 1, ilo_n, ihi_n, base_n);  // lands while this diagonal computes
+            if (s + 1 < n_diag) {
+                // lands while this diagonal computes.  The index is hidden from the compiler's uniformity analysis:
+                // it would otherwise move the loaded values to uniform registers at once (R2UR) and wait for them here.
+                int sn = s + 1;
+#ifndef PG2_HOST_EMU
+                asm volatile("" : "+r"(sn));
+#endif
+                diag_geometry(c, sn, ilo_n, ihi_n, base_n);
+            }
             wave_ring_begin(c, s, ilo);
             wave_chain_cell(c, m, flags, lng2, s, ilo, ihi, base, P, (int)threadIdx.x, track);
             __syncthreads();
