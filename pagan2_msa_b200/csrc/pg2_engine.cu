@@ -151,6 +151,8 @@ constexpr int PIPE_SLOTS = 4;  // chunks of one pg2_align_batch call in flight a
 struct pg2_ctx {
     int device = 0;
     cudaStream_t stream = 0;
+    cudaStream_t hi_stream = 0;  // high priority: the traceback of a pipelined chunk must not queue behind the resident
+                                 // fill CTAs of the following chunks (they hold every SM's registers until their tail)
     cudaDeviceProp prop;
     std::vector<ModelRec> models;
     bool models_dirty = true;
@@ -205,6 +207,11 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
         return fail(PG2_ERR_NO_DEVICE, "device is not sm_100 class; the kernels are built for sm_100a only");
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(PG2_ERR_CUDA, "stream creation failed"); }
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&c->hi_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { cudaGetLastError(); c->hi_stream = 0; }
+    }
     for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
     const char *fw = getenv("PG2_FORCE_WAVEFRONT");
     c->force_wavefront = fw && atoi(fw) != 0;
@@ -235,6 +242,7 @@ extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
     c->d_steps.release(); c->d_ptr16.release(); c->d_lane_scratch.release(); c->d_tasks.release();
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
+    if (c->hi_stream) cudaStreamDestroy(c->hi_stream);
     delete c;
 }
 
@@ -1070,10 +1078,15 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
             st.fill_launches++;
         }
         CU(cudaEventRecord(c->ev[3], c->stream));
+        // pipelined chunks: the walk goes to the high-priority stream (after the fills, before anything later on the
+        // ctx stream), so that its CTAs take the first SM slots that free up
+        cudaStream_t tb_stream = (async && c->hi_stream) ? c->hi_stream : c->stream;
+        if (tb_stream != c->stream) CU(cudaStreamWaitEvent(tb_stream, c->ev[3], 0));
         launch_traceback(phase_jobs, phase_wave_jobs, c->d_order.p + b->groups[gi].first, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p, c->d_off.p, c->d_estart.p,
                          c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_steps.p, c->d_results.p,
-                         c->stream);
-        CU(cudaEventRecord(c->ev[4], c->stream));
+                         tb_stream);
+        CU(cudaEventRecord(c->ev[4], tb_stream));
+        if (tb_stream != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev[4], 0));
         if (!async) {
             CU(cudaEventSynchronize(c->ev[4]));
             CU(cudaGetLastError());
@@ -1288,6 +1301,10 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
     if (rc != PG2_OK) return rc;
     const bool async_d2h = host_pointer_is_pinned(steps);
     timer.lap("= group + chunk");
+    // PG2_TIMING: device timeline of the chunks against one origin (tuning aid)
+    cudaEvent_t origin = nullptr;
+    const auto host_origin = std::chrono::steady_clock::now();
+    if (timer.on) { cudaEventCreate(&origin); cudaEventRecord(origin, c->stream); }
 
     // Chunk k runs on slot k % n_slots: pack, upload, kernels and (into pinned caller memory) the copy back are all
     // enqueued without waiting; the host only waits for a chunk when its slot is needed again or at the end.
@@ -1305,6 +1322,17 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         int r = PG2_OK;
         if (!f.batch->fetch_enqueued) r = fetch_enqueue(f.ctx, f.batch, steps + f.step_base, step_cap - f.step_base);
         if (r == PG2_OK) r = fetch_complete(f.ctx, f.batch, chunk_res.data());
+        if (r == PG2_OK && origin) {
+            float t_up = 0, t_k0 = 0, t_fill = 0, t_tb = 0, t_d2h = 0;
+            cudaEventElapsedTime(&t_up, origin, f.ctx->ev[0]);
+            cudaEventElapsedTime(&t_k0, origin, f.ctx->ev[7]);
+            cudaEventElapsedTime(&t_fill, origin, f.ctx->ev[3]);
+            cudaEventElapsedTime(&t_tb, origin, f.ctx->ev[4]);
+            cudaEventElapsedTime(&t_d2h, origin, f.ctx->ev[6]);
+            fprintf(stderr, "pg2 chunk [%6d,%6d): upload starts %6.2f  kernels start %6.2f  fill ends %6.2f  traceback ends %6.2f  d2h ends %6.2f  "
+                            "(host: collected at %6.2f ms)\n", f.lo, f.hi, t_up, t_k0, t_fill, t_tb, t_d2h,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_origin).count());
+        }
         if (r == PG2_OK) {
             for (int k = 0; k < n; k++) {
                 pg2_result &o = results[perm[f.lo + k]];
@@ -1343,6 +1371,9 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         rc = pg2_batch_create(f.ctx, f.hi - f.lo, chunk_jobs.data(), &f.batch);
         if (rc == PG2_OK) rc = batch_run_impl(f.ctx, f.batch, true);
         if (rc == PG2_OK && async_d2h) rc = fetch_enqueue(f.ctx, f.batch, steps + f.step_base, step_cap - f.step_base);
+        if (timer.on)
+            fprintf(stderr, "pg2 chunk [%6d,%6d): enqueued at %6.2f ms (host)\n", f.lo, f.hi,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_origin).count());
         if (rc != PG2_OK && f.batch) { pg2_batch_destroy(f.ctx, f.batch); f.batch = nullptr; }
     }
     for (size_t k = 0; k < (size_t)n_slots; k++) {
@@ -1352,6 +1383,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         if (rc == PG2_OK) rc = r;
     }
     if (rc == PG2_OK) c->stats = agg;
+    if (origin) cudaEventDestroy(origin);
     timer.lap("= pipelined chunks");
     return rc;
 }
