@@ -372,7 +372,7 @@ def main():
     # ---------------- end to end: host buffers in, host results out, every step ----------------
     # the caller's host buffers (pg2_job array over the numpy arrays, result + step buffers) exist before
     # the clock starts; each timed step is exactly one pg2_align_batch call
-    prep = eng.prepare(jobs, pinned=True)
+    prep = eng.prepare(jobs, pinned=True, compact=True)  # reads and leaf targets in the compact chain form of the C-ABI
     eng.align_prepared(prep)  # warm-up: grows the pinned staging and device buffers once
     barrier()
     e2e_t = []

@@ -63,7 +63,13 @@ enum { PG2_X_MAT = 0, PG2_Y_MAT = 1, PG2_M_MAT = 2 };
 /* One sequence graph (reference: Sequence = vector<Site> + vector<Edge>, sequence.h:663-671) as a CSR
  * of BACKWARD edges.  Site 0 is the start site, site n_sites-1 the stop site.  For site s its edges
  * are k in [bwd_off[s], bwd_off[s+1]) IN THE REFERENCE'S LIST ORDER (Site::get_first_bwd_edge /
- * get_next_bwd_edge, sequence.h:395-417) -- the order decides ties.  Every edge_start[k] < s. */
+ * get_next_bwd_edge, sequence.h:395-417) -- the order decides ties.  Every edge_start[k] < s.
+ *
+ * COMPACT FORM of a plain chain (a leaf or a read as Sequence::create_default_sequence builds it, sequence.cpp:152-303:
+ * site s >= 1 is entered by the one edge (s-1 -> s) of weight 1): bwd_off == edge_start == edge_logw == NULL and
+ * n_edges == n_sites - 1.  The engine then reads only `state` (nothing else is packed or uploaded for the graph).
+ * edge_index may still be given for pg2_expand_path; NULL means edge k has index k + 1 (edge 0 of a default sequence
+ * is the dummy first edge). */
 typedef struct pg2_graph {
     int32_t n_sites;
     int32_t n_edges;           /* == bwd_off[n_sites] */

@@ -141,11 +141,24 @@ class FlatGraph:
     def n_sites(self):
         return int(self.state.shape[0])
 
-    def as_struct(self):
+    def is_plain_chain(self):
+        """Site s >= 1 entered by the one edge (s-1 -> s) with log weight +0.0: what the compact form describes."""
+        n = self.n_sites
+        if self.start.shape[0] != n - 1:
+            return False
+        return bool(self.off[0] == 0 and (self.off[1:] == np.arange(n, dtype=np.int32)).all()
+                    and (self.start == np.arange(n - 1, dtype=np.int32)).all() and not self.logw.view(np.uint32).any())
+
+    def as_struct(self, compact=False):
+        """compact=True: a plain chain is passed in the compact form of pagan2_b200.h (states only; the edge indices stay
+        for pg2_expand_path)."""
         g = Graph()
         g.n_sites = self.n_sites
         g.n_edges = int(self.start.shape[0])
         g.state = _ptr(self.state, C.c_int32)
+        if compact and self.is_plain_chain():
+            g.edge_index = _ptr(self.eidx, C.c_int32)
+            return g
         g.bwd_off = _ptr(self.off, C.c_int32)
         g.edge_start = _ptr(self.start, C.c_int32)
         g.edge_logw = _ptr(self.logw, C.c_float)
@@ -208,10 +221,10 @@ class FlatJob:
         hi = np.minimum(self.lower, ly - 1)
         return int(np.maximum(hi - lo + 1, 0).sum())
 
-    def as_struct(self, model_handle=0):
+    def as_struct(self, model_handle=0, compact=False):
         j = Job()
-        j.left = self.left.as_struct()
-        j.right = self.right.as_struct()
+        j.left = self.left.as_struct(compact)
+        j.right = self.right.as_struct(compact)
         j.model = model_handle
         j.flags = self.flags
         if self.upper is not None:

@@ -320,7 +320,9 @@ struct GraphTable {
 
 // Packing step 1 (serial): de-duplicate by host-array identity.  Touches the job records only, never the arrays.
 static int intern_graph(pg2_batch *b, const pg2_graph &g, GraphTable &seen, std::vector<const pg2_graph *> &sources, int *gid) {
-    if (g.n_sites < 2 || g.n_edges < 0 || !g.state || !g.bwd_off || (g.n_edges > 0 && (!g.edge_start || !g.edge_logw || !g.edge_index)))
+    const bool compact = !g.bwd_off && !g.edge_start && !g.edge_logw;  // plain chain described by its states only
+    if (g.n_sites < 2 || g.n_edges < 0 || !g.state || (compact && g.n_edges != g.n_sites - 1) ||
+        (!compact && (!g.bwd_off || (g.n_edges > 0 && (!g.edge_start || !g.edge_logw || !g.edge_index)))))
         return fail(PG2_ERR_INVALID, "graph with null arrays or fewer than 2 sites");
     GraphKey key = {g.state, g.bwd_off, g.edge_start, g.edge_logw, g.n_sites};
     GraphTable::Slot &slot = seen.find(key, sources);
@@ -350,6 +352,13 @@ static void classify_graph(DevGraph &dg, const pg2_graph &g) {
     const int n_edges = g.n_edges;
     const int *po = g.bwd_off, *pe = g.edge_start;
     const float *pw = g.edge_logw;
+    if (!po) {  // compact form: the caller states that the graph is a plain unit-weight chain
+        dg.max_indeg = 1;
+        dg.simple = 1;
+        dg.zero_w = 1;
+        dg.implicit = 1;
+        return;
+    }
     if (po[g.n_sites] != n_edges) { dg.max_indeg = -2; return; }
     if (n_edges == g.n_sites - 1) {
         // the common case first, as three branch-free passes the compiler vectorises: a plain chain with unit weights has
@@ -652,7 +661,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             // the arrays of a read are small separate allocations: start the next graphs' cache misses early
             const pg2_graph &nx = *sources[gi + 2];
             const int bytes = nx.n_sites * 4;
-            for (int o = 0; o < bytes; o += 256) {
+            for (int o = 0; nx.bwd_off && o < bytes; o += 256) {
                 __builtin_prefetch(reinterpret_cast<const char *>(nx.bwd_off) + o);
                 __builtin_prefetch(reinterpret_cast<const char *>(nx.edge_start) + o);
                 __builtin_prefetch(reinterpret_cast<const char *>(nx.edge_logw) + o);

@@ -66,6 +66,30 @@ extern "C" int pg2_expand_path(const pg2_job *job, const pg2_model_desc *model, 
     if (n_used_left) *n_used_left = 0;
     if (n_used_right) *n_used_right = 0;
     if (result->status != PG2_JOB_OK) return PG2_ERR_INVALID;
+    // compact plain chains (pagan2_b200.h): write their CSR out once, the walk below reads explicit arrays
+    pg2_job explicit_job = *job;
+    std::vector<int32_t> chain_store[2][3];
+    std::vector<float> chain_w[2];
+    for (int side = 0; side < 2; ++side) {
+        pg2_graph &g = side == 0 ? explicit_job.left : explicit_job.right;
+        if (g.bwd_off) continue;
+        if (g.edge_start || g.edge_logw || g.n_edges != g.n_sites - 1 || g.n_sites < 2) return PG2_ERR_INVALID;
+        std::vector<int32_t> &off = chain_store[side][0], &es = chain_store[side][1], &ei = chain_store[side][2];
+        off.resize((size_t)g.n_sites + 1);
+        es.resize((size_t)g.n_edges);
+        chain_w[side].assign((size_t)g.n_edges, 0.0f);
+        for (int s2 = 0; s2 <= g.n_sites; ++s2) off[(size_t)s2] = s2 > 0 ? s2 - 1 : 0;
+        for (int k = 0; k < g.n_edges; ++k) es[(size_t)k] = k;
+        g.bwd_off = off.data();
+        g.edge_start = es.data();
+        g.edge_logw = chain_w[side].data();
+        if (!g.edge_index) {
+            ei.resize((size_t)g.n_edges);
+            for (int k = 0; k < g.n_edges; ++k) ei[(size_t)k] = k + 1;
+            g.edge_index = ei.data();
+        }
+    }
+    job = &explicit_job;
     const pg2_graph &L = job->left, &R = job->right;
     const int lx = L.n_sites - 1, ly = R.n_sites - 1;
     const int cap = L.n_sites + R.n_sites;

@@ -66,13 +66,13 @@ assert RESULT_DTYPE.itemsize == C.sizeof(abi.Result)
 class Batch:
     """A launch batch resident on the device (pg2_batch_*)."""
 
-    def __init__(self, engine, jobs):
+    def __init__(self, engine, jobs, compact=False):
         self.engine = engine
         self.jobs = jobs
         self.n = len(jobs)
         self._structs = (abi.Job * max(self.n, 1))()
         for k, j in enumerate(jobs):
-            self._structs[k] = j.as_struct(engine.model_handle(j.model))
+            self._structs[k] = j.as_struct(engine.model_handle(j.model), compact)
         self._h = C.c_void_p()
         engine._check(engine.lib.pg2_batch_create(engine.ctx, self.n, self._structs, C.byref(self._h)))
         self.step_capacity = int(engine.lib.pg2_batch_step_capacity(self._h))
@@ -150,19 +150,20 @@ class Engine:
             self._models[key] = (h.value, model)
         return self._models[key][0]
 
-    def batch(self, jobs):
-        return Batch(self, jobs)
+    def batch(self, jobs, compact=False):
+        return Batch(self, jobs, compact)
 
-    def prepare(self, jobs, pinned=False):
+    def prepare(self, jobs, pinned=False, compact=False):
         """Builds the pg2_job array (the caller-side host buffers of the C-ABI) once; the arrays of the
         FlatJob objects stay owned by `jobs`.  pinned=True puts the result / step buffers in page-locked
-        host memory (torch), which lets the device->host copy run at full PCIe rate.
+        host memory (torch), which lets the device->host copy run at full PCIe rate.  compact=True describes plain
+        chains (reads, leaves) by their states only (the compact pg2_graph form).
         Returns an opaque tuple for align_prepared()."""
         n = len(jobs)
         structs = (abi.Job * max(n, 1))()
         cap = 0
         for k, j in enumerate(jobs):
-            structs[k] = j.as_struct(self.model_handle(j.model))
+            structs[k] = j.as_struct(self.model_handle(j.model), compact)
             cap += j.left.n_sites + j.right.n_sites
         if pinned:
             import torch
@@ -187,14 +188,14 @@ class Engine:
         """pg2_align_batch on a list of FlatJob -> (results[RESULT_DTYPE], packed steps uint32)."""
         return self.align_prepared(self.prepare(jobs))
 
-    def expand(self, job, result, steps):
+    def expand(self, job, result, steps, compact=False):
         """pg2_expand_path -> (steps[STEP_DTYPE] forward order, used_left, used_right)."""
         cap = job.left.n_sites + job.right.n_sites
         out = np.zeros(cap, dtype=abi.STEP_DTYPE)
         ul = np.zeros(cap, np.int32)
         ur = np.zeros(cap, np.int32)
         n, nl, nr = C.c_int32(), C.c_int32(), C.c_int32()
-        js = job.as_struct(0)
+        js = job.as_struct(0, compact)
         ms = job.model.as_struct()
         r = abi.Result()
         for f, _ in abi.Result._fields_:

@@ -200,3 +200,35 @@ def test_pipelined_align_batch_matches_single_shot(emu_lib, chunks):
     finally:
         os.environ.pop("PG2_PIPELINE_MIN_JOBS", None)
         os.environ.pop("PG2_PIPELINE_CHUNKS", None)
+
+
+def test_compact_chain_form(emu_lib, golden):
+    """Plain chains passed in the compact form of pagan2_b200.h (states only, CSR arrays NULL): same results, same packed
+    paths, same expanded paths as the explicit form; fewer bytes staged; a compact graph that is no chain is refused."""
+    rng = np.random.default_rng(91)
+    jobs = list(golden["place_dna"][:24]) + randjobs.random_shared_target_jobs(rng, 40, weights=False)
+    jobs += [randjobs.random_job(rng, kind) for kind in ("banded_chain", "strip") for _ in range(8)]
+    jobs += randjobs.random_shared_target_jobs(rng, 20, plain_left=True, weights=False)
+    assert sum(j.right.is_plain_chain() for j in jobs) > 80 and any(j.left.is_plain_chain() for j in jobs)
+    assert any(not j.right.is_plain_chain() for j in jobs)  # weighted chains keep the explicit form
+    with make_engine(emu_lib, False) as eng:
+        ra, sa = eng.align(jobs)
+        ra, sa = ra.copy(), sa.copy()
+        bytes_explicit = eng.stats()["h2d_bytes"]
+        rb, sb = eng.align_prepared(eng.prepare(jobs, compact=True))
+        assert eng.stats()["h2d_bytes"] <= bytes_explicit
+        assert ra.tobytes() == rb.tobytes()
+        for k, job in enumerate(jobs):
+            if ra["status"][k] != 0:
+                continue
+            pa, la, ua = eng.expand(job, ra[k], sa)
+            pb, lb, ub = eng.expand(job, rb[k], sb, compact=True)
+            assert pa.tobytes() == pb.tobytes() and la.tobytes() == lb.tobytes() and ua.tobytes() == ub.tobytes()
+        # n_edges must be n_sites - 1 in the compact form
+        bad = jobs[0].as_struct(eng.model_handle(jobs[0].model), compact=True)
+        assert not bad.right.bwd_off
+        bad.right.n_edges += 1
+        arr = (abi.Job * 1)(bad)
+        res = (abi.Result * 1)()
+        stp = np.zeros(4096, np.uint16)
+        assert eng.lib.pg2_align_batch(eng.ctx, 1, arr, res, stp.ctypes.data, 4096) == abi.PG2_ERR_INVALID

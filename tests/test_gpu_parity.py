@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import enginecheck
+import oracle_lib
 import randjobs
 from pagan2_msa_b200 import abi, engine, synth
 
@@ -227,3 +228,18 @@ def test_pipelined_align_batch_on_device(eng):
     finally:
         os.environ.pop("PG2_PIPELINE_MIN_JOBS", None)
         os.environ.pop("PG2_PIPELINE_CHUNKS", None)
+
+
+def test_compact_chain_form_on_device(eng, golden):
+    """Plain chains in the compact pg2_graph form (states only) against the explicit form and the oracle."""
+    rng = np.random.default_rng(191)
+    jobs = list(golden["place_dna"][:30]) + randjobs.random_shared_target_jobs(rng, 70, weights=False)
+    jobs += [randjobs.random_job(rng, kind) for kind in ("banded_chain", "strip") for _ in range(10)]
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    ra = enginecheck.check_batch(eng, jobs).copy()
+    rb, sb = eng.align_prepared(eng.prepare(jobs, compact=True))
+    assert ra.tobytes() == rb.tobytes()
+    for k, job in enumerate(jobs):
+        if rb["status"][k] == 0:
+            st, _, _ = eng.expand(job, rb[k], sb, compact=True)
+            assert oracle_lib.steps_equal(st, job.expected_path, job.expected_path_score) == []

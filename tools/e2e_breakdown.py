@@ -9,7 +9,7 @@ import bench
 from pagan2_msa_b200 import engine
 jobs, info = bench.build_workload(100000, 7)
 eng = engine.Engine(0)
-prep = eng.prepare(jobs, pinned=True)
+prep = eng.prepare(jobs, pinned=True, compact="--explicit" not in sys.argv)
 for rep in range(4):
     t0 = time.perf_counter(); eng.align_prepared(prep); t1 = time.perf_counter()
     st = eng.stats()
