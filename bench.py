@@ -306,7 +306,7 @@ def main():
     # the host packing threads of all ranks share this box's cores
     n_cores_box = len(os.sched_getaffinity(0))
     near_cores = bind_to_gpu_numa_node(local, world)
-    os.environ.setdefault("PG2_PACK_THREADS", str(max(1, min(16, n_cores_box // max(world, 1)))))
+    os.environ.setdefault("PG2_PACK_THREADS", str(max(1, min(4, n_cores_box // max(world, 1)))))
     if rank == 0:
         __graft_entry__.build()
     if dist is not None:

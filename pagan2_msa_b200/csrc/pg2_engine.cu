@@ -641,7 +641,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         for (int gi = 0; gi < ng; gi++) sites += (size_t)b->graphs[gi].n_sites;
         if (sites * 16 > ((size_t)8 << 20) && ng >= 64) {
             unsigned hw = std::thread::hardware_concurrency();
-            nthreads = (int)std::min<unsigned>(hw ? hw : 4, 16);
+            nthreads = (int)std::min<unsigned>(hw ? hw : 4, 4);  // measured: 2-4 threads beat 16 (spawn cost, memory-bound passes)
             const char *pt = getenv("PG2_PACK_THREADS");
             if (pt && atoi(pt) > 0) nthreads = atoi(pt);
         }
