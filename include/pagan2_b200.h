@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PG2_ABI_VERSION 1
+#define PG2_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -104,15 +104,18 @@ typedef struct pg2_job {
 
 /* ---- outputs ------------------------------------------------------------------------------- */
 
-/* Result header of one job.  The traceback itself is returned compactly: n_steps packed back-pointers
- * (uint16 each: the encoding below needs 14 bits) in WALK order (end corner first), at
- * steps[step_off .. step_off+n_steps).
- * pg2_expand_path() turns them into the reference's vector<Path_pointer>. */
+/* Result header of one job.  The traceback itself is returned compactly: packed back-pointers (the encoding below
+ * needs 14 bits) in WALK order (end corner first: the end pointer, then the pointer of every visited cell), run-length
+ * encoded in uint16 words at steps[step_off .. step_off+n_steps): a word with bit 15 clear is a pointer, a word with
+ * bit 15 set repeats the previous pointer (word & 0x7fff) more times.  The words of all jobs of a call lie back to back
+ * in job order (step_off is the running sum of n_steps), at the start of the caller's step buffer; the buffer itself
+ * must still hold left.n_sites + right.n_sites words per job (pg2_batch_step_capacity), the bound of an incompressible
+ * walk.  pg2_expand_path() turns the words into the reference's vector<Path_pointer>. */
 typedef struct pg2_result {
     double score;              /* Viterbi log-score == max_end.score (viterbi_alignment.cpp:1558-1566) */
     int64_t cells;             /* in-band DP cells filled */
     int64_t step_off;          /* offset of this job's packed pointers in the caller's step buffer */
-    int32_t n_steps;           /* number of packed pointers (end pointer + one per visited cell) */
+    int32_t n_steps;           /* number of encoded uint16 words of this job's walk */
     int32_t status;            /* PG2_JOB_* */
     uint32_t end_ptr;          /* packed end-corner pointer (same encoding as steps[]) */
     int32_t kernel;            /* which fill kernel ran: 0 = wavefront (general), 1 = strip (warp per alignment),
@@ -207,9 +210,9 @@ typedef struct pg2_stats {
 int pg2_get_stats(pg2_ctx *ctx, pg2_stats *out);
 
 /* Device addresses of the last run's result records (24-byte records {double score; uint32 end_ptr;
- * int32 n_steps; int32 status; int32 pad}, job order) and packed-pointer buffer, for callers that forward
- * results GPU-to-GPU (multi-GPU gather to rank 0 over NCCL, no host bounce).  Valid until the next batch
- * is created on this ctx. */
+ * int32 n_steps; int32 status; int32 raw_steps}, job order) and of the compacted path words (all jobs back to back in
+ * job order, *n_steps_total words), for callers that forward results GPU-to-GPU (multi-GPU gather to rank 0 over NCCL,
+ * no host bounce).  Waits for the run.  Valid until the next batch is created on this ctx. */
 int pg2_batch_device_buffers(pg2_ctx *ctx, pg2_batch *batch, void **results_dev, void **steps_dev, int64_t *n_steps_total);
 int pg2_stream_synchronize(pg2_ctx *ctx);
 

@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-PG2_ABI_VERSION = 1
+PG2_ABI_VERSION = 2
 
 PG2_OK, PG2_ERR_INVALID, PG2_ERR_NO_DEVICE, PG2_ERR_CUDA, PG2_ERR_NOMEM, PG2_ERR_UNSUPPORTED, PG2_ERR_CAPACITY = range(7)
 PG2_JOB_OK, PG2_JOB_NO_PATH, PG2_JOB_BAD_BAND, PG2_JOB_BAD_GRAPH, PG2_JOB_BROKEN_PATH = range(5)

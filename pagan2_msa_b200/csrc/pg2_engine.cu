@@ -27,6 +27,8 @@ void launch_expand_implicit(int n_graphs, const DevGraph *graphs, int *d_off, in
 void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
                      const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
                      DevResult *results, cudaStream_t stream);
+void launch_compact_steps(int n_jobs, const DevJob *jobs, const DevResult *results, long long *block_scratch, long long *total,
+                          const unsigned short *steps_in, unsigned short *steps_out, cudaStream_t stream);
 void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                            const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                            const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff, const int *d_vlast,
@@ -176,7 +178,10 @@ struct pg2_ctx {
     DevBuf<DevResult> d_results;
     DevBuf<double4> d_scores;
     DevBuf<unsigned> d_ptr32;
-    DevBuf<unsigned short> d_steps;
+    DevBuf<unsigned short> d_steps;          // per job a region of lx + ly words (what the walk may need at most)
+    DevBuf<unsigned short> d_steps_compact;  // the run-length encoded words of all jobs back to back, job order
+    DevBuf<long long> d_step_scan;           // block sums of the compaction scan; the last element is the total
+    PinVec<long long> h_step_total;
     DevBuf<unsigned short> d_ptr16;
     PinVec<DevResult> h_results;
     cudaEvent_t ev[8];
@@ -239,7 +244,7 @@ extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
     c->d_state.release(); c->d_off.release(); c->d_estart.release(); c->d_blo.release(); c->d_bhi.release(); c->d_dlo.release();
     c->d_order.release(); c->d_graph_status.release(); c->d_elogw.release(); c->d_doff.release(); c->d_jobs.release();
     c->d_graphs.release(); c->d_models.release(); c->d_results.release(); c->d_scores.release(); c->d_ptr32.release();
-    c->d_steps.release(); c->d_ptr16.release(); c->d_lane_scratch.release(); c->d_tasks.release();
+    c->d_steps.release(); c->d_steps_compact.release(); c->d_step_scan.release(); c->h_step_total.release(); c->d_ptr16.release(); c->d_lane_scratch.release(); c->d_tasks.release();
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
     if (c->hi_stream) cudaStreamDestroy(c->hi_stream);
@@ -947,6 +952,7 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     ENS(c->d_blo, c->h_blo.n + 1); ENS(c->d_bhi, c->h_bhi.n + 1); ENS(c->d_dlo, c->h_dlo.n + 1); ENS(c->d_doff, c->h_doff.n + 1);
     ENS(c->d_jobs, b->jobs.size() + 1); ENS(c->d_graphs, b->graphs.size() + 1); ENS(c->d_order, b->order.size() + 1);
     ENS(c->d_graph_status, b->graphs.size() + 1); ENS(c->d_results, b->jobs.size() + 1); ENS(c->d_steps, (size_t)b->total_steps + 1);
+    ENS(c->d_steps_compact, (size_t)b->total_steps + 1); ENS(c->d_step_scan, b->jobs.size() / 256 + 4);
     ENS(c->d_models, c->models.size() + 1); ENS(c->d_tasks, b->tasks.size() + 1);
     long long bytes = 0;
 #define H2D(dst, src, n, T)                                                                                 \
@@ -1108,7 +1114,15 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
         st.traceback_launches++;
         gi = ge;
     }
-    st.kernel_launches = 3 + st.fill_launches + st.traceback_launches + st.jobs_strip_groups;
+    // the run-length encoded paths of all jobs back to back (job order): what goes back to the host or to rank 0
+    {
+        const size_t nb = b->jobs.size() / 256 + 2;
+        launch_compact_steps(b->n_jobs, c->d_jobs.p, c->d_results.p, c->d_step_scan.p, c->d_step_scan.p + nb, c->d_steps.p,
+                             c->d_steps_compact.p, c->stream);
+        CU(cudaEventRecord(c->ev[4], c->stream));  // run_ms includes the compaction
+        if (!async) CU(cudaEventSynchronize(c->ev[4]));
+    }
+    st.kernel_launches = 6 + st.fill_launches + st.traceback_launches + st.jobs_strip_groups;
     st.run_ms = 0;
     if (!async && !b->groups.empty()) {
         float ms = 0;
@@ -1121,46 +1135,57 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
 
 extern "C" int pg2_batch_run(pg2_ctx *c, pg2_batch *b) { return batch_run_impl(c, b, false); }
 
-// Results come back in two steps: fetch_enqueue puts the device->host copies of the result records (into the ctx's
-// pinned staging) and of the packed paths (straight into the caller's buffer) on the ctx stream behind the kernels;
-// fetch_complete waits for them and fills the caller's pg2_result records.
-static int fetch_enqueue(pg2_ctx *c, pg2_batch *b, uint16_t *steps, int64_t step_cap) {
+// Results come back in two steps: fetch_enqueue puts the device->host copies of the result records and of the total
+// number of path words (into the ctx's pinned staging) on the ctx stream behind the kernels; fetch_complete waits for
+// them, copies exactly that many words of the compacted, run-length encoded paths into the caller's buffer and fills
+// the caller's pg2_result records (step_off = running sum of n_steps in job order, as the device compacted them).
+static int fetch_enqueue(pg2_ctx *c, pg2_batch *b, int64_t step_cap) {
     CU(cudaSetDevice(c->device));
     if (step_cap < b->total_steps) return fail(PG2_ERR_CAPACITY, "step buffer too small");
     c->h_results.clear();
+    c->h_step_total.clear();
     DevResult *hr = c->h_results.extend((size_t)b->n_jobs + 1);
-    if (!hr) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    long long *ht = c->h_step_total.extend(1);
+    if (!hr || !ht) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    *ht = 0;
     CU(cudaEventRecord(c->ev[5], c->stream));
     if (b->n_jobs > 0) {
         CU(cudaMemcpyAsync(hr, c->d_results.p, sizeof(DevResult) * b->n_jobs, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(steps, c->d_steps.p, sizeof(unsigned short) * (size_t)b->total_steps, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(ht, c->d_step_scan.p + (b->jobs.size() / 256 + 2), sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     }
-    CU(cudaEventRecord(c->ev[6], c->stream));
     b->fetch_enqueued = true;
     return PG2_OK;
 }
 
-static int fetch_complete(pg2_ctx *c, pg2_batch *b, pg2_result *results) {
+static int fetch_complete(pg2_ctx *c, pg2_batch *b, pg2_result *results, uint16_t *steps) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     const DevResult *hr = c->h_results.p;
+    const long long total = b->n_jobs > 0 ? c->h_step_total.p[0] : 0;
+    if (total < 0 || total > b->total_steps) return fail(PG2_ERR_CUDA, "path compaction returned an impossible word count");
+    if (total > 0) CU(cudaMemcpyAsync(steps, c->d_steps_compact.p, sizeof(unsigned short) * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev[6], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]);
     c->stats.d2h_ms = ms;
-    c->stats.d2h_bytes = (long long)sizeof(DevResult) * b->n_jobs + (long long)sizeof(unsigned short) * b->total_steps;
+    c->stats.d2h_bytes = (long long)sizeof(DevResult) * b->n_jobs + (long long)sizeof(unsigned short) * total + (long long)sizeof(long long);
+    long long off = 0;
     for (int t = 0; t < b->n_jobs; t++) {
         const DevJob &J = b->jobs[t];
         pg2_result &r = results[t];
         r.score = hr[t].score;
         r.cells = J.cells;
-        r.step_off = J.step_base;
+        r.step_off = off;
         r.n_steps = hr[t].n_steps;
+        off += hr[t].n_steps;
         r.status = hr[t].status == JOB_UNSUPPORTED ? PG2_JOB_BAD_GRAPH : hr[t].status;
         r.end_ptr = hr[t].end_ptr;
         r.kernel = J.kernel;
         if (hr[t].status == JOB_UNSUPPORTED) { g_last_error = "a graph exceeds PG2_MAX_IN_DEGREE backward edges per site"; }
     }
+    if (off != total) return fail(PG2_ERR_CUDA, "path compaction: word counts do not add up");
     return PG2_OK;
 }
 
@@ -1170,9 +1195,9 @@ extern "C" int pg2_batch_fetch(pg2_ctx *c, pg2_batch *b, pg2_result *results, ui
         for (int t = 0; t < b->n_jobs; t++) results[t].n_steps = b->jobs[t].step_cap;
         return fail(PG2_ERR_CAPACITY, "step buffer too small");
     }
-    int rc = fetch_enqueue(c, b, steps, step_cap);
+    int rc = fetch_enqueue(c, b, step_cap);
     if (rc != PG2_OK) return rc;
-    return fetch_complete(c, b, results);
+    return fetch_complete(c, b, results, steps);
 }
 
 extern "C" void pg2_batch_destroy(pg2_ctx *c, pg2_batch *b) {
@@ -1188,7 +1213,7 @@ extern "C" void pg2_batch_destroy(pg2_ctx *c, pg2_batch *b) {
 // One launch batch from host buffers to host buffers.  Large batches are cut into chunks that rotate over the ctx
 // and its siblings (further sets of staging / device buffers, each with its own stream): the host packs chunk k+1
 // while the device computes chunk k, the kernels of consecutive chunks overlap on the device (the tail of one
-// launch is filled by the next), and results stream back while later chunks compute.  Jobs that share the left
+// launch is filled by the next), and the (compacted) results of a chunk are collected while later chunks compute.  Jobs that share the left
 // graph stay in one chunk, so the lane kernel keeps full tasks.
 static int align_batch_single(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint16_t *steps, int64_t step_cap) {
     pg2_batch *b = nullptr;
@@ -1220,18 +1245,6 @@ static int ensure_siblings(pg2_ctx *c, int n_slots) {
         c->sibling[k]->models_dirty = true;
     }
     return PG2_OK;
-}
-
-// page-locked host memory takes asynchronous device->host copies; a copy into pageable memory would block the caller
-static bool host_pointer_is_pinned(const void *p) {
-#ifdef PG2_HOST_EMU
-    (void)p;
-    return true;
-#else
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-#endif
 }
 
 extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, pg2_result *results, uint16_t *steps, int64_t step_cap) {
@@ -1308,7 +1321,6 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
     n_slots = std::min<int>(n_slots, (int)cut.size() - 1);
     int rc = ensure_siblings(c, n_slots);
     if (rc != PG2_OK) return rc;
-    const bool async_d2h = host_pointer_is_pinned(steps);
     timer.lap("= group + chunk");
     // PG2_TIMING: device timeline of the chunks against one origin (tuning aid)
     cudaEvent_t origin = nullptr;
@@ -1329,8 +1341,8 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         const int n = f.hi - f.lo;
         chunk_res.resize((size_t)n);
         int r = PG2_OK;
-        if (!f.batch->fetch_enqueued) r = fetch_enqueue(f.ctx, f.batch, steps + f.step_base, step_cap - f.step_base);
-        if (r == PG2_OK) r = fetch_complete(f.ctx, f.batch, chunk_res.data());
+        if (!f.batch->fetch_enqueued) r = fetch_enqueue(f.ctx, f.batch, step_cap - f.step_base);
+        if (r == PG2_OK) r = fetch_complete(f.ctx, f.batch, chunk_res.data(), steps + f.step_base);
         if (r == PG2_OK && origin) {
             float t_up = 0, t_k0 = 0, t_fill = 0, t_tb = 0, t_d2h = 0;
             cudaEventElapsedTime(&t_up, origin, f.ctx->ev[0]);
@@ -1379,7 +1391,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         step_base += cap;
         rc = pg2_batch_create(f.ctx, f.hi - f.lo, chunk_jobs.data(), &f.batch);
         if (rc == PG2_OK) rc = batch_run_impl(f.ctx, f.batch, true);
-        if (rc == PG2_OK && async_d2h) rc = fetch_enqueue(f.ctx, f.batch, steps + f.step_base, step_cap - f.step_base);
+        if (rc == PG2_OK) rc = fetch_enqueue(f.ctx, f.batch, step_cap - f.step_base);
         if (timer.on)
             fprintf(stderr, "pg2 chunk [%6d,%6d): enqueued at %6.2f ms (host)\n", f.lo, f.hi,
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_origin).count());
@@ -1403,8 +1415,16 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
 extern "C" int pg2_batch_device_buffers(pg2_ctx *c, pg2_batch *b, void **results_dev, void **steps_dev, int64_t *n_steps_total) {
     if (!c || !b || c->current != b || !b->ran) return fail(PG2_ERR_INVALID, "pg2_batch_device_buffers: batch not run");
     if (results_dev) *results_dev = c->d_results.p;
-    if (steps_dev) *steps_dev = c->d_steps.p;
-    if (n_steps_total) *n_steps_total = b->total_steps;
+    if (steps_dev) *steps_dev = c->d_steps_compact.p;
+    if (n_steps_total) {
+        long long total = 0;
+        CU(cudaSetDevice(c->device));
+        if (b->n_jobs > 0) {
+            CU(cudaMemcpyAsync(&total, c->d_step_scan.p + (b->jobs.size() / 256 + 2), sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        *n_steps_total = total;
+    }
     return PG2_OK;
 }
 

@@ -93,8 +93,20 @@ extern "C" int pg2_expand_path(const pg2_job *job, const pg2_model_desc *model, 
     const pg2_graph &L = job->left, &R = job->right;
     const int lx = L.n_sites - 1, ly = R.n_sites - 1;
     const int cap = L.n_sites + R.n_sites;
-    const uint16_t *rec = steps + result->step_off;
-    const int n_rec = result->n_steps;
+    // run-length decoding (pagan2_b200.h): a word with bit 15 set repeats the previous pointer (word & 0x7fff) times
+    std::vector<uint16_t> raw;
+    {
+        const uint16_t *enc = steps + result->step_off;
+        raw.reserve((size_t)cap);
+        for (int k = 0; k < result->n_steps; ++k) {
+            const uint16_t w = enc[k];
+            if (!(w & 0x8000u)) { raw.push_back(w); continue; }
+            if (raw.empty() || raw.size() + (size_t)(w & 0x7fffu) > (size_t)cap + 1) return PG2_ERR_INVALID;
+            raw.insert(raw.end(), (size_t)(w & 0x7fffu), raw.back());
+        }
+    }
+    const uint16_t *rec = raw.data();
+    const int n_rec = (int)raw.size();
     if (n_rec < 1) return PG2_ERR_INVALID;
 
     int nl = 0, nr = 0;

@@ -9,6 +9,7 @@
 // backtrack_new_path does (reference src/main/viterbi_alignment.cpp:1038-1189) and emits the pointer of
 // every visited cell in walk order.  The host unpacker (pg2_expand.cpp) turns that into the reference's
 // vector<Path_pointer>, including the skipped-site steps of insert_preexisting_gap.
+#include <string.h>
 #include "pg2_device.cuh"
 #include "pg2_strip_geom.cuh"
 
@@ -111,6 +112,29 @@ __global__ void validate_jobs_kernel(int n_jobs, const DevJob *jobs, const DevGr
 }
 #endif
 
+// Path words are run-length encoded as they are emitted (pagan2_b200.h): a word with bit 15 clear is a packed pointer,
+// a word with bit 15 set repeats the previous pointer (word & 0x7fff) more times.  A run of L equal pointers costs
+// min(L, 2) words, so the encoding never needs more room than the raw walk (<= Lx + Ly words per job).
+struct StepEmit {
+    unsigned short *out;
+    int n;         // words written
+    int raw;       // pointers emitted (what the reference's path length bounds)
+    unsigned last; // previous pointer (0xffffffff: none)
+    int rep;       // pending repeats of `last`
+};
+__device__ __forceinline__ void emit_begin(StepEmit &e, unsigned short *out) { e.out = out; e.n = 0; e.raw = 0; e.last = 0xffffffffu; e.rep = 0; }
+__device__ __forceinline__ void emit_flush(StepEmit &e) {
+    if (e.rep > 0) { e.out[e.n++] = (unsigned short)(0x8000u | (unsigned)e.rep); e.rep = 0; }
+}
+__device__ __forceinline__ void emit_step(StepEmit &e, unsigned q) {
+    q &= 0x3fffu;
+    ++e.raw;
+    if (q == e.last && e.rep < 0x7fff) { ++e.rep; return; }
+    emit_flush(e);
+    e.out[e.n++] = (unsigned short)q;
+    e.last = q;
+}
+
 // Cell pointer lookup for both fill kernels' layouts.
 struct TraceCtx {
     const DevJob *J;
@@ -170,8 +194,8 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
     tc.doff = J.banded ? d_doff + J.diag_base : nullptr;
     tc.ptr32 = ptr32;
     tc.ptr16 = ptr16;
-    unsigned short *out = steps + J.step_base;
-    int n = 0;
+    StepEmit em;
+    emit_begin(em, steps + J.step_base);
 
     // end pointer -> last alignment column (viterbi_alignment.cpp:1047-1069)
     unsigned p = res->end_ptr;
@@ -181,7 +205,7 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
     else if (vit == X_MAT) { i = l_es[l_off[J.lx] + ((p >> 2) & 63u)]; j = J.ly - 1; }
     else if (vit == Y_MAT) { i = J.lx - 1; j = r_es[r_off[J.ly] + ((p >> 8) & 63u)]; }
     else { res->status = JOB_NO_PATH; return; }
-    out[n++] = (unsigned short)p;
+    emit_step(em, p);
 
     int status = JOB_OK;
     // the reference loop ends when (i<1 && j<1) AFTER reading the cell it stands on (:1073-1181)
@@ -205,8 +229,8 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
                 q = lane_decode_ptr(w, vit);
             }
         } else if (vit == NO_MAT || !fetch_ptr(tc, vit, i, j, q, chain_left)) { status = JOB_BROKEN_PATH; break; }
-        if (n >= J.step_cap) { status = JOB_BROKEN_PATH; break; }
-        out[n++] = (unsigned short)q;
+        if (em.raw >= J.step_cap) { status = JOB_BROKEN_PATH; break; }
+        emit_step(em, q);
         int src = (int)(q & 3u);
         if (vit == M_MAT || vit == X_MAT) {
             if (src == NO_MAT) i = -1;
@@ -218,7 +242,9 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
         vit = src;
         if (i < 1 && j < 1) break;
     }
-    res->n_steps = n;
+    emit_flush(em);
+    res->n_steps = em.n;
+    res->pad = em.raw;
     res->status = status;
 }
 
@@ -259,7 +285,8 @@ __device__ __forceinline__ void win_load(const DevJob &J, const TraceCtx &t, Tra
 
 // walk state of one path (held by lane 0)
 struct TraceState {
-    int i, j, vit, n, status;
+    int i, j, vit, status;
+    StepEmit em;
     bool done;
 };
 
@@ -268,7 +295,7 @@ __device__ __forceinline__ void trace_wave_begin(const DevJob &J, DevResult *res
     // end pointer -> last alignment column (viterbi_alignment.cpp:1047-1069)
     const unsigned p = res->end_ptr;
     st.vit = (int)(p & 3u);
-    st.n = 0;
+    emit_begin(st.em, out);
     st.status = JOB_OK;
     st.done = false;
     st.i = st.j = 0;
@@ -276,7 +303,7 @@ __device__ __forceinline__ void trace_wave_begin(const DevJob &J, DevResult *res
     else if (st.vit == X_MAT) { st.i = l_es[l_off[J.lx] + ((p >> 2) & 63u)]; st.j = J.ly - 1; }
     else if (st.vit == Y_MAT) { st.i = J.lx - 1; st.j = r_es[r_off[J.ly] + ((p >> 8) & 63u)]; }
     else { st.status = JOB_NO_PATH; st.done = true; return; }
-    out[st.n++] = (unsigned short)p;
+    emit_step(st.em, p);
 }
 
 // walks while the cells are inside the window; returns with st.done set, or at a cell outside the window
@@ -288,10 +315,10 @@ __device__ __forceinline__ void trace_wave_walk(const DevJob &J, const TraceWin 
         const int d = W.s0 - (i + j), r = W.i0 - i;
         if (d < 0 || d >= TWD || r < 0 || r >= TW) return;  // next window
         if (i < W.lo[d] || i > W.hi[d]) { st.status = JOB_BROKEN_PATH; st.done = true; return; }  // outside the band
-        if (st.n >= J.step_cap) { st.status = JOB_BROKEN_PATH; st.done = true; return; }
+        if (st.em.raw >= J.step_cap) { st.status = JOB_BROKEN_PATH; st.done = true; return; }
         const unsigned w = W.w[d * TW + r];
         const unsigned q = word_ptr(w, st.vit);
-        out[st.n++] = (unsigned short)q;
+        emit_step(st.em, q);
         const int src = (int)(q & 3u);
         // the reference loop ends when (i<1 && j<1) AFTER reading the cell it stands on (:1073-1181)
         if (st.vit == M_MAT || st.vit == X_MAT)
@@ -327,7 +354,8 @@ __global__ void __launch_bounds__(128) traceback_wave_kernel(int n_jobs, const i
     tc.ptr32 = ptr32; tc.ptr16 = nullptr;
     unsigned short *out = steps + J.step_base;
     TraceState st;
-    st.i = st.j = 0; st.vit = NO_MAT; st.n = 0; st.status = JOB_OK; st.done = false;
+    st.i = st.j = 0; st.vit = NO_MAT; st.status = JOB_OK; st.done = false;
+    emit_begin(st.em, out);
     if (lane == 0) trace_wave_begin(J, res, l_off, r_off, l_es, r_es, out, st);
     for (;;) {
         const int done = __shfl_sync(0xffffffffu, (int)st.done, 0);
@@ -348,7 +376,7 @@ __global__ void __launch_bounds__(128) traceback_wave_kernel(int n_jobs, const i
         if (lane == 0) trace_wave_walk(J, W, l_off, r_off, l_es, r_es, out, st);
         __syncwarp();
     }
-    if (lane == 0) { res->n_steps = st.n; res->status = st.status; }
+    if (lane == 0) { emit_flush(st.em); res->n_steps = st.em.n; res->pad = st.em.raw; res->status = st.status; }
 }
 
 __global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast,
@@ -465,9 +493,79 @@ void launch_traceback(int n_jobs, int n_wave, const int *job_ids, const DevJob *
                 for (int lane = 0; lane < TW; ++lane) win_load(J, tc, W, d, lane);
             trace_wave_walk(J, W, l_off, r_off, l_es, r_es, out, st);
         }
-        res->n_steps = st.n;
+        emit_flush(st.em);
+        res->n_steps = st.em.n;
+        res->pad = st.em.raw;
         res->status = st.status;
     }
+#endif
+}
+
+// ---- compaction: the encoded words of all jobs back to back, in job order ----
+// offsets = exclusive prefix sum of n_steps over the job index; three small kernels (block sums, scan of the block sums,
+// block-local scan + copy, one warp per 32 jobs).
+constexpr int CS_BLOCK = 256;
+#ifndef PG2_HOST_EMU
+__global__ void __launch_bounds__(CS_BLOCK) steps_block_sum_kernel(int n_jobs, const DevResult *results, long long *block_sum) {
+    __shared__ int warp_sum[CS_BLOCK / 32];
+    const int t = blockIdx.x * CS_BLOCK + threadIdx.x;
+    int v = t < n_jobs ? results[t].n_steps : 0;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long s = 0;
+        for (int w = 0; w < CS_BLOCK / 32; ++w) s += warp_sum[w];
+        block_sum[blockIdx.x] = s;
+    }
+}
+__global__ void steps_scan_blocks_kernel(int n_blocks, long long *block_sum, long long *total) {
+    // in place: block_sum[b] becomes the offset of block b; one thread, n_blocks is n_jobs / 256
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long run = 0;
+    for (int b = 0; b < n_blocks; ++b) { const long long v = block_sum[b]; block_sum[b] = run; run += v; }
+    *total = run;
+}
+__global__ void __launch_bounds__(CS_BLOCK) steps_compact_kernel(int n_jobs, const DevJob *jobs, const DevResult *results,
+                                                                 const long long *block_off, const unsigned short *steps_in,
+                                                                 unsigned short *steps_out) {
+    __shared__ long long s_off[CS_BLOCK];
+    __shared__ int s_n[CS_BLOCK];
+    const int t = blockIdx.x * CS_BLOCK + threadIdx.x;
+    s_n[threadIdx.x] = t < n_jobs ? results[t].n_steps : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = block_off[blockIdx.x];
+        for (int k = 0; k < CS_BLOCK; ++k) { s_off[k] = run; run += s_n[k]; }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp * 32; k < warp * 32 + 32; ++k) {
+        const int job = blockIdx.x * CS_BLOCK + k;
+        if (job >= n_jobs) break;
+        const unsigned short *src = steps_in + jobs[job].step_base;
+        unsigned short *dst = steps_out + s_off[k];
+        for (int e = lane; e < s_n[k]; e += 32) dst[e] = src[e];
+    }
+}
+#endif
+void launch_compact_steps(int n_jobs, const DevJob *jobs, const DevResult *results, long long *block_scratch, long long *total,
+                          const unsigned short *steps_in, unsigned short *steps_out, cudaStream_t stream) {
+#ifndef PG2_HOST_EMU
+    if (n_jobs <= 0) { cudaMemsetAsync(total, 0, sizeof(long long), stream); return; }
+    const int nb = (n_jobs + CS_BLOCK - 1) / CS_BLOCK;
+    steps_block_sum_kernel<<<nb, CS_BLOCK, 0, stream>>>(n_jobs, results, block_scratch);
+    steps_scan_blocks_kernel<<<1, 32, 0, stream>>>(nb, block_scratch, total);
+    steps_compact_kernel<<<nb, CS_BLOCK, 0, stream>>>(n_jobs, jobs, results, block_scratch, steps_in, steps_out);
+#else
+    (void)stream; (void)block_scratch;
+    long long run = 0;
+    for (int t = 0; t < n_jobs; ++t) {
+        const int n = results[t].n_steps;
+        memcpy(steps_out + run, steps_in + jobs[t].step_base, sizeof(unsigned short) * (size_t)n);
+        run += n;
+    }
+    *total = run;
 #endif
 }
 

@@ -3,7 +3,7 @@
 Alignments of a launch batch are independent (a guide-tree wave, node.cpp:240-264; the trial / final
 alignments of many reads, reads_aligner.cpp:983-1216), so the batch is cut by index range over the ranks,
 every rank runs its shard on its own pg2_ctx, and ONE exchange step brings the fixed-size result records
-and the packed traceback pointers to rank 0, which is where the reference's serial host step
+and the run-length encoded, compacted traceback pointers to rank 0, which is where the reference's serial host step
 (build_ancestral_sequence, basic_alignment.cpp:36-59) consumes them.  No collective runs inside an
 alignment.  The exchange is torch.distributed (NCCL over NVLink on the GPU box, straight from the device
 buffers pg2_batch_device_buffers exposes; gloo in the CPU tests).
@@ -12,7 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-RECORD_BYTES = 24  # pg2_device.cuh DevResult {double score; uint32 end_ptr; int32 n_steps; int32 status; int32 pad}
+RECORD_BYTES = 24  # pg2_device.cuh DevResult {double score; uint32 end_ptr; int32 n_steps; int32 status; int32 pad = raw step count}
 RECORD_DTYPE = np.dtype([("score", "<f8"), ("end_ptr", "<u4"), ("n_steps", "<i4"), ("status", "<i4"), ("pad", "<i4")])
 assert RECORD_DTYPE.itemsize == RECORD_BYTES
 
@@ -93,9 +93,10 @@ def assemble(parts, shards, jobs):
         rec = rec.cpu().numpy().view(RECORD_DTYPE)
         st = st.cpu().numpy().view(np.uint16)
         assert rec.shape[0] == len(idx)
-        caps = np.array([step_capacity(jobs[i]) for i in idx], dtype=np.int64)
-        offs = np.concatenate([[0], np.cumsum(caps)[:-1]]) if len(idx) else np.zeros(0, np.int64)
-        assert st.shape[0] == int(caps.sum())
+        # the shard's path words lie back to back in shard-job order (the engine compacts them on the device)
+        words = rec["n_steps"].astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(words)[:-1]]) if len(idx) else np.zeros(0, np.int64)
+        assert st.shape[0] == int(words.sum())
         records[idx] = rec
         step_off[idx] = base + offs
         bufs.append(st)

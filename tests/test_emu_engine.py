@@ -232,3 +232,16 @@ def test_compact_chain_form(emu_lib, golden):
         res = (abi.Result * 1)()
         stp = np.zeros(4096, np.uint16)
         assert eng.lib.pg2_align_batch(eng.ctx, 1, arr, res, stp.ctypes.data, 4096) == abi.PG2_ERR_INVALID
+
+
+def test_path_runs_longer_than_one_repeat_word(emu_lib):
+    """A 40 000-site target against a 5-nt read: the walk holds one gap run longer than the 32 767 a repeat word can
+    carry; the encoded path is a few words and expands to the oracle's path."""
+    rng = np.random.default_rng(404)
+    model = randjobs.random_model(rng, 4)
+    left = abi.FlatGraph.chain(rng.integers(0, 4, size=40000).astype(np.int32))
+    right = abi.FlatGraph.chain(rng.integers(0, 4, size=5).astype(np.int32))
+    job = enginecheck.expect_from_oracle(abi.FlatJob(left, right, model, 2))
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, [job])
+        assert res["n_steps"][0] < 64 and len(job.expected_path) > 39000
