@@ -1148,7 +1148,6 @@ static int fetch_enqueue(pg2_ctx *c, pg2_batch *b, int64_t step_cap) {
     long long *ht = c->h_step_total.extend(1);
     if (!hr || !ht) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
     *ht = 0;
-    CU(cudaEventRecord(c->ev[5], c->stream));
     if (b->n_jobs > 0) {
         CU(cudaMemcpyAsync(hr, c->d_results.p, sizeof(DevResult) * b->n_jobs, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(ht, c->d_step_scan.p + (b->jobs.size() / 256 + 2), sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
@@ -1164,6 +1163,7 @@ static int fetch_complete(pg2_ctx *c, pg2_batch *b, pg2_result *results, uint16_
     const DevResult *hr = c->h_results.p;
     const long long total = b->n_jobs > 0 ? c->h_step_total.p[0] : 0;
     if (total < 0 || total > b->total_steps) return fail(PG2_ERR_CUDA, "path compaction returned an impossible word count");
+    CU(cudaEventRecord(c->ev[5], c->stream));  // d2h_ms: the copy of the path words
     if (total > 0) CU(cudaMemcpyAsync(steps, c->d_steps_compact.p, sizeof(unsigned short) * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev[6], c->stream));
     CU(cudaStreamSynchronize(c->stream));
