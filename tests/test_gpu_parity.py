@@ -243,3 +243,39 @@ def test_compact_chain_form_on_device(eng, golden):
         if rb["status"][k] == 0:
             st, _, _ = eng.expand(job, rb[k], sb, compact=True)
             assert oracle_lib.steps_equal(st, job.expected_path, job.expected_path_score) == []
+
+
+def test_pipelined_call_equals_resident_batch_at_scale(eng, golden):
+    """12 000 reads against 8 targets: pg2_align_batch takes its chunked, multi-context path by itself (>= 8192 jobs);
+    every score, status and encoded path must equal what one resident batch (pg2_batch_create / run / fetch) gives, and
+    a sample must equal the oracle."""
+    model = golden["place_dna"][0].model
+    rng = np.random.default_rng(4242)
+    targets = [synth.leaf_graph(synth.random_dna(1500, rng)) for _ in range(8)]
+    tseqs = [t.state[1:-1] for t in targets]
+    reads, assign = [], []
+    for k in range(12000):
+        a = int(rng.integers(0, 8))
+        st = int(rng.integers(0, 1350))
+        r = tseqs[a][st:st + 150].copy()
+        mut = rng.random(150) < 0.03
+        r[mut] = rng.integers(0, 4, size=int(mut.sum()))
+        reads.append(r)
+        assign.append(a)
+    jobs = synth.placement_jobs(targets, reads, assign, model)
+    with eng.batch(jobs) as b:
+        b.run()
+        ra, sa = b.fetch()
+    rb, sb = eng.align_prepared(eng.prepare(jobs, pinned=True, compact=True))
+    rc, sc = eng.align(jobs)  # pageable buffers, explicit graphs
+    for res, stp in ((rb, sb), (rc, sc)):
+        assert (res["score"].view(np.uint64) == ra["score"].view(np.uint64)).all()
+        assert (res["status"] == ra["status"]).all() and (res["n_steps"] == ra["n_steps"]).all()
+        for k in range(0, len(jobs), 97):
+            x = stp[res["step_off"][k]: res["step_off"][k] + res["n_steps"][k]]
+            y = sa[ra["step_off"][k]: ra["step_off"][k] + ra["n_steps"][k]]
+            assert x.tobytes() == y.tobytes()
+    for k in range(0, len(jobs), 1500):
+        job = enginecheck.expect_from_oracle(jobs[k])
+        st, _, _ = eng.expand(job, rb[k], sb, compact=True)
+        assert oracle_lib.steps_equal(st, job.expected_path, job.expected_path_score) == []
