@@ -377,13 +377,23 @@ def main():
     barrier()
     e2e_t = []
     h2d = d2h = 0
+    e2e_res = None
     for _ in range(args.steps):
         t1 = time.perf_counter()
-        eng.align_prepared(prep)
+        e2e_res, e2e_steps = eng.align_prepared(prep)
         e2e_t.append(time.perf_counter() - t1)
         st = eng.stats()
         h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
     barrier()
+    # outside the clock: the host -> host call must return what the resident batch returned, bit for bit
+    e2e_same = bool((e2e_res["score"].view(np.uint64) == results["score"].view(np.uint64)).all()
+                    and (e2e_res["status"] == results["status"]).all() and (e2e_res["n_steps"] == results["n_steps"]).all())
+    for k in range(0, len(jobs), max(1, len(jobs) // 64)):
+        a = e2e_steps[e2e_res["step_off"][k]: e2e_res["step_off"][k] + e2e_res["n_steps"][k]]
+        b = steps_buf[results["step_off"][k]: results["step_off"][k] + results["n_steps"][k]]
+        e2e_same = e2e_same and a.tobytes() == b.tobytes()
+    if not e2e_same:
+        raise SystemExit("bench: pg2_align_batch (e2e) and the resident batch disagree")
 
     print("rank %d: e2e %.1f ms/step, device %.1f ms/step, %d near cores" % (
         rank, sum(e2e_t) / args.steps * 1e3, dev_ms / args.steps, len(near_cores)), file=sys.stderr, flush=True)
@@ -426,7 +436,8 @@ def main():
                        "host": "%d cores, %d packing threads per rank, rank bound to the %d cores next to its GPU" % (
                            n_cores_box, int(os.environ["PG2_PACK_THREADS"]), len(near_cores))},
             "e2e": {"value": total_cells / (ms_e2e * 1e-3) * 1e-9, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                    "results_equal_resident_batch": e2e_same},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
