@@ -90,7 +90,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tag", default="r1")
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--only", default="")
+    ap.add_argument("--only", default="C1", help="substring of the runs to do; '' = all (C2 tests every node for every read and "
+                    "C3 / C5 take minutes of host time in the reference program: budget accordingly)")
     args = ap.parse_args()
     rows = []
     for name, fn, seed in scenarios(args.full):
