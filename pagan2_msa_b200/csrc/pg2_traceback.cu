@@ -251,7 +251,7 @@ __device__ void traceback_one(int jid, const DevJob *jobs, const DevGraph *graph
 // ---- wavefront-layout jobs: one warp per path, the pointer words around the walk fetched a window at a time ----
 // The walk is a chain of dependent loads; with one thread per path every step costs two L2/HBM round trips (band
 // geometry, then the pointer word) -- 0.5 s for the 400 000 steps of a 200 kb anchored alignment.  Here the warp
-// loads the words of diagonals s0-63..s0, rows i0-31..i0 (64 coalesced loads, 16 in flight at once) into shared memory
+// loads the words of diagonals s0-63..s0, rows i0-31..i0 (64 coalesced loads, all in flight at once) into shared memory
 // and lane 0 walks inside the window: at least 16 steps per round trip.
 constexpr int TW = 32;   // rows per window (one per lane)
 constexpr int TWD = 64;  // diagonals per window: a run of 32 match steps goes up 32 rows and 64 diagonals
@@ -370,8 +370,20 @@ __global__ void __launch_bounds__(128) traceback_wave_kernel(int n_jobs, const i
         win_geometry(J, tc, W, lane);
         win_geometry(J, tc, W, lane + 32);
         __syncwarp();
-#pragma unroll 16
-        for (int d = 0; d < TWD; ++d) win_load(J, tc, W, d, lane);
+        {
+            // all 64 loads of the lane in flight at once: addresses first, then the loads, then the stores
+            const unsigned *src[TWD];
+#pragma unroll
+            for (int d = 0; d < TWD; ++d) {
+                const int i = W.i0 - lane;
+                src[d] = (i >= W.lo[d] && i <= W.hi[d]) ? tc.ptr32 + J.cell_base + W.base[d] + (i - W.lo[d]) : nullptr;
+            }
+            unsigned v[TWD];
+#pragma unroll
+            for (int d = 0; d < TWD; ++d) v[d] = src[d] ? __ldg(src[d]) : 0u;
+#pragma unroll
+            for (int d = 0; d < TWD; ++d) W.w[d * TW + lane] = v[d];
+        }
         __syncwarp();
         if (lane == 0) trace_wave_walk(J, W, l_off, r_off, l_es, r_es, out, st);
         __syncwarp();

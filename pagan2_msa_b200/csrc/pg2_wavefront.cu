@@ -435,28 +435,26 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
 
     const int n_diag = c.lx + c.ly - 1;
     if (ring_cap > 0 && GL.simple && GR.simple && ring_cap <= (int)blockDim.x) {
-        // chain x chain: per-thread site tracking, band geometry fetched one diagonal ahead
+        // chain x chain: per-thread site tracking; the band geometry of 32 diagonals is fetched by the 32 lanes of a
+        // warp in one round trip and handed out by shuffles, so no global load sits between two diagonals
         c.chain_job = true;
         ChainTrack track;
         track.i = track.j = -2;
-        int ilo, ihi, ilo_n = 0, ihi_n = 0;
-        long long base, base_n = 0;
-        diag_geometry(c, 1, ilo, ihi, base);
-        for (int s = 1; s < n_diag; ++s) {
-            if (s + 1 < n_diag) {
-                // lands while this diagonal computes.  The index is hidden from the compiler's uniformity analysis:
-                // it would otherwise move the loaded values to uniform registers at once (R2UR) and wait for them here.
-                int sn = s + 1;
-#ifndef PG2_HOST_EMU
-                asm volatile("" : "+r"(sn));
-#endif
-                diag_geometry(c, sn, ilo_n, ihi_n, base_n);
+        const int lane = (int)threadIdx.x & 31;
+        for (int s0 = 1; s0 < n_diag; s0 += 32) {
+            int g_lo, g_hi;
+            long long g_base;
+            diag_geometry(c, min(s0 + lane, n_diag - 1), g_lo, g_hi, g_base);
+            const int nd = min(32, n_diag - s0);
+            for (int d = 0; d < nd; ++d) {
+                const int s = s0 + d;
+                const int ilo = __shfl_sync(0xffffffffu, g_lo, d), ihi = __shfl_sync(0xffffffffu, g_hi, d);
+                const long long base = __shfl_sync(0xffffffffu, g_base, d);
+                wave_ring_begin(c, s, ilo);
+                wave_chain_cell(c, m, flags, lng2, s, ilo, ihi, base, P, (int)threadIdx.x, track);
+                __syncthreads();
+                wave_ring_end(c, ilo, ihi);
             }
-            wave_ring_begin(c, s, ilo);
-            wave_chain_cell(c, m, flags, lng2, s, ilo, ihi, base, P, (int)threadIdx.x, track);
-            __syncthreads();
-            wave_ring_end(c, ilo, ihi);
-            ilo = ilo_n; ihi = ihi_n; base = base_n;
         }
     } else
     for (int s = 1; s < n_diag; ++s) {
