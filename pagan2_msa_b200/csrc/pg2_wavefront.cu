@@ -26,7 +26,7 @@ struct WaveRing {
     double *buf;         // nullptr: the diagonals of this job do not fit; every read goes to the global scratch
     int cap;             // cells per diagonal the ring holds
     int s;               // diagonal being computed; cells on s-1 and s-2 are served from the ring
-    int slot0, slot1, slot2;
+    int off0, off1, off2;  // offsets (in doubles) of the ring slots of diagonals s, s-1, s-2; they rotate, nothing is recomputed
     int lo0, lo1, hi1, lo2, hi2;  // first row of diagonal s; row ranges of diagonals s-1 and s-2
     bool global_scores;  // false: both graphs are plain chains, the global scratch is never read
 };
@@ -69,7 +69,7 @@ __device__ __forceinline__ double4 load_cell(const WaveCtx &c, int p, int q) {
                 double ninf = neg_inf();
                 return make_double4(ninf, ninf, ninf, 0.0);
             }
-            const double *b = c.ring.buf + (ds == 1 ? c.ring.slot1 : c.ring.slot2) * 3 * c.ring.cap + (p - lo);
+            const double *b = c.ring.buf + (ds == 1 ? c.ring.off1 : c.ring.off2) + (p - lo);
             return make_double4(b[0], b[c.ring.cap], b[2 * c.ring.cap], 0.0);
         }
     }
@@ -219,17 +219,20 @@ __device__ __forceinline__ void wave_use_ring(WaveCtx &c, double *buf, int cap, 
     c.ring.global_scores = !(GL.simple && GR.simple);
     c.ring.lo1 = 0; c.ring.hi1 = 0;   // diagonal 0 is the start corner
     c.ring.lo2 = 0; c.ring.hi2 = -1;  // there is no diagonal -1
+    // the first diagonal computed is s = 1: it goes to slot 1, diagonal 0 sits in slot 0, slot 2 is free
+    c.ring.off0 = 3 * cap; c.ring.off1 = 0; c.ring.off2 = 6 * cap;
 }
 __device__ __forceinline__ void wave_ring_begin(WaveCtx &c, int s, int ilo) {
     c.ring.s = s;
-    c.ring.slot0 = s % 3;
-    c.ring.slot1 = (s + 2) % 3;
-    c.ring.slot2 = (s + 1) % 3;
     c.ring.lo0 = ilo;
 }
 __device__ __forceinline__ void wave_ring_end(WaveCtx &c, int ilo, int ihi) {
     c.ring.lo2 = c.ring.lo1; c.ring.hi2 = c.ring.hi1;
     c.ring.lo1 = ilo; c.ring.hi1 = ihi;
+    const int freed = c.ring.off2;  // the slot of diagonal s-2 takes diagonal s+1
+    c.ring.off2 = c.ring.off1;
+    c.ring.off1 = c.ring.off0;
+    c.ring.off0 = freed;
 }
 
 // initialise_array_corner (:725-733)
@@ -271,7 +274,7 @@ __device__ __forceinline__ void wave_cell(const WaveCtx &c, const DevModel &m, u
         match_pairs(c, c.l_off[i], c.l_off[i + 1], c.r_off[j], c.r_off[j + 1], m_log, x_log, x_log, false, sm, pm);
     }
     if (c.ring.buf) {
-        double *b = c.ring.buf + c.ring.slot0 * 3 * c.ring.cap + (i - c.ring.lo0);
+        double *b = c.ring.buf + c.ring.off0 + (i - c.ring.lo0);
         b[0] = sx; b[c.ring.cap] = sy; b[2 * c.ring.cap] = sm;
     }
     if (c.ring.global_scores) {
@@ -291,7 +294,7 @@ __device__ __forceinline__ void wave_cell(const WaveCtx &c, const DevModel &m, u
 __device__ __forceinline__ void ring_near(const WaveCtx &c, int ds, int p, double &x, double &y, double &m) {
     const int lo = ds == 1 ? c.ring.lo1 : c.ring.lo2, hi = ds == 1 ? c.ring.hi1 : c.ring.hi2;
     if (p < lo || p > hi) { x = y = m = neg_inf(); return; }
-    const double *b = c.ring.buf + (ds == 1 ? c.ring.slot1 : c.ring.slot2) * 3 * c.ring.cap + (p - lo);
+    const double *b = c.ring.buf + (ds == 1 ? c.ring.off1 : c.ring.off2) + (p - lo);
     x = b[0]; y = b[c.ring.cap]; m = b[2 * c.ring.cap];
 }
 
@@ -339,7 +342,7 @@ __device__ __forceinline__ void wave_cell_plain_core(const WaveCtx &c, const Dev
     if (s > sm) { sm = s; pm = X_MAT; }
     s = __dadd_rn(__dadd_rn(__dadd_rn(dy, x_log), wl), wr);
     if (s > sm) { sm = s; pm = Y_MAT; }
-    double *b = c.ring.buf + c.ring.slot0 * 3 * c.ring.cap + (i - c.ring.lo0);
+    double *b = c.ring.buf + c.ring.off0 + (i - c.ring.lo0);
     b[0] = sx; b[c.ring.cap] = sy; b[2 * c.ring.cap] = sm;
     if (c.ring.global_scores) {
         double2 *dst = reinterpret_cast<double2 *>(c.scores + idx);
