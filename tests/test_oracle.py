@@ -41,6 +41,24 @@ def test_oracle_matches_live_reference_on_random_jobs(kind):
         check_job(job)
 
 
+@pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("shape", ["banded_chain", "shared_target"])
+def test_oracle_matches_live_reference_on_more_shapes(shape):
+    """Further pins of the restatement against the reference library run live: plain chains inside a band (the anchored
+    leaf x leaf shape), reads against one shared ancestor-shaped target (the placement shape) and parameter sets made of a few repeated values (ties everywhere: the first-wins order is what is being checked)."""
+    rng = np.random.default_rng({"banded_chain": 31, "shared_target": 33}[shape])
+    jobs = []
+    if shape == "banded_chain":
+        jobs = [randjobs.random_job(rng, "banded_chain") for _ in range(30)]
+    else:
+        for _ in range(3):
+            jobs += randjobs.random_shared_target_jobs(rng, 12)
+    for job in jobs:
+        score, path, pscore = oracle_lib.ref_align_flat(job)
+        job.expected_score, job.expected_path, job.expected_path_score = score, path, pscore
+        check_job(job)
+
+
 def test_oracle_rejects_bad_band():
     rng = np.random.default_rng(5)
     job = randjobs.random_job(rng, "banded")
