@@ -107,10 +107,12 @@ typedef struct pg2_job {
 /* Result header of one job.  The traceback itself is returned compactly: packed back-pointers (the encoding below
  * needs 14 bits) in WALK order (end corner first: the end pointer, then the pointer of every visited cell), run-length
  * encoded in uint16 words at steps[step_off .. step_off+n_steps): a word with bit 15 clear is a pointer, a word with
- * bit 15 set repeats the previous pointer (word & 0x7fff) more times.  The words of all jobs of a call lie back to back
- * in job order (step_off is the running sum of n_steps), at the start of the caller's step buffer; the buffer itself
- * must still hold left.n_sites + right.n_sites words per job (pg2_batch_step_capacity), the bound of an incompressible
- * walk.  pg2_expand_path() turns the words into the reference's vector<Path_pointer>. */
+ * bit 15 set repeats the previous pointer (word & 0x7fff) more times.  step_off is AUTHORITATIVE: the words of the jobs
+ * of a call lie compacted in the caller's step buffer, but in an order the engine chooses (pg2_batch_fetch: job order;
+ * pg2_align_batch on large batches: chunk by chunk, jobs grouped by left graph).  The buffer itself must still hold
+ * left.n_sites + right.n_sites words per job (pg2_batch_step_capacity), the bound of an incompressible walk; on
+ * PG2_ERR_CAPACITY nothing ran and that sum is what the caller must provide (pg2_batch_fetch also writes each job's
+ * bound into results[].n_steps).  pg2_expand_path() turns the words into the reference's vector<Path_pointer>. */
 typedef struct pg2_result {
     double score;              /* Viterbi log-score == max_end.score (viterbi_alignment.cpp:1558-1566) */
     int64_t cells;             /* in-band DP cells filled */
@@ -118,8 +120,9 @@ typedef struct pg2_result {
     int32_t n_steps;           /* number of encoded uint16 words of this job's walk */
     int32_t status;            /* PG2_JOB_* */
     uint32_t end_ptr;          /* packed end-corner pointer (same encoding as steps[]) */
-    int32_t kernel;            /* which fill kernel ran: 0 = wavefront (general), 1 = strip (warp per alignment),
-                                  2 = lanes (lane per alignment, jobs sharing the left graph) */
+    int32_t kernel;            /* which fill kernel ran: 0 = wavefront (general fallback), 1 = strip (warp per alignment),
+                                  2 = lanes (lane per alignment, jobs sharing the left graph), 3 = pipelined strips (CTA per
+                                  alignment, general graphs on both sides, anchor bands) */
 } pg2_result;
 
 /* Packed back-pointer: bits 0-1 source matrix (PG2_*_MAT, 3 = none), bits 2-7 ordinal of the LEFT
@@ -205,7 +208,7 @@ typedef struct pg2_stats {
     int32_t kernel_launches;   /* kernels launched by the last pg2_batch_run */
     int32_t jobs_strip_groups;
     int32_t jobs_lanes;        /* jobs the lane-per-alignment kernel took (shared row graph) */
-    int32_t reserved;
+    int32_t jobs_pstrip;       /* jobs the pipelined-strip kernel took (CTA per alignment: general x general, banded, small waves) */
 } pg2_stats;
 int pg2_get_stats(pg2_ctx *ctx, pg2_stats *out);
 

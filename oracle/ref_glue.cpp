@@ -154,6 +154,15 @@ void flatten(Sequence *s, Flat_graph *g) {
     g->off[n] = (int)g->start.size();
 }
 
+// indices of the edges whose is_used() flag is set (the marks backtrack_new_path leaves, viterbi_alignment.cpp:1054-1155)
+void used_edges(Sequence *s, vector<int> *out) {
+    out->clear();
+    vector<Edge> *edges = s->get_edges();
+    for (size_t e = 0; e < edges->size(); e++)
+        if (edges->at(e).is_used()) out->push_back((int)e);
+}
+vector<int> g_flat_used[2];  // used edges of the last pagan2_ref_align_flat call (left, right)
+
 uint64_t fnv1a(const void *p, size_t n) {
     const unsigned char *b = (const unsigned char *)p;
     uint64_t h = 1469598103934665603ull;
@@ -217,8 +226,9 @@ extern "C" void CAT(__wrap_, ALIGN_SYM)(Viterbi_alignment *self, Sequence *left,
     // inputs must be captured before the call: align() marks child edges and the caller may
     // later edit the graphs.
     Flat_graph L, R;
+    vector<int> l_used_before, r_used_before;
     bool dumping = g_dump != 0;
-    if (dumping) { flatten(left, &L); flatten(right, &R); }
+    if (dumping) { flatten(left, &L); flatten(right, &R); used_edges(left, &l_used_before); used_edges(right, &r_used_before); }
 
     g_build_seconds = 0;
     double t0 = now_seconds();
@@ -289,6 +299,14 @@ extern "C" void CAT(__wrap_, ALIGN_SYM)(Viterbi_alignment *self, Sequence *left,
         f.push_back({"score", 2, 1, &score});
         f.push_back({"path", 0, (uint64_t)p.size(), p.data()});
         f.push_back({"path_score", 2, (uint64_t)ps.size(), ps.data()});
+        // edge marks: what was set before the call and what is set after it (the call only ever sets marks)
+        vector<int> l_used_after, r_used_after;
+        used_edges(left, &l_used_after);
+        used_edges(right, &r_used_after);
+        f.push_back({"l_used_before", 0, (uint64_t)l_used_before.size(), l_used_before.data()});
+        f.push_back({"l_used_after", 0, (uint64_t)l_used_after.size(), l_used_after.data()});
+        f.push_back({"r_used_before", 0, (uint64_t)r_used_before.size(), r_used_before.data()});
+        f.push_back({"r_used_after", 0, (uint64_t)r_used_after.size(), r_used_after.data()});
         f.push_back({"time", 2, 2, times});
         write_record(f);
     }
@@ -413,8 +431,18 @@ extern "C" int pagan2_ref_align_flat(int fas, const float *table, const float *s
         if (!p.empty()) memcpy(path_out, p.data(), p.size() * sizeof(int));
         if (!ps.empty()) memcpy(path_score_out, ps.data(), ps.size() * sizeof(double));
     }
+    used_edges(L, &g_flat_used[0]);
+    used_edges(R, &g_flat_used[1]);
     delete va.ancestral_sequence;
     delete L;
     delete R;
     return rc;
+}
+
+// Edge indices marked is_used(true) by the last pagan2_ref_align_flat call (side 0 = left, 1 = right), ascending.
+// Returns the count (the first `cap` are written).
+extern "C" int pagan2_ref_last_used(int side, int *out, int cap) {
+    const vector<int> &v = g_flat_used[side ? 1 : 0];
+    for (int k = 0; k < (int)v.size() && k < cap; k++) out[k] = v[k];
+    return (int)v.size();
 }

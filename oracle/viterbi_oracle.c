@@ -7,7 +7,7 @@
  *
  * Parity pin: the reference ships no tests or golden vectors, so this file is
  * pinned against the reference ITSELF: oracle/_ref (the unmodified reference sources compiled here,
- * oracle/Makefile) dumps every job it runs; tests/test_oracle_vs_ref.py demands bit-identical scores
+ * oracle/Makefile) dumps every job it runs; tests/test_oracle.py demands bit-identical scores
  * and paths on those dumps, and tests/golden/ holds committed dumps for boxes without /root/reference.
  *
  * Every function cites the reference lines it restates (paths relative to /root/reference/src).
@@ -238,11 +238,28 @@ static int preexisting_gap(stack_t *s, int *i, int *j, int x_ind, int y_ind) {
     return 0;
 }
 
-/* backtrack_new_path (main/viterbi_alignment.cpp:1038-1189).  Edge marks are replayed by the caller
- * from the emitted steps; returns PG2_JOB_* status. */
-static int backtrack(dp_t *d, const cell_t *fp, stack_t *st) {
+/* is_used(true) marks in the order backtrack_new_path sets them (:1054-1057, 1079-1101, 1128, 1155) */
+typedef struct {
+    int32_t *l, *r;
+    int nl, nr, cap;
+} marks_t;
+static void mark(int32_t *v, int *n, int cap, int e) {
+    if (v && e >= 0 && *n < cap) v[(*n)++] = e;
+}
+/* Sequence::get_fwd_edge_index_at_site(from, Edge(from, stop)): the edge from `from` into the stop site, or -1 */
+static int terminal_fwd_edge(const pg2_graph *g, int from, int stop_site) {
+    for (int k = g->bwd_off[stop_site]; k < g->bwd_off[stop_site + 1]; k++)
+        if (g->edge_start[k] == from) return g->edge_index[k];
+    return -1;
+}
+
+/* backtrack_new_path (main/viterbi_alignment.cpp:1038-1189); returns PG2_JOB_* status. */
+static int backtrack(dp_t *d, const cell_t *fp, stack_t *st, marks_t *mk) {
     int vit = fp->matrix, x_ind = fp->x_ind, y_ind = fp->y_ind;
     int j = d->ly - 1, i = d->lx - 1;
+    int first_x = 1, first_y = 1;
+    mark(mk->l, &mk->nl, mk->cap, fp->x_edge_ind); /* :1054-1057 */
+    mark(mk->r, &mk->nr, mk->cap, fp->y_edge_ind);
     if (preexisting_gap(st, &i, &j, x_ind, y_ind)) return -1;
     if (i > 0 || j > 0)
         if (push(st, fp, 1)) return -1;
@@ -254,6 +271,16 @@ static int backtrack(dp_t *d, const cell_t *fp, stack_t *st) {
             else if (vit == PG2_Y_MAT) { c = rd(d, d->Y, i, j); }
             else return PG2_JOB_BROKEN_PATH;
             int was = vit;
+            if ((was == PG2_M_MAT || was == PG2_X_MAT) && first_x) { /* :1079-1086, :1118-1125 */
+                mark(mk->l, &mk->nl, mk->cap, terminal_fwd_edge(d->L, x_ind, d->lx));
+                first_x = 0;
+            }
+            if ((was == PG2_M_MAT || was == PG2_Y_MAT) && first_y) { /* :1087-1094, :1145-1152 */
+                mark(mk->r, &mk->nr, mk->cap, terminal_fwd_edge(d->R, y_ind, d->ly));
+                first_y = 0;
+            }
+            if (was == PG2_M_MAT || was == PG2_X_MAT) mark(mk->l, &mk->nl, mk->cap, c->x_edge_ind); /* :1100, :1128 */
+            if (was == PG2_M_MAT || was == PG2_Y_MAT) mark(mk->r, &mk->nr, mk->cap, c->y_edge_ind); /* :1101, :1155 */
             vit = c->matrix; x_ind = c->x_ind; y_ind = c->y_ind;
             if (was == PG2_M_MAT) { i--; j--; }
             else if (was == PG2_X_MAT) i--;
@@ -283,9 +310,22 @@ static int band_ok(const int32_t *up, const int32_t *lo, int lx) {
  * order: 0 = reference's unbanded loop order (j outer, :275-281), 1 = row-major (banded order, :262-271);
  * results do not depend on it (every dependency precedes in both).
  */
+int pg2o_align_marks(const pg2_job *job, const pg2_model_desc *model, double *score, pg2_step *out_steps,
+                     int32_t step_cap, int32_t *n_steps, int64_t *cells_out, int32_t *used_left, int32_t *n_used_left,
+                     int32_t *used_right, int32_t *n_used_right);
 int pg2o_align(const pg2_job *job, const pg2_model_desc *model, double *score, pg2_step *out_steps,
                int32_t step_cap, int32_t *n_steps, int64_t *cells_out) {
+    return pg2o_align_marks(job, model, score, out_steps, step_cap, n_steps, cells_out, 0, 0, 0, 0);
+}
+
+/* The same, also returning the edge indices marked is_used(true), in marking order (capacity step_cap each). */
+int pg2o_align_marks(const pg2_job *job, const pg2_model_desc *model, double *score, pg2_step *out_steps,
+                     int32_t step_cap, int32_t *n_steps, int64_t *cells_out, int32_t *used_left, int32_t *n_used_left,
+                     int32_t *used_right, int32_t *n_used_right) {
     dp_t d;
+    marks_t mk = {used_left, used_right, 0, 0, step_cap};
+    if (n_used_left) *n_used_left = 0;
+    if (n_used_right) *n_used_right = 0;
     memset(&d, 0, sizeof d);
     d.L = &job->left;
     d.R = &job->right;
@@ -337,8 +377,10 @@ int pg2o_align(const pg2_job *job, const pg2_model_desc *model, double *score, p
         if (max_end.score == -HUGE_VAL) rc = PG2_JOB_NO_PATH;
         else {
             stack_t st = {out_steps, 0, step_cap};
-            rc = backtrack(&d, &max_end, &st);
+            rc = backtrack(&d, &max_end, &st, &mk);
             if (rc == PG2_JOB_OK) {
+                if (n_used_left) *n_used_left = mk.nl;
+                if (n_used_right) *n_used_right = mk.nr;
                 /* stack -> forward order (:1183-1187) */
                 for (int a = 0, b = st.n - 1; a < b; a++, b--) {
                     pg2_step t = out_steps[a];

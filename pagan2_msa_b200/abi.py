@@ -112,7 +112,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int32),
         ("jobs_strip_groups", C.c_int32),
         ("jobs_lanes", C.c_int32),
-        ("reserved", C.c_int32),
+        ("jobs_pstrip", C.c_int32),
     ]
 
 

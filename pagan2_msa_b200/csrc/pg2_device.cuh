@@ -47,6 +47,13 @@ struct DevGraph {
     int np_base;     // into d_vlast: sorted list of the DP sites that are NOT plain (site 0, and every site whose backward
     int n_np;        //   edges are not exactly one edge from the site before it); -1 until a wavefront job uses the graph
     int npmask_base; // into d_vlast: bit s & 31 of word s >> 5 set when DP site s is plain
+    // column program of a graph used as the COLUMN graph of the pipelined-strip kernel (pg2_pstrip_geom.cuh); -1 until built
+    int cp_ci_base;  // into d_vlast: one info word per DP column (general / parked / end column, slots, block index)
+    int cp_ei_base;  // into d_vlast: per backward edge (CSR order), the history slot of its source column
+    int cp_blk_base; // into d_vlast: column range [c0, c1) of every block, 2 ints per block
+    int cp_n_blocks;
+    int cp_k;        // columns per lane the program was cut for (0: the graph cannot be a pstrip column graph)
+    int cp_park;     // parked columns of the block that has most of them (sizes the kernel's shared-memory history)
 };
 
 struct DevModel {
@@ -61,7 +68,7 @@ struct DevJob {
     int model;           // index into the DevModel array
     unsigned flags;
     int banded;
-    short kernel;        // 0 wavefront, 1 strip, 2 lanes
+    short kernel;        // 0 wavefront, 1 strip, 2 lanes, 3 pipelined strips
     short strip_general; // strip kernel: 1 = left graph needs the general row body, 0 = plain unit-weight chain
     long long band_base; // into d_blo / d_bhi (lx entries)
     long long diag_base; // into d_dlo / d_doff (lx+ly-1 entries)
@@ -74,7 +81,9 @@ struct DevJob {
     int lane;            // lane kernel: the job's lane in its task (cell_base = the task's pointer region)
     int task;            // lane kernel: task index
     int max_diag;        // banded jobs: cells on the longest in-band anti-diagonal
-    int pad;
+    int n_blocks;        // pipelined-strip kernel: column blocks of the job
+    int blk_base;        // pipelined-strip kernel: into d_vlast, PB_INTS ints per block
+    int ps_ring;         // pipelined-strip kernel: virtual rows of the job's tallest block
 };
 
 // Lane kernel work item: up to 32 alignments that share the LEFT (row) graph, model and flags; every right

@@ -21,8 +21,15 @@
 #include "../../include/pagan2_b200.h"
 #include "pg2_device.cuh"
 #include "pg2_strip_geom.cuh"
+#include "pg2_pstrip_geom.cuh"
 
 namespace pg2 {
+int pstrip_warps(int n_blocks, int park_cap, bool smalltab);
+long long pstrip_cta_double4(int K, int nw, int max_lx, int ring, int max_slots);
+void launch_pstrip_fill(int K, bool smalltab, int nw, int n_jobs, int n_ctas, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
+                        const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
+                        const int4 *d_vrow, const int *d_vlast, const int *d_blo, const int *d_bhi, unsigned *ptrs, DevResult *results,
+                        double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int *queue, cudaStream_t stream);
 void launch_expand_implicit(int n_graphs, const DevGraph *graphs, int *d_off, int *d_estart, float *d_elogw, cudaStream_t stream);
 void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
                      const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
@@ -44,9 +51,10 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
                       int max_lx, int max_slots, int *queue, int n_ctas, cudaStream_t stream);
 int lane_ctas_per_sm();
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
-void launch_traceback(int n_jobs, int n_wave, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
+void launch_traceback(int n_jobs, int n_wave, int n_ps, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
-                      const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps, DevResult *results, cudaStream_t stream);
+                      const unsigned *ptr32, const unsigned short *ptr16, const unsigned *ptrps, unsigned short *steps, DevResult *results,
+                      cudaStream_t stream);
 }  // namespace pg2
 
 using namespace pg2;
@@ -130,6 +138,8 @@ struct Group {
     int max_diag;
     int max_slots, max_lx;  // strip kernel per-warp scratch: saved rows, boundary column
     int max_nv = 1;         // lane kernel: longest row program
+    int ps_ring = 1, ps_nw = 1;  // pipelined-strip kernel: boundary ring (virtual rows, power of two), warps per CTA
+    int ps_park = 1, ps_blocks = 1;  // ... history slots per block, most blocks of a job
     int phase = 0;          // groups of one phase keep their pointer buffers side by side and share one traceback launch
     long long ptr_off = 0;  // offset of the group's region in its pointer buffer (d_ptr16 or d_ptr32 / d_scores)
 };
@@ -161,6 +171,9 @@ struct pg2_ctx {
     size_t scratch_bytes = (size_t)64 << 30;  // pointer/score scratch per launch group (PG2_SCRATCH_MB overrides)
     bool force_wavefront = false;  // PG2_FORCE_WAVEFRONT=1: route every job through the general kernel (tests)
     bool no_lanes = false;         // PG2_NO_LANES=1: keep shared-target jobs on the warp-per-alignment strip kernel (tests)
+    bool no_pstrip = false;        // PG2_NO_PSTRIP=1: never use the pipelined-strip kernel (tests: the older kernels stay covered)
+    int pstrip_max_jobs = 600;     // strip-eligible jobs of a batch go to the pipelined-strip kernel when there are at most this
+                                   // many of them (a warp per alignment cannot fill the chip; PG2_PSTRIP_MAX_JOBS)
     size_t lane_scratch_bytes = (size_t)8 << 30;  // cap of the lane kernel's per-CTA wrap / end-column / parked-row scratch
     // staging (pinned) and device arrays of the current batch
     PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_vrow, h_vlast;
@@ -178,12 +191,15 @@ struct pg2_ctx {
     DevBuf<DevResult> d_results;
     DevBuf<double4> d_scores;
     DevBuf<unsigned> d_ptr32;
+    DevBuf<unsigned> d_ptrps;      // pipelined-strip kernel: one 32-bit pointer word per cell of its block layout
+    DevBuf<double4> d_ps_scratch;  // pipelined-strip kernel: per CTA end columns, boundary rings, parked rows
     DevBuf<unsigned short> d_steps;          // per job a region of lx + ly words (what the walk may need at most)
     DevBuf<unsigned short> d_steps_compact;  // the run-length encoded words of all jobs back to back, job order
     DevBuf<long long> d_step_scan;           // block sums of the compaction scan; the last element is the total
     PinVec<long long> h_step_total;
     DevBuf<unsigned short> d_ptr16;
     PinVec<DevResult> h_results;
+    PinVec<DevModel> h_models;  // staging of the model records (ctx-owned, so the upload needs no host wait)
     cudaEvent_t ev[8];
     pg2_stats stats;
     pg2_batch *current = nullptr;
@@ -222,6 +238,10 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
     c->force_wavefront = fw && atoi(fw) != 0;
     const char *nl = getenv("PG2_NO_LANES");
     c->no_lanes = nl && atoi(nl) != 0;
+    const char *nps = getenv("PG2_NO_PSTRIP");
+    c->no_pstrip = nps && atoi(nps) != 0;
+    const char *pmj = getenv("PG2_PSTRIP_MAX_JOBS");
+    if (pmj && atoi(pmj) >= 0) c->pstrip_max_jobs = atoi(pmj);
     const char *mb = getenv("PG2_SCRATCH_MB");
     if (mb && atoll(mb) > 0) c->scratch_bytes = (size_t)atoll(mb) << 20;
     size_t cap = c->prop.totalGlobalMem / 100 * 45;  // leave room for inputs, steps and the caller
@@ -239,12 +259,12 @@ extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
     if (!c->borrowed_models)
         for (auto &m : c->models) if (m.live && m.d_table) cudaFree(m.d_table);
     c->h_state.release(); c->h_off.release(); c->h_estart.release(); c->h_blo.release(); c->h_bhi.release(); c->h_dlo.release();
-    c->h_elogw.release(); c->h_doff.release(); c->h_results.release(); c->h_vrow.release(); c->h_vlast.release();
+    c->h_elogw.release(); c->h_doff.release(); c->h_results.release(); c->h_models.release(); c->h_vrow.release(); c->h_vlast.release();
     c->d_vrow.release(); c->d_vlast.release(); c->d_queue.release(); c->d_saved.release(); c->d_bcol.release();
     c->d_state.release(); c->d_off.release(); c->d_estart.release(); c->d_blo.release(); c->d_bhi.release(); c->d_dlo.release();
     c->d_order.release(); c->d_graph_status.release(); c->d_elogw.release(); c->d_doff.release(); c->d_jobs.release();
     c->d_graphs.release(); c->d_models.release(); c->d_results.release(); c->d_scores.release(); c->d_ptr32.release();
-    c->d_steps.release(); c->d_steps_compact.release(); c->d_step_scan.release(); c->h_step_total.release(); c->d_ptr16.release(); c->d_lane_scratch.release(); c->d_tasks.release();
+    c->d_ptrps.release(); c->d_ps_scratch.release(); c->d_steps.release(); c->d_steps_compact.release(); c->d_step_scan.release(); c->h_step_total.release(); c->d_ptr16.release(); c->d_lane_scratch.release(); c->d_tasks.release();
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
     if (c->hi_stream) cudaStreamDestroy(c->hi_stream);
@@ -340,6 +360,7 @@ static int intern_graph(pg2_batch *b, const pg2_graph &g, GraphTable &seen, std:
     dg.n_vrows = g.n_sites - 1;
     dg.vlast_base = -1;
     dg.vplain_base = -1;
+    dg.cp_ci_base = -1;
     *gid = (int)b->graphs.size();
     b->graphs.push_back(dg);
     sources.push_back(&g);
@@ -465,7 +486,9 @@ static int build_row_program(pg2_ctx *c, DevGraph &dg) {
             if (!free_slots.empty()) { slot = free_slots.back(); free_slots.pop_back(); }
             else slot = n_slots++;
             slot_of[s] = slot;
-            release[std::min(last_use[s] + 2, n + 2)].push_back(slot);
+            // the warp-per-alignment kernel reads a parked row one step late on the next lane; a general column of the
+            // pipelined-strip kernel reads the portion of a lane up to PS_HIST - 2 lanes ahead
+            release[std::min(last_use[s] + PS_HIST, n + 2)].push_back(slot);
         }
     }
     if (n_slots > STRIP_MAX_SLOTS) return PG2_ERR_UNSUPPORTED;
@@ -593,6 +616,166 @@ static int build_nonplain(pg2_ctx *c, DevGraph &dg) {
     int *md = c->h_vlast.extend(mask.size());
     if (!md) return PG2_ERR_NOMEM;
     memcpy(md, mask.data(), mask.size() * sizeof(unsigned));
+    return PG2_OK;
+}
+
+// Column program of a graph used as the COLUMN graph of the pipelined-strip kernel (pg2_pstrip_geom.cuh): general /
+// parked / end columns, blocks that start at cut points, history slots.  Built once per distinct graph.  Returns
+// PG2_ERR_UNSUPPORTED (remembered in cp_k == 0) when the graph does not fit the kernel's limits: an edge into a general
+// column spans more than (PS_HIST - 3) * 4 columns, no cut point within a block's width, more than PS_MAX_END end columns.
+static int build_col_program(pg2_ctx *c, DevGraph &dg) {
+    if (dg.cp_ci_base >= 0) return dg.cp_k > 0 ? PG2_OK : PG2_ERR_UNSUPPORTED;
+    dg.cp_ci_base = 0;
+    dg.cp_k = 0;
+    const int n = dg.n_sites, cols = n - 1;
+    const HostCsr csr = host_csr(c, dg);
+    std::vector<char> general((size_t)cols, 0), parked((size_t)cols, 0);
+    std::vector<int> forbid((size_t)cols + 2, 0);  // difference array over block boundaries: a block may not start at c when forbid sums > 0
+    int maxspan = 1;
+    for (int j = 1; j < cols; j++) {
+        const int k0 = csr.off(j), k1 = csr.off(j + 1);
+        if (k1 < k0) return PG2_ERR_UNSUPPORTED;  // malformed: the general kernel's validation reports it
+        if (k1 - k0 == 1 && csr.start(k0) == j - 1) continue;
+        general[(size_t)j] = 1;
+        int minsrc = j;
+        for (int k = k0; k < k1; k++) {
+            const int p = csr.start(k);
+            if (p < 0 || p >= j) return PG2_ERR_UNSUPPORTED;
+            parked[(size_t)p] = 1;
+            minsrc = std::min(minsrc, p);
+        }
+        if (k1 - k0 > PS_MAX_RIGHT_INDEG) return PG2_ERR_UNSUPPORTED;
+        if (minsrc < j) {  // every source of a general column lies in the column's own block
+            maxspan = std::max(maxspan, j - minsrc);
+            forbid[(size_t)minsrc + 1]++;
+            forbid[(size_t)j + 1]--;
+        }
+    }
+    int K = maxspan <= (PS_HIST - 3) * 2 ? 2 : (maxspan <= (PS_HIST - 3) * 4 ? 4 : 0);
+    if (const char *fk = getenv("PG2_PSTRIP_K")) if (atoi(fk) == 4 && K == 2) K = 4;
+    if (K == 0) return PG2_ERR_UNSUPPORTED;
+    // columns the end corner reads: the predecessors of the stop site and the last DP column
+    std::vector<int> endcols(1, cols - 1);
+    for (int k = csr.off(n - 1); k < csr.off(n); k++) {
+        const int p = csr.start(k);
+        if (p < 0 || p >= cols) return PG2_ERR_UNSUPPORTED;
+        if (std::find(endcols.begin(), endcols.end(), p) == endcols.end()) endcols.push_back(p);
+    }
+    if ((int)endcols.size() > PS_MAX_END) return PG2_ERR_UNSUPPORTED;
+    // blocks: greedy, as wide as the lanes, the parked-column budget and the cut points allow
+    // (narrow strips first: fewer cells per step; the wider strips when no cut point lies within 64 columns somewhere)
+    std::vector<int> blocks;
+    {
+        std::vector<char> cut((size_t)cols + 1, 0);
+        int run = 0;
+        for (int cc = 0; cc <= cols; cc++) { run += forbid[(size_t)cc]; cut[(size_t)cc] = run == 0; }
+        for (; K <= 4; K += 2) {
+            blocks.clear();
+            int c0 = 0;
+            while (c0 < cols) {
+                const int limit = std::min(c0 + 32 * K, cols);
+                int count = 0, best = -1;
+                for (int cc = c0; cc < limit; cc++) {
+                    if (parked[(size_t)cc] && ++count > PS_MAX_PARK) break;
+                    if (cc + 1 == cols || cut[(size_t)cc + 1]) best = cc + 1;
+                }
+                if (best < 0) break;
+                blocks.push_back(c0);
+                blocks.push_back(best);
+                c0 = best;
+            }
+            if (c0 >= cols) break;
+        }
+        if (K > 4) return PG2_ERR_UNSUPPORTED;
+    }
+    const int nb = (int)blocks.size() / 2;
+    if (nb >= (1 << (31 - PC_BLOCK_SHIFT))) return PG2_ERR_UNSUPPORTED;
+    const int n_edges = csr.off(n);
+    const int ci_base = (int)c->h_vlast.n;
+    int *ci = c->h_vlast.extend((size_t)cols);
+    if (!ci) return PG2_ERR_NOMEM;
+    int max_park = 1;
+    for (int bi = 0; bi < nb; bi++) {
+        int slot = 0;
+        for (int j = blocks[(size_t)2 * bi]; j < blocks[(size_t)2 * bi + 1]; j++) {
+            int w = (general[(size_t)j] ? PC_GENERAL : 0) | (bi << PC_BLOCK_SHIFT);
+            if (parked[(size_t)j]) w |= PC_PARKED | (slot++ << PC_SLOT_SHIFT);
+            ci[j] = w;
+        }
+        max_park = std::max(max_park, slot);
+    }
+    for (size_t e = 0; e < endcols.size(); e++) ci[endcols[e]] |= PC_ENDCOL | ((int)e << PC_END_SHIFT);
+    int ei_base = ci_base;
+    if (!dg.implicit) {  // per edge: the history slot of its source column (read for edges into general columns only)
+        ei_base = (int)c->h_vlast.n;
+        int *ei = c->h_vlast.extend((size_t)n_edges + 1);
+        if (!ei) return PG2_ERR_NOMEM;
+        ci = c->h_vlast.p + ci_base;
+        for (int j = 0; j < n; j++)
+            for (int k = csr.off(j); k < csr.off(j + 1); k++) {
+                const int p = csr.start(k);
+                ei[k] = (p >= 0 && p < cols) ? ((ci[p] >> PC_SLOT_SHIFT) & PC_SLOT_MASK) : 0;
+            }
+    }
+    const int blk_base = (int)c->h_vlast.n;
+    int *bl = c->h_vlast.extend(blocks.size());
+    if (!bl) return PG2_ERR_NOMEM;
+    memcpy(bl, blocks.data(), blocks.size() * sizeof(int));
+    dg.cp_ci_base = ci_base;
+    dg.cp_ei_base = ei_base;
+    dg.cp_blk_base = blk_base;
+    dg.cp_n_blocks = nb;
+    dg.cp_k = K;
+    dg.cp_park = max_park;
+    return PG2_OK;
+}
+
+// Routes one job to the pipelined-strip kernel: row program of the left graph, column program of the right graph, the
+// job's block table (column range, virtual-row range inside the band, pointer offsets).  Returns PG2_ERR_UNSUPPORTED when
+// the job stays where it was.
+static int try_pstrip(pg2_ctx *c, pg2_batch *b, DevJob &J) {
+    DevGraph &GL = b->graphs[J.left];
+    DevGraph &GR = b->graphs[J.right];
+    if (GL.max_indeg > PG2_MAX_IN_DEGREE || GR.max_indeg > PS_MAX_RIGHT_INDEG || GL.max_indeg < 0 || GR.max_indeg < 0) return PG2_ERR_UNSUPPORTED;
+    if (c->models[J.model].fas > VR_STATE_MASK || J.lx < 1 || J.ly < 1) return PG2_ERR_UNSUPPORTED;
+    int rc = build_row_program(c, GL);
+    if (rc != PG2_OK) return rc;
+    rc = build_col_program(c, GR);
+    if (rc != PG2_OK) return rc;
+    const int K = GR.cp_k, nb = GR.cp_n_blocks;
+    const int blk_base = (int)c->h_vlast.n;
+    int *out = c->h_vlast.extend((size_t)nb * PB_INTS);
+    if (!out) return PG2_ERR_NOMEM;
+    const int *cb = c->h_vlast.p + GR.cp_blk_base;
+    const int *vl = c->h_vlast.p + GL.vlast_base;
+    const int *blo = J.banded ? c->h_blo.p + J.band_base : nullptr, *bhi = J.banded ? c->h_bhi.p + J.band_base : nullptr;
+    long long words = 0;
+    int tallest = 1, ifirst = 0, ilast = -1;
+    for (int bi = 0; bi < nb; bi++) {
+        const int c0 = cb[2 * bi], c1 = cb[2 * bi + 1];
+        int v0 = 0, v1 = GL.n_vrows, i0 = 0;
+        if (J.banded) {
+            // rows that meet the block: bhi[i] >= c0 - 1 (column c0 - 1 counts: a long-span edge may read it) and blo[i] <= c1 - 1;
+            // both bounds are non-decreasing in i
+            while (ifirst < J.lx && bhi[ifirst] < c0 - 1) ifirst++;
+            while (ilast + 1 < J.lx && blo[ilast + 1] <= c1 - 1) ilast++;
+            i0 = ifirst;
+            v0 = ifirst == 0 ? 0 : vl[ifirst - 1] + 1;
+            v1 = ilast >= ifirst ? vl[ilast] + 1 : v0;
+        }
+        if (words > 0x7fffffffLL - ps_block_words(v0, v1, K)) { c->h_vlast.n = (size_t)blk_base; return PG2_ERR_UNSUPPORTED; }
+        int *e = out + (size_t)bi * PB_INTS;
+        e[0] = c0; e[1] = c1; e[2] = v0; e[3] = v1; e[4] = i0; e[5] = (int)words;
+        words += ps_block_words(v0, v1, K);
+        tallest = std::max(tallest, v1 - v0);
+    }
+    J.kernel = 3;
+    J.strip_k = K;
+    J.strip_general = c->models[J.model].fas <= STRIP_SMALL_FAS ? 2 : 0;
+    J.n_blocks = nb;
+    J.blk_base = blk_base;
+    J.ps_ring = tallest;
+    J.ptr_cells = words;
     return PG2_OK;
 }
 
@@ -737,11 +920,6 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             if (rc == PG2_ERR_UNSUPPORTED) J.kernel = 0;  // too many parked rows: the general kernel takes it
             else if (rc != PG2_OK) { delete b; return fail(rc, "pinned staging allocation failed"); }
         }
-        if (J.kernel == 0) {
-            rc = build_nonplain(c, GL);
-            if (rc == PG2_OK) rc = build_nonplain(c, b->graphs[J.right]);
-            if (rc != PG2_OK) { delete b; return fail(rc, "pinned staging allocation failed"); }
-        }
         if (J.kernel == 1 && J.ly != pick_ly) { pick_ly = J.ly; pick_k = strip_pick_k(J.ly); }
         J.strip_k = J.kernel == 1 ? pick_k : 0;
         J.strip_general = (J.kernel == 1 && !(GL.simple && GL.zero_w)) ? 1 : 0;
@@ -873,7 +1051,28 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         }
     }
 
-    timer.lap("6 lane tasks");
+    // ---- pipelined strips: every job the register-strip kernels cannot take (banded, general right graph), and the
+    //      strip-eligible jobs of a batch too small to fill the chip with one warp per alignment ----
+    if (!c->force_wavefront && !c->no_pstrip) {
+        int n_strip = 0;
+        for (int t = 0; t < n_jobs; t++) n_strip += b->jobs[t].kernel == 1;
+        const bool small = n_strip <= c->pstrip_max_jobs;
+        for (int t = 0; t < n_jobs; t++) {
+            DevJob &J = b->jobs[t];
+            if (J.kernel == 0 || (J.kernel == 1 && small)) {
+                const int rc = try_pstrip(c, b, J);
+                if (rc == PG2_ERR_NOMEM) { delete b; return fail(rc, "pinned staging allocation failed"); }
+            }
+        }
+    }
+    for (int t = 0; t < n_jobs; t++) {
+        DevJob &J = b->jobs[t];
+        if (J.kernel != 0) continue;
+        int rc = build_nonplain(c, b->graphs[J.left]);
+        if (rc == PG2_OK) rc = build_nonplain(c, b->graphs[J.right]);
+        if (rc != PG2_OK) { delete b; return fail(rc, "pinned staging allocation failed"); }
+    }
+    timer.lap("6 lane tasks, pipelined strips");
     // order: lane jobs (task by task), then strip jobs, then wavefront jobs; larger jobs first inside a class
     // (tail balance)
     b->order = lane_order;
@@ -898,7 +1097,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         g.max_diag = 1;
         g.max_slots = 0;
         g.max_lx = 1;
-        size_t per_cell = g.kernel == 0 ? 36 : 2;
+        size_t per_cell = g.kernel == 0 ? 36 : (g.kernel == 3 ? 4 : 2);
         while (pos < b->order.size()) {
             DevJob &J = b->jobs[b->order[pos]];
             if (J.kernel != g.kernel || J.strip_k != g.strip_k || J.strip_general != g.strip_general) break;
@@ -909,6 +1108,12 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             g.max_diag = std::max(g.max_diag, J.banded ? J.max_diag : std::min(J.lx, J.ly));
             g.max_slots = std::max(g.max_slots, b->graphs[J.left].n_slots);
             g.max_lx = std::max(g.max_lx, J.lx);
+            if (g.kernel == 3) {
+                while (g.ps_ring < J.ps_ring) g.ps_ring <<= 1;
+                g.ps_park = std::max(g.ps_park, b->graphs[J.right].cp_park);
+                g.ps_blocks = std::max(g.ps_blocks, J.n_blocks);
+                g.ps_nw = pstrip_warps(g.ps_blocks, g.ps_park, (g.strip_general & 2) != 0);
+            }
             g.count++;
             pos++;
         }
@@ -919,13 +1124,14 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     {
         int phase = 0;
         size_t bytes = 0;
-        long long off16 = 0, off32 = 0;
+        long long off16 = 0, off32 = 0, offps = 0;
         for (auto &g : b->groups) {
-            const size_t need = (size_t)g.cells * (g.kernel == 0 ? 36 : 2);
-            if (bytes > 0 && bytes + need > c->scratch_bytes) { phase++; bytes = 0; off16 = off32 = 0; }
+            const size_t need = (size_t)g.cells * (g.kernel == 0 ? 36 : (g.kernel == 3 ? 4 : 2));
+            if (bytes > 0 && bytes + need > c->scratch_bytes) { phase++; bytes = 0; off16 = off32 = offps = 0; }
             g.phase = phase;
-            g.ptr_off = g.kernel == 0 ? off32 : off16;
-            (g.kernel == 0 ? off32 : off16) += g.cells;
+            long long &off = g.kernel == 0 ? off32 : (g.kernel == 3 ? offps : off16);
+            g.ptr_off = off;
+            off += g.cells;
             bytes += need;
             if (g.kernel == 2) {
                 for (int t = g.task_first; t < g.task_first + g.task_count; t++) {
@@ -971,13 +1177,13 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     H2D(c->d_graphs, b->graphs.data(), b->graphs.size(), DevGraph);
     H2D(c->d_order, b->order.data(), b->order.size(), int);
     H2D(c->d_tasks, b->tasks.data(), b->tasks.size(), LaneTask);
-    {
-        std::vector<DevModel> dm(c->models.size());
-        for (size_t i = 0; i < dm.size(); i++) dm[i] = c->models[i].dev;
-        if (!dm.empty()) {
-            CU(cudaMemcpyAsync(c->d_models.p, dm.data(), dm.size() * sizeof(DevModel), cudaMemcpyHostToDevice, c->stream));
-            CU(cudaStreamSynchronize(c->stream));  // dm is a stack temporary
-        }
+    if (!c->models.empty()) {
+        // staged in pinned memory the ctx owns: the copy is asynchronous and the host goes on packing the next chunk
+        c->h_models.clear();
+        DevModel *dm = c->h_models.extend(c->models.size());
+        if (!dm) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+        for (size_t i = 0; i < c->models.size(); i++) dm[i] = c->models[i].dev;
+        CU(cudaMemcpyAsync(c->d_models.p, dm, c->models.size() * sizeof(DevModel), cudaMemcpyHostToDevice, c->stream));
         c->models_dirty = false;
     }
     // the CSR of implicit chains (plain leaves and reads) is generated where it is used
@@ -1010,8 +1216,12 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
         st.h2d_bytes = b->h2d_bytes;
     }
     // scratch for the largest phase of each buffer class (strip and lane groups share d_ptr16)
-    long long max_w = 0, max_s = 0;
-    for (auto &g : b->groups) (g.kernel == 0 ? max_w : max_s) = std::max(g.kernel == 0 ? max_w : max_s, g.ptr_off + g.cells);
+    long long max_w = 0, max_s = 0, max_ps = 0;
+    for (auto &g : b->groups) {
+        long long &m = g.kernel == 0 ? max_w : (g.kernel == 3 ? max_ps : max_s);
+        m = std::max(m, g.ptr_off + g.cells);
+    }
+    if (max_ps > 0 && (rc = c->d_ptrps.ensure((size_t)max_ps)) != PG2_OK) return fail(rc, "pointer buffer allocation failed");
     if (max_w > 0) {
         if ((rc = c->d_scores.ensure((size_t)max_w)) != PG2_OK) return fail(rc, "score scratch allocation failed");
         if ((rc = c->d_ptr32.ensure((size_t)max_w)) != PG2_OK) return fail(rc, "pointer buffer allocation failed");
@@ -1033,6 +1243,16 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
             size_t need = (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots) * lane_ctas(g);
             if ((rc = c->d_lane_scratch.ensure(need)) != PG2_OK) return fail(rc, "lane scratch allocation failed");
         }
+    // pipelined strips: one CTA per job in flight; CTAs per SM by the warps a CTA holds
+    auto ps_ctas = [&](const Group &g) {
+        const int per_sm = g.ps_nw > 8 ? 1 : (g.ps_nw > 4 ? 2 : 4);
+        return std::max(1, std::min(g.count, c->prop.multiProcessorCount * per_sm));
+    };
+    for (auto &g : b->groups)
+        if (g.kernel == 3) {
+            const size_t need = (size_t)pstrip_cta_double4(g.strip_k, g.ps_nw, g.max_lx, g.ps_ring, g.max_slots) * (size_t)ps_ctas(g);
+            if ((rc = c->d_ps_scratch.ensure(need)) != PG2_OK) return fail(rc, "pipelined-strip scratch allocation failed");
+        }
     for (auto &g : b->groups)
         if (g.kernel == 1) {
             int warps = (std::min(resident_warps, std::max(g.count, 1)) + 3) & ~3;  // whole CTAs of 4 warps: every launched warp owns scratch
@@ -1047,7 +1267,7 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                     c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, c->stream);
     st.fill_ms = st.traceback_ms = 0;
     st.fill_launches = st.traceback_launches = 0;
-    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = 0;
+    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = st.jobs_pstrip = 0;
     st.jobs_strip_groups = 0;
     st.cells = b->total_cells;
     st.traceback_bytes = 0;
@@ -1057,13 +1277,21 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
         size_t ge = gi;
         while (ge < b->groups.size() && b->groups[ge].phase == b->groups[gi].phase) ge++;
         CU(cudaEventRecord(c->ev[2], c->stream));
-        int phase_jobs = 0, phase_wave_jobs = 0;
+        int phase_jobs = 0, phase_wave_jobs = 0, phase_ps_jobs = 0;
         for (size_t k = gi; k < ge; k++) {
             const Group &g = b->groups[k];
             const int *ids = c->d_order.p + g.first;
             phase_jobs += g.count;
             if (g.kernel == 0) phase_wave_jobs += g.count;
-            if (g.kernel == 0) {
+            if (g.kernel == 3) {
+                phase_ps_jobs += g.count;
+                launch_pstrip_fill(g.strip_k, (g.strip_general & 2) != 0, g.ps_nw, g.count, ps_ctas(g), c->d_jobs.p, ids, c->d_graphs.p,
+                                   c->d_models.p, c->d_state.p, c->d_off.p, c->d_estart.p, c->d_elogw.p,
+                                   reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_vlast.p, c->d_blo.p, c->d_bhi.p, c->d_ptrps.p,
+                                   c->d_results.p, c->d_ps_scratch.p, g.max_lx, g.ps_ring, g.max_slots, g.ps_park, c->d_queue.p, c->stream);
+                st.jobs_pstrip += g.count;
+                st.traceback_bytes += g.cells * 4;
+            } else if (g.kernel == 0) {
                 int threads = g.max_diag <= 32 ? 32 : g.max_diag <= 64 ? 64 : g.max_diag <= 128 ? 128 : g.max_diag <= 256 ? 256
                               : g.max_diag <= 512 ? 512 : 1024;
                 launch_wavefront_fill(g.count, threads, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_off.p,
@@ -1097,9 +1325,9 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
         // ctx stream), so that its CTAs take the first SM slots that free up
         cudaStream_t tb_stream = (async && c->hi_stream) ? c->hi_stream : c->stream;
         if (tb_stream != c->stream) CU(cudaStreamWaitEvent(tb_stream, c->ev[3], 0));
-        launch_traceback(phase_jobs, phase_wave_jobs, c->d_order.p + b->groups[gi].first, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p, c->d_off.p, c->d_estart.p,
-                         c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_steps.p, c->d_results.p,
-                         tb_stream);
+        launch_traceback(phase_jobs, phase_wave_jobs, phase_ps_jobs, c->d_order.p + b->groups[gi].first, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p,
+                         c->d_off.p, c->d_estart.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_ptrps.p,
+                         c->d_steps.p, c->d_results.p, tb_stream);
         CU(cudaEventRecord(c->ev[4], tb_stream));
         if (tb_stream != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev[4], 0));
         if (!async) {
@@ -1239,6 +1467,8 @@ static int ensure_siblings(pg2_ctx *c, int n_slots) {
             s->scratch_bytes = c->scratch_bytes / PIPE_SLOTS;
             s->force_wavefront = c->force_wavefront;
             s->no_lanes = c->no_lanes;
+            s->no_pstrip = c->no_pstrip;
+            s->pstrip_max_jobs = c->pstrip_max_jobs;
             c->sibling[k] = s;
         }
         c->sibling[k]->models = c->models;  // same device tables
@@ -1307,6 +1537,9 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         wacc += weight[(size_t)k - 1];
         const long long want = (long long)((double)total * (wacc / wsum));
         int pos = (int)(std::lower_bound(cells_prefix.begin(), cells_prefix.end(), want) - cells_prefix.begin());
+        // cells_prefix has n_jobs + 1 entries: a dominant last job puts the search at n_jobs, where there is nothing to cut
+        // (and perm[] ends)
+        if (pos >= n_jobs) continue;
         // prefer a boundary between two left graphs; inside a big group cut at a multiple of 32 jobs
         int lo = pos;
         while (lo > cut.back() && jobs[perm[lo]].left.state == jobs[perm[lo - 1]].left.state && pos - lo < 1024) lo--;
@@ -1321,6 +1554,13 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
     n_slots = std::min<int>(n_slots, (int)cut.size() - 1);
     int rc = ensure_siblings(c, n_slots);
     if (rc != PG2_OK) return rc;
+    // every slot gets the same share of the scratch budget while chunks are in flight side by side (the siblings were made
+    // with budget / PIPE_SLOTS; the primary goes back to its full budget afterwards)
+    struct BudgetGuard {
+        pg2_ctx *c; size_t saved;
+        ~BudgetGuard() { c->scratch_bytes = saved; }
+    } budget_guard = {c, c->scratch_bytes};
+    if (n_slots > 1) c->scratch_bytes = budget_guard.saved / PIPE_SLOTS;
     timer.lap("= group + chunk");
     // PG2_TIMING: device timeline of the chunks against one origin (tuning aid)
     cudaEvent_t origin = nullptr;
@@ -1363,7 +1603,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
             const pg2_stats &st = f.ctx->stats;
             agg.h2d_bytes += st.h2d_bytes; agg.d2h_bytes += st.d2h_bytes; agg.cells += st.cells; agg.traceback_bytes += st.traceback_bytes;
             agg.fill_launches += st.fill_launches; agg.traceback_launches += st.traceback_launches; agg.kernel_launches += st.kernel_launches;
-            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes;
+            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes; agg.jobs_pstrip += st.jobs_pstrip;
             agg.jobs_strip_groups += st.jobs_strip_groups; agg.d2h_ms += st.d2h_ms;
         }
         pg2_batch_destroy(f.ctx, f.batch);

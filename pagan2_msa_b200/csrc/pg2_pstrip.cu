@@ -1,0 +1,654 @@
+// pg2_pstrip.cu -- pipelined-strip fill kernel: one CTA per alignment, the column blocks of the alignment pipelined over
+// the warps of the CTA.  General graphs on BOTH sides, with or without an anchor band.
+//
+// This is the kernel of the guide-tree waves (node.cpp:240-264: few, large alignments; from the second wave on both
+// children are ancestor graphs), of the pileup (reads_aligner.cpp: one growing root against one 454 read graph at a
+// time) and of anchored alignments (Tunnel_matrix bands, utils/tunnel_matrix.h:45-344).  Geometry, column program and
+// block table: pg2_pstrip_geom.cuh.
+//
+// A block of <= 32*K columns is swept by one warp: lane l owns K consecutive columns and keeps X / Y / M of its strip
+// for the row it handled last in registers; the lanes are skewed by one virtual row (lane l is on virtual row t - l at
+// step t), so the strip's last column is handed to lane l + 1 by shuffles.  The row graph is the left graph's row
+// program (pg2_strip_geom.cuh: one virtual row per backward edge; rows that start long-span edges are parked in a
+// per-warp scratch).  Column j of the right graph is PLAIN when its only backward edge comes from column j - 1 (its
+// sources are then the neighbouring registers) and GENERAL otherwise: a general column walks its backward edges and
+// reads the cells (i, pr), (i - 1, pr) from a shared-memory history of the block's PARKED columns, (pl, pr) of a
+// long-span left edge from the parked row.
+//
+// The warp of block b + 1 follows the warp of block b: the last column of block b goes to a boundary-column ring in
+// global memory (one entry per virtual row), a progress counter in shared memory says how far it is valid, and lane 0
+// of block b + 1 fetches its entries a few steps ahead.  No CTA-wide barrier runs inside an alignment.
+//
+// Arithmetic follows the reference candidate by candidate (src/main/viterbi_alignment.cpp:856-971, 1328-1436,
+// 2029-2219): same order, same FP64 association, strict '>' (first candidate wins ties).  "+ 0.0" terms are dropped
+// (exact: the DP never produces -0.0).
+#include "pg2_device.cuh"
+#include "pg2_strip_geom.cuh"
+#include "pg2_pstrip_geom.cuh"
+#ifdef PG2_HOST_EMU
+#include <vector>
+#endif
+
+namespace pg2 {
+
+// warp-uniform constants of one job and of the block being swept
+struct PsCtx {
+    // row graph (left)
+    const int4 *l_vrow;
+    const int *l_off, *l_estart;
+    const float *l_elogw;
+    int nv;
+    // column graph (right)
+    const int *r_state, *r_off, *r_estart, *r_einfo, *colinfo;
+    const float *r_elogw;
+    // model
+    const float *table;
+    const double2 *stab;
+    int fas;
+    double open, ext, end_ext, lng, lng2;
+    bool term, reduced, banded, weights;
+    int lx, ly;
+    const int *blo, *bhi;
+    // block
+    int c0, c1, v0, v1, i0;
+    // scratch
+    double4 *saved;      // [n_slots][1 + 32*K]: entry 0 is column c0 - 1
+    double *hist;        // shared: [PS_HIST][park_cap][3]
+    int park_cap;        // history slots per block (the launch group's largest block need)
+    double4 *endstore;   // [PS_MAX_END][lx]
+    int saved_stride;    // 1 + 32*K
+};
+
+template <int K> struct PsLane {
+    double X[K], Y[K], M[K];   // own strip, row handled last
+    double bX, bY, bM;         // column to the left of the strip, same row
+    double extX[K];            // X-extension term per column (:864-868)
+    double wr[K];              // log weight of the edge into a plain column
+    int colbase[K];            // state_r[j] * fas (SMALLTAB: the same)
+    int cinfo[K];              // column info words; -1 for padding columns (j >= c1)
+    int j0;                    // first column of the strip
+};
+
+template <int K> struct PsAcc {
+    double nX[K], nM[K];
+    unsigned pX[K], pM[K];
+};
+
+template <bool SMALLTAB>
+__device__ __forceinline__ void ps_subst(const PsCtx &c, int sl, int colbase, double &mlog, double &xlog) {
+    if (SMALLTAB) {
+        const double2 v = c.stab[sl + colbase];
+        mlog = v.x;
+        xlog = v.y;
+    } else {
+        const double ls = (double)__ldg(c.table + sl + colbase);
+        mlog = __dadd_rn(c.lng2, ls);
+        xlog = __dadd_rn(c.lng, ls);
+    }
+}
+
+// double4 through L2 (written by another lane or warp of the CTA a moment ago: not to be served from a stale L1 line)
+__device__ __forceinline__ double4 ps_ldcg(const double4 *p) {
+    const double2 a = __ldcg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ void ps_cand(double s, unsigned code, double &best, unsigned &ptr) {
+    if (s > best) { best = s; ptr = code; }
+}
+
+// history of the parked columns: entry (site i, slot) holds X, Y, M of cell (i, parked column)
+__device__ __forceinline__ const double *ps_hist(const PsCtx &c, int i, int slot) {
+    return c.hist + ((((i + PS_HIST) % PS_HIST) * c.park_cap + slot) * 3);
+}
+
+// One virtual row (one backward edge of the left site) of one lane.  Returns true when the site was completed: st then
+// holds row i (cells outside the band forced to -inf) and out[] the pointer words of its K cells.
+//   any_saved (warp-uniform): some lane's edge starts at a parked row this step
+//   rX, rY, rM: cell (i, j0 - 1), the strip's left neighbour in the row being completed
+template <int K, bool SMALLTAB>
+__device__ __forceinline__ bool ps_step(const PsCtx &c, PsLane<K> &st, PsAcc<K> &acc, int lane, int4 vr, bool any_saved, double rX,
+                                        double rY, double rM, unsigned *out) {
+    const double ninf = neg_inf();
+    const int info = vr.x, i = vr.z;
+    const int sl = info & VR_STATE_MASK;
+    if (info & VR_FIRST) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { acc.nX[k] = ninf; acc.nM[k] = ninf; acc.pX[k] = NO_MAT; acc.pM[k] = NO_MAT; }
+    }
+    if (!(info & VR_NOEDGE)) {
+        const bool reg = (info & VR_REG) != 0;
+        const int p = reg ? i - 1 : c.l_estart[vr.y];
+        const double wl = (info & VR_ZERO_W) ? 0.0 : (double)c.l_elogw[vr.y];
+        const unsigned lord = ((unsigned)vr.w >> 16) << 2;
+        const double pen = (c.reduced && p == 0) ? 0.0 : c.open;  // get_log_gap_open_penalty (basic_alignment.h:490-513)
+        // source row p: column j0 - 1 in [0], column j0 + k in [k + 1]
+        double sX[K + 1], sY[K + 1], sM[K + 1];
+        sX[0] = st.bX; sY[0] = st.bY; sM[0] = st.bM;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { sX[k + 1] = st.X[k]; sY[k + 1] = st.Y[k]; sM[k + 1] = st.M[k]; }
+        const double4 *prow = nullptr;  // the parked source row, when the edge does not start at the row above
+        bool pvalid = true;
+        if (any_saved && !reg) {
+            // a row above the block's first row lies outside the band for every column of the block (and for c0 - 1)
+            pvalid = p >= c.i0;
+            prow = c.saved + (long long)(vr.w & 0xffff) * c.saved_stride;
+#pragma unroll
+            for (int k = 0; k <= K; ++k) {
+                double4 v = make_double4(ninf, ninf, ninf, 0.0);
+                if (pvalid) v = ps_ldcg(prow + (st.j0 - c.c0) + k);
+                sX[k] = v.x; sY[k] = v.y; sM[k] = v.z;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            // X: ext, double, open out of (p, j) (:2116-2211)
+            ps_cand(__dadd_rn(sX[k + 1], st.extX[k]), X_MAT | lord, acc.nX[k], acc.pX[k]);
+            ps_cand(__dadd_rn(sY[k + 1], c.open), Y_MAT | lord, acc.nX[k], acc.pX[k]);
+            ps_cand(__dadd_rn(__dadd_rn(sM[k + 1], c.lng), pen), M_MAT | lord, acc.nX[k], acc.pX[k]);
+            // M: from M, X, Y of (p, pr) for every backward edge pr -> j (:1353-1436, :2029-2112)
+            double mlog, xlog;
+            ps_subst<SMALLTAB>(c, sl, st.colbase[k], mlog, xlog);
+            if (!(st.cinfo[k] & PC_GENERAL)) {
+                double a = __dadd_rn(sM[k], mlog), b = __dadd_rn(sX[k], xlog), d = __dadd_rn(sY[k], xlog);
+                if (c.weights) {
+                    a = __dadd_rn(__dadd_rn(a, wl), st.wr[k]);
+                    b = __dadd_rn(__dadd_rn(b, wl), st.wr[k]);
+                    d = __dadd_rn(__dadd_rn(d, wl), st.wr[k]);
+                }
+                ps_cand(a, M_MAT | lord, acc.nM[k], acc.pM[k]);
+                ps_cand(b, X_MAT | lord, acc.nM[k], acc.pM[k]);
+                ps_cand(d, Y_MAT | lord, acc.nM[k], acc.pM[k]);
+            } else if (st.cinfo[k] >= 0) {
+                const int j = st.j0 + k;
+                const int kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
+                for (int kr = kr0; kr < kr1; ++kr) {
+                    double vx, vy, vm;
+                    if (reg) {
+                        const double *h = ps_hist(c, i - 1, c.r_einfo[kr]);
+                        vx = h[0]; vy = h[1]; vm = h[2];
+                    } else if (prow && pvalid) {
+                        const double4 v = ps_ldcg(prow + (c.r_estart[kr] - c.c0) + 1);
+                        vx = v.x; vy = v.y; vm = v.z;
+                    } else {
+                        vx = vy = vm = ninf;
+                    }
+                    const double wrk = (double)c.r_elogw[kr];
+                    const unsigned code = lord | ((unsigned)(kr - kr0) << 8);
+                    ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vm, mlog), wl), wrk), M_MAT | code, acc.nM[k], acc.pM[k]);
+                    ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vx, xlog), wl), wrk), X_MAT | code, acc.nM[k], acc.pM[k]);
+                    ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vy, xlog), wl), wrk), Y_MAT | code, acc.nM[k], acc.pM[k]);
+                }
+            }
+        }
+    }
+    if (!(info & VR_LAST)) return false;
+
+    // ---- the site's last virtual row: Y chain along the strip, band mask, pointer words ----
+    if (st.j0 == 0) {  // DP column 0 has no M; (0,0) is the start corner (:725-733, :956-969)
+        acc.nM[0] = (i == 0) ? 0.0 : ninf;
+        acc.pM[0] = NO_MAT;
+    }
+    const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : c.ext;
+    int blo = 0, bhi = 0x7fffffff;
+    if (c.banded) { blo = c.blo[i]; bhi = c.bhi[i]; }
+    const unsigned plain_row = ((info & VR_FAST) == VR_FAST && !(info & VR_NOEDGE)) ? PSW_PLAIN_ROW : 0u;
+    double lX = rX, lY = rY, lM = rM;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = st.j0 + k;
+        double best = ninf;
+        unsigned ptr = NO_MAT;
+        unsigned plain_col = 0;
+        if (!(st.cinfo[k] & PC_GENERAL)) {
+            // Y: ext, double, open out of (i, j - 1) (:2116-2211 with the roles of X and Y swapped)
+            const double penY = (c.reduced && j == 1) ? 0.0 : c.open;
+            ps_cand(__dadd_rn(lY, extY), Y_MAT, best, ptr);
+            ps_cand(__dadd_rn(lX, c.open), X_MAT, best, ptr);
+            ps_cand(__dadd_rn(__dadd_rn(lM, c.lng), penY), M_MAT, best, ptr);
+            plain_col = j > 0 ? PSW_PLAIN_COL : 0u;
+        } else if (st.cinfo[k] >= 0) {
+            const int kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
+            for (int kr = kr0; kr < kr1; ++kr) {
+                const double *h = ps_hist(c, i, c.r_einfo[kr]);
+                const double penY = (c.reduced && c.r_estart[kr] == 0) ? 0.0 : c.open;
+                const unsigned ord = (unsigned)(kr - kr0) << 2;
+                ps_cand(__dadd_rn(h[1], extY), Y_MAT | ord, best, ptr);
+                ps_cand(__dadd_rn(h[0], c.open), X_MAT | ord, best, ptr);
+                ps_cand(__dadd_rn(__dadd_rn(h[2], c.lng), penY), M_MAT | ord, best, ptr);
+            }
+        }
+        double nx = acc.nX[k], nm = acc.nM[k];
+        if (j < blo || j > bhi) { nx = ninf; best = ninf; nm = ninf; }  // Tunnel_slice::at: -inf outside the band
+        out[k] = cell_word(acc.pX[k], ptr, acc.pM[k]) | plain_row | plain_col;
+        st.X[k] = nx; st.Y[k] = best; st.M[k] = nm;
+        if (st.cinfo[k] >= 0 && (st.cinfo[k] & PC_PARKED)) {
+            double *h = const_cast<double *>(ps_hist(c, i, (st.cinfo[k] >> PC_SLOT_SHIFT) & PC_SLOT_MASK));
+            h[0] = nx; h[1] = best; h[2] = nm;
+        }
+        if (st.cinfo[k] >= 0 && (st.cinfo[k] & PC_ENDCOL) && (info & VR_ENDPRED))
+            c.endstore[(long long)((st.cinfo[k] >> PC_END_SHIFT) & 3) * c.lx + i] = make_double4(nx, best, nm, 0.0);
+        lX = nx; lY = best; lM = nm;
+    }
+    st.bX = rX; st.bY = rY; st.bM = rM;
+    return true;
+}
+
+// per-lane constants of one block
+template <int K>
+__device__ __forceinline__ void ps_init_lane(const PsCtx &c, PsLane<K> &st, int lane) {
+    const double ninf = neg_inf();
+    st.j0 = c.c0 + lane * K;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = st.j0 + k;
+        const bool v = j < c.c1;
+        st.X[k] = st.Y[k] = st.M[k] = ninf;
+        st.extX[k] = (c.term && (j == 0 || j == c.ly - 1)) ? c.end_ext : c.ext;
+        st.cinfo[k] = v ? c.colinfo[j] : -1;
+        const bool plain = v && j >= 1 && !(st.cinfo[k] & PC_GENERAL);
+        st.wr[k] = plain ? (double)c.r_elogw[c.r_off[j]] : 0.0;
+        st.colbase[k] = (v && j >= 1) ? c.r_state[j] * c.fas : 0;
+    }
+    st.bX = st.bY = st.bM = ninf;
+}
+
+// iterate_bwd_edges_for_end_corner (:1440-1552) from the stored end columns.  Run by one thread after the last block.
+__device__ void ps_end_corner(const PsCtx &c, const double4 *endstore, DevResult *res) {
+    const int kl0 = c.l_off[c.lx], kl1 = c.l_off[c.lx + 1], kr0 = c.r_off[c.ly], kr1 = c.r_off[c.ly + 1];
+    const double ninf = neg_inf();
+    double best = ninf;
+    unsigned ptr = NO_MAT;
+    auto cell = [&](int p, int q) {
+        const int ci = c.colinfo[q];
+        return ps_ldcg(endstore + (long long)((ci >> PC_END_SHIFT) & 3) * c.lx + p);
+    };
+    if (kl1 > kl0 && kr1 > kr0) {
+        auto m_pair = [&](int kl, int kr) {
+            const double4 v = cell(c.l_estart[kl], c.r_estart[kr]);
+            const double s = __dadd_rn(__dadd_rn(__dadd_rn(v.z, c.lng), (double)c.l_elogw[kl]), (double)c.r_elogw[kr]);
+            if (s > best) { best = s; ptr = pack_ptr(M_MAT, kl - kl0, kr - kr0); }
+        };
+        auto x_close = [&](int kl) {  // score_gap_close :2221-2255, close penalty 0
+            const double s = cell(c.l_estart[kl], c.ly - 1).x;
+            if (s > best) { best = s; ptr = pack_ptr(X_MAT, kl - kl0, 0); }
+        };
+        auto y_close = [&](int kr) {
+            const double s = cell(c.lx - 1, c.r_estart[kr]).y;
+            if (s > best) { best = s; ptr = pack_ptr(Y_MAT, 0, kr - kr0); }
+        };
+        m_pair(kl0, kr0);
+        x_close(kl0);
+        y_close(kr0);
+        for (int kr = kr0 + 1; kr < kr1; ++kr) { m_pair(kl0, kr); y_close(kr); }
+        for (int kl = kl0 + 1; kl < kl1; ++kl) {
+            m_pair(kl, kr0);
+            x_close(kl);
+            for (int kr = kr0 + 1; kr < kr1; ++kr) { m_pair(kl, kr); y_close(kr); }
+        }
+    }
+    res->score = best;
+    res->end_ptr = ptr;
+    res->status = (best == ninf) ? JOB_NO_PATH : JOB_OK;
+}
+
+// entries of the end columns the end corner may read: the rows that start an edge into the left stop site, and row lx - 1
+__device__ __forceinline__ void ps_end_init(const PsCtx &c, double4 *endstore, int tid, int nthreads) {
+    const double4 empty = make_double4(neg_inf(), neg_inf(), neg_inf(), 0.0);
+    const int kl0 = c.l_off[c.lx], n = c.l_off[c.lx + 1] - kl0;
+    for (int e = tid; e < (n + 1) * PS_MAX_END; e += nthreads) {
+        const int which = e / PS_MAX_END, slot = e - which * PS_MAX_END;
+        const int row = which < n ? c.l_estart[kl0 + which] : c.lx - 1;
+        endstore[(long long)slot * c.lx + row] = empty;
+    }
+}
+
+__device__ __forceinline__ void ps_make_ctx(PsCtx &c, const DevJob &J, const DevGraph &GL, const DevGraph &GR, const DevModel &m,
+                                            const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
+                                            const int4 *d_vrow, const int *d_vlast, const int *d_blo, const int *d_bhi) {
+    c.l_vrow = d_vrow + GL.vrow_base;
+    c.nv = GL.n_vrows;
+    c.l_off = d_off + GL.off_base;
+    c.l_estart = d_estart + GL.edge_base;
+    c.l_elogw = d_elogw + GL.edge_base;
+    c.r_state = d_state + GR.state_base;
+    c.r_off = d_off + GR.off_base;
+    c.r_estart = d_estart + GR.edge_base;
+    c.r_elogw = d_elogw + GR.edge_base;
+    c.r_einfo = d_vlast + GR.cp_ei_base;
+    c.colinfo = d_vlast + GR.cp_ci_base;
+    c.table = m.table;
+    c.stab = nullptr;
+    c.fas = m.fas;
+    c.open = (double)m.open;
+    c.ext = (double)m.ext;
+    c.end_ext = (double)m.end_ext;
+    c.lng = (double)m.lng;
+    c.lng2 = (double)__fmul_rn(2.0f, m.lng);
+    c.term = !(J.flags & FLAG_NO_TERMINAL_EDGES);
+    c.reduced = (J.flags & FLAG_REDUCED) != 0;
+    c.banded = J.banded != 0;
+    c.weights = !(GL.zero_w && GR.zero_w);
+    c.lx = J.lx;
+    c.ly = J.ly;
+    c.blo = c.banded ? d_blo + J.band_base : nullptr;
+    c.bhi = c.banded ? d_bhi + J.band_base : nullptr;
+}
+
+__device__ __forceinline__ void ps_load_block(PsCtx &c, const int *blk) {
+    c.c0 = blk[0]; c.c1 = blk[1]; c.v0 = blk[2]; c.v1 = blk[3]; c.i0 = blk[4];
+}
+
+#ifndef PG2_HOST_EMU
+__device__ __forceinline__ int ps_load_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ps_store_release(int *p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+template <int K, bool SMALLTAB>
+__global__ void __launch_bounds__(PS_MAX_WARPS * 32, 1)
+pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models, const int *d_state,
+                   const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow, const int *d_vlast, const int *d_blo,
+                   const int *d_bhi, unsigned *ptrs, DevResult *results, double4 *scratch, long long cta_d4, long long end_d4, int ring,
+                   int max_slots, int park_cap, int *queue) {
+    extern __shared__ __align__(16) unsigned char ps_smem[];
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *hist_all = reinterpret_cast<double *>(ps_smem);
+    const int hist_doubles = PS_HIST * park_cap * 3;
+    double2 *s_tab = reinterpret_cast<double2 *>(hist_all + (size_t)nw * hist_doubles);
+    __shared__ int s_job;
+    __shared__ int s_prog[PS_MAX_WARPS];
+    // the warp-uniform constants live in shared memory, one copy per warp (the block fields differ): in registers they
+    // would cost every lane some sixty registers
+    __shared__ PsCtx s_ctx[PS_MAX_WARPS];
+    const double ninf = neg_inf();
+    const int ring_mask = ring - 1;
+    double4 *cta_scratch = scratch + (long long)blockIdx.x * cta_d4;
+    double4 *endstore = cta_scratch;  // [PS_MAX_END][max lx]
+    const long long warp_d4 = 2LL * ring + (long long)(max_slots > 0 ? max_slots : 1) * (1 + 32 * K);
+    double4 *my = cta_scratch + end_d4 + (long long)w * warp_d4;            // this warp: 2 boundary rings, parked rows
+    double4 *prev = cta_scratch + end_d4 + (long long)((w + nw - 1) % nw) * warp_d4;
+    int tab_model = -1;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_job = atomicAdd(queue, 1);
+        if (threadIdx.x < PS_MAX_WARPS) s_prog[threadIdx.x] = 0;
+        __syncthreads();
+        const int q = s_job;
+        if (q >= n_jobs) break;
+        const int jid = job_ids[q];
+        const DevJob &J = jobs[jid];
+        DevResult *res = results + jid;
+        if (res->status != JOB_OK) continue;  // rejected by the validation kernel (block-uniform)
+        const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+        const DevModel m = models[J.model];
+        PsCtx &c = s_ctx[w];
+        if (lane == 0) {
+            ps_make_ctx(c, J, GL, GR, m, d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, d_blo, d_bhi);
+            c.hist = hist_all + (size_t)w * hist_doubles;
+            c.park_cap = park_cap;
+            c.endstore = endstore;
+            c.saved = my + 2LL * ring;
+            c.saved_stride = 1 + 32 * K;
+            c.stab = SMALLTAB ? s_tab : nullptr;
+        }
+        __syncwarp();
+        if (SMALLTAB) {
+            if (tab_model != J.model) {  // block-uniform
+                for (int e = threadIdx.x; e < m.fas * m.fas; e += blockDim.x) {
+                    const double ls = (double)m.table[e];
+                    s_tab[e] = make_double2(__dadd_rn(c.lng2, ls), __dadd_rn(c.lng, ls));
+                }
+                tab_model = J.model;
+                __syncthreads();
+            }
+        }
+        const int *blocks = d_vlast + J.blk_base;
+        const int n_blocks = J.n_blocks;
+        const int stride = c.nv + 2;  // progress values of one round
+        unsigned *P = ptrs + J.cell_base;
+        // rows the end corner reads: -inf until a block writes them (a row above a banded block never is)
+        ps_end_init(c, endstore, threadIdx.x, blockDim.x);
+        __syncthreads();
+
+        for (int b = w; b < n_blocks; b += nw) {
+            const int round = b / nw;
+            __syncwarp();
+            if (lane == 0) ps_load_block(c, blocks + b * PB_INTS);
+            __syncwarp();
+            const int ptr_off = blocks[b * PB_INTS + 5];
+            int pv0 = 0, pv1 = 0;
+            if (b > 0) { pv0 = blocks[(b - 1) * PB_INTS + 2]; pv1 = blocks[(b - 1) * PB_INTS + 3]; }
+            // the producer of this block's left boundary: warp w - 1 in this round, or the last warp one round earlier
+            const int *prod = s_prog + (w + nw - 1) % nw;
+            const int prod_base = (w == 0 ? round - 1 : round) * stride;
+            const double4 *bcol_prev = prev + (long long)(((w == 0 ? round - 1 : round) & 1) ? ring : 0);
+            double4 *bcol_cur = my + (long long)((round & 1) ? ring : 0);
+            PsLane<K> st;
+            PsAcc<K> acc;
+            ps_init_lane<K>(c, st, lane);
+#pragma unroll
+            for (int k = 0; k < K; ++k) { acc.nX[k] = acc.nM[k] = ninf; acc.pX[k] = acc.pM[k] = NO_MAT; }
+            for (int e = lane; e < hist_doubles; e += 32) c.hist[e] = ninf;
+            __syncwarp();
+            const int last_col = c.c1 - 1 - c.c0, last_lane = last_col / K, last_k = last_col % K;
+            const bool feeds_next = b + 1 < n_blocks;
+            // boundary column, fetched PS_PREFETCH steps ahead by lane 0
+            int avail = 0;  // producer progress seen so far
+            struct Bnd { double x, y, z; };
+            auto fetch = [&](int v) -> Bnd {
+                Bnd r = {ninf, ninf, ninf};
+                if (lane != 0 || b == 0 || v < pv0 || v >= pv1) return r;
+                const int need = prod_base + v + 1;
+                while (avail < need) avail = ps_load_acquire(prod);
+                const double4 q4 = ps_ldcg(bcol_prev + (v & ring_mask));
+                r.x = q4.x; r.y = q4.y; r.z = q4.z;
+                return r;
+            };
+            Bnd pf[PS_PREFETCH];
+#pragma unroll
+            for (int d = 0; d < PS_PREFETCH; ++d) pf[d] = fetch(c.v0 + d);
+            unsigned *out = P + ptr_off + lane * K;
+            const int n_steps = (c.v1 - c.v0) + last_lane;
+            for (int t = 0; t < n_steps; ++t) {
+                double rX = __shfl_up_sync(0xffffffffu, st.X[K - 1], 1);
+                double rY = __shfl_up_sync(0xffffffffu, st.Y[K - 1], 1);
+                double rM = __shfl_up_sync(0xffffffffu, st.M[K - 1], 1);
+                if (lane == 0) { rX = pf[0].x; rY = pf[0].y; rM = pf[0].z; }
+#pragma unroll
+                for (int d = 0; d + 1 < PS_PREFETCH; ++d) pf[d] = pf[d + 1];
+                pf[PS_PREFETCH - 1] = fetch(c.v0 + t + PS_PREFETCH);
+                const int v = c.v0 + t - lane;
+                const bool active = (v >= c.v0 && v < c.v1 && lane <= last_lane);
+                int4 vr = make_int4(VR_FAST | VR_ZERO_W, -1, 0, 0);
+                if (active) vr = __ldg(c.l_vrow + v);
+                const bool any_saved = __any_sync(0xffffffffu, active && !(vr.x & (VR_REG | VR_NOEDGE)));
+                if (active) {
+                    unsigned wds[K];
+                    const bool done = ps_step<K, SMALLTAB>(c, st, acc, lane, vr, any_saved, rX, rY, rM, wds);
+                    if (done) {
+                        unsigned *dst = out + (long long)t * 32 * K;
+                        if (K == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(wds[0], wds[1]);
+                        else if (K == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                        else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) dst[k] = wds[k];
+                        }
+                        const int slot = (int)((unsigned)vr.x >> VR_SLOT_SHIFT) - 1;
+                        if (slot >= 0) {  // park the row for long-span edges
+                            double4 *row = c.saved + (long long)slot * c.saved_stride + (st.j0 - c.c0);
+                            if (lane == 0) row[0] = make_double4(st.bX, st.bY, st.bM, 0.0);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) row[k + 1] = make_double4(st.X[k], st.Y[k], st.M[k], 0.0);
+                        }
+                        if (lane == last_lane && feeds_next) {
+                            double vx = ninf, vy = ninf, vm = ninf;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) if (k == last_k) { vx = st.X[k]; vy = st.Y[k]; vm = st.M[k]; }
+                            bcol_cur[v & ring_mask] = make_double4(vx, vy, vm, 0.0);
+                        }
+                    }
+                    if (lane == last_lane && feeds_next) ps_store_release(s_prog + w, round * stride + (v + 1));
+                }
+                __syncwarp();
+            }
+            if (lane == 0) ps_store_release(s_prog + w, round * stride + c.nv + 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) ps_end_corner(c, endstore, res);
+    }
+}
+#endif
+
+// smem of one CTA: the parked-column histories of its warps (+ the shared substitution table)
+static size_t ps_smem_bytes(int nw, int park_cap, bool smalltab) {
+    return (size_t)nw * PS_HIST * park_cap * 3 * sizeof(double) + (smalltab ? STRIP_SMALL_FAS * STRIP_SMALL_FAS * sizeof(double2) : 0);
+}
+// warps per CTA: as many as the job has blocks, the kernel allows and the histories fit
+int pstrip_warps(int n_blocks, int park_cap, bool smalltab) {
+    int nw = n_blocks < PS_MAX_WARPS ? n_blocks : PS_MAX_WARPS;
+    while (nw > 1 && ps_smem_bytes(nw, park_cap, smalltab) > (size_t)PS_SMEM_BUDGET) --nw;
+    return nw < 1 ? 1 : nw;
+}
+
+#ifdef PG2_HOST_EMU
+// CPU test emulation of one job: the same step body; the blocks one after the other (one of the interleavings the
+// progress counters admit), lanes one after the other inside a step with the shuffle replaced by a snapshot.
+template <int K>
+static void ps_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &GR, const DevModel &m, const int *d_state, const int *d_off,
+                           const int *d_estart, const float *d_elogw, const int4 *d_vrow, const int *d_vlast, const int *d_blo,
+                           const int *d_bhi, unsigned *ptrs, DevResult *res, double4 *scratch, long long end_d4, int ring, int max_slots,
+                           int park_cap) {
+    const double ninf = neg_inf();
+    PsCtx c;
+    ps_make_ctx(c, J, GL, GR, m, d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, d_blo, d_bhi);
+    std::vector<double> hist((size_t)PS_HIST * park_cap * 3);
+    c.hist = hist.data();
+    c.park_cap = park_cap;
+    c.endstore = scratch;
+    double4 *ringbuf[2] = {scratch + end_d4, scratch + end_d4 + ring};
+    c.saved = scratch + end_d4 + 2LL * ring;
+    c.saved_stride = 1 + 32 * K;
+    (void)max_slots;
+    std::vector<double2> tab;
+    const bool smalltab = m.fas <= STRIP_SMALL_FAS;
+    if (smalltab) {
+        tab.resize((size_t)m.fas * m.fas);
+        for (int e = 0; e < m.fas * m.fas; ++e) {
+            const double ls = (double)m.table[e];
+            tab[e] = make_double2(c.lng2 + ls, c.lng + ls);
+        }
+        c.stab = tab.data();
+    }
+    const int *blocks = d_vlast + J.blk_base;
+    unsigned *P = ptrs + J.cell_base;
+    const int ring_mask = ring - 1;
+    ps_end_init(c, c.endstore, 0, 1);
+    for (int b = 0; b < J.n_blocks; ++b) {
+        ps_load_block(c, blocks + b * PB_INTS);
+        const int ptr_off = blocks[b * PB_INTS + 5];
+        int pv0 = 0, pv1 = 0;
+        if (b > 0) { pv0 = blocks[(b - 1) * PB_INTS + 2]; pv1 = blocks[(b - 1) * PB_INTS + 3]; }
+        const double4 *bcol_prev = ringbuf[(b + 1) & 1];
+        double4 *bcol_cur = ringbuf[b & 1];
+        PsLane<K> st[32];
+        PsAcc<K> acc[32];
+        for (int l = 0; l < 32; ++l) {
+            ps_init_lane<K>(c, st[l], l);
+            for (int k = 0; k < K; ++k) { acc[l].nX[k] = acc[l].nM[k] = ninf; acc[l].pX[k] = acc[l].pM[k] = NO_MAT; }
+        }
+        for (auto &h : hist) h = ninf;
+        const int last_col = c.c1 - 1 - c.c0, last_lane = last_col / K, last_k = last_col % K;
+        const bool feeds_next = b + 1 < J.n_blocks;
+        const int n_steps = (c.v1 - c.v0) + last_lane;
+        for (int t = 0; t < n_steps; ++t) {
+            double sx[32], sy[32], sm[32];
+            int4 vr[32];
+            bool any_saved = false;
+            for (int l = 0; l < 32; ++l) {
+                sx[l] = st[l].X[K - 1]; sy[l] = st[l].Y[K - 1]; sm[l] = st[l].M[K - 1];
+                const int v = c.v0 + t - l;
+                const bool active = v >= c.v0 && v < c.v1 && l <= last_lane;
+                vr[l] = active ? c.l_vrow[v] : make_int4(VR_FAST | VR_ZERO_W, -1, 0, 0);
+                if (active && !(vr[l].x & (VR_REG | VR_NOEDGE))) any_saved = true;
+            }
+            for (int l = 0; l < 32; ++l) {
+                const int v = c.v0 + t - l;
+                if (v < c.v0 || v >= c.v1 || l > last_lane) continue;
+                double rX, rY, rM;
+                if (l == 0) {
+                    rX = rY = rM = ninf;
+                    if (b > 0 && v >= pv0 && v < pv1) { const double4 bv = bcol_prev[v & ring_mask]; rX = bv.x; rY = bv.y; rM = bv.z; }
+                } else { rX = sx[l - 1]; rY = sy[l - 1]; rM = sm[l - 1]; }
+                unsigned wds[K];
+                bool done;
+                if (smalltab) done = ps_step<K, true>(c, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
+                else done = ps_step<K, false>(c, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
+                if (!done) continue;
+                unsigned *dst = P + ptr_off + ((long long)t * 32 + l) * K;
+                for (int k = 0; k < K; ++k) dst[k] = wds[k];
+                const int slot = (int)((unsigned)vr[l].x >> VR_SLOT_SHIFT) - 1;
+                if (slot >= 0) {
+                    double4 *row = c.saved + (long long)slot * c.saved_stride + (st[l].j0 - c.c0);
+                    if (l == 0) row[0] = make_double4(st[l].bX, st[l].bY, st[l].bM, 0.0);
+                    for (int k = 0; k < K; ++k) row[k + 1] = make_double4(st[l].X[k], st[l].Y[k], st[l].M[k], 0.0);
+                }
+                if (l == last_lane && feeds_next)
+                    bcol_cur[v & ring_mask] = make_double4(st[l].X[last_k], st[l].Y[last_k], st[l].M[last_k], 0.0);
+            }
+        }
+    }
+    ps_end_corner(c, c.endstore, res);
+}
+#endif
+
+int pstrip_max_warps() { return PS_MAX_WARPS; }
+
+// per-CTA scratch in double4: end columns, then per warp two boundary rings and the parked rows
+long long pstrip_cta_double4(int K, int nw, int max_lx, int ring, int max_slots) {
+    return (long long)PS_MAX_END * max_lx + (long long)nw * (2LL * ring + (long long)(max_slots > 0 ? max_slots : 1) * (1 + 32 * K));
+}
+
+// Launches one group of pipelined-strip jobs that share the strip width K and the table variant.
+void launch_pstrip_fill(int K, bool smalltab, int nw, int n_jobs, int n_ctas, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
+                        const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
+                        const int4 *d_vrow, const int *d_vlast, const int *d_blo, const int *d_bhi, unsigned *ptrs, DevResult *results,
+                        double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int *queue, cudaStream_t stream) {
+    if (n_jobs <= 0) return;
+    const long long end_d4 = (long long)PS_MAX_END * max_lx;
+    const long long cta_d4 = pstrip_cta_double4(K, nw, max_lx, ring, max_slots);
+#ifndef PG2_HOST_EMU
+    cudaMemsetAsync(queue, 0, sizeof(int), stream);
+    const int smem = (int)ps_smem_bytes(nw, park_cap, smalltab);
+#define PG2_PS_LAUNCH(KK, S)                                                                                                      \
+    do {                                                                                                                          \
+        cudaFuncSetAttribute(pstrip_fill_kernel<KK, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
+        pstrip_fill_kernel<KK, S><<<n_ctas, nw * 32, smem, stream>>>(n_jobs, jobs, job_ids, graphs, models, d_state, d_off, d_estart, \
+                                                                    d_elogw, d_vrow, d_vlast, d_blo, d_bhi, ptrs, results, scratch,  \
+                                                                    cta_d4, end_d4, ring, max_slots, park_cap, queue);              \
+    } while (0)
+    if (K == 2) { if (smalltab) PG2_PS_LAUNCH(2, true); else PG2_PS_LAUNCH(2, false); }
+    else { if (smalltab) PG2_PS_LAUNCH(4, true); else PG2_PS_LAUNCH(4, false); }
+#undef PG2_PS_LAUNCH
+#else
+    (void)queue; (void)stream; (void)n_ctas; (void)nw; (void)smalltab; (void)cta_d4;
+    for (int q = 0; q < n_jobs; ++q) {
+        const int jid = job_ids[q];
+        const DevJob &J = jobs[jid];
+        DevResult *res = results + jid;
+        if (res->status != JOB_OK) continue;
+        if (K == 2) ps_emulate_job<2>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast,
+                                      d_blo, d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap);
+        else ps_emulate_job<4>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, d_blo,
+                               d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap);
+    }
+#endif
+}
+
+}  // namespace pg2

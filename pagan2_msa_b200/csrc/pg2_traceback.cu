@@ -12,6 +12,7 @@
 #include <string.h>
 #include "pg2_device.cuh"
 #include "pg2_strip_geom.cuh"
+#include "pg2_pstrip_geom.cuh"
 
 namespace pg2 {
 
@@ -398,8 +399,140 @@ __global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *j
                                  DevResult *results) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
-    if (jobs[job_ids[t]].kernel == 0) return;  // wavefront-layout jobs: traceback_wave_kernel
+    if (jobs[job_ids[t]].kernel == 0 || jobs[job_ids[t]].kernel == 3) return;  // traceback_wave_kernel / traceback_pstrip_kernel
     traceback_one(job_ids[t], jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
+}
+#endif
+
+// ---- pipelined-strip layout (pg2_pstrip_geom.cuh): one warp per path, a window of one block's step rows at a time ----
+// The pointer words of a block lie step-major ([step][lane][K], step = virtual row - v0 + lane).  The warp loads the
+// PTW_WORDS / (32 K) step rows that end at the walk's current step into shared memory (coalesced, all loads in flight)
+// and lane 0 walks inside them; a plain row / plain column flag in the word saves the CSR lookup of the next site.
+constexpr int PTW_WORDS = 4096;
+struct PsTraceWin {
+    unsigned w[PTW_WORDS];
+    int b, t_hi;  // block and last step held (b < 0: nothing loaded)
+};
+struct PsTraceJob {
+    const int *blocks, *colinfo, *vlast;
+    const unsigned *P;
+    int K, rows;  // step rows per window
+};
+struct PsTraceState {
+    TraceState s;
+    int v;                      // virtual row that completed site s.i, or -1: not known
+    int b, c0, c1, v0, v1, off; // block of column s.j (b < 0: not known)
+    int need_t;                 // the step the walk stopped at (to be the last step of the next window)
+};
+
+__device__ __forceinline__ void ps_trace_block(const PsTraceJob &tj, PsTraceState &st, int j) {
+    if (st.b >= 0 && j >= st.c0 && j < st.c1) return;
+    st.b = tj.colinfo[j] >> PC_BLOCK_SHIFT;
+    const int *e = tj.blocks + st.b * PB_INTS;
+    st.c0 = e[0]; st.c1 = e[1]; st.v0 = e[2]; st.v1 = e[3]; st.off = e[5];
+}
+
+// walks while the cells are inside the window; returns with st.s.done set, or at a cell outside the window
+__device__ __forceinline__ void ps_trace_walk(const DevJob &J, const PsTraceJob &tj, const PsTraceWin &W, const int *l_off, const int *r_off,
+                                              const int *l_es, const int *r_es, PsTraceState &st) {
+    TraceState &s = st.s;
+    for (;;) {
+        const int i = s.i, j = s.j;
+        if (s.vit == NO_MAT || i < 0 || j < 0 || i >= J.lx || j >= J.ly) { s.status = JOB_BROKEN_PATH; s.done = true; return; }
+        ps_trace_block(tj, st, j);
+        if (st.v < 0) st.v = tj.vlast[i];
+        if (st.v < st.v0 || st.v >= st.v1) { s.status = JOB_BROKEN_PATH; s.done = true; return; }  // a row the band keeps out of the block
+        const int jj = j - st.c0, l = jj / tj.K, k = jj - l * tj.K;
+        const int t = st.v - st.v0 + l;
+        if (W.b != st.b || t > W.t_hi || t <= W.t_hi - tj.rows) { st.need_t = t; return; }  // next window
+        if (s.em.raw >= J.step_cap) { s.status = JOB_BROKEN_PATH; s.done = true; return; }
+        const unsigned w = W.w[((W.t_hi - t) * 32 + l) * tj.K + k];
+        const unsigned q = word_ptr(w, s.vit);
+        emit_step(s.em, q);
+        const int src = (int)(q & 3u);
+        // the reference loop ends when (i<1 && j<1) AFTER reading the cell it stands on (:1073-1181)
+        if (s.vit == M_MAT || s.vit == X_MAT) {
+            if (src == NO_MAT) { s.i = -1; st.v = -1; }
+            else if (w & PSW_PLAIN_ROW) { s.i = i - 1; st.v -= 1; }
+            else { s.i = l_es[l_off[i] + ((q >> 2) & 63u)]; st.v = -1; }
+        }
+        if (s.vit == M_MAT || s.vit == Y_MAT)
+            s.j = (src == NO_MAT) ? -1 : ((w & PSW_PLAIN_COL) ? j - 1 : r_es[r_off[j] + ((q >> 8) & 63u)]);
+        s.vit = src;
+        if (s.i < 1 && s.j < 1) { s.done = true; return; }
+    }
+}
+
+// one lane's share of a window load: step rows t_hi, t_hi - 1, ... of block b; rows outside the block read as 0
+template <int K>
+__device__ __forceinline__ void ps_trace_load(const PsTraceJob &tj, PsTraceWin &W, int b, int t_hi, int lane) {
+    const int *e = tj.blocks + b * PB_INTS;
+    const int n_steps = e[3] - e[2] + 31;
+    const unsigned *base = tj.P + e[5] + lane * K;
+    constexpr int ROWS = PTW_WORDS / (32 * K), U = 16;
+#pragma unroll 1
+    for (int r0 = 0; r0 < ROWS; r0 += U) {
+        unsigned v[U][K];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int ts = t_hi - (r0 + u);
+            const bool ok = ts >= 0 && ts < n_steps;
+#pragma unroll
+            for (int k = 0; k < K; ++k) v[u][k] = ok ? __ldg(base + (long long)ts * 32 * K + k) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) W.w[((r0 + u) * 32 + lane) * K + k] = v[u][k];
+    }
+}
+
+__device__ __forceinline__ void ps_trace_setup(const DevJob &J, const DevGraph &GL, const DevGraph &GR, const int *d_vlast, const unsigned *ptrps,
+                                               PsTraceJob &tj) {
+    tj.blocks = d_vlast + J.blk_base;
+    tj.colinfo = d_vlast + GR.cp_ci_base;
+    tj.vlast = d_vlast + GL.vlast_base;
+    tj.P = ptrps + J.cell_base;
+    tj.K = J.strip_k;
+    tj.rows = PTW_WORDS / (32 * J.strip_k);
+}
+
+#ifndef PG2_HOST_EMU
+__global__ void __launch_bounds__(64) traceback_pstrip_kernel(int n_jobs, const int *job_ids, const DevJob *jobs, const DevGraph *graphs,
+                                                              const int *d_vlast, const int *d_off, const int *d_estart, const unsigned *ptrps,
+                                                              unsigned short *steps, DevResult *results) {
+    __shared__ PsTraceWin wins[2];
+    const int lane = threadIdx.x & 31, t = blockIdx.x * 2 + (threadIdx.x >> 5);
+    if (t >= n_jobs) return;
+    const int jid = job_ids[t];
+    const DevJob J = jobs[jid];
+    DevResult *res = results + jid;
+    if (J.kernel != 3 || res->status != JOB_OK) return;  // warp-uniform
+    PsTraceWin &W = wins[threadIdx.x >> 5];
+    const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+    const int *l_off = d_off + GL.off_base, *r_off = d_off + GR.off_base;
+    const int *l_es = d_estart + GL.edge_base, *r_es = d_estart + GR.edge_base;
+    PsTraceJob tj;
+    ps_trace_setup(J, GL, GR, d_vlast, ptrps, tj);
+    unsigned short *out = steps + J.step_base;
+    PsTraceState st;
+    st.s.i = st.s.j = 0; st.s.vit = NO_MAT; st.s.status = JOB_OK; st.s.done = false;
+    st.v = -1; st.b = -1; st.c0 = st.c1 = st.v0 = st.v1 = st.off = 0; st.need_t = 0;
+    emit_begin(st.s.em, out);
+    if (lane == 0) { W.b = -1; W.t_hi = 0; trace_wave_begin(J, res, l_off, r_off, l_es, r_es, out, st.s); }
+    __syncwarp();
+    for (;;) {
+        if (lane == 0 && !st.s.done) ps_trace_walk(J, tj, W, l_off, r_off, l_es, r_es, st);
+        const int done = __shfl_sync(0xffffffffu, (int)st.s.done, 0);
+        if (done) break;
+        const int nb = __shfl_sync(0xffffffffu, st.b, 0), nt = __shfl_sync(0xffffffffu, st.need_t, 0);
+        __syncwarp();
+        if (tj.K == 2) ps_trace_load<2>(tj, W, nb, nt, lane);
+        else ps_trace_load<4>(tj, W, nb, nt, lane);
+        if (lane == 0) { W.b = nb; W.t_hi = nt; }
+        __syncwarp();
+    }
+    if (lane == 0) { emit_flush(st.s.em); res->n_steps = st.s.em.n; res->pad = st.s.em.raw; res->status = st.s.status; }
 }
 #endif
 
@@ -460,23 +593,56 @@ void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *j
 }
 
 // n_wave: how many of the jobs were filled by the wavefront kernel (they get the warp-per-path walk)
-void launch_traceback(int n_jobs, int n_wave, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
+void launch_traceback(int n_jobs, int n_wave, int n_ps, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
-                      const unsigned *ptr32, const unsigned short *ptr16, unsigned short *steps, DevResult *results, cudaStream_t stream) {
+                      const unsigned *ptr32, const unsigned short *ptr16, const unsigned *ptrps, unsigned short *steps, DevResult *results,
+                      cudaStream_t stream) {
     if (n_jobs <= 0) return;
 #ifndef PG2_HOST_EMU
     const int threads = 64;
-    if (n_wave < n_jobs)
+    if (n_ps > 0)
+        traceback_pstrip_kernel<<<(n_jobs + 1) / 2, 64, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_vlast, d_off, d_estart, ptrps, steps, results);
+    if (n_wave + n_ps < n_jobs)
         traceback_kernel<<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_vlast, d_off, d_estart, d_blo,
                                                                                   d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
     if (n_wave > 0)
         traceback_wave_kernel<<<(n_jobs + 3) / 4, 128, 0, stream>>>(n_jobs, job_ids, jobs, graphs, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff,
                                                                    ptr32, steps, results);
 #else
-    (void)stream; (void)n_wave;
+    (void)stream; (void)n_wave; (void)n_ps;
     for (int t = 0; t < n_jobs; ++t) {
         const int jid = job_ids[t];
         const DevJob J = jobs[jid];
+        if (J.kernel == 3) {
+            // the warp-per-path walk of the pipelined-strip layout, lanes one after the other
+            DevResult *res = results + jid;
+            if (res->status != JOB_OK) continue;
+            const DevGraph GL = graphs[J.left], GR = graphs[J.right];
+            const int *l_off = d_off + GL.off_base, *r_off = d_off + GR.off_base;
+            const int *l_es = d_estart + GL.edge_base, *r_es = d_estart + GR.edge_base;
+            PsTraceJob tj;
+            ps_trace_setup(J, GL, GR, d_vlast, ptrps, tj);
+            unsigned short *out = steps + J.step_base;
+            PsTraceState st;
+            st.v = -1; st.b = -1; st.c0 = st.c1 = st.v0 = st.v1 = st.off = 0; st.need_t = 0;
+            static PsTraceWin W;
+            W.b = -1; W.t_hi = 0;
+            trace_wave_begin(J, res, l_off, r_off, l_es, r_es, out, st.s);
+            while (!st.s.done) {
+                ps_trace_walk(J, tj, W, l_off, r_off, l_es, r_es, st);
+                if (st.s.done) break;
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (tj.K == 2) ps_trace_load<2>(tj, W, st.b, st.need_t, lane);
+                    else ps_trace_load<4>(tj, W, st.b, st.need_t, lane);
+                }
+                W.b = st.b; W.t_hi = st.need_t;
+            }
+            emit_flush(st.s.em);
+            res->n_steps = st.s.em.n;
+            res->pad = st.s.em.raw;
+            res->status = st.s.status;
+            continue;
+        }
         if (J.kernel != 0) {
             traceback_one(jid, jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
             continue;

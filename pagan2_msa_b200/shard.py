@@ -115,6 +115,12 @@ def align_sharded(eng, jobs, dist, rank, world, device, root=0):
         batch.run()
         rec, st = buffer_views(batch, device)
         parts = gather_to_root(dist, rank, world, rec, st, root)
+        if device.type == "cuda":
+            # rec / st are views of the engine's own buffers and the gather is asynchronous (NCCL stream): every rank
+            # waits for its sends before the batch is closed and the next batch may rewrite or free those buffers
+            import torch
+
+            torch.cuda.current_stream(device).synchronize()
     finally:
         batch.close()
     if rank != root:

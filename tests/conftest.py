@@ -16,8 +16,19 @@ def pytest_configure(config):
 GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.pjob.gz")))
 
 
+class _Golden(dict):
+    """name -> list[FlatJob], loaded on first use (the BASELINE-size streams are large)."""
+
+    def __missing__(self, name):
+        from pagan2_msa_b200 import jobio
+
+        path = os.path.join(ROOT, "tests", "golden", name + ".pjob.gz")
+        if not os.path.exists(path):
+            raise KeyError(name)
+        self[name] = jobio.load_jobs(path)
+        return self[name]
+
+
 @pytest.fixture(scope="session")
 def golden():
-    from pagan2_msa_b200 import jobio
-
-    return {os.path.basename(p).split(".")[0]: jobio.load_jobs(p) for p in GOLDEN}
+    return _Golden()

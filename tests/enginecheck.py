@@ -5,7 +5,8 @@ import oracle_lib
 
 
 def expect_from_oracle(job):
-    status, score, steps, cells = oracle_lib.oracle_align(job)
+    status, score, steps, cells, ul, ur = oracle_lib.oracle_align(job, marks=True)
+    job.oracle_marks = (ul, ur)
     job.expected_status = status
     job.expected_score = score
     job.expected_path = np.stack([steps[n] for n in ("matrix", "x_ind", "y_ind", "x_edge_ind", "y_edge_ind", "real_site")],
@@ -14,12 +15,20 @@ def expect_from_oracle(job):
     return job
 
 
-def used_edges_from_path(job, path):
-    """Edges the reference marks used, derived from the expected path (real steps carry the indices)."""
-    real = path[path[:, 5] == 1]
-    left = set(int(e) for e in real[:, 3] if e >= 0)
-    right = set(int(e) for e in real[:, 4] if e >= 0)
-    return left, right
+def check_marks(job, ul, ur, k=0):
+    """The is_used(true) marks pg2_expand_path replays (viterbi_alignment.cpp:1054-1155): equal, in order, to the oracle's
+    restatement of backtrack_new_path; and as a set equal to what the REFERENCE itself left marked (fixtures dumped by the
+    interposer carry the flags before and after the reference's call)."""
+    marks = getattr(job, "oracle_marks", None)
+    if marks is None:
+        marks = oracle_lib.oracle_align(job, marks=True)[4:6]
+    assert ul.tolist() == marks[0].tolist(), "job %d: left edge marks differ from the oracle's (order included)" % k
+    assert ur.tolist() == marks[1].tolist(), "job %d: right edge marks differ from the oracle's (order included)" % k
+    used = getattr(job, "expected_used", None)
+    if used is not None:
+        for side, mine in (("l", ul), ("r", ur)):
+            before, after = set(used[side][0].tolist()), set(used[side][1].tolist())
+            assert before | set(mine.tolist()) == after, "job %d: %s edge marks differ from the reference's" % (k, side)
 
 
 def check_batch(eng, jobs, expect_kernel=None):
@@ -38,10 +47,9 @@ def check_batch(eng, jobs, expect_kernel=None):
         assert np.float64(r["score"]).view(np.uint64) == np.float64(job.expected_score).view(np.uint64), \
             "job %d: score %r vs %r" % (k, r["score"], job.expected_score)
         st, ul, ur = eng.expand(job, r, steps)
-        diffs = oracle_lib.steps_equal(st, job.expected_path, job.expected_path_score)
+        diffs = oracle_lib.steps_equal(st, job.expected_path, job.expected_path_score, getattr(job, 'expected_path_score_sha', None))
         assert diffs == [], "job %d (kernel %d): %s" % (k, r["kernel"], diffs)
-        wl, wr = used_edges_from_path(job, job.expected_path)
-        assert wl <= set(ul.tolist()) and wr <= set(ur.tolist())
+        check_marks(job, ul, ur, k)
         if expect_kernel is not None:
             assert r["kernel"] == expect_kernel
     return res

@@ -108,8 +108,60 @@ def bench_targets(tmp):
     return jobs[:127]
 
 
+# ---- BASELINE-size job streams of the reference (VERDICT r1, next #1b): stored compactly (jobio, compact=True) ----
+
+def c1_full(tmp):
+    """config 1 at BASELINE size: 16 taxa x 1 kb, all 15 alignments (leaf x leaf, ancestor x ancestor up to the root)."""
+    rng = np.random.default_rng(1101)
+    tree, seqs = synth.balanced_tree(4, synth.random_dna(1000, rng), rng)
+    synth.write_fasta(os.path.join(tmp, "s.fas"), seqs)
+    open(os.path.join(tmp, "t.nwk"), "w").write(tree + "\n")
+    jobs, _ = oracle_lib.run_ref(["-s", "s.fas", "-t", "t.nwk", "-o", "out", "--no-anchors", "--silent"], tmp)
+    return jobs
+
+
+def c3_full(tmp):
+    """config 3 at BASELINE read size: --pileup-alignment --homopolymer of 220 454-like 400-nt reads from a 2 kb template;
+    the root grows with every read.  Every 10th alignment plus the last four are kept."""
+    rng = np.random.default_rng(1303)
+    t = list(synth.random_dna(2000, rng))
+    for i in range(1, len(t)):
+        if rng.random() < 0.35:
+            t[i] = t[i - 1]
+    reads = synth.reads_454("".join(t), 220, 400, rng)
+    synth.write_fasta(os.path.join(tmp, "r.fas"), reads)
+    jobs, _ = oracle_lib.run_ref(["--pileup-alignment", "--homopolymer", "--queryfile", "r.fas", "-o", "pile", "--no-anchors",
+                                  "--silent"], tmp, timeout=7200)
+    keep = sorted(set(range(0, len(jobs), 10)) | set(range(len(jobs) - 4, len(jobs))))
+    return [jobs[k] for k in keep]
+
+
+def c4_full(tmp):
+    """config 4 at BASELINE sequence size: --codons, 8 taxa x 1000 codons, all 7 alignments (fas 1892)."""
+    rng = np.random.default_rng(1404)
+    tree, seqs = synth.balanced_codon_tree(3, synth.random_codons(1000, rng), rng)
+    synth.write_fasta(os.path.join(tmp, "s.fas"), seqs)
+    open(os.path.join(tmp, "t.nwk"), "w").write(tree + "\n")
+    jobs, _ = oracle_lib.run_ref(["-s", "s.fas", "-t", "t.nwk", "-o", "out", "--codons", "--no-anchors", "--silent"], tmp, timeout=7200)
+    return jobs
+
+
+def c5_full(tmp):
+    """config 5 at BASELINE sequence size: 4 x 200 kb with prefix anchors: two leaf x leaf and one ancestor x ancestor
+    alignment inside their bands, run by the reference itself (~80 s of CPU each)."""
+    rng = np.random.default_rng(1505)
+    tree, seqs = synth.balanced_tree(2, synth.random_dna(200000, rng), rng, sub=0.01, indel=0.001)
+    synth.write_fasta(os.path.join(tmp, "s.fas"), seqs)
+    open(os.path.join(tmp, "t.nwk"), "w").write(tree + "\n")
+    # the ancestor x ancestor band is wide (the reference predicts more than its default 4 GB of matrices)
+    jobs, _ = oracle_lib.run_ref(["-s", "s.fas", "-t", "t.nwk", "-o", "out", "--use-prefix-anchors", "--anchors-offset", "15",
+                                  "--memory-for-single-alignment", "50000", "--silent"], tmp, timeout=14400)
+    return jobs
+
+
 FIXTURES = [("prog_dna", progressive_dna), ("place_dna", placement_dna), ("pileup_hp", pileup_homopolymer),
-            ("codon", codons), ("anchored", anchored), ("bench_targets", bench_targets)]
+            ("codon", codons), ("anchored", anchored), ("bench_targets", bench_targets),
+            ("c1_full", c1_full), ("c3_full", c3_full), ("c4_full", c4_full), ("c5_full", c5_full)]
 
 
 def main():
@@ -121,7 +173,7 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             jobs = fn(tmp)
         path = os.path.join(HERE, name + ".pjob.gz")
-        jobio.save_jobs(path, jobs)
+        jobio.save_jobs(path, jobs, compact=name.endswith("_full"))
         cells = sum(j.cells for j in jobs)
         banded = sum(1 for j in jobs if j.upper is not None)
         print("%-10s %4d jobs %10d cells %3d banded  fas=%d  %8.1f KB" % (name, len(jobs), cells, banded, jobs[0].model.fas,

@@ -36,12 +36,15 @@ def oracle():
         lib.pg2o_align.restype = C.c_int
         lib.pg2o_align.argtypes = [C.POINTER(abi.Job), C.POINTER(abi.ModelDesc), C.POINTER(C.c_double),
                                    C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        lib.pg2o_align_marks.restype = C.c_int
+        lib.pg2o_align_marks.argtypes = lib.pg2o_align.argtypes + [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]
         _oracle = lib
     return _oracle
 
 
-def oracle_align(job):
-    """Runs the C restatement on one FlatJob -> (status, score, steps[STEP_DTYPE], cells)."""
+def oracle_align(job, marks=False):
+    """Runs the C restatement on one FlatJob -> (status, score, steps[STEP_DTYPE], cells); with marks=True also the
+    edge indices backtrack_new_path marks is_used(true), in marking order: (..., used_left, used_right)."""
     lib = oracle()
     cap = job.left.n_sites + job.right.n_sites + 2
     steps = np.zeros(cap, dtype=abi.STEP_DTYPE)
@@ -50,9 +53,14 @@ def oracle_align(job):
     score = C.c_double()
     n = C.c_int32()
     cells = C.c_int64()
-    rc = lib.pg2o_align(C.byref(js), C.byref(ms), C.byref(score), steps.ctypes.data, cap, C.byref(n), C.byref(cells))
+    ul, ur = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    nl, nr = C.c_int32(), C.c_int32()
+    rc = lib.pg2o_align_marks(C.byref(js), C.byref(ms), C.byref(score), steps.ctypes.data, cap, C.byref(n), C.byref(cells),
+                              ul.ctypes.data, C.byref(nl), ur.ctypes.data, C.byref(nr))
     if rc < 0:
         raise RuntimeError("oracle: capacity/allocation failure")
+    if marks:
+        return rc, score.value, steps[: n.value].copy(), cells.value, ul[: nl.value].copy(), ur[: nr.value].copy()
     return rc, score.value, steps[: n.value].copy(), cells.value
 
 
@@ -78,6 +86,8 @@ def ref_lib():
                                               C.c_int, i32p, i32p, i32p, f32p, i32p,
                                               i32p, i32p, C.c_int,
                                               C.POINTER(C.c_double), i32p, C.POINTER(C.c_double), C.c_int, i32p]
+        lib.pagan2_ref_last_used.restype = C.c_int
+        lib.pagan2_ref_last_used.argtypes = [C.c_int, i32p, C.c_int]
         _ref = lib
     return _ref
 
@@ -105,8 +115,22 @@ def ref_align_flat(job):
     return score.value, path[: n.value * 6].reshape(-1, 6).copy(), ps[: n.value].copy()
 
 
-def steps_equal(steps, path, path_score):
-    """Bit-exact comparison of STEP_DTYPE steps with reference (n,6) path + scores; returns list of diffs."""
+def ref_last_used():
+    """Edge indices the last ref_align_flat call left marked is_used (fresh graphs: exactly the call's marks):
+    (left, right), ascending."""
+    lib = ref_lib()
+    out = []
+    for side in (0, 1):
+        n = lib.pagan2_ref_last_used(side, None, 0)
+        buf = np.zeros(max(n, 1), np.int32)
+        lib.pagan2_ref_last_used(side, abi._ptr(buf, C.c_int32), n)
+        out.append(buf[:n].copy())
+    return out[0], out[1]
+
+
+def steps_equal(steps, path, path_score, path_score_sha=None):
+    """Bit-exact comparison of STEP_DTYPE steps with reference (n,6) path + scores (or, for long fixture paths, the
+    SHA-256 of the scores' bytes); returns list of diffs."""
     diffs = []
     if len(steps) != len(path):
         return ["length %d vs %d" % (len(steps), len(path))]
@@ -121,6 +145,11 @@ def steps_equal(steps, path, path_score):
         bad = np.nonzero(a != b)[0]
         if len(bad):
             diffs.append("score bits differ at %d steps (first %d: %r vs %r)" % (len(bad), bad[0], steps["score"][bad[0]], path_score[bad[0]]))
+    elif path_score_sha is not None:
+        from pagan2_msa_b200 import jobio
+
+        if jobio.sha_words(np.ascontiguousarray(steps["score"], dtype="<f8")).tolist() != np.asarray(path_score_sha).tolist():
+            diffs.append("per-step scores: SHA-256 differs from the reference's")
     return diffs
 
 

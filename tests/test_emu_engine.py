@@ -23,14 +23,19 @@ def emu_lib():
     return EMU_LIB
 
 
-def make_engine(lib, force_wavefront, no_lanes=False):
+def make_engine(lib, force_wavefront, no_lanes=False, no_pstrip=False, pstrip_k=None):
+    """no_pstrip: keep the pipelined-strip kernel out, so that the warp-per-alignment strip kernel and the general
+    wavefront kernel (its fallback) stay covered; pstrip_k=4 forces the wider strips."""
     os.environ["PG2_FORCE_WAVEFRONT"] = "1" if force_wavefront else "0"
     os.environ["PG2_NO_LANES"] = "1" if no_lanes else "0"
+    os.environ["PG2_NO_PSTRIP"] = "1" if no_pstrip else "0"
+    if pstrip_k:
+        os.environ["PG2_PSTRIP_K"] = str(pstrip_k)
     try:
         return engine.Engine(0, lib)
     finally:
-        os.environ.pop("PG2_FORCE_WAVEFRONT", None)
-        os.environ.pop("PG2_NO_LANES", None)
+        for name in ("PG2_FORCE_WAVEFRONT", "PG2_NO_LANES", "PG2_NO_PSTRIP", "PG2_PSTRIP_K"):
+            os.environ.pop(name, None)
 
 
 @pytest.mark.parametrize("force_wavefront", [True, False])
@@ -43,12 +48,28 @@ def test_golden(emu_lib, golden, name, force_wavefront):
 
 
 def test_strip_kernel_is_chosen_for_placement(emu_lib, golden):
-    with make_engine(emu_lib, False, no_lanes=True) as eng:
+    with make_engine(emu_lib, False, no_lanes=True, no_pstrip=True) as eng:
         res = enginecheck.check_batch(eng, golden["place_dna"])
         assert (res["kernel"] == 1).all()
-    with make_engine(emu_lib, False) as eng:
+    with make_engine(emu_lib, False, no_pstrip=True) as eng:
         res = enginecheck.check_batch(eng, golden["place_dna"])
         assert np.isin(res["kernel"], (1, 2)).all()
+    with make_engine(emu_lib, False, no_lanes=True) as eng:  # a batch this small goes to the CTA-per-alignment kernel
+        res = enginecheck.check_batch(eng, golden["place_dna"])
+        assert (res["kernel"] == 3).all()
+
+
+@pytest.mark.parametrize("name", ["prog_dna", "place_dna", "pileup_hp", "codon", "anchored"])
+@pytest.mark.parametrize("k", [2, 4])
+def test_golden_pstrip(emu_lib, golden, name, k):
+    """Every reference job stream through the pipelined-strip kernel (general graphs on both sides, bands), both strip
+    widths; and with the older kernels only."""
+    with make_engine(emu_lib, False, no_lanes=True, pstrip_k=k) as eng:
+        res = enginecheck.check_batch(eng, golden[name])
+        assert (res["kernel"] == 3).all()
+    with make_engine(emu_lib, False, no_pstrip=True) as eng:
+        res = enginecheck.check_batch(eng, golden[name])
+        assert (res["kernel"] != 3).all()
 
 
 @pytest.mark.parametrize("seed,plain_left,n_jobs", [(61, False, 70), (62, True, 40), (63, False, 33), (64, False, 16), (65, True, 100)])
@@ -61,7 +82,7 @@ def test_lane_kernel_shared_target_vs_oracle(emu_lib, seed, plain_left, n_jobs):
         jobs += randjobs.random_shared_target_jobs(rng, n_jobs, plain_left=plain_left)
     jobs += [randjobs.random_job(rng, "strip") for _ in range(5)]  # singletons stay on the strip kernel
     jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
-    with make_engine(emu_lib, False) as eng:
+    with make_engine(emu_lib, False, no_pstrip=True) as eng:
         res = enginecheck.check_batch(eng, jobs)
         st = eng.stats()
     assert (res["kernel"][:3 * n_jobs] == 2).all()
@@ -194,7 +215,7 @@ def test_pipelined_align_batch_matches_single_shot(emu_lib, chunks):
         with make_engine(emu_lib, False) as eng:
             res = enginecheck.check_batch(eng, jobs)
             assert (res["kernel"] == 2).sum() >= 4 * 32
-            assert eng.stats()["jobs_lanes"] + eng.stats()["jobs_strip"] + eng.stats()["jobs_wavefront"] == len(jobs)
+            assert sum(eng.stats()[k] for k in ("jobs_lanes", "jobs_strip", "jobs_wavefront", "jobs_pstrip")) == len(jobs)
             # twice on the same engine: the sibling context and its buffers are reused
             enginecheck.check_batch(eng, jobs[::-1])
     finally:
@@ -245,3 +266,48 @@ def test_path_runs_longer_than_one_repeat_word(emu_lib):
     with make_engine(emu_lib, False) as eng:
         res = enginecheck.check_batch(eng, [job])
         assert res["n_steps"][0] < 64 and len(job.expected_path) > 39000
+
+
+@pytest.mark.parametrize("kind,seed,k", [("general", 81, 2), ("general", 82, 4), ("banded", 83, 2), ("banded", 84, 4),
+                                         ("strip", 85, 2), ("banded_chain", 86, 2)])
+def test_pstrip_random_jobs_vs_oracle(emu_lib, kind, seed, k):
+    """Pipelined-strip kernel on seeded random jobs: multi-edge graphs with long spans and weights on both sides, tie-prone
+    parameter sets, random monotone bands, every flag combination."""
+    rng = np.random.default_rng(seed)
+    jobs = [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for _ in range(60)]
+    with make_engine(emu_lib, False, no_lanes=True, pstrip_k=k) as eng:
+        res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 3).mean() > 0.9
+
+
+@pytest.mark.parametrize("seed,banded", [(91, False), (92, True), (93, False), (94, True)])
+def test_pstrip_many_blocks(emu_lib, seed, banded):
+    """Jobs wide enough for several column blocks per alignment (the blocks of the CTA pipeline): general x general graphs
+    of a few hundred sites, long-span edges that cross lanes, parked rows read across a block's lanes, bands that leave
+    some blocks without rows."""
+    rng = np.random.default_rng(seed)
+    jobs = []
+    for _ in range(6):
+        model = randjobs.random_model(rng, 15, ties=rng.random() < 0.4)
+        nl, nr = int(rng.integers(150, 420)), int(rng.integers(150, 420))
+        left = randjobs.random_graph(rng, nl, 15, p_extra=0.1, max_span=int(rng.integers(3, 25)))
+        right = randjobs.random_graph(rng, nr, 15, p_extra=float(rng.choice([0.03, 0.12])), max_span=int(rng.integers(3, 20)))
+        job = abi.FlatJob(left, right, model, int(rng.integers(0, 4)))
+        if banded:
+            job.upper, job.lower = randjobs.random_band(rng, left.n_sites - 1, right.n_sites - 1, min_w=3, max_w=40)
+        jobs.append(enginecheck.expect_from_oracle(job))
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, jobs)
+        st = eng.stats()
+    # (a right graph without a cut point within a block's width stays on the general wavefront kernel)
+    assert (res["kernel"] == 3).sum() >= len(jobs) - 1 and st["jobs_pstrip"] == int((res["kernel"] == 3).sum())
+
+
+@pytest.mark.parametrize("name", ["c1_full", "c3_full", "c5_full"])
+def test_reference_streams_at_baseline_size(emu_lib, golden, name):
+    """The engine's host logic and the pipelined-strip kernel body on job streams the reference ran at BASELINE sizes
+    (several column blocks per alignment, real anchor bands, 200 kb graphs)."""
+    jobs = golden[name] if name != "c3_full" else golden[name][::3]
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 3).sum() >= len(jobs) - 2

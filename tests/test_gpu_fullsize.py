@@ -21,6 +21,20 @@ def eng():
     e.close()
 
 
+@pytest.fixture(scope="module")
+def eng_old():
+    """Without the pipelined-strip kernel (strip + wavefront kernels only)."""
+    import os
+
+    os.environ["PG2_NO_PSTRIP"] = "1"
+    try:
+        e = engine.Engine(0)
+    finally:
+        os.environ.pop("PG2_NO_PSTRIP", None)
+    yield e
+    e.close()
+
+
 def indel_copy(a, rng, sub, n_indels, max_len):
     """b = a with substitutions and a few indels; returns (b, col) with col[i] = column of b facing row i of a."""
     pos = np.sort(rng.choice(np.arange(100, len(a) - 100), size=n_indels, replace=False))
@@ -46,7 +60,7 @@ def indel_copy(a, rng, sub, n_indels, max_len):
     return b, col
 
 
-def test_config5_anchored_200kb(eng, golden):
+def test_config5_anchored_200kb(eng, eng_old, golden):
     """configs[4]: one 200 kb x 200 kb alignment inside an anchor band (banded wavefront kernel, 10 M in-band cells)."""
     rng = np.random.default_rng(5005)
     model = golden["anchored"][0].model
@@ -62,11 +76,14 @@ def test_config5_anchored_200kb(eng, golden):
     job.upper = np.maximum.accumulate(job.upper).astype(np.int32)
     job.lower = np.maximum.accumulate(job.lower).astype(np.int32)
     assert 9_000_000 < job.cells < 12_000_000
-    res = enginecheck.check_batch(eng, [enginecheck.expect_from_oracle(job)])
+    job = enginecheck.expect_from_oracle(job)
+    res = enginecheck.check_batch(eng, [job])
+    assert res["kernel"][0] == 3 and res["status"][0] == 0
+    res = enginecheck.check_batch(eng_old, [job])
     assert res["kernel"][0] == 0 and res["status"][0] == 0
 
 
-def test_config4_codons_1000(eng, golden):
+def test_config4_codons_1000(eng, eng_old, golden):
     """configs[3]: 1002 x 1002 codon sites, 1892-state table (strip kernel, global float table), leaf vs leaf and
     an ancestor-shaped graph vs leaf."""
     rng = np.random.default_rng(4004)
@@ -80,11 +97,14 @@ def test_config4_codons_1000(eng, golden):
     anc = randjobs.random_graph(rng, 1000, 61, p_extra=0.05)
     jobs = [abi.FlatJob(abi.FlatGraph.chain(a), abi.FlatGraph.chain(b), model, 2),
             abi.FlatJob(anc, abi.FlatGraph.chain(b), model, 2)]
-    res = enginecheck.check_batch(eng, [enginecheck.expect_from_oracle(j) for j in jobs])
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 3).all()
+    res = enginecheck.check_batch(eng_old, jobs)
     assert (res["kernel"] == 1).all()
 
 
-def test_config3_pileup_shape(eng, golden):
+def test_config3_pileup_shape(eng, eng_old, golden):
     """configs[2]: a grown pileup root (2 k sites, multi-edge) against a 400-nt 454 read graph (multi-edge): the
     general wavefront kernel, both graphs with long-span edges and weights."""
     rng = np.random.default_rng(3003)
@@ -94,11 +114,14 @@ def test_config3_pileup_shape(eng, golden):
         left = randjobs.random_graph(rng, 2000, 4, p_extra=0.15, max_span=6)
         right = randjobs.random_graph(rng, 400, 4, p_extra=0.3, max_span=4)
         jobs.append(abi.FlatJob(left, right, model, 2))
-    res = enginecheck.check_batch(eng, [enginecheck.expect_from_oracle(j) for j in jobs])
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
+    res = enginecheck.check_batch(eng, jobs)
+    assert np.isin(res["kernel"], (0, 3)).all()
+    res = enginecheck.check_batch(eng_old, jobs)
     assert (res["kernel"] == 0).all()
 
 
-def test_config1_progressive_1kb_wave(eng, golden):
+def test_config1_progressive_1kb_wave(eng, eng_old, golden):
     """configs[0]: the 8 + 4 + 2 + 1 alignments of a 16-taxon x 1 kb guide tree as launch batches: leaves (plain
     chains) and ancestor-shaped graphs on both sides."""
     rng = np.random.default_rng(1001)
@@ -106,15 +129,22 @@ def test_config1_progressive_1kb_wave(eng, golden):
     root = synth.random_dna(1000, rng)
     leaves = [synth.dna_states(synth.evolve(root, rng)) for _ in range(16)]
     wave1 = [abi.FlatJob(abi.FlatGraph.chain(leaves[2 * k]), abi.FlatGraph.chain(leaves[2 * k + 1]), model, 2) for k in range(8)]
-    res = enginecheck.check_batch(eng, [enginecheck.expect_from_oracle(j) for j in wave1])
+    wave1 = [enginecheck.expect_from_oracle(j) for j in wave1]
+    res = enginecheck.check_batch(eng, wave1)
+    assert (res["kernel"] == 3).all()
+    res = enginecheck.check_batch(eng_old, wave1)
     assert (res["kernel"] == 1).all()
     anc = [randjobs.random_graph(rng, 1100, 4, p_extra=0.06, max_span=8) for _ in range(6)]
     wave2 = [abi.FlatJob(anc[2 * k], anc[2 * k + 1], model, 2) for k in range(3)]
-    res = enginecheck.check_batch(eng, [enginecheck.expect_from_oracle(j) for j in wave2])
+    wave2 = [enginecheck.expect_from_oracle(j) for j in wave2]
+    res = enginecheck.check_batch(eng, wave2)
+    assert (res["kernel"] == 3).all()
+    res = enginecheck.check_batch(eng_old, wave2)
     assert (res["kernel"] == 0).all()
 
 
-def test_wavefront_diagonals_longer_than_the_ring(eng, golden):
+def test_wavefront_diagonals_longer_than_the_ring(eng_old, golden):
+    eng = eng_old
     """A general x general job whose anti-diagonals (3000 cells) exceed the wavefront kernel's shared-memory ring
     (WAVE_RING_MAX = 2816): every score read goes to the global scratch, the original path."""
     rng = np.random.default_rng(2816)

@@ -24,13 +24,44 @@ def eng():
     e.close()
 
 
+def engine_with(**env):
+    """An Engine created under the given PG2_* switches (read once, at pg2_ctx_create)."""
+    for k, v in env.items():
+        os.environ[k] = str(v)
+    try:
+        return engine.Engine(0)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+
+
 @pytest.fixture(scope="module")
 def eng_wave():
-    os.environ["PG2_FORCE_WAVEFRONT"] = "1"
-    try:
-        e = engine.Engine(0)
-    finally:
-        os.environ.pop("PG2_FORCE_WAVEFRONT", None)
+    e = engine_with(PG2_FORCE_WAVEFRONT=1)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_old():
+    """Without the pipelined-strip kernel: the warp-per-alignment strip kernel and the general wavefront kernel (the
+    fallback for graphs outside the pipelined-strip kernel's limits) stay covered."""
+    e = engine_with(PG2_NO_PSTRIP=1)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_ps():
+    """Every job that is not a lane task goes to the pipelined-strip kernel."""
+    e = engine_with(PG2_NO_LANES=1, PG2_PSTRIP_MAX_JOBS=1000000)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_ps4():
+    e = engine_with(PG2_NO_LANES=1, PG2_PSTRIP_MAX_JOBS=1000000, PG2_PSTRIP_K=4)
     yield e
     e.close()
 
@@ -46,20 +77,40 @@ def test_golden_wavefront_kernel(eng_wave, golden, name):
     assert (res["kernel"] == 0).all()
 
 
+@pytest.mark.parametrize("name", ["prog_dna", "place_dna", "pileup_hp", "codon", "anchored"])
+def test_golden_pstrip_kernel(eng_ps, eng_ps4, eng_old, golden, name):
+    """The reference's job streams of all five config shapes through the pipelined-strip kernel (both strip widths) and
+    through the older kernels only."""
+    for e in (eng_ps, eng_ps4):
+        res = enginecheck.check_batch(e, golden[name])
+        assert (res["kernel"] == 3).all()
+    res = enginecheck.check_batch(eng_old, golden[name])
+    assert (res["kernel"] != 3).all()
+
+
+@pytest.mark.parametrize("name", ["c1_full", "c3_full", "c4_full", "c5_full"])
+def test_reference_streams_at_baseline_size(eng, eng_old, golden, name):
+    """BASELINE-size job streams dumped from the REFERENCE itself (tests/golden/make_golden.py): 16 x 1 kb progressive (all
+    15 alignments), the growing pileup root against 400-nt 454 read graphs, 1000-codon alignments with the 1892-state
+    table, and 200 kb x 200 kb anchored alignments incl. ancestor x ancestor inside its band.  Score bits, every path
+    field, every per-step score (or their SHA-256 for the 400 000-step paths) and the used-edge marks."""
+    jobs = golden[name]
+    res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 3).sum() >= len(jobs) - 2
+    if name != "c5_full":  # the wavefront kernel needs 36 bytes per cell: minutes for the widest 200 kb band
+        enginecheck.check_batch(eng_old, jobs)
+
+
 @pytest.fixture(scope="module")
 def eng_nolanes():
-    os.environ["PG2_NO_LANES"] = "1"
-    try:
-        e = engine.Engine(0)
-    finally:
-        os.environ.pop("PG2_NO_LANES", None)
+    e = engine_with(PG2_NO_LANES=1, PG2_NO_PSTRIP=1)
     yield e
     e.close()
 
 
 def test_placement_uses_register_strip_kernels(eng, eng_nolanes, golden):
     res = enginecheck.check_batch(eng, golden["place_dna"])
-    assert np.isin(res["kernel"], (1, 2)).all()
+    assert np.isin(res["kernel"], (1, 2, 3)).all() and (res["kernel"] == 2).any()
     res = enginecheck.check_batch(eng_nolanes, golden["place_dna"])
     assert (res["kernel"] == 1).all()
 
@@ -76,7 +127,7 @@ def test_lane_kernel_shared_target_vs_oracle(eng, seed, plain_left, n_jobs):
     jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
     res = enginecheck.check_batch(eng, jobs)
     assert (res["kernel"][:6 * n_jobs] == 2).all()
-    assert (res["kernel"][-5:] == 1).all()
+    assert np.isin(res["kernel"][-5:], (1, 3)).all()
 
 
 def test_lane_kernel_long_reads_and_bad_job(eng):
@@ -116,10 +167,34 @@ def test_lane_and_strip_kernels_agree_bitwise(eng, eng_nolanes, golden):
 
 
 @pytest.mark.parametrize("kind,seed", [("general", 121), ("banded", 122), ("strip", 123), ("banded_chain", 124)])
-def test_random_jobs_vs_oracle(eng, kind, seed):
+def test_random_jobs_vs_oracle(eng, eng_old, eng_ps4, kind, seed):
     rng = np.random.default_rng(seed)
     jobs = [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for _ in range(300)]
-    enginecheck.check_batch(eng, jobs)
+    res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 3).mean() > 0.9
+    enginecheck.check_batch(eng_ps4, jobs)
+    res = enginecheck.check_batch(eng_old, jobs)
+    assert (res["kernel"] != 3).all()
+
+
+@pytest.mark.parametrize("seed,banded", [(191, False), (192, True), (193, False), (194, True)])
+def test_pstrip_many_blocks(eng, eng_ps4, seed, banded):
+    """Several column blocks per alignment pipelined over the warps of a CTA: general x general graphs of a few hundred
+    to 1500 sites, long-span edges across lanes, parked rows, bands that leave some blocks without rows."""
+    rng = np.random.default_rng(seed)
+    jobs = []
+    for n_max in (420, 420, 420, 1500, 1500, 3000):
+        model = randjobs.random_model(rng, 15, ties=rng.random() < 0.4)
+        nl, nr = int(rng.integers(150, n_max)), int(rng.integers(150, n_max))
+        left = randjobs.random_graph(rng, nl, 15, p_extra=0.1, max_span=int(rng.integers(3, 25)))
+        right = randjobs.random_graph(rng, nr, 15, p_extra=float(rng.choice([0.03, 0.12])), max_span=int(rng.integers(3, 20)))
+        job = abi.FlatJob(left, right, model, int(rng.integers(0, 4)))
+        if banded:
+            job.upper, job.lower = randjobs.random_band(rng, left.n_sites - 1, right.n_sites - 1, min_w=3, max_w=40)
+        jobs.append(enginecheck.expect_from_oracle(job))
+    for e in (eng, eng_ps4):
+        res = enginecheck.check_batch(e, jobs)
+        assert (res["kernel"] == 3).sum() >= len(jobs) - 1
 
 
 def test_both_kernels_agree_on_strip_jobs(eng, eng_wave):
@@ -127,7 +202,7 @@ def test_both_kernels_agree_on_strip_jobs(eng, eng_wave):
     jobs = [randjobs.random_job(rng, "strip") for _ in range(200)]
     ra, sa = eng.align(jobs)
     rb, sb = eng_wave.align(jobs)
-    assert np.isin(ra["kernel"], (1, 2)).all() and (rb["kernel"] == 0).all()
+    assert np.isin(ra["kernel"], (1, 2, 3)).all() and (rb["kernel"] == 0).all()
     assert (ra["score"].view(np.uint64) == rb["score"].view(np.uint64)).all()
     for k, job in enumerate(jobs):
         pa, _, _ = eng.expand(job, ra[k], sa)
@@ -185,7 +260,7 @@ def test_placement_config_scale_properties(eng, golden):
     enginecheck.check_batch(eng, sample)
 
 
-def test_progressive_config_scale_vs_oracle(eng):
+def test_progressive_config_scale_vs_oracle(eng, eng_old):
     """BASELINE configs[0] shape: 1 kb x 1 kb leaf alignments (multi-block strip) and a banded
     200 kb-style corridor job on the wavefront kernel, both against the oracle."""
     rng = np.random.default_rng(9)
@@ -198,6 +273,8 @@ def test_progressive_config_scale_vs_oracle(eng):
     banded.upper, banded.lower = randjobs.random_band(rng, lx, ly, 20, 40)
     jobs = [enginecheck.expect_from_oracle(job), enginecheck.expect_from_oracle(banded)]
     res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"] == 3).all()
+    res = enginecheck.check_batch(eng_old, jobs)
     assert res["kernel"][0] == 1 and res["kernel"][1] == 0
 
 

@@ -7,16 +7,33 @@ import oracle_lib
 import randjobs
 
 
-def check_job(job):
-    status, score, steps, cells = oracle_lib.oracle_align(job)
+def check_job(job, ref_used=None):
+    status, score, steps, cells, ul, ur = oracle_lib.oracle_align(job, marks=True)
     assert status == 0
     assert cells == job.cells
     assert np.float64(score).view(np.uint64) == np.float64(job.expected_score).view(np.uint64)
-    assert oracle_lib.steps_equal(steps, job.expected_path, job.expected_path_score) == []
+    assert oracle_lib.steps_equal(steps, job.expected_path, job.expected_path_score, getattr(job, 'expected_path_score_sha', None)) == []
+    # is_used edge marks (viterbi_alignment.cpp:1054-1155): the restatement's marks, as a set, are what the reference
+    # itself left marked -- on fresh graphs (live reference) or as the difference the dump recorded around its call
+    if ref_used is not None:
+        assert sorted(set(ul.tolist())) == ref_used[0].tolist() and sorted(set(ur.tolist())) == ref_used[1].tolist()
+    used = getattr(job, "expected_used", None)
+    if used is not None:
+        for side, mine in (("l", ul), ("r", ur)):
+            before, after = set(used[side][0].tolist()), set(used[side][1].tolist())
+            assert before | set(mine.tolist()) == after
 
 
 @pytest.mark.parametrize("name", ["prog_dna", "place_dna", "pileup_hp", "codon", "anchored"])
 def test_oracle_matches_reference_dump(golden, name):
+    for job in golden[name]:
+        check_job(job)
+
+
+@pytest.mark.parametrize("name", ["c1_full", "c3_full", "c4_full", "c5_full"])
+def test_oracle_matches_reference_at_baseline_size(golden, name):
+    """The restatement against job streams the REFERENCE ran at BASELINE sizes (16 x 1 kb, 400-nt pileup, 1000 codons,
+    200 kb anchored incl. ancestor x ancestor inside its band -- where FP64 rounding first matters)."""
     for job in golden[name]:
         check_job(job)
 
@@ -38,7 +55,7 @@ def test_oracle_matches_live_reference_on_random_jobs(kind):
         job = randjobs.random_job(rng, kind)
         score, path, pscore = oracle_lib.ref_align_flat(job)
         job.expected_score, job.expected_path, job.expected_path_score = score, path, pscore
-        check_job(job)
+        check_job(job, oracle_lib.ref_last_used())
 
 
 @pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built (reference sources absent)")
@@ -56,7 +73,7 @@ def test_oracle_matches_live_reference_on_more_shapes(shape):
     for job in jobs:
         score, path, pscore = oracle_lib.ref_align_flat(job)
         job.expected_score, job.expected_path, job.expected_path_score = score, path, pscore
-        check_job(job)
+        check_job(job, oracle_lib.ref_last_used())
 
 
 def test_oracle_rejects_bad_band():
