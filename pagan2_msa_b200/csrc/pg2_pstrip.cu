@@ -59,12 +59,20 @@ struct PsCtx {
     int saved_stride;    // 1 + 32*K
 };
 
+// the three scalars every candidate needs, in registers (everything else of PsCtx is read from shared memory on demand)
+struct PsHot {
+    double open, ext, lng;
+};
+
 template <int K> struct PsLane {
     double X[K], Y[K], M[K];   // own strip, row handled last
+    double Mo[K];              // (M + log_non_gap) + log_gap_open: what a gap move out of the cell starts from.  The reference
+                               // forms it twice per cell (X move :2190-2211, Y move); the reduced terminal penalty
+                               // (basic_alignment.h:490-513) only ever meets a finite M at the start corner, where it is planted
     double bX, bY, bM;         // column to the left of the strip, same row
     double extX[K];            // X-extension term per column (:864-868)
     double wr[K];              // log weight of the edge into a plain column
-    int colbase[K];            // state_r[j] * fas (SMALLTAB: the same)
+    int colbase[K];            // state_r[j] * fas
     int cinfo[K];              // column info words; -1 for padding columns (j >= c1)
     int j0;                    // first column of the strip
 };
@@ -94,13 +102,52 @@ __device__ __forceinline__ double4 ps_ldcg(const double4 *p) {
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// first-wins running maximum: the candidate replaces the best only when strictly greater (basic_alignment.h:449-462)
 __device__ __forceinline__ void ps_cand(double s, unsigned code, double &best, unsigned &ptr) {
-    if (s > best) { best = s; ptr = code; }
+    const bool p = s > best;
+    best = p ? s : best;
+    ptr = p ? code : ptr;
 }
 
 // history of the parked columns: entry (site i, slot) holds X, Y, M of cell (i, parked column)
-__device__ __forceinline__ const double *ps_hist(const PsCtx &c, int i, int slot) {
-    return c.hist + ((((i + PS_HIST) % PS_HIST) * c.park_cap + slot) * 3);
+__device__ __forceinline__ double *ps_hist(const PsCtx &c, int i, int slot) {
+    return c.hist + ((((i + PS_HIST) & (PS_HIST - 1)) * c.park_cap + slot) * 3);
+}
+
+// M of a GENERAL column for one left edge: every backward edge pr -> j, sources (p, pr) from the history (the edge starts
+// at the row above) or from the parked row
+__device__ __forceinline__ void ps_general_m(const PsCtx &c, int i, int j, bool reg, const double4 *prow, double mlog, double xlog, double wl,
+                                             unsigned lord, double &best, unsigned &ptr) {
+    const double ninf = neg_inf();
+    const int kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
+    for (int kr = kr0; kr < kr1; ++kr) {
+        double vx = ninf, vy = ninf, vm = ninf;
+        if (reg) {
+            const double *h = ps_hist(c, i - 1, c.r_einfo[kr]);
+            vx = h[0]; vy = h[1]; vm = h[2];
+        } else if (prow) {
+            const double4 v = ps_ldcg(prow + (c.r_estart[kr] - c.c0) + 1);
+            vx = v.x; vy = v.y; vm = v.z;
+        }
+        const double wrk = (double)c.r_elogw[kr];
+        const unsigned code = lord | ((unsigned)(kr - kr0) << 8);
+        ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vm, mlog), wl), wrk), M_MAT | code, best, ptr);   // :2029-2112
+        ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vx, xlog), wl), wrk), X_MAT | code, best, ptr);
+        ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vy, xlog), wl), wrk), Y_MAT | code, best, ptr);
+    }
+}
+
+// Y of a GENERAL column: every backward edge pr -> j, sources (i, pr) from the history
+__device__ __forceinline__ void ps_general_y(const PsCtx &c, const PsHot &h3, int i, int j, double extY, double &best, unsigned &ptr) {
+    const int kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
+    for (int kr = kr0; kr < kr1; ++kr) {
+        const double *h = ps_hist(c, i, c.r_einfo[kr]);
+        const double penY = (c.reduced && c.r_estart[kr] == 0) ? 0.0 : h3.open;
+        const unsigned ord = (unsigned)(kr - kr0) << 2;
+        ps_cand(__dadd_rn(h[1], extY), Y_MAT | ord, best, ptr);
+        ps_cand(__dadd_rn(h[0], h3.open), X_MAT | ord, best, ptr);
+        ps_cand(__dadd_rn(__dadd_rn(h[2], h3.lng), penY), M_MAT | ord, best, ptr);
+    }
 }
 
 // One virtual row (one backward edge of the left site) of one lane.  Returns true when the site was completed: st then
@@ -108,50 +155,63 @@ __device__ __forceinline__ const double *ps_hist(const PsCtx &c, int i, int slot
 //   any_saved (warp-uniform): some lane's edge starts at a parked row this step
 //   rX, rY, rM: cell (i, j0 - 1), the strip's left neighbour in the row being completed
 template <int K, bool SMALLTAB>
-__device__ __forceinline__ bool ps_step(const PsCtx &c, PsLane<K> &st, PsAcc<K> &acc, int lane, int4 vr, bool any_saved, double rX,
-                                        double rY, double rM, unsigned *out) {
+__device__ __forceinline__ bool ps_step(const PsCtx &c, const PsHot &h3, PsLane<K> &st, PsAcc<K> &acc, int lane, int4 vr, bool any_saved,
+                                        double rX, double rY, double rM, unsigned *out) {
     const double ninf = neg_inf();
     const int info = vr.x, i = vr.z;
     const int sl = info & VR_STATE_MASK;
-    if (info & VR_FIRST) {
+    const bool first = (info & VR_FIRST) != 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) { acc.nX[k] = ninf; acc.nM[k] = ninf; acc.pX[k] = NO_MAT; acc.pM[k] = NO_MAT; }
+    for (int k = 0; k < K; ++k) {
+        acc.nX[k] = first ? ninf : acc.nX[k];
+        acc.nM[k] = first ? ninf : acc.nM[k];
+        acc.pX[k] = first ? (unsigned)NO_MAT : acc.pX[k];
+        acc.pM[k] = first ? (unsigned)NO_MAT : acc.pM[k];
     }
-    if (!(info & VR_NOEDGE)) {
-        const bool reg = (info & VR_REG) != 0;
-        const int p = reg ? i - 1 : c.l_estart[vr.y];
-        const double wl = (info & VR_ZERO_W) ? 0.0 : (double)c.l_elogw[vr.y];
-        const unsigned lord = ((unsigned)vr.w >> 16) << 2;
-        const double pen = (c.reduced && p == 0) ? 0.0 : c.open;  // get_log_gap_open_penalty (basic_alignment.h:490-513)
-        // source row p: column j0 - 1 in [0], column j0 + k in [k + 1]
-        double sX[K + 1], sY[K + 1], sM[K + 1];
-        sX[0] = st.bX; sY[0] = st.bY; sM[0] = st.bM;
-#pragma unroll
-        for (int k = 0; k < K; ++k) { sX[k + 1] = st.X[k]; sY[k + 1] = st.Y[k]; sM[k + 1] = st.M[k]; }
-        const double4 *prow = nullptr;  // the parked source row, when the edge does not start at the row above
-        bool pvalid = true;
-        if (any_saved && !reg) {
+    const bool reg = (info & VR_REG) != 0;
+    const bool edge = !(info & VR_NOEDGE);
+    const double4 *prow = nullptr;
+    // An edge that starts at a parked row: the lane's strip registers take the parked row for this step and get the
+    // previous row back afterwards (nothing is copied on steps without such an edge)
+    double tX[K], tY[K], tM[K], tMo[K], tbX = 0, tbY = 0, tbM = 0;
+    const bool swap = any_saved && edge && !reg;
+    if (any_saved) {
+        if (swap) {
+            const int p = c.l_estart[vr.y];
             // a row above the block's first row lies outside the band for every column of the block (and for c0 - 1)
-            pvalid = p >= c.i0;
-            prow = c.saved + (long long)(vr.w & 0xffff) * c.saved_stride;
+            const bool pvalid = p >= c.i0;
+            const double pen = (c.reduced && p == 0) ? 0.0 : h3.open;  // get_log_gap_open_penalty (basic_alignment.h:490-513)
+            const double4 *row = c.saved + (long long)(vr.w & 0xffff) * c.saved_stride;
+            prow = pvalid ? row : nullptr;
+            tbX = st.bX; tbY = st.bY; tbM = st.bM;
+            double4 v = make_double4(ninf, ninf, ninf, 0.0);
+            if (pvalid) v = ps_ldcg(row + (st.j0 - c.c0));
+            st.bX = v.x; st.bY = v.y; st.bM = v.z;
 #pragma unroll
-            for (int k = 0; k <= K; ++k) {
-                double4 v = make_double4(ninf, ninf, ninf, 0.0);
-                if (pvalid) v = ps_ldcg(prow + (st.j0 - c.c0) + k);
-                sX[k] = v.x; sY[k] = v.y; sM[k] = v.z;
+            for (int k = 0; k < K; ++k) {
+                tX[k] = st.X[k]; tY[k] = st.Y[k]; tM[k] = st.M[k]; tMo[k] = st.Mo[k];
+                v = make_double4(ninf, ninf, ninf, 0.0);
+                if (pvalid) v = ps_ldcg(row + (st.j0 - c.c0) + k + 1);
+                st.X[k] = v.x; st.Y[k] = v.y; st.M[k] = v.z;
+                st.Mo[k] = __dadd_rn(__dadd_rn(v.z, h3.lng), pen);
             }
         }
+    }
+    if (edge) {
+        const double wl = (info & VR_ZERO_W) ? 0.0 : (double)c.l_elogw[vr.y];
+        const unsigned lord = ((unsigned)vr.w >> 16) << 2;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             // X: ext, double, open out of (p, j) (:2116-2211)
-            ps_cand(__dadd_rn(sX[k + 1], st.extX[k]), X_MAT | lord, acc.nX[k], acc.pX[k]);
-            ps_cand(__dadd_rn(sY[k + 1], c.open), Y_MAT | lord, acc.nX[k], acc.pX[k]);
-            ps_cand(__dadd_rn(__dadd_rn(sM[k + 1], c.lng), pen), M_MAT | lord, acc.nX[k], acc.pX[k]);
+            ps_cand(__dadd_rn(st.X[k], st.extX[k]), X_MAT | lord, acc.nX[k], acc.pX[k]);
+            ps_cand(__dadd_rn(st.Y[k], h3.open), Y_MAT | lord, acc.nX[k], acc.pX[k]);
+            ps_cand(st.Mo[k], M_MAT | lord, acc.nX[k], acc.pX[k]);
             // M: from M, X, Y of (p, pr) for every backward edge pr -> j (:1353-1436, :2029-2112)
             double mlog, xlog;
             ps_subst<SMALLTAB>(c, sl, st.colbase[k], mlog, xlog);
             if (!(st.cinfo[k] & PC_GENERAL)) {
-                double a = __dadd_rn(sM[k], mlog), b = __dadd_rn(sX[k], xlog), d = __dadd_rn(sY[k], xlog);
+                const double qM = k ? st.M[k - 1] : st.bM, qX = k ? st.X[k - 1] : st.bX, qY = k ? st.Y[k - 1] : st.bY;
+                double a = __dadd_rn(qM, mlog), b = __dadd_rn(qX, xlog), d = __dadd_rn(qY, xlog);
                 if (c.weights) {
                     a = __dadd_rn(__dadd_rn(a, wl), st.wr[k]);
                     b = __dadd_rn(__dadd_rn(b, wl), st.wr[k]);
@@ -161,26 +221,15 @@ __device__ __forceinline__ bool ps_step(const PsCtx &c, PsLane<K> &st, PsAcc<K> 
                 ps_cand(b, X_MAT | lord, acc.nM[k], acc.pM[k]);
                 ps_cand(d, Y_MAT | lord, acc.nM[k], acc.pM[k]);
             } else if (st.cinfo[k] >= 0) {
-                const int j = st.j0 + k;
-                const int kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
-                for (int kr = kr0; kr < kr1; ++kr) {
-                    double vx, vy, vm;
-                    if (reg) {
-                        const double *h = ps_hist(c, i - 1, c.r_einfo[kr]);
-                        vx = h[0]; vy = h[1]; vm = h[2];
-                    } else if (prow && pvalid) {
-                        const double4 v = ps_ldcg(prow + (c.r_estart[kr] - c.c0) + 1);
-                        vx = v.x; vy = v.y; vm = v.z;
-                    } else {
-                        vx = vy = vm = ninf;
-                    }
-                    const double wrk = (double)c.r_elogw[kr];
-                    const unsigned code = lord | ((unsigned)(kr - kr0) << 8);
-                    ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vm, mlog), wl), wrk), M_MAT | code, acc.nM[k], acc.pM[k]);
-                    ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vx, xlog), wl), wrk), X_MAT | code, acc.nM[k], acc.pM[k]);
-                    ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vy, xlog), wl), wrk), Y_MAT | code, acc.nM[k], acc.pM[k]);
-                }
+                ps_general_m(c, i, st.j0 + k, reg, prow, mlog, xlog, wl, lord, acc.nM[k], acc.pM[k]);
             }
+        }
+    }
+    if (any_saved) {
+        if (swap) {
+            st.bX = tbX; st.bY = tbY; st.bM = tbM;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { st.X[k] = tX[k]; st.Y[k] = tY[k]; st.M[k] = tM[k]; st.Mo[k] = tMo[k]; }
         }
     }
     if (!(info & VR_LAST)) return false;
@@ -190,46 +239,49 @@ __device__ __forceinline__ bool ps_step(const PsCtx &c, PsLane<K> &st, PsAcc<K> 
         acc.nM[0] = (i == 0) ? 0.0 : ninf;
         acc.pM[0] = NO_MAT;
     }
-    const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : c.ext;
+    const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : h3.ext;
     int blo = 0, bhi = 0x7fffffff;
     if (c.banded) { blo = c.blo[i]; bhi = c.bhi[i]; }
-    const unsigned plain_row = ((info & VR_FAST) == VR_FAST && !(info & VR_NOEDGE)) ? PSW_PLAIN_ROW : 0u;
-    double lX = rX, lY = rY, lM = rM;
+    const unsigned plain_row = ((info & VR_FAST) == VR_FAST && edge) ? PSW_PLAIN_ROW : 0u;
+    // Y: ext, double, open out of (i, j - 1) (:2116-2211 with the roles of X and Y swapped).  The two candidates that do
+    // not depend on the chain are folded first: (g > a ? g : a) with g = first-wins(double, open) equals the sequential
+    // first-wins over ext, double, open
+    double lXo = __dadd_rn(rX, h3.open), lMo = __dadd_rn(__dadd_rn(rM, h3.lng), h3.open), lY = rY;
+    if (st.j0 == 1 && i == 0 && c.reduced) lMo = __dadd_rn(__dadd_rn(rM, h3.lng), 0.0);  // the neighbour is the start corner
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = st.j0 + k;
-        double best = ninf;
-        unsigned ptr = NO_MAT;
-        unsigned plain_col = 0;
+        double ny;
+        unsigned py, plain_col = 0;
         if (!(st.cinfo[k] & PC_GENERAL)) {
-            // Y: ext, double, open out of (i, j - 1) (:2116-2211 with the roles of X and Y swapped)
-            const double penY = (c.reduced && j == 1) ? 0.0 : c.open;
-            ps_cand(__dadd_rn(lY, extY), Y_MAT, best, ptr);
-            ps_cand(__dadd_rn(lX, c.open), X_MAT, best, ptr);
-            ps_cand(__dadd_rn(__dadd_rn(lM, c.lng), penY), M_MAT, best, ptr);
+            const bool p2 = lMo > lXo;
+            const double g = p2 ? lMo : lXo;
+            const double a = __dadd_rn(lY, extY);
+            const bool p1 = g > a;
+            ny = p1 ? g : a;
+            py = p1 ? (p2 ? (unsigned)M_MAT : (unsigned)X_MAT) : (unsigned)Y_MAT;
+            py = (ny == ninf) ? (unsigned)NO_MAT : py;  // no candidate: the cell keeps no pointer (it is never walked)
             plain_col = j > 0 ? PSW_PLAIN_COL : 0u;
-        } else if (st.cinfo[k] >= 0) {
-            const int kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
-            for (int kr = kr0; kr < kr1; ++kr) {
-                const double *h = ps_hist(c, i, c.r_einfo[kr]);
-                const double penY = (c.reduced && c.r_estart[kr] == 0) ? 0.0 : c.open;
-                const unsigned ord = (unsigned)(kr - kr0) << 2;
-                ps_cand(__dadd_rn(h[1], extY), Y_MAT | ord, best, ptr);
-                ps_cand(__dadd_rn(h[0], c.open), X_MAT | ord, best, ptr);
-                ps_cand(__dadd_rn(__dadd_rn(h[2], c.lng), penY), M_MAT | ord, best, ptr);
-            }
+        } else {
+            ny = ninf;
+            py = NO_MAT;
+            if (st.cinfo[k] >= 0) ps_general_y(c, h3, i, j, extY, ny, py);
         }
         double nx = acc.nX[k], nm = acc.nM[k];
-        if (j < blo || j > bhi) { nx = ninf; best = ninf; nm = ninf; }  // Tunnel_slice::at: -inf outside the band
-        out[k] = cell_word(acc.pX[k], ptr, acc.pM[k]) | plain_row | plain_col;
-        st.X[k] = nx; st.Y[k] = best; st.M[k] = nm;
-        if (st.cinfo[k] >= 0 && (st.cinfo[k] & PC_PARKED)) {
-            double *h = const_cast<double *>(ps_hist(c, i, (st.cinfo[k] >> PC_SLOT_SHIFT) & PC_SLOT_MASK));
-            h[0] = nx; h[1] = best; h[2] = nm;
+        if (j < blo || j > bhi) { nx = ninf; ny = ninf; nm = ninf; }  // Tunnel_slice::at: -inf outside the band
+        double nmo = __dadd_rn(__dadd_rn(nm, h3.lng), h3.open);
+        if (j == 0 && i == 0 && c.reduced) nmo = __dadd_rn(__dadd_rn(nm, h3.lng), 0.0);  // the start corner's gap moves
+        out[k] = cell_word(acc.pX[k], py, acc.pM[k]) | plain_row | plain_col;
+        st.X[k] = nx; st.Y[k] = ny; st.M[k] = nm; st.Mo[k] = nmo;
+        if (st.cinfo[k] >= 0 && (st.cinfo[k] & (PC_PARKED | PC_ENDCOL))) {
+            if (st.cinfo[k] & PC_PARKED) {
+                double *h = ps_hist(c, i, (st.cinfo[k] >> PC_SLOT_SHIFT) & PC_SLOT_MASK);
+                h[0] = nx; h[1] = ny; h[2] = nm;
+            }
+            if ((st.cinfo[k] & PC_ENDCOL) && (info & VR_ENDPRED))
+                c.endstore[(long long)((st.cinfo[k] >> PC_END_SHIFT) & 3) * c.lx + i] = make_double4(nx, ny, nm, 0.0);
         }
-        if (st.cinfo[k] >= 0 && (st.cinfo[k] & PC_ENDCOL) && (info & VR_ENDPRED))
-            c.endstore[(long long)((st.cinfo[k] >> PC_END_SHIFT) & 3) * c.lx + i] = make_double4(nx, best, nm, 0.0);
-        lX = nx; lY = best; lM = nm;
+        lXo = __dadd_rn(nx, h3.open); lMo = nmo; lY = ny;
     }
     st.bX = rX; st.bY = rY; st.bM = rM;
     return true;
@@ -244,7 +296,7 @@ __device__ __forceinline__ void ps_init_lane(const PsCtx &c, PsLane<K> &st, int 
     for (int k = 0; k < K; ++k) {
         const int j = st.j0 + k;
         const bool v = j < c.c1;
-        st.X[k] = st.Y[k] = st.M[k] = ninf;
+        st.X[k] = st.Y[k] = st.M[k] = st.Mo[k] = ninf;
         st.extX[k] = (c.term && (j == 0 || j == c.ly - 1)) ? c.end_ext : c.ext;
         st.cinfo[k] = v ? c.colinfo[j] : -1;
         const bool plain = v && j >= 1 && !(st.cinfo[k] & PC_GENERAL);
@@ -366,6 +418,8 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
     // the warp-uniform constants live in shared memory, one copy per warp (the block fields differ): in registers they
     // would cost every lane some sixty registers
     __shared__ PsCtx s_ctx[PS_MAX_WARPS];
+    // boundary column entries on their way in (cp.async, PS_PREFETCH steps ahead), a ring of 8 per warp: {X, Y, M, -}
+    __shared__ __align__(16) double s_bnd[PS_MAX_WARPS][8][4];
     const double ninf = neg_inf();
     const int ring_mask = ring - 1;
     double4 *cta_scratch = scratch + (long long)blockIdx.x * cta_d4;
@@ -432,6 +486,8 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
             double4 *bcol_cur = my + (long long)((round & 1) ? ring : 0);
             PsLane<K> st;
             PsAcc<K> acc;
+            PsHot h3;
+            h3.open = c.open; h3.ext = c.ext; h3.lng = c.lng;
             ps_init_lane<K>(c, st, lane);
 #pragma unroll
             for (int k = 0; k < K; ++k) { acc.nX[k] = acc.nM[k] = ninf; acc.pX[k] = acc.pM[k] = NO_MAT; }
@@ -439,39 +495,46 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
             __syncwarp();
             const int last_col = c.c1 - 1 - c.c0, last_lane = last_col / K, last_k = last_col % K;
             const bool feeds_next = b + 1 < n_blocks;
-            // boundary column, fetched PS_PREFETCH steps ahead by lane 0
+            const int v0 = c.v0, v1 = c.v1;
+            // boundary column: lane 0 starts the copy of the entry of virtual row v into the ring PS_PREFETCH steps before it
+            // is used; an entry the previous block does not hold (rows outside its share of the band) is -inf
             int avail = 0;  // producer progress seen so far
-            struct Bnd { double x, y, z; };
-            auto fetch = [&](int v) -> Bnd {
-                Bnd r = {ninf, ninf, ninf};
-                if (lane != 0 || b == 0 || v < pv0 || v >= pv1) return r;
-                const int need = prod_base + v + 1;
-                while (avail < need) avail = ps_load_acquire(prod);
-                const double4 q4 = ps_ldcg(bcol_prev + (v & ring_mask));
-                r.x = q4.x; r.y = q4.y; r.z = q4.z;
-                return r;
+            double *ringp = &s_bnd[w][0][0];
+            auto issue = [&](int v) {
+                if (lane == 0) {
+                    double *dst = ringp + ((v - v0) & 7) * 4;
+                    if (b == 0 || v < pv0 || v >= pv1) {
+                        dst[0] = ninf; dst[1] = ninf; dst[2] = ninf;
+                    } else {
+                        const int need = prod_base + v + 1;
+                        while (avail < need) avail = ps_load_acquire(prod);
+                        const double4 *src = bcol_prev + (v & ring_mask);
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16), "l"(reinterpret_cast<const char *>(src) + 16) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            Bnd pf[PS_PREFETCH];
 #pragma unroll
-            for (int d = 0; d < PS_PREFETCH; ++d) pf[d] = fetch(c.v0 + d);
+            for (int d = 0; d < PS_PREFETCH; ++d) issue(v0 + d);
             unsigned *out = P + ptr_off + lane * K;
-            const int n_steps = (c.v1 - c.v0) + last_lane;
+            const int n_steps = (v1 - v0) + last_lane;
             for (int t = 0; t < n_steps; ++t) {
                 double rX = __shfl_up_sync(0xffffffffu, st.X[K - 1], 1);
                 double rY = __shfl_up_sync(0xffffffffu, st.Y[K - 1], 1);
                 double rM = __shfl_up_sync(0xffffffffu, st.M[K - 1], 1);
-                if (lane == 0) { rX = pf[0].x; rY = pf[0].y; rM = pf[0].z; }
-#pragma unroll
-                for (int d = 0; d + 1 < PS_PREFETCH; ++d) pf[d] = pf[d + 1];
-                pf[PS_PREFETCH - 1] = fetch(c.v0 + t + PS_PREFETCH);
-                const int v = c.v0 + t - lane;
-                const bool active = (v >= c.v0 && v < c.v1 && lane <= last_lane);
+                asm volatile("cp.async.wait_group %0;" ::"n"(PS_PREFETCH - 1) : "memory");
+                if (lane == 0) { const double *e = ringp + (t & 7) * 4; rX = e[0]; rY = e[1]; rM = e[2]; }
+                issue(v0 + t + PS_PREFETCH);
+                const int v = v0 + t - lane;
+                const bool active = (v >= v0 && v < v1 && lane <= last_lane);
                 int4 vr = make_int4(VR_FAST | VR_ZERO_W, -1, 0, 0);
                 if (active) vr = __ldg(c.l_vrow + v);
                 const bool any_saved = __any_sync(0xffffffffu, active && !(vr.x & (VR_REG | VR_NOEDGE)));
                 if (active) {
                     unsigned wds[K];
-                    const bool done = ps_step<K, SMALLTAB>(c, st, acc, lane, vr, any_saved, rX, rY, rM, wds);
+                    const bool done = ps_step<K, SMALLTAB>(c, h3, st, acc, lane, vr, any_saved, rX, rY, rM, wds);
                     if (done) {
                         unsigned *dst = out + (long long)t * 32 * K;
                         if (K == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(wds[0], wds[1]);
@@ -494,10 +557,12 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
                             bcol_cur[v & ring_mask] = make_double4(vx, vy, vm, 0.0);
                         }
                     }
-                    if (lane == last_lane && feeds_next) ps_store_release(s_prog + w, round * stride + (v + 1));
+                    // progress: every 8th virtual row (a release store orders the thread's earlier stores: not every step)
+                    if (lane == last_lane && feeds_next && ((v & 7) == 7 || v == v1 - 1)) ps_store_release(s_prog + w, round * stride + (v + 1));
                 }
                 __syncwarp();
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
             if (lane == 0) ps_store_release(s_prog + w, round * stride + c.nv + 1);
         }
         __syncthreads();
@@ -549,6 +614,8 @@ static void ps_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &
     const int *blocks = d_vlast + J.blk_base;
     unsigned *P = ptrs + J.cell_base;
     const int ring_mask = ring - 1;
+    PsHot h3;
+    h3.open = c.open; h3.ext = c.ext; h3.lng = c.lng;
     ps_end_init(c, c.endstore, 0, 1);
     for (int b = 0; b < J.n_blocks; ++b) {
         ps_load_block(c, blocks + b * PB_INTS);
@@ -588,8 +655,8 @@ static void ps_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &
                 } else { rX = sx[l - 1]; rY = sy[l - 1]; rM = sm[l - 1]; }
                 unsigned wds[K];
                 bool done;
-                if (smalltab) done = ps_step<K, true>(c, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
-                else done = ps_step<K, false>(c, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
+                if (smalltab) done = ps_step<K, true>(c, h3, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
+                else done = ps_step<K, false>(c, h3, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
                 if (!done) continue;
                 unsigned *dst = P + ptr_off + ((long long)t * 32 + l) * K;
                 for (int k = 0; k < K; ++k) dst[k] = wds[k];

@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "viterbi_alignment_b200.h"
+#include "main/node.h"
+#include "main/reads_aligner.h"
 #include "utils/check_version.h"
 #include "utils/exonerate_queries.h"
 
@@ -37,6 +39,21 @@ extern "C" void CAT(__wrap_, ALIGN_SYM)(Viterbi_alignment *self, Sequence *left,
     ppa_b200::align_on_device(self, left, right, model, lbl, rbl, is_reads);
 }
 
+// The schedulers.  `--threads N` (N > 1) sends the guide-tree traversal through Node::start_openmp_alignment or, with
+// --boost, Node::start_threaded_alignment (main.cpp:185-191): both become the wave scheduler.  Reads_aligner::align
+// (main.cpp) is bracketed by the placement prefetch.  Both reach the reference's own code for everything but the DP.
+#define OMP_SYM _ZN3ppa4Node22start_openmp_alignmentEPNS_13Model_factoryEi
+#define THR_SYM _ZN3ppa4Node24start_threaded_alignmentEPNS_13Model_factoryEi
+#define RAL_SYM _ZN3ppa13Reads_aligner5alignEPNS_4NodeEPNS_13Model_factoryEi
+extern "C" void CAT(__wrap_, OMP_SYM)(Node *root, Model_factory *mf, int n_threads) { ppa_b200::align_tree_in_waves(root, mf, n_threads); }
+extern "C" void CAT(__wrap_, THR_SYM)(Node *root, Model_factory *mf, int n_threads) { ppa_b200::align_tree_in_waves(root, mf, n_threads, true); }
+extern "C" void CAT(__real_, RAL_SYM)(Reads_aligner *self, Node *root, Model_factory *mf, int count);
+extern "C" void CAT(__wrap_, RAL_SYM)(Reads_aligner *self, Node *root, Model_factory *mf, int count) {
+    ppa_b200::placement_begin(self, root);
+    CAT(__real_, RAL_SYM)(self, root, mf, count);
+    ppa_b200::placement_end();
+}
+
 namespace {
 struct Stats_at_exit {
     ~Stats_at_exit() {
@@ -45,8 +62,9 @@ struct Stats_at_exit {
             ppa_b200::Totals t = ppa_b200::totals();
             FILE *f = fopen(p, "w");
             if (f) {
-                fprintf(f, "{\"jobs\": %lld, \"cells\": %lld, \"batches\": %lld, \"fill_ms\": %.6f, \"traceback_ms\": %.6f}\n", t.jobs, t.cells,
-                        t.batches, t.fill_ms, t.traceback_ms);
+                fprintf(f, "{\"jobs\": %lld, \"cells\": %lld, \"batches\": %lld, \"fill_ms\": %.6f, \"traceback_ms\": %.6f, "
+                           "\"wave_batches\": %lld, \"prefetch_batches\": %lld, \"cache_hits\": %lld, \"sharded_batches\": %lld}\n",
+                        t.jobs, t.cells, t.batches, t.fill_ms, t.traceback_ms, t.wave_batches, t.prefetch_batches, t.cache_hits, t.sharded_batches);
                 fclose(f);
             }
         }

@@ -18,6 +18,16 @@
 //       the launch-batch form for the schedulers (a guide-tree wave, node.cpp:240-264; the trial / final
 //       alignments of many reads, reads_aligner.cpp:983-1216): add() jobs, run() them in ONE pg2_align_batch,
 //       then every `va` is finished exactly as above, in the order the jobs were added.
+//   ppa_b200::align_tree_in_waves(root, mf, n_threads)
+//       the batch scheduler of the guide-tree traversal: stands where Node::start_openmp_alignment /
+//       Node::start_threaded_alignment stand (node.cpp:196-285).  Every ready node of a wave runs the reference's own
+//       per-node code on a host thread; their align() calls are combined into one launch batch per wave.
+//   ppa_b200::placement_begin(ra, root) / placement_end()
+//       bracket Reads_aligner::align (reads_aligner.cpp:35): while active, a trial alignment of query placement that
+//       is not cached yet triggers ONE launch batch over the next reads of the query file x every candidate node; the
+//       reference's own loops then find their alignments in the cache and only post-process them, in their own order.
+//   With PAGAN2_B200_DEVICES=0-7 a launch batch is cut by index range over the devices (one pg2_ctx and one host
+//   thread each) and the results meet in host memory.
 //
 // Modes that are not part of the device contract (--full-probability, --sample-path,
 // --sample-additional-paths, posterior plots) are refused with the reference's own style of fatal message; there
@@ -41,6 +51,12 @@
 #include "main/sequence.h"
 #include "main/viterbi_alignment.h"
 #include "utils/evol_model.h"
+
+namespace ppa {
+class Node;
+class Model_factory;
+class Reads_aligner;
+}
 
 namespace ppa_b200 {
 
@@ -73,10 +89,21 @@ void align_on_device(ppa::Viterbi_alignment *va, ppa::Sequence *left, ppa::Seque
 // CUDA device the engine binds to (default 0; also PAGAN2_B200_DEVICE).  Call before the first alignment.
 void set_device(int device);
 
-// Device-side totals since process start (for the drop-in binary's --b200-stats line).
+// Guide-tree alignment in waves: one launch batch per wave of ready nodes (node.cpp:227-285).
+void align_tree_in_waves(ppa::Node *root, ppa::Model_factory *mf, int n_threads, bool boost_variant = false);
+
+// Query placement: batched prefetch of the trial alignments while Reads_aligner::align runs.
+void placement_begin(ppa::Reads_aligner *ra, ppa::Node *root);
+void placement_end();
+
+// Device-side totals since process start (for the drop-in binary's stats file, PAGAN2_B200_STATS).
 struct Totals {
     long long jobs, cells, batches;
     double fill_ms, traceback_ms;
+    long long wave_batches;      // launch batches that combined the alignments of a guide-tree wave
+    long long prefetch_batches;  // launch batches of prefetched placement trial alignments
+    long long cache_hits;        // align() calls served from a prefetched batch
+    long long sharded_batches;   // launch batches cut over more than one device
 };
 Totals totals();
 

@@ -19,7 +19,7 @@ import randjobs  # noqa: E402
 import test_gpu_fullsize as fs  # noqa: E402
 from pagan2_msa_b200 import abi, engine, jobio, synth  # noqa: E402
 
-KERNEL = {0: "wavefront", 1: "strip", 2: "lanes"}
+KERNEL = {0: "wavefront", 1: "strip", 2: "lanes", 3: "pstrip"}
 
 
 def golden(name):
@@ -74,6 +74,23 @@ def batches():
         job.lower = np.maximum.accumulate(job.lower).astype(np.int32)
         jobs.append(job)
     out.append(("C5 wave 1: 16 x (200 kb x 200 kb inside a +-25 anchor band)", jobs))
+    # the reference's own job streams at BASELINE sizes (tests/golden/*_full: dumped from the reference program)
+    c1 = golden("c1_full")
+    depth = {}
+    for k, j in enumerate(c1):  # a node's wave = how many of its two children are ancestors, by graph shape: leaves are plain chains
+        plain = lambda g: bool((np.diff(g.off)[1:] == 1).all())
+        depth[k] = 0 if plain(j.left) and plain(j.right) else 1
+    out.append(("C1 (reference stream) wave 1: 8 leaf x leaf, 1 kb", [j for k, j in enumerate(c1) if depth[k] == 0]))
+    out.append(("C1 (reference stream) waves 2-4: 7 ancestor x ancestor", [j for k, j in enumerate(c1) if depth[k] == 1]))
+    out.append(("C1 (reference stream) root: 1 alignment, 1.2 k x 1.2 k sites", [c1[-1]]))
+    c3 = golden("c3_full")
+    out.append(("C3 (reference stream): 1 x (root after 220 reads x 400-nt 454 read)", [c3[-1]]))
+    c4 = golden("c4_full")
+    out.append(("C4 (reference stream): 4 leaf x leaf, 1000 codons", c4[:1] + c4[1:2] + [j for j in c4[2:] if (np.diff(j.left.off)[1:] == 1).all()][:2]))
+    out.append(("C4 (reference stream) root: 1 ancestor x ancestor, 1000 codons", [c4[-1]]))
+    c5 = golden("c5_full")
+    out.append(("C5 (reference stream): 2 x (200 kb leaf x leaf, reference's anchor band)", c5[:2]))
+    out.append(("C5 (reference stream): 1 x (200 kb ancestor x ancestor, reference's anchor band)", c5[2:]))
     return out
 
 
@@ -81,10 +98,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tag", default="r1")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--only", default="", help="substring filter on the batch name")
+    ap.add_argument("--max-cells", type=float, default=0, help="skip batches with more cells (the wavefront kernel needs 36 B/cell)")
     args = ap.parse_args()
     eng = engine.Engine(0)
     rows = []
     for name, jobs in batches():
+        if args.only and args.only not in name:
+            continue
+        if args.max_cells and sum(j.cells for j in jobs) > args.max_cells:
+            continue
         cells = int(sum(j.cells for j in jobs))
         b = eng.batch(jobs)
         best = None
