@@ -625,7 +625,7 @@ void launch_traceback(int n_jobs, int n_wave, int n_ps, const int *job_ids, cons
             unsigned short *out = steps + J.step_base;
             PsTraceState st;
             st.v = -1; st.b = -1; st.c0 = st.c1 = st.v0 = st.v1 = st.off = 0; st.need_t = 0;
-            static PsTraceWin W;
+            static thread_local PsTraceWin W;  // 16 KB: not on the stack; one per host thread (several contexts may run side by side)
             W.b = -1; W.t_hi = 0;
             trace_wave_begin(J, res, l_off, r_off, l_es, r_es, out, st.s);
             while (!st.s.done) {
