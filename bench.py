@@ -185,25 +185,85 @@ def dist_setup(n_gpus):
     return rank, world, local, None
 
 
-def cpu_baseline_sample(jobs, budget_s=12.0):
+def cpu_baseline_sample(jobs, eng, results, steps_buf, budget_s=12.0):
     """The reference's own code (oracle/_ref, kind 'reference') or the oracle port, 1 thread, on the first
-    jobs of the workload until ~budget_s seconds are spent."""
+    jobs of the workload until ~budget_s seconds are spent.  Its outputs are the checker of this very run: every job
+    of the sample must equal the GPU's result -- score bits, the expanded path in every field, every per-step score.
+    Returns (cpu_baseline object, number of jobs compared)."""
     import oracle_lib
 
     use_ref = oracle_lib.ref_available()
-    fn = (lambda j: oracle_lib.ref_align_flat(j)) if use_ref else (lambda j: oracle_lib.oracle_align(j))
     t0 = time.perf_counter()
     cells = 0
-    n = 0
+    ref = []
     for j in jobs:
-        fn(j)
+        if use_ref:
+            score, path, pscore = oracle_lib.ref_align_flat(j)
+        else:
+            _, score, st, _ = oracle_lib.oracle_align(j)
+            path = np.stack([st[n] for n in ("matrix", "x_ind", "y_ind", "x_edge_ind", "y_edge_ind", "real_site")], axis=1)
+            pscore = st["score"]
+        ref.append((score, path, pscore))
         cells += j.cells
-        n += 1
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
+    n = len(ref)
+    for k, (score, path, pscore) in enumerate(ref):  # outside the clock
+        if np.float64(score).view(np.uint64) != results["score"][k].view(np.uint64):
+            raise SystemExit("bench: job %d: GPU score %r differs from the CPU %s's %r" % (k, results["score"][k], "reference" if use_ref else "oracle", score))
+        st, _, _ = eng.expand(jobs[k], results[k], steps_buf)
+        diffs = oracle_lib.steps_equal(st, path, pscore)
+        if diffs:
+            raise SystemExit("bench: job %d: GPU path differs from the CPU checker's: %s" % (k, diffs))
     return {"value": cells / dt * 1e-9, "unit": "GCUPS", "cores": 1, "kind": "reference" if use_ref else "port",
-            "sample": "first %d jobs of the workload (%d cells) in %.1f s, 1 thread" % (n, cells, dt)}
+            "sample": "first %d jobs of the workload (%d cells) in %.1f s, 1 thread; all %d compared with the GPU results "
+                      "(score bits, path, per-step scores)" % (n, cells, dt, n)}, n
+
+
+def other_configs(eng, reps=3):
+    """Device time and GCUPS of the launch batches of the other BASELINE configs, from the reference's own job streams at
+    BASELINE sizes (tests/golden/*_full.pjob.gz); every score is compared with the reference's (bit for bit)."""
+    out = {}
+    def plain(g):
+        return bool((np.diff(g.off)[1:] == 1).all())
+    streams = {}
+    for name in ("c1_full", "c3_full", "c4_full", "c5_full"):
+        path = os.path.join(ROOT, "tests", "golden", name + ".pjob.gz")
+        if os.path.exists(path):
+            streams[name] = jobio.load_jobs(path)
+    batches = []
+    if "c1_full" in streams:
+        c1 = streams["c1_full"]
+        batches.append(("c1_wave1_8_leaf_pairs_1kb", [j for j in c1 if plain(j.left) and plain(j.right)]))
+        batches.append(("c1_waves2to4_7_ancestor_pairs", [j for j in c1 if not (plain(j.left) and plain(j.right))]))
+    if "c3_full" in streams:
+        batches.append(("c3_pileup_one_alignment_root_after_220_reads", streams["c3_full"][-1:]))
+    if "c4_full" in streams:
+        batches.append(("c4_codons_7_alignments_1000_codons", streams["c4_full"]))
+    if "c5_full" in streams:
+        batches.append(("c5_anchored_2_leaf_pairs_200kb", streams["c5_full"][:2]))
+        batches.append(("c5_anchored_ancestor_pair_200kb", streams["c5_full"][2:]))
+    for name, jobs in batches:
+        if not jobs:
+            continue
+        b = eng.batch(jobs)
+        best = None
+        for _ in range(reps + 1):
+            b.run()
+            st = eng.stats()
+            if best is None or st["run_ms"] < best["run_ms"]:
+                best = st
+        res, _ = b.fetch()
+        b.close()
+        same = all(np.float64(j.expected_score).view(np.uint64) == res["score"][k].view(np.uint64) for k, j in enumerate(jobs))
+        if not same or not (res["status"] == 0).all():
+            raise SystemExit("bench: config batch %s: GPU scores differ from the reference's" % name)
+        cells = int(sum(j.cells for j in jobs))
+        out[name] = {"jobs": len(jobs), "cells": cells, "device_ms": best["run_ms"], "fill_ms": best["fill_ms"],
+                     "traceback_ms": best["traceback_ms"], "gcups": cells / best["run_ms"] * 1e-6,
+                     "kernels": sorted(set(int(k) for k in res["kernel"])), "scores_equal_reference": True}
+    return out
 
 
 _REF_JOBS = None
@@ -247,6 +307,11 @@ def run_reference_arm(args):
     use_ref = oracle_lib.ref_available()
     bounds = [(k * per_core, (k + 1) * per_core) for k in range(cores)]
     times, cells_step = [], 0
+    # one thread alone (the reference's default mode, main.cpp:100-106), beside the all-cores figure
+    _ref_init(n, args.seed)
+    t0 = time.perf_counter()
+    single_cells = _ref_worker((0, min(per_core * 2, n)))
+    single_gcups = single_cells / (time.perf_counter() - t0) * 1e-9
     with mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(n, args.seed)) as pool:
         pool.map(_ref_worker, [(0, 0)] * cores)  # every worker up and initialised before the clock starts
         for it in range(args.warmup + args.steps):
@@ -264,7 +329,8 @@ def run_reference_arm(args):
         "config": {"workload": "query placement: 150-nt reads vs 64-taxon x 1.5 kb reference (BASELINE configs[1]); "
                                "bounded sample of %d alignments per step" % n, "cells_per_step": int(cells_step)},
         "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": cores, "kind": "reference" if use_ref else "port",
-                         "sample": "%d alignments per step over %d processes (fork), model build excluded" % (n, cores)},
+                         "sample": "%d alignments per step over %d processes (fork), model build excluded" % (n, cores),
+                         "single_thread_gcups": single_gcups},
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -291,6 +357,8 @@ def main():
     ap.add_argument("--reads", type=int, default=100000, help="reads (= alignments) per GPU per step")
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (--reads in total over all GPUs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config launch batches (C1, C3, C4, C5 at BASELINE sizes)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -395,6 +463,41 @@ def main():
     if not e2e_same:
         raise SystemExit("bench: pg2_align_batch (e2e) and the resident batch disagree")
 
+    # ---------------- strong scaling: the SAME --reads alignments in total, cut by index range over the ranks ----------------
+    strong_vals = None
+    if world > 1 and not args.no_strong:
+        gjobs, _ = build_workload(args.reads, args.seed, 0)  # every rank builds the same job list
+        mine = [gjobs[i] for i in shard.partition([j.cells for j in gjobs], world)[rank]]
+        sbatch = eng.batch(mine)
+        sprep = eng.prepare(mine, pinned=True, compact=True)
+        for _ in range(3):
+            sbatch.run()
+        eng.align_prepared(sprep)
+        barrier()
+        s_dev = 0.0
+        for _ in range(args.steps):
+            sbatch.run()
+            s_dev += eng.stats()["run_ms"]
+            if dist is not None:
+                rec, stp = shard.buffer_views(sbatch, tdev)
+                ev0.record()
+                parts = shard.gather_to_root(dist, rank, world, rec, stp)
+                ev1.record()
+                ev1.synchronize()
+                del parts
+                s_dev += ev0.elapsed_time(ev1)
+        barrier()
+        s_e2e = []
+        for _ in range(args.steps):
+            t1 = time.perf_counter()
+            eng.align_prepared(sprep)
+            s_e2e.append(time.perf_counter() - t1)
+        barrier()
+        sbatch.close()
+        strong_vals = np.array([s_dev / args.steps, sum(s_e2e) / args.steps * 1e3], dtype=np.float64)
+        strong_cells = int(sum(j.cells for j in gjobs))
+        del gjobs, mine, sprep
+
     print("rank %d: e2e %.1f ms/step, device %.1f ms/step, %d near cores" % (
         rank, sum(e2e_t) / args.steps * 1e3, dev_ms / args.steps, len(near_cores)), file=sys.stderr, flush=True)
     cells = info["cells_per_step"]
@@ -407,6 +510,10 @@ def main():
         c = torch.tensor([cells], dtype=torch.int64).cuda()
         dist.all_reduce(c)
         total_cells = int(c.item())
+        if strong_vals is not None:
+            t = torch.from_numpy(strong_vals).cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            strong_vals = t.cpu().numpy()
     else:
         total_cells = cells
     ms_dev, ms_fill, ms_e2e, ms_wall = [float(x) for x in local_vals]
@@ -440,37 +547,52 @@ def main():
                     "results_equal_resident_batch": e2e_same},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic,
+            # the fill kernel is bound by the FP64 / issue port, not by HBM: `frac` is the contract figure (the
+            # reference's 22 FP64-pipe instructions per cell against the chip's measured FP64 issue rate), `frac_executed`
+            # the same with the instructions the kernel really issues; the HBM view of the same launch is under "hbm"
+            "roofline": {"bound": "fp64_issue", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "1e9 FP64-pipe warp-instr/s",
+                         "frac": fp64_achieved / fp64_peak if fp64_peak else None,
+                         "instr_per_cell": FP64_INSTR_PER_CELL,
+                         "frac_executed": fp64_executed / fp64_peak if fp64_peak else None,
+                         "instr_per_cell_executed": FP64_INSTR_EXECUTED,
+                         "peak_source": "pg2_measure_fp64_issue (independent DADDs, this run; theory 148 SM x 4 x clock / 2)",
+                         "candidate_update_peak": cand.value,
+                         "traffic": traffic,
                          "traffic_note": "DRAM read+write bytes per fill launch, ncu capture profiles/" + TRAFFIC_PROFILE + "; "
                                          "algorithmic bytes per launch = %d" % int(per_launch_cells * PTR_BYTES_PER_CELL),
-                         "peak_source": peaks_kind,
                          "kernel": "lane_fill_kernel" if stats["jobs_lanes"] >= stats["jobs_strip"] else "strip_fill_kernel",
-                         "algorithmic_bytes_per_cell": PTR_BYTES_PER_CELL,
                          "launch_ms": launch_ms,
-                         "dp_issue": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "1e9 FP64-pipe warp-instr/s",
-                                      "frac": fp64_achieved / fp64_peak if fp64_peak else None,
-                                      "instr_per_cell": FP64_INSTR_PER_CELL,
-                                      "executed": {"achieved": fp64_executed, "frac": fp64_executed / fp64_peak if fp64_peak else None,
-                                                   "instr_per_cell": FP64_INSTR_EXECUTED,
-                                                   "note": "FP64-pipe instructions the kernel really issues (common terms shared)"},
-                                      "peak_source": "pg2_measure_fp64_issue (DADD loop, this run)",
-                                      "candidate_update_peak": cand.value,
-                                      "issue_slots": {
-                                          "cycles_8dadd_16fadd_both": [mix[0], mix[1], mix[2]],
-                                          "busy_frac_ncu": dispatch_busy["issue_active_pct"] / 100.0 if dispatch_busy else None,
-                                          "fp64_pipe_frac_ncu": dispatch_busy["fp64_pipe_active_pct"] / 100.0 if dispatch_busy else None,
-                                          "alu_pipe_frac_ncu": dispatch_busy.get("alu_pipe_active_pct", 0.0) / 100.0 if dispatch_busy else None,
-                                          "warp_instr_per_32_cells_ncu": dispatch_busy["warp_instructions"] / (cells / 32.0) if dispatch_busy else None,
-                                          "note": "8 DADD + 16 FADD per loop iteration cost cycles[2] ~ 24 issue cycles, not "
-                                                  "cycles[0] + cycles[1]: FP64 instructions (2 pipe cycles each) overlap other issue, so "
-                                                  "the fill kernel's bound is the issue port (1 warp-instruction / cycle / sub-partition); "
-                                                  "busy_frac_ncu = smsp__issue_active of the fill launches in the committed ncu capture"}}},
+                         "hbm": {"achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
+                                 "peak_source": peaks_kind, "algorithmic_bytes_per_cell": PTR_BYTES_PER_CELL},
+                         "issue_slots": {
+                             "cycles_8dadd_16fadd_both": [mix[0], mix[1], mix[2]],
+                             "busy_frac_ncu": dispatch_busy["issue_active_pct"] / 100.0 if dispatch_busy else None,
+                             "fp64_pipe_frac_ncu": dispatch_busy["fp64_pipe_active_pct"] / 100.0 if dispatch_busy else None,
+                             "alu_pipe_frac_ncu": dispatch_busy.get("alu_pipe_active_pct", 0.0) / 100.0 if dispatch_busy else None,
+                             "warp_instr_per_32_cells_ncu": dispatch_busy["warp_instructions"] / (cells / 32.0) if dispatch_busy else None,
+                             "note": "8 DADD + 16 FADD per loop iteration cost cycles[2] ~ 24 issue cycles, not cycles[0] + cycles[1]: "
+                                     "FP64 instructions (2 pipe cycles each) overlap other issue, so the kernel's bound is the issue "
+                                     "port (1 warp-instruction / cycle / sub-partition); busy_frac_ncu = smsp__issue_active of the "
+                                     "fill launches in the committed ncu capture"}},
             "fill_ms_per_step": ms_fill, "traceback_ms_per_step": tb_ms / args.steps, "wall_ms_per_step": ms_wall,
-            "jobs_ok": ok, "jobs": len(jobs), "kernels": {"lanes": stats["jobs_lanes"], "strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"]},
+            "jobs_ok": ok, "jobs": len(jobs),
+            "kernels": {"lanes": stats["jobs_lanes"], "strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"], "pstrip": stats["jobs_pstrip"]},
         }
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample(jobs)
+        # strong scaling: --reads alignments in TOTAL over the ranks (BASELINE configs[1] is one 100k-read job); at N=1 it is
+        # the main line itself
+        if strong_vals is not None:
+            line["strong"] = {"reads_total": args.reads, "cells_total": strong_cells,
+                              "value": strong_cells / (float(strong_vals[0]) * 1e-3) * 1e-9, "unit": "GCUPS", "ms_per_step": float(strong_vals[0]),
+                              "e2e": {"value": strong_cells / (float(strong_vals[1]) * 1e-3) * 1e-9, "ms_per_step": float(strong_vals[1])}}
+        elif world == 1:
+            line["strong"] = {"reads_total": args.reads, "cells_total": cells, "value": line["value"], "unit": "GCUPS", "ms_per_step": ms_dev,
+                              "e2e": {"value": line["e2e"]["value"], "ms_per_step": ms_e2e}}
+        if not args.no_configs:
+            line["configs"] = other_configs(eng)
+        # the CPU leg runs at N=1 only (rank 0 would otherwise keep the other ranks waiting in a barrier) and doubles as the
+        # parity check of this run
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"], line["parity_checked_jobs"] = cpu_baseline_sample(jobs, eng, results, steps_buf)
         emit(line)
     eng.close()
     if dist is not None:
