@@ -54,6 +54,13 @@ extern "C" void CAT(__wrap_, RAL_SYM)(Reads_aligner *self, Node *root, Model_fac
     ppa_b200::placement_end();
 }
 
+// Model_factory::alignment_model: models kept by distance (the reference rebuilds them per node and per trial alignment)
+#define AMD_SYM _ZN3ppa13Model_factory15alignment_modelEd
+extern "C" Evol_model CAT(__real_, AMD_SYM)(Model_factory *self, double distance);
+extern "C" Evol_model CAT(__wrap_, AMD_SYM)(Model_factory *self, double distance) {
+    return ppa_b200::cached_alignment_model(self, distance, &CAT(__real_, AMD_SYM));
+}
+
 namespace {
 struct Stats_at_exit {
     ~Stats_at_exit() {
@@ -63,8 +70,10 @@ struct Stats_at_exit {
             FILE *f = fopen(p, "w");
             if (f) {
                 fprintf(f, "{\"jobs\": %lld, \"cells\": %lld, \"batches\": %lld, \"fill_ms\": %.6f, \"traceback_ms\": %.6f, "
-                           "\"wave_batches\": %lld, \"prefetch_batches\": %lld, \"cache_hits\": %lld, \"sharded_batches\": %lld}\n",
-                        t.jobs, t.cells, t.batches, t.fill_ms, t.traceback_ms, t.wave_batches, t.prefetch_batches, t.cache_hits, t.sharded_batches);
+                           "\"wave_batches\": %lld, \"prefetch_batches\": %lld, \"cache_hits\": %lld, \"sharded_batches\": %lld, "
+                           "\"model_cache_hits\": %lld}\n",
+                        t.jobs, t.cells, t.batches, t.fill_ms, t.traceback_ms, t.wave_batches, t.prefetch_batches, t.cache_hits, t.sharded_batches,
+                        t.model_cache_hits);
                 fclose(f);
             }
         }

@@ -121,7 +121,7 @@ struct Engine {
         pg2_model_desc desc;
     };
     std::map<Model_key, Model_entry> models;
-    ppa_b200::Totals totals = {0, 0, 0, 0.0, 0.0, 0, 0, 0, 0};
+    ppa_b200::Totals totals = {0, 0, 0, 0.0, 0.0, 0, 0, 0, 0, 0};
 
     void fatal(const char *what, int rc) {
         Log_output::write_out(std::string("pagan2_b200: ") + what + " failed (" + std::to_string(rc) + "): " + pg2_last_error() +
@@ -804,6 +804,78 @@ void placement_end() {
     P.cache.clear();
     P.items.clear();
     P.reads.clear();
+}
+
+// Model_factory::alignment_model (model_factory.cpp:1871-2230) is a pure function of the distance: the reference
+// rebuilds the substitution tables for every node (node.cpp:70-71) and twice for every trial alignment of a read
+// (reads_aligner.cpp:3487, 3493) -- 0.23 s per call for the 1892-state codon tables.  Here the first model built for a
+// distance is kept and later calls get a deep copy (same doubles, bit for bit: they were computed by the reference's code).
+namespace {
+struct Model_cache {
+    std::mutex m;
+    std::map<std::pair<Model_factory *, uint64_t>, Evol_model *> models;
+    size_t bytes = 0;
+} g_model_cache;
+
+size_t model_bytes(const Evol_model &m) {
+    const size_t f = (size_t)m.logCharPr->x;
+    return f * f * (2 * sizeof(double) + sizeof(int)) + f * 2 * sizeof(double) + (size_t)m.char_as * m.char_as * sizeof(int);
+}
+
+void copy_model(const Evol_model &src, Evol_model &dst) {
+    auto copy_db = [](Db_matrix *d, const Db_matrix *s) { memcpy(d->data, s->data, sizeof(double) * (size_t)s->x * (size_t)s->y); };  // (y == 1 for vectors)
+    copy_db(dst.charPi, src.charPi);
+    copy_db(dst.charPr, src.charPr);
+    copy_db(dst.logCharPi, src.logCharPi);
+    copy_db(dst.logCharPr, src.logCharPr);
+    memcpy(dst.parsimony_table->data, src.parsimony_table->data, sizeof(int) * (size_t)src.parsimony_table->x * (size_t)src.parsimony_table->y);
+    memcpy(dst.mostcommon_table->data, src.mostcommon_table->data, sizeof(int) * (size_t)src.mostcommon_table->x * (size_t)src.mostcommon_table->y);
+    dst.data_type = src.data_type; dst.char_as = src.char_as; dst.distance = src.distance;
+    dst.id_prob = src.id_prob; dst.ext_prob = src.ext_prob; dst.end_ext_prob = src.end_ext_prob; dst.break_ext_prob = src.break_ext_prob;
+    dst.match_prob = src.match_prob;
+    dst.log_id_prob = src.log_id_prob; dst.log_ext_prob = src.log_ext_prob; dst.log_end_ext_prob = src.log_end_ext_prob;
+    dst.log_break_ext_prob = src.log_break_ext_prob; dst.log_match_prob = src.log_match_prob;
+    dst.ins_rate = src.ins_rate; dst.del_rate = src.del_rate; dst.ins_prob = src.ins_prob; dst.del_prob = src.del_prob;
+    dst.full_char_alphabet = src.full_char_alphabet;
+    dst.ambiguity_type = src.ambiguity_type;
+}
+}  // namespace
+
+// (Evol_model has no copy constructor of its own -- the implicit one shares the tables -- so, like the reference's code,
+// this relies on the returned local being constructed in place: ONE return statement, naming the local.)
+static Evol_model clone_cached_model(Model_factory *mf, double distance, Evol_model (*build)(Model_factory *, double));
+
+Evol_model cached_alignment_model(Model_factory *mf, double distance, Evol_model (*build)(Model_factory *, double)) {
+    static const bool off = getenv("PAGAN2_B200_NO_MODEL_CACHE") && atoi(getenv("PAGAN2_B200_NO_MODEL_CACHE"));
+    if (off) return build(mf, distance);
+    return clone_cached_model(mf, distance, build);
+}
+
+static Evol_model clone_cached_model(Model_factory *mf, double distance, Evol_model (*build)(Model_factory *, double)) {
+    uint64_t bits;
+    memcpy(&bits, &distance, 8);
+    const std::pair<Model_factory *, uint64_t> key(mf, bits);
+    std::lock_guard<std::mutex> lk(g_model_cache.m);
+    auto it = g_model_cache.models.find(key);
+    if (it == g_model_cache.models.end()) {
+        Evol_model built = build(mf, distance);  // (as the reference's callers take it)
+        Evol_model *master = new Evol_model(built.data_type, built.distance);
+        copy_model(built, *master);
+        const size_t b = model_bytes(*master);
+        if (g_model_cache.bytes + b > ((size_t)2 << 30)) {  // bounded: a tree of distinct branch lengths gains nothing from the cache
+            for (auto &kv : g_model_cache.models) delete kv.second;
+            g_model_cache.models.clear();
+            g_model_cache.bytes = 0;
+        }
+        g_model_cache.bytes += b;
+        it = g_model_cache.models.emplace(key, master).first;
+    } else {
+        engine().totals.model_cache_hits++;
+    }
+    const Evol_model &src = *it->second;
+    Evol_model out(src.data_type, src.distance);
+    copy_model(src, out);
+    return out;
 }
 
 }  // namespace ppa_b200

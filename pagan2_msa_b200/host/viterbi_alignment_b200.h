@@ -96,6 +96,10 @@ void align_tree_in_waves(ppa::Node *root, ppa::Model_factory *mf, int n_threads,
 void placement_begin(ppa::Reads_aligner *ra, ppa::Node *root);
 void placement_end();
 
+// Model_factory::alignment_model with the models kept by distance (model_factory.cpp:1871): `build`
+// is the reference's own function; a later call for the same distance gets a deep copy of what it returned.
+ppa::Evol_model cached_alignment_model(ppa::Model_factory *mf, double distance, ppa::Evol_model (*build)(ppa::Model_factory *, double));
+
 // Device-side totals since process start (for the drop-in binary's stats file, PAGAN2_B200_STATS).
 struct Totals {
     long long jobs, cells, batches;
@@ -104,6 +108,7 @@ struct Totals {
     long long prefetch_batches;  // launch batches of prefetched placement trial alignments
     long long cache_hits;        // align() calls served from a prefetched batch
     long long sharded_batches;   // launch batches cut over more than one device
+    long long model_cache_hits;  // Model_factory::alignment_model calls answered with a copy of an earlier model
 };
 Totals totals();
 

@@ -145,6 +145,9 @@ def check_schedulers(binary):
     cuts every launch batch over several contexts."""
     st = compare(binary, "progressive16", extra_args=["--threads", "4"])
     assert st["jobs"] == 15 and st["wave_batches"] == 3 and st["batches"] == 4, st  # waves of 8, 4, 2 and the root
+    assert st["model_cache_hits"] == 14, st  # one branch length everywhere: alignment_model runs once, 14 deep copies
+    st2 = compare(binary, "progressive16", extra_env={"PAGAN2_B200_NO_MODEL_CACHE": "1"})
+    assert st2["model_cache_hits"] == 0 and st2["batches"] == 15, st2  # (and the serial traversal: one alignment per batch)
     st = compare(binary, "progressive16", extra_args=["--threads", "3", "--boost"])
     assert st["jobs"] == 15 and st["batches"] == 4, st
     st = compare(binary, "anchored", extra_args=["--threads", "2"])

@@ -31,10 +31,11 @@ def make_engine(lib, force_wavefront, no_lanes=False, no_pstrip=False, pstrip_k=
     os.environ["PG2_NO_PSTRIP"] = "1" if no_pstrip else "0"
     if pstrip_k:
         os.environ["PG2_PSTRIP_K"] = str(pstrip_k)
+        os.environ["PG2_PSTRIP_BANDED_CHAINS"] = "1"  # (by default banded chain x chain jobs stay on the wavefront kernel)
     try:
         return engine.Engine(0, lib)
     finally:
-        for name in ("PG2_FORCE_WAVEFRONT", "PG2_NO_LANES", "PG2_NO_PSTRIP", "PG2_PSTRIP_K"):
+        for name in ("PG2_FORCE_WAVEFRONT", "PG2_NO_LANES", "PG2_NO_PSTRIP", "PG2_PSTRIP_K", "PG2_PSTRIP_BANDED_CHAINS"):
             os.environ.pop(name, None)
 
 

@@ -35,6 +35,20 @@ def eng_old():
     e.close()
 
 
+@pytest.fixture(scope="module")
+def eng_ps():
+    """Banded chain x chain jobs on the pipelined-strip kernel too (by default they stay on the wavefront kernel)."""
+    import os
+
+    os.environ["PG2_PSTRIP_BANDED_CHAINS"] = "1"
+    try:
+        e = engine.Engine(0)
+    finally:
+        os.environ.pop("PG2_PSTRIP_BANDED_CHAINS", None)
+    yield e
+    e.close()
+
+
 def indel_copy(a, rng, sub, n_indels, max_len):
     """b = a with substitutions and a few indels; returns (b, col) with col[i] = column of b facing row i of a."""
     pos = np.sort(rng.choice(np.arange(100, len(a) - 100), size=n_indels, replace=False))
@@ -60,7 +74,7 @@ def indel_copy(a, rng, sub, n_indels, max_len):
     return b, col
 
 
-def test_config5_anchored_200kb(eng, eng_old, golden):
+def test_config5_anchored_200kb(eng, eng_old, eng_ps, golden):
     """configs[4]: one 200 kb x 200 kb alignment inside an anchor band (banded wavefront kernel, 10 M in-band cells)."""
     rng = np.random.default_rng(5005)
     model = golden["anchored"][0].model
@@ -78,6 +92,8 @@ def test_config5_anchored_200kb(eng, eng_old, golden):
     assert 9_000_000 < job.cells < 12_000_000
     job = enginecheck.expect_from_oracle(job)
     res = enginecheck.check_batch(eng, [job])
+    assert res["kernel"][0] == 0 and res["status"][0] == 0
+    res = enginecheck.check_batch(eng_ps, [job])
     assert res["kernel"][0] == 3 and res["status"][0] == 0
     res = enginecheck.check_batch(eng_old, [job])
     assert res["kernel"][0] == 0 and res["status"][0] == 0

@@ -54,14 +54,14 @@ def eng_old():
 @pytest.fixture(scope="module")
 def eng_ps():
     """Every job that is not a lane task goes to the pipelined-strip kernel."""
-    e = engine_with(PG2_NO_LANES=1, PG2_PSTRIP_MAX_JOBS=1000000)
+    e = engine_with(PG2_NO_LANES=1, PG2_PSTRIP_MAX_JOBS=1000000, PG2_PSTRIP_BANDED_CHAINS=1)
     yield e
     e.close()
 
 
 @pytest.fixture(scope="module")
 def eng_ps4():
-    e = engine_with(PG2_NO_LANES=1, PG2_PSTRIP_MAX_JOBS=1000000, PG2_PSTRIP_K=4)
+    e = engine_with(PG2_NO_LANES=1, PG2_PSTRIP_MAX_JOBS=1000000, PG2_PSTRIP_K=4, PG2_PSTRIP_BANDED_CHAINS=1)
     yield e
     e.close()
 
@@ -171,8 +171,12 @@ def test_random_jobs_vs_oracle(eng, eng_old, eng_ps4, kind, seed):
     rng = np.random.default_rng(seed)
     jobs = [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for _ in range(300)]
     res = enginecheck.check_batch(eng, jobs)
+    if kind == "banded_chain":
+        assert (res["kernel"] == 0).all()  # plain chains inside a band: the wavefront kernel's chain path
+    else:
+        assert (res["kernel"] == 3).mean() > 0.9
+    res = enginecheck.check_batch(eng_ps4, jobs)
     assert (res["kernel"] == 3).mean() > 0.9
-    enginecheck.check_batch(eng_ps4, jobs)
     res = enginecheck.check_batch(eng_old, jobs)
     assert (res["kernel"] != 3).all()
 
@@ -260,7 +264,7 @@ def test_placement_config_scale_properties(eng, golden):
     enginecheck.check_batch(eng, sample)
 
 
-def test_progressive_config_scale_vs_oracle(eng, eng_old):
+def test_progressive_config_scale_vs_oracle(eng, eng_old, eng_ps):
     """BASELINE configs[0] shape: 1 kb x 1 kb leaf alignments (multi-block strip) and a banded
     200 kb-style corridor job on the wavefront kernel, both against the oracle."""
     rng = np.random.default_rng(9)
@@ -273,6 +277,8 @@ def test_progressive_config_scale_vs_oracle(eng, eng_old):
     banded.upper, banded.lower = randjobs.random_band(rng, lx, ly, 20, 40)
     jobs = [enginecheck.expect_from_oracle(job), enginecheck.expect_from_oracle(banded)]
     res = enginecheck.check_batch(eng, jobs)
+    assert res["kernel"][0] == 3 and res["kernel"][1] == 0
+    res = enginecheck.check_batch(eng_ps, jobs)
     assert (res["kernel"] == 3).all()
     res = enginecheck.check_batch(eng_old, jobs)
     assert res["kernel"][0] == 1 and res["kernel"][1] == 0
