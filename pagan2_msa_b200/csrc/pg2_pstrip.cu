@@ -62,7 +62,11 @@ struct PsCtx {
 // the three scalars every candidate needs, in registers (everything else of PsCtx is read from shared memory on demand)
 struct PsHot {
     double open, ext, lng;
+    unsigned flags;      // PH_*
+    int lx1;             // lx - 1
+    unsigned stab_s;     // shared-memory address of the {2 lng + ls, lng + ls} table (SMALLTAB)
 };
+constexpr unsigned PH_TERM = 1u, PH_REDUCED = 2u, PH_BANDED = 4u, PH_WEIGHTS = 8u;
 
 template <int K> struct PsLane {
     double X[K], Y[K], M[K];   // own strip, row handled last
@@ -83,11 +87,16 @@ template <int K> struct PsAcc {
 };
 
 template <bool SMALLTAB>
-__device__ __forceinline__ void ps_subst(const PsCtx &c, int sl, int colbase, double &mlog, double &xlog) {
+__device__ __forceinline__ void ps_subst(const PsCtx &c, const PsHot &h3, int sl, int colbase, double &mlog, double &xlog) {
     if (SMALLTAB) {
+#ifdef PG2_HOST_EMU
         const double2 v = c.stab[sl + colbase];
         mlog = v.x;
         xlog = v.y;
+#else
+        // (an explicit shared-memory load: through the pointer kept in the shared-memory context it would be a generic one)
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mlog), "=d"(xlog) : "r"(h3.stab_s + (unsigned)(sl + colbase) * 16u));
+#endif
     } else {
         const double ls = (double)__ldg(c.table + sl + colbase);
         mlog = __dadd_rn(c.lng2, ls);
@@ -142,7 +151,7 @@ __device__ __forceinline__ void ps_general_y(const PsCtx &c, const PsHot &h3, in
     const int kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
     for (int kr = kr0; kr < kr1; ++kr) {
         const double *h = ps_hist(c, i, c.r_einfo[kr]);
-        const double penY = (c.reduced && c.r_estart[kr] == 0) ? 0.0 : h3.open;
+        const double penY = ((h3.flags & PH_REDUCED) && c.r_estart[kr] == 0) ? 0.0 : h3.open;
         const unsigned ord = (unsigned)(kr - kr0) << 2;
         ps_cand(__dadd_rn(h[1], extY), Y_MAT | ord, best, ptr);
         ps_cand(__dadd_rn(h[0], h3.open), X_MAT | ord, best, ptr);
@@ -180,7 +189,7 @@ __device__ __forceinline__ bool ps_step(const PsCtx &c, const PsHot &h3, PsLane<
             const int p = c.l_estart[vr.y];
             // a row above the block's first row lies outside the band for every column of the block (and for c0 - 1)
             const bool pvalid = p >= c.i0;
-            const double pen = (c.reduced && p == 0) ? 0.0 : h3.open;  // get_log_gap_open_penalty (basic_alignment.h:490-513)
+            const double pen = ((h3.flags & PH_REDUCED) && p == 0) ? 0.0 : h3.open;  // get_log_gap_open_penalty (basic_alignment.h:490-513)
             const double4 *row = c.saved + (long long)(vr.w & 0xffff) * c.saved_stride;
             prow = pvalid ? row : nullptr;
             tbX = st.bX; tbY = st.bY; tbM = st.bM;
@@ -208,11 +217,11 @@ __device__ __forceinline__ bool ps_step(const PsCtx &c, const PsHot &h3, PsLane<
             ps_cand(st.Mo[k], M_MAT | lord, acc.nX[k], acc.pX[k]);
             // M: from M, X, Y of (p, pr) for every backward edge pr -> j (:1353-1436, :2029-2112)
             double mlog, xlog;
-            ps_subst<SMALLTAB>(c, sl, st.colbase[k], mlog, xlog);
+            ps_subst<SMALLTAB>(c, h3, sl, st.colbase[k], mlog, xlog);
             if (!(st.cinfo[k] & PC_GENERAL)) {
                 const double qM = k ? st.M[k - 1] : st.bM, qX = k ? st.X[k - 1] : st.bX, qY = k ? st.Y[k - 1] : st.bY;
                 double a = __dadd_rn(qM, mlog), b = __dadd_rn(qX, xlog), d = __dadd_rn(qY, xlog);
-                if (c.weights) {
+                if (h3.flags & PH_WEIGHTS) {
                     a = __dadd_rn(__dadd_rn(a, wl), st.wr[k]);
                     b = __dadd_rn(__dadd_rn(b, wl), st.wr[k]);
                     d = __dadd_rn(__dadd_rn(d, wl), st.wr[k]);
@@ -239,15 +248,15 @@ __device__ __forceinline__ bool ps_step(const PsCtx &c, const PsHot &h3, PsLane<
         acc.nM[0] = (i == 0) ? 0.0 : ninf;
         acc.pM[0] = NO_MAT;
     }
-    const double extY = (c.term && (i == 0 || i == c.lx - 1)) ? c.end_ext : h3.ext;
+    const double extY = ((h3.flags & PH_TERM) && (i == 0 || i == h3.lx1)) ? c.end_ext : h3.ext;
     int blo = 0, bhi = 0x7fffffff;
-    if (c.banded) { blo = c.blo[i]; bhi = c.bhi[i]; }
+    if (h3.flags & PH_BANDED) { blo = c.blo[i]; bhi = c.bhi[i]; }
     const unsigned plain_row = ((info & VR_FAST) == VR_FAST && edge) ? PSW_PLAIN_ROW : 0u;
     // Y: ext, double, open out of (i, j - 1) (:2116-2211 with the roles of X and Y swapped).  The two candidates that do
     // not depend on the chain are folded first: (g > a ? g : a) with g = first-wins(double, open) equals the sequential
     // first-wins over ext, double, open
     double lXo = __dadd_rn(rX, h3.open), lMo = __dadd_rn(__dadd_rn(rM, h3.lng), h3.open), lY = rY;
-    if (st.j0 == 1 && i == 0 && c.reduced) lMo = __dadd_rn(__dadd_rn(rM, h3.lng), 0.0);  // the neighbour is the start corner
+    if (st.j0 == 1 && i == 0 && (h3.flags & PH_REDUCED)) lMo = __dadd_rn(__dadd_rn(rM, h3.lng), 0.0);  // the neighbour is the start corner
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = st.j0 + k;
@@ -270,7 +279,7 @@ __device__ __forceinline__ bool ps_step(const PsCtx &c, const PsHot &h3, PsLane<
         double nx = acc.nX[k], nm = acc.nM[k];
         if (j < blo || j > bhi) { nx = ninf; ny = ninf; nm = ninf; }  // Tunnel_slice::at: -inf outside the band
         double nmo = __dadd_rn(__dadd_rn(nm, h3.lng), h3.open);
-        if (j == 0 && i == 0 && c.reduced) nmo = __dadd_rn(__dadd_rn(nm, h3.lng), 0.0);  // the start corner's gap moves
+        if (j == 0 && i == 0 && (h3.flags & PH_REDUCED)) nmo = __dadd_rn(__dadd_rn(nm, h3.lng), 0.0);  // the start corner's gap moves
         out[k] = cell_word(acc.pX[k], py, acc.pM[k]) | plain_row | plain_col;
         st.X[k] = nx; st.Y[k] = ny; st.M[k] = nm; st.Mo[k] = nmo;
         if (st.cinfo[k] >= 0 && (st.cinfo[k] & (PC_PARKED | PC_ENDCOL))) {
@@ -488,6 +497,9 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
             PsAcc<K> acc;
             PsHot h3;
             h3.open = c.open; h3.ext = c.ext; h3.lng = c.lng;
+            h3.flags = (c.term ? PH_TERM : 0u) | (c.reduced ? PH_REDUCED : 0u) | (c.banded ? PH_BANDED : 0u) | (c.weights ? PH_WEIGHTS : 0u);
+            h3.lx1 = c.lx - 1;
+            h3.stab_s = SMALLTAB ? (unsigned)__cvta_generic_to_shared(s_tab) : 0u;
             ps_init_lane<K>(c, st, lane);
 #pragma unroll
             for (int k = 0; k < K; ++k) { acc.nX[k] = acc.nM[k] = ninf; acc.pX[k] = acc.pM[k] = NO_MAT; }
@@ -507,7 +519,10 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
                         dst[0] = ninf; dst[1] = ninf; dst[2] = ninf;
                     } else {
                         const int need = prod_base + v + 1;
-                        while (avail < need) avail = ps_load_acquire(prod);
+                        while (avail < need) {
+                            avail = ps_load_acquire(prod);
+                            if (avail < need) __nanosleep(64);  // the waiting warp leaves the issue slots to the warps that work
+                        }
                         const double4 *src = bcol_prev + (v & ring_mask);
                         const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
@@ -520,6 +535,10 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
             for (int d = 0; d < PS_PREFETCH; ++d) issue(v0 + d);
             unsigned *out = P + ptr_off + lane * K;
             const int n_steps = (v1 - v0) + last_lane;
+            // the row program entry of the NEXT step is fetched a step ahead
+            const int4 vr_idle = make_int4(VR_FAST | VR_ZERO_W, -1, 0, 0);
+            int4 vr_next = vr_idle;
+            if (lane == 0 && v1 > v0) vr_next = __ldg(c.l_vrow + v0);
             for (int t = 0; t < n_steps; ++t) {
                 double rX = __shfl_up_sync(0xffffffffu, st.X[K - 1], 1);
                 double rY = __shfl_up_sync(0xffffffffu, st.Y[K - 1], 1);
@@ -529,8 +548,12 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
                 issue(v0 + t + PS_PREFETCH);
                 const int v = v0 + t - lane;
                 const bool active = (v >= v0 && v < v1 && lane <= last_lane);
-                int4 vr = make_int4(VR_FAST | VR_ZERO_W, -1, 0, 0);
-                if (active) vr = __ldg(c.l_vrow + v);
+                const int4 vr = vr_next;
+                {
+                    const int vn = v + 1;
+                    vr_next = vr_idle;
+                    if (vn >= v0 && vn < v1 && lane <= last_lane) vr_next = __ldg(c.l_vrow + vn);
+                }
                 const bool any_saved = __any_sync(0xffffffffu, active && !(vr.x & (VR_REG | VR_NOEDGE)));
                 if (active) {
                     unsigned wds[K];
@@ -616,6 +639,9 @@ static void ps_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &
     const int ring_mask = ring - 1;
     PsHot h3;
     h3.open = c.open; h3.ext = c.ext; h3.lng = c.lng;
+    h3.flags = (c.term ? PH_TERM : 0u) | (c.reduced ? PH_REDUCED : 0u) | (c.banded ? PH_BANDED : 0u) | (c.weights ? PH_WEIGHTS : 0u);
+    h3.lx1 = c.lx - 1;
+    h3.stab_s = 0;
     ps_end_init(c, c.endstore, 0, 1);
     for (int b = 0; b < J.n_blocks; ++b) {
         ps_load_block(c, blocks + b * PB_INTS);
