@@ -158,7 +158,8 @@ struct pg2_batch {
     bool uploaded = false, ran = false, fetch_enqueued = false;
 };
 
-constexpr int PIPE_SLOTS = 4;  // chunks of one pg2_align_batch call in flight at once (packing / H2D / kernels / D2H overlap)
+constexpr int PIPE_SLOTS = 8;  // chunks of one pg2_align_batch call in flight at once (packing / H2D / kernels / D2H overlap): one slot per
+                               // chunk of the default cut, so the host never waits for a traceback that sits behind the next chunks' fills
 
 struct pg2_ctx {
     int device = 0;
@@ -204,6 +205,7 @@ struct pg2_ctx {
     cudaEvent_t ev[8];
     pg2_stats stats;
     pg2_batch *current = nullptr;
+    bool prio_set = false;  // sibling: its stream carries the priority of its pipeline slot
     pg2_ctx *sibling[PIPE_SLOTS - 1] = {};  // further sets of staging / device buffers + streams for pipelined pg2_align_batch calls
     bool borrowed_models = false;  // a sibling shares the primary's model tables and must not free them
 };
@@ -214,6 +216,11 @@ extern "C" const char *pg2_last_error(void) { return g_last_error.c_str(); }
 extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
     if (!out) return fail(PG2_ERR_INVALID, "pg2_ctx_create: null out pointer");
     *out = nullptr;
+    // Pipelined pg2_align_batch calls keep up to PIPE_SLOTS chunks in flight on two streams each.  With the driver's default of 8
+    // hardware work queues several of those streams share a queue, and an upload then waits behind another chunk's traceback that
+    // is itself waiting for SM slots (measured: chunk 6 of 8 started 14 ms late).  Only effective before the process creates its
+    // CUDA context; a caller that initialised CUDA earlier sets the variable itself (bench.py, engine.py do).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
         cudaGetLastError();
@@ -228,10 +235,15 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
         delete c;
         return fail(PG2_ERR_NO_DEVICE, "device is not sm_100 class; the kernels are built for sm_100a only");
     }
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(PG2_ERR_CUDA, "stream creation failed"); }
     {
+        // the ctx stream sits one level below the traceback stream (slot 0 of a pipelined call: the oldest chunk, see ensure_siblings)
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, std::min(prio_hi + 1, prio_lo)) != cudaSuccess) {
+            cudaGetLastError();
+            delete c;
+            return fail(PG2_ERR_CUDA, "stream creation failed");
+        }
         if (cudaStreamCreateWithPriority(&c->hi_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { cudaGetLastError(); c->hi_stream = 0; }
     }
     for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
@@ -1479,6 +1491,23 @@ static int ensure_siblings(pg2_ctx *c, int n_slots) {
             s->pstrip_banded_chains = c->pstrip_banded_chains;
             c->sibling[k] = s;
         }
+        // Chunk k of a pipelined call runs on slot k: the earlier chunk's stream gets the higher priority, so that the SM slots
+        // a finishing launch gives back go to the OLDEST launch that still has CTAs waiting.  Without this the last three
+        // launches of a call share the slots evenly and all end raggedly (measured: ends at 60.3 / 62.2 / 64.4 ms).
+        if (!c->sibling[k]->prio_set) {
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority; prio_hi is the tracebacks'
+            const int levels = prio_lo - prio_hi;                  // levels below the traceback streams
+            if (levels >= 2) {
+                const int prio = prio_hi + 1 + ((k + 1) * levels) / PIPE_SLOTS;
+                cudaStream_t st = 0;
+                if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, std::min(prio, prio_lo)) == cudaSuccess) {
+                    cudaStreamDestroy(c->sibling[k]->stream);
+                    c->sibling[k]->stream = st;
+                } else cudaGetLastError();
+            }
+            c->sibling[k]->prio_set = true;
+        }
         c->sibling[k]->models = c->models;  // same device tables
         c->sibling[k]->models_dirty = true;
     }
@@ -1497,32 +1526,58 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
     std::vector<long long> cells_prefix((size_t)n_jobs + 1, 0);
     {
         // open-addressing table on the left graph's `state` pointer -> group id
+        // (the table grows with the number of DISTINCT left graphs -- 127 in a placement batch of 100 000 reads)
         size_t cap = 1024;
-        while (cap < (size_t)n_jobs * 2) cap <<= 1;
         struct Slot { const void *key; int gid; };
         std::vector<Slot> table(cap, Slot{nullptr, -1});
-        std::vector<int> gid(n_jobs), count;
+        auto probe = [&](const void *key) {
+            size_t i = ((((size_t)key >> 4) * 0x9E3779B97F4A7C15ull) >> 24) & (cap - 1);
+            while (table[i].gid >= 0 && table[i].key != key) i = (i + 1) & (cap - 1);
+            return i;
+        };
+        std::vector<int> gid(n_jobs), count, gsize;
+        std::vector<long long> cells(n_jobs);  // read in job order here; the permuted prefix sum below stays inside this array
         const void *last_key = nullptr;
         int last_gid = -1;
         for (int t = 0; t < n_jobs; t++) {
-            const void *key = jobs[t].left.state;
+            const pg2_job &j = jobs[t];
+            const void *key = j.left.state;
             if (key != last_key) {
-                size_t i = ((((size_t)key >> 4) * 0x9E3779B97F4A7C15ull) >> 24) & (cap - 1);
-                while (table[i].gid >= 0 && table[i].key != key) i = (i + 1) & (cap - 1);
-                if (table[i].gid < 0) { table[i].key = key; table[i].gid = (int)count.size(); count.push_back(0); }
+                size_t i = probe(key);
+                if (table[i].gid < 0) {
+                    if ((count.size() + 1) * 2 > cap) {  // keep the load under one half
+                        std::vector<Slot> old_table;
+                        old_table.swap(table);
+                        cap <<= 2;
+                        table.assign(cap, Slot{nullptr, -1});
+                        for (const Slot &o : old_table) if (o.gid >= 0) table[probe(o.key)] = o;
+                        i = probe(key);
+                    }
+                    table[i].key = key;
+                    table[i].gid = (int)count.size();
+                    count.push_back(0);
+                    gsize.push_back(j.left.n_sites);
+                }
                 last_key = key;
                 last_gid = table[i].gid;
             }
             gid[t] = last_gid;
             count[last_gid]++;
+            cells[t] = (long long)std::max(j.left.n_sites, 1) * std::max(j.right.n_sites, 1);
         }
+        // groups with the longest left graph first: the launches of the last chunks then hold the shortest tasks (the
+        // tail of the call), as a single launch's longest-first task order would
+        std::vector<int> gorder(count.size());
+        for (size_t g = 0; g < gorder.size(); g++) gorder[g] = (int)g;
+        if (!getenv("PG2_PIPELINE_KEEP_ORDER"))
+            std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b2) { return gsize[a] > gsize[b2]; });
         std::vector<int> start(count.size() + 1, 0);
-        for (size_t g = 0; g < count.size(); g++) start[g + 1] = start[g] + count[g];
-        for (int t = 0; t < n_jobs; t++) perm[start[gid[t]]++] = t;
-        for (int k = 0; k < n_jobs; k++) {
-            const pg2_job &j = jobs[perm[k]];
-            cells_prefix[k + 1] = cells_prefix[k] + (long long)std::max(j.left.n_sites, 1) * std::max(j.right.n_sites, 1);
+        {
+            int acc = 0;
+            for (int g : gorder) { start[g] = acc; acc += count[g]; }
         }
+        for (int t = 0; t < n_jobs; t++) perm[start[gid[t]]++] = t;
+        for (int k = 0; k < n_jobs; k++) cells_prefix[k + 1] = cells_prefix[k] + cells[perm[k]];
     }
     const long long total = cells_prefix[n_jobs];
     int n_chunks = (int)std::min<long long>(8, std::max<long long>(2, total / 2500000000LL));

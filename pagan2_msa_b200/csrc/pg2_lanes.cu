@@ -561,6 +561,9 @@ __device__ __forceinline__ void lane_publish(int *p, int value, int lane) {
     }
 }
 
+// CTAs placed on each SM so far (never reset: only its value modulo LANE_W is used)
+__device__ int g_lane_sm_rotation[256];
+
 template <int K, bool GENERAL, bool SMALLTAB, bool WR>
 __global__ void __launch_bounds__(LANE_W * 32, PG2_LANE_MINB)
 lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs, const DevModel *models,
@@ -576,10 +579,23 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
     // pipeline stage of this warp.  Hardware warp k of every CTA lives on SM sub-partition k % 4; rotating the
     // stages by the CTA index puts one warp of each stage on every sub-partition (stage 0 carries the wrap
     // prefetch, the last stage idles in a short last round), so the sub-partitions stay evenly loaded.
-#ifdef PG2_LANE_NOROT
+#if defined(PG2_LANE_NOROT)
     const int w = threadIdx.x >> 5;
-#else
+#elif !defined(PG2_LANE_ROT_SM)
     const int w = ((threadIdx.x >> 5) + blockIdx.x) % LANE_W;
+#else
+    // (tuning variant, measured and not adopted: the rotation counted per SM instead of taken from the CTA index, for the case
+    // that several launches share the chip -- e2e 70.0 vs 69.4 ms, resident fill 55.2 vs 54.1 ms: the stage index stops being
+    // a uniform-datapath value)
+    __shared__ int s_rot;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rot = atomicAdd(&g_lane_sm_rotation[smid & 255u], 1);
+    }
+    __syncthreads();
+    const int w = ((threadIdx.x >> 5) + s_rot) & (LANE_W - 1);
+    static_assert((LANE_W & (LANE_W - 1)) == 0, "stage rotation assumes a power-of-two warp count");
 #endif
     double *wrap = scratch + (long long)blockIdx.x * (wrap_doubles + endcol_doubles + LANE_W * slot_doubles);
     double *endcol = wrap + wrap_doubles;
