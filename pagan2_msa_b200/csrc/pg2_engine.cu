@@ -26,7 +26,7 @@
 namespace pg2 {
 int pstrip_warps(int n_blocks, int park_cap, bool smalltab);
 long long pstrip_cta_double4(int K, int nw, int max_lx, int ring, int max_slots);
-void launch_pstrip_fill(int K, bool smalltab, int nw, int n_jobs, int n_ctas, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
+void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_clusters, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                         const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                         const int4 *d_vrow, const int *d_vlast, const int *d_blo, const int *d_bhi, unsigned *ptrs, DevResult *results,
                         double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int *queue, cudaStream_t stream);
@@ -173,7 +173,8 @@ struct pg2_ctx {
     bool force_wavefront = false;  // PG2_FORCE_WAVEFRONT=1: route every job through the general kernel (tests)
     bool no_lanes = false;         // PG2_NO_LANES=1: keep shared-target jobs on the warp-per-alignment strip kernel (tests)
     bool no_pstrip = false;        // PG2_NO_PSTRIP=1: never use the pipelined-strip kernel (tests: the older kernels stay covered)
-    bool pstrip_banded_chains = false;  // PG2_PSTRIP_BANDED_CHAINS=1: banded chain x chain jobs too (tests)
+    bool pstrip_banded_chains = false;
+    int pstrip_cluster_max = 8;     // CTAs (SMs) one pipelined-strip alignment may be spread over (PG2_PSTRIP_CLUSTER; 1 = one CTA per job)  // PG2_PSTRIP_BANDED_CHAINS=1: banded chain x chain jobs too (tests)
     int pstrip_max_jobs = 600;     // strip-eligible jobs of a batch go to the pipelined-strip kernel when there are at most this
                                    // many of them (a warp per alignment cannot fill the chip; PG2_PSTRIP_MAX_JOBS)
     size_t lane_scratch_bytes = (size_t)8 << 30;  // cap of the lane kernel's per-CTA wrap / end-column / parked-row scratch
@@ -255,6 +256,8 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
     c->no_pstrip = nps && atoi(nps) != 0;
     const char *pbc = getenv("PG2_PSTRIP_BANDED_CHAINS");
     c->pstrip_banded_chains = pbc && atoi(pbc) != 0;
+    const char *pcl = getenv("PG2_PSTRIP_CLUSTER");
+    if (pcl && atoi(pcl) >= 1 && atoi(pcl) <= 8) c->pstrip_cluster_max = atoi(pcl);
     const char *pmj = getenv("PG2_PSTRIP_MAX_JOBS");
     if (pmj && atoi(pmj) >= 0) c->pstrip_max_jobs = atoi(pmj);
     const char *mb = getenv("PG2_SCRATCH_MB");
@@ -1262,14 +1265,33 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
             size_t need = (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots) * lane_ctas(g);
             if ((rc = c->d_lane_scratch.ensure(need)) != PG2_OK) return fail(rc, "lane scratch allocation failed");
         }
-    // pipelined strips: one CTA per job in flight; CTAs per SM by the warps a CTA holds
-    auto ps_ctas = [&](const Group &g) {
-        const int per_sm = g.ps_nw > 8 ? 1 : (g.ps_nw > 4 ? 2 : 4);
-        return std::max(1, std::min(g.count, c->prop.multiProcessorCount * per_sm));
+    // pipelined strips: one CLUSTER per job in flight.  A launch with few jobs (a guide-tree wave, a pileup step) spreads every
+    // job over G SMs with 4 warps per CTA -- one warp per SM sub-partition, all column blocks of a 1.5 k-column alignment in
+    // flight at once; a launch that fills the chip by itself keeps one CTA of up to 12 warps per job.
+    struct PsShape { int G, nw, clusters; };
+    auto ps_shape = [&](const Group &g) {
+        PsShape s;
+        const int sms = c->prop.multiProcessorCount;
+        s.G = 1;
+        s.nw = g.ps_nw;
+        const int per_job = sms / std::max(g.count, 1);  // SMs one job may take
+        if (per_job >= 2 && g.ps_blocks > 4 && c->pstrip_cluster_max > 1) {
+            const int nw = std::min(4, g.ps_nw);
+            const int want = (g.ps_blocks + nw - 1) / nw;
+            const int G = std::min(std::min(c->pstrip_cluster_max, want), per_job);
+            if (G > 1) { s.G = G; s.nw = nw; }
+        }
+        if (s.G > 1) s.clusters = std::max(1, std::min(g.count, sms / s.G));
+        else {
+            const int per_sm = s.nw > 8 ? 1 : (s.nw > 4 ? 2 : 4);
+            s.clusters = std::max(1, std::min(g.count, sms * per_sm));
+        }
+        return s;
     };
     for (auto &g : b->groups)
         if (g.kernel == 3) {
-            const size_t need = (size_t)pstrip_cta_double4(g.strip_k, g.ps_nw, g.max_lx, g.ps_ring, g.max_slots) * (size_t)ps_ctas(g);
+            const PsShape sh = ps_shape(g);
+            const size_t need = (size_t)pstrip_cta_double4(g.strip_k, sh.nw * sh.G, g.max_lx, g.ps_ring, g.max_slots) * (size_t)sh.clusters;
             if ((rc = c->d_ps_scratch.ensure(need)) != PG2_OK) return fail(rc, "pipelined-strip scratch allocation failed");
         }
     for (auto &g : b->groups)
@@ -1304,7 +1326,8 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
             if (g.kernel == 0) phase_wave_jobs += g.count;
             if (g.kernel == 3) {
                 phase_ps_jobs += g.count;
-                launch_pstrip_fill(g.strip_k, (g.strip_general & 2) != 0, g.ps_nw, g.count, ps_ctas(g), c->d_jobs.p, ids, c->d_graphs.p,
+                const PsShape sh = ps_shape(g);
+                launch_pstrip_fill(g.strip_k, (g.strip_general & 2) != 0, sh.nw, sh.G, g.count, sh.clusters, c->d_jobs.p, ids, c->d_graphs.p,
                                    c->d_models.p, c->d_state.p, c->d_off.p, c->d_estart.p, c->d_elogw.p,
                                    reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_vlast.p, c->d_blo.p, c->d_bhi.p, c->d_ptrps.p,
                                    c->d_results.p, c->d_ps_scratch.p, g.max_lx, g.ps_ring, g.max_slots, g.ps_park, c->d_queue.p, c->stream);
@@ -1489,6 +1512,7 @@ static int ensure_siblings(pg2_ctx *c, int n_slots) {
             s->no_pstrip = c->no_pstrip;
             s->pstrip_max_jobs = c->pstrip_max_jobs;
             s->pstrip_banded_chains = c->pstrip_banded_chains;
+            s->pstrip_cluster_max = c->pstrip_cluster_max;
             c->sibling[k] = s;
         }
         // Chunk k of a pipelined call runs on slot k: the earlier chunk's stream gets the higher priority, so that the SM slots

@@ -27,6 +27,8 @@
 #include "pg2_pstrip_geom.cuh"
 #ifdef PG2_HOST_EMU
 #include <vector>
+#else
+#include <cooperative_groups.h>
 #endif
 
 namespace pg2 {
@@ -402,13 +404,19 @@ __device__ __forceinline__ void ps_load_block(PsCtx &c, const int *blk) {
 }
 
 #ifndef PG2_HOST_EMU
-__device__ __forceinline__ int ps_load_acquire(const int *p) {
+// Progress counters of the block pipeline live in global memory (the warps of one alignment may sit on several SMs of a
+// thread-block cluster).  `wide`: producer and consumer may be on different SMs -- gpu scope; otherwise cta scope.
+__device__ __forceinline__ int ps_load_acquire(const int *p, bool wide) {
     int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    // (relaxed, not acquire: a gpu-scope acquire invalidates the SM's L1 on every poll; what the flag guards is read with
+    // cp.async.cg / ld.cg, which go to L2 anyway, and is issued only after the polling loop has seen the value)
+    if (wide) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else asm volatile("ld.acquire.cta.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void ps_store_release(int *p, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+__device__ __forceinline__ void ps_store_release(int *p, int v, bool wide) {
+    if (wide) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else asm volatile("st.release.cta.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <int K, bool SMALLTAB>
@@ -418,12 +426,19 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
                    const int *d_bhi, unsigned *ptrs, DevResult *results, double4 *scratch, long long cta_d4, long long end_d4, int ring,
                    int max_slots, int park_cap, int *queue) {
     extern __shared__ __align__(16) unsigned char ps_smem[];
+    // One alignment is swept by the warps of a whole thread-block CLUSTER: G CTAs of nw warps on G SMs (a guide-tree wave
+    // holds a handful of alignments and 148 SMs; with 4 warps per CTA every warp has an SM sub-partition to itself).
+    // Consecutive column blocks go to consecutive CTAs of the cluster: pipeline slot gw = w * G + rank takes blocks gw, gw + NW, ...
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int G = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const bool wide = G > 1;
     const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NW = G * nw, gw = w * G + rank;
     double *hist_all = reinterpret_cast<double *>(ps_smem);
     const int hist_doubles = PS_HIST * park_cap * 3;
     double2 *s_tab = reinterpret_cast<double2 *>(hist_all + (size_t)nw * hist_doubles);
     __shared__ int s_job;
-    __shared__ int s_prog[PS_MAX_WARPS];
     // the warp-uniform constants live in shared memory, one copy per warp (the block fields differ): in registers they
     // would cost every lane some sixty registers
     __shared__ PsCtx s_ctx[PS_MAX_WARPS];
@@ -431,24 +446,32 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
     __shared__ __align__(16) double s_bnd[PS_MAX_WARPS][8][4];
     const double ninf = neg_inf();
     const int ring_mask = ring - 1;
-    double4 *cta_scratch = scratch + (long long)blockIdx.x * cta_d4;
-    double4 *endstore = cta_scratch;  // [PS_MAX_END][max lx]
+    double4 *cl_scratch = scratch + (long long)(blockIdx.x / G) * cta_d4;  // one region per cluster
+    double4 *endstore = cl_scratch;  // [PS_MAX_END][max lx]
     const long long warp_d4 = 2LL * ring + (long long)(max_slots > 0 ? max_slots : 1) * (1 + 32 * K);
-    double4 *my = cta_scratch + end_d4 + (long long)w * warp_d4;            // this warp: 2 boundary rings, parked rows
-    double4 *prev = cta_scratch + end_d4 + (long long)((w + nw - 1) % nw) * warp_d4;
+    double4 *my = cl_scratch + end_d4 + (long long)gw * warp_d4;            // this pipeline slot: 2 boundary rings, parked rows
+    double4 *prev = cl_scratch + end_d4 + (long long)((gw + NW - 1) % NW) * warp_d4;
+    int *g_prog = reinterpret_cast<int *>(cl_scratch + end_d4 + (long long)NW * warp_d4);  // progress of every pipeline slot
     int tab_model = -1;
 
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_job = atomicAdd(queue, 1);
-        if (threadIdx.x < PS_MAX_WARPS) s_prog[threadIdx.x] = 0;
+        cluster.sync();  // every CTA is done with the previous job (its end corner included)
+        // the job index travels through global memory, not through rank 0's shared memory: a CTA that leaves the loop must not be
+        // read by its cluster mates afterwards
+        if (rank == 0) {
+            if (threadIdx.x == 0) g_prog[NW] = atomicAdd(queue, 1);
+            for (int e = threadIdx.x; e < NW; e += blockDim.x) g_prog[e] = 0;
+            __threadfence();
+        }
+        cluster.sync();
+        if (threadIdx.x == 0) s_job = ps_load_acquire(g_prog + NW, wide);
         __syncthreads();
         const int q = s_job;
         if (q >= n_jobs) break;
         const int jid = job_ids[q];
         const DevJob &J = jobs[jid];
         DevResult *res = results + jid;
-        if (res->status != JOB_OK) continue;  // rejected by the validation kernel (block-uniform)
+        if (res->status != JOB_OK) continue;  // rejected by the validation kernel (cluster-uniform)
         const DevGraph GL = graphs[J.left], GR = graphs[J.right];
         const DevModel m = models[J.model];
         PsCtx &c = s_ctx[w];
@@ -477,21 +500,21 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
         const int stride = c.nv + 2;  // progress values of one round
         unsigned *P = ptrs + J.cell_base;
         // rows the end corner reads: -inf until a block writes them (a row above a banded block never is)
-        ps_end_init(c, endstore, threadIdx.x, blockDim.x);
-        __syncthreads();
+        if (rank == 0) { ps_end_init(c, endstore, threadIdx.x, blockDim.x); __threadfence(); }
+        cluster.sync();
 
-        for (int b = w; b < n_blocks; b += nw) {
-            const int round = b / nw;
+        for (int b = gw; b < n_blocks; b += NW) {
+            const int round = b / NW;
             __syncwarp();
             if (lane == 0) ps_load_block(c, blocks + b * PB_INTS);
             __syncwarp();
             const int ptr_off = blocks[b * PB_INTS + 5];
             int pv0 = 0, pv1 = 0;
             if (b > 0) { pv0 = blocks[(b - 1) * PB_INTS + 2]; pv1 = blocks[(b - 1) * PB_INTS + 3]; }
-            // the producer of this block's left boundary: warp w - 1 in this round, or the last warp one round earlier
-            const int *prod = s_prog + (w + nw - 1) % nw;
-            const int prod_base = (w == 0 ? round - 1 : round) * stride;
-            const double4 *bcol_prev = prev + (long long)(((w == 0 ? round - 1 : round) & 1) ? ring : 0);
+            // the producer of this block's left boundary: slot gw - 1 in this round, or the last slot one round earlier
+            const int *prod = g_prog + (gw + NW - 1) % NW;
+            const int prod_base = (gw == 0 ? round - 1 : round) * stride;
+            const double4 *bcol_prev = prev + (long long)(((gw == 0 ? round - 1 : round) & 1) ? ring : 0);
             double4 *bcol_cur = my + (long long)((round & 1) ? ring : 0);
             PsLane<K> st;
             PsAcc<K> acc;
@@ -520,7 +543,7 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
                     } else {
                         const int need = prod_base + v + 1;
                         while (avail < need) {
-                            avail = ps_load_acquire(prod);
+                            avail = ps_load_acquire(prod, wide);
                             if (avail < need) __nanosleep(64);  // the waiting warp leaves the issue slots to the warps that work
                         }
                         const double4 *src = bcol_prev + (v & ring_mask);
@@ -581,15 +604,16 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
                         }
                     }
                     // progress: every 8th virtual row (a release store orders the thread's earlier stores: not every step)
-                    if (lane == last_lane && feeds_next && ((v & 7) == 7 || v == v1 - 1)) ps_store_release(s_prog + w, round * stride + (v + 1));
+                    if (lane == last_lane && feeds_next && ((v & 7) == 7 || v == v1 - 1)) ps_store_release(g_prog + gw, round * stride + (v + 1), wide);
                 }
                 __syncwarp();
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
-            if (lane == 0) ps_store_release(s_prog + w, round * stride + c.nv + 1);
+            if (lane == 0) ps_store_release(g_prog + gw, round * stride + c.nv + 1, wide);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) ps_end_corner(c, endstore, res);
+        __threadfence();  // the end columns this CTA wrote, before the cluster meets
+        cluster.sync();
+        if (rank == 0 && threadIdx.x == 0) ps_end_corner(c, endstore, res);
     }
 }
 #endif
@@ -703,34 +727,48 @@ static void ps_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &
 
 int pstrip_max_warps() { return PS_MAX_WARPS; }
 
-// per-CTA scratch in double4: end columns, then per warp two boundary rings and the parked rows
+// per-cluster scratch in double4: end columns, then per pipeline slot (nw = warps of the whole cluster) two boundary rings and
+// the parked rows, then the progress counters of the slots
 long long pstrip_cta_double4(int K, int nw, int max_lx, int ring, int max_slots) {
-    return (long long)PS_MAX_END * max_lx + (long long)nw * (2LL * ring + (long long)(max_slots > 0 ? max_slots : 1) * (1 + 32 * K));
+    return (long long)PS_MAX_END * max_lx + (long long)nw * (2LL * ring + (long long)(max_slots > 0 ? max_slots : 1) * (1 + 32 * K)) + (nw + 7) / 8 + 1;
 }
 
-// Launches one group of pipelined-strip jobs that share the strip width K and the table variant.
-void launch_pstrip_fill(int K, bool smalltab, int nw, int n_jobs, int n_ctas, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
+// Launches one group of pipelined-strip jobs that share the strip width K and the table variant: n_clusters clusters of G CTAs
+// of nw warps each, one alignment per cluster at a time.
+void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_clusters, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                         const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                         const int4 *d_vrow, const int *d_vlast, const int *d_blo, const int *d_bhi, unsigned *ptrs, DevResult *results,
                         double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int *queue, cudaStream_t stream) {
     if (n_jobs <= 0) return;
     const long long end_d4 = (long long)PS_MAX_END * max_lx;
-    const long long cta_d4 = pstrip_cta_double4(K, nw, max_lx, ring, max_slots);
+    const long long cta_d4 = pstrip_cta_double4(K, nw * G, max_lx, ring, max_slots);
 #ifndef PG2_HOST_EMU
     cudaMemsetAsync(queue, 0, sizeof(int), stream);
     const int smem = (int)ps_smem_bytes(nw, park_cap, smalltab);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_clusters * G));
+    cfg.blockDim = dim3((unsigned)(nw * 32));
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)G;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
 #define PG2_PS_LAUNCH(KK, S)                                                                                                      \
     do {                                                                                                                          \
         cudaFuncSetAttribute(pstrip_fill_kernel<KK, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
-        pstrip_fill_kernel<KK, S><<<n_ctas, nw * 32, smem, stream>>>(n_jobs, jobs, job_ids, graphs, models, d_state, d_off, d_estart, \
-                                                                    d_elogw, d_vrow, d_vlast, d_blo, d_bhi, ptrs, results, scratch,  \
-                                                                    cta_d4, end_d4, ring, max_slots, park_cap, queue);              \
+        cudaLaunchKernelEx(&cfg, pstrip_fill_kernel<KK, S>, n_jobs, jobs, job_ids, graphs, models, d_state, d_off, d_estart,       \
+                           d_elogw, d_vrow, d_vlast, d_blo, d_bhi, ptrs, results, scratch, cta_d4, end_d4, ring, max_slots,       \
+                           park_cap, queue);                                                                                      \
     } while (0)
     if (K == 2) { if (smalltab) PG2_PS_LAUNCH(2, true); else PG2_PS_LAUNCH(2, false); }
     else { if (smalltab) PG2_PS_LAUNCH(4, true); else PG2_PS_LAUNCH(4, false); }
 #undef PG2_PS_LAUNCH
 #else
-    (void)queue; (void)stream; (void)n_ctas; (void)nw; (void)smalltab; (void)cta_d4;
+    (void)queue; (void)stream; (void)n_clusters; (void)nw; (void)G; (void)smalltab; (void)cta_d4;
     for (int q = 0; q < n_jobs; ++q) {
         const int jid = job_ids[q];
         const DevJob &J = jobs[jid];
