@@ -231,6 +231,24 @@ int pg2_measure_fp64_issue(int device, double *dadd_gips, double *cand_gips);
  * sm_clock_mhz: the clock the cycle counts were derived with. */
 int pg2_measure_dispatch_mix(int device, double cycles[3], double *sm_clock_mhz);
 
+/* ---- prefix anchors (host) ------------------------------------------------------------------ */
+
+/* One anchor: seq1[start_1 .. start_1+length) == seq2[start_2 .. start_2+length) (reference: Substring_hit,
+ * src/utils/substring_hit.h:32-46, with score == length and both strands plus). */
+typedef struct pg2_anchor_hit {
+    int32_t start_1, start_2, length;
+} pg2_anchor_hit;
+
+/* Replaces Find_anchors::find_long_substrings (src/utils/find_anchors.cpp:35-127; --use-prefix-anchors, called from
+ * Viterbi_alignment::define_tunnel, src/main/viterbi_alignment.cpp:70-74): the exact substrings of at least min_length
+ * characters that are neighbours in the common suffix order of the two sequences, longest first, greedily thinned so
+ * that no two share a site.  Same hits in the same order as the reference (same suffix order, same sort, same greedy
+ * walk); linear in the number of candidate hits where the reference's vector::erase loop is quadratic.  Host code (the
+ * band the reference derives from the hits is what the device gets, pg2_job.upper / lower).  Returns PG2_ERR_CAPACITY
+ * with *n_hits = the number of hits when `cap` is too small. */
+int pg2_find_prefix_anchors(const char *seq1, int32_t len1, const char *seq2, int32_t len2, int32_t min_length,
+                            pg2_anchor_hit *hits, int32_t cap, int32_t *n_hits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -446,3 +446,22 @@ extern "C" int pagan2_ref_last_used(int side, int *out, int cap) {
     for (int k = 0; k < (int)v.size() && k < cap; k++) out[k] = v[k];
     return (int)v.size();
 }
+
+// --------------------------------------------------------------------------------------------
+// pagan2_ref_prefix_anchors(): the reference's own Find_anchors::find_long_substrings
+// (find_anchors.cpp:35-127) on two plain character strings; hits come back as (start_1, start_2, length) triples
+// in the reference's order.  Returns the number of hits (which may exceed cap: only cap are written).
+// --------------------------------------------------------------------------------------------
+#include "utils/find_anchors.h"
+extern "C" int pagan2_ref_prefix_anchors(const char *seq1, int len1, const char *seq2, int len2, int min_length, int *out, int cap) {
+    std::string s1(seq1, (size_t)len1), s2(seq2, (size_t)len2);
+    std::vector<Substring_hit> hits;
+    Find_anchors fa;
+    fa.find_long_substrings(&s1, &s2, &hits, min_length);
+    for (int k = 0; k < (int)hits.size() && k < cap; k++) {
+        out[3 * k] = hits[k].start_site_1;
+        out[3 * k + 1] = hits[k].start_site_2;
+        out[3 * k + 2] = hits[k].length;
+    }
+    return (int)hits.size();
+}

@@ -43,6 +43,7 @@ def _bind(lib):
     lib.pg2_stream_synchronize.argtypes = [vp]
     lib.pg2_measure_fp64_issue.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.pg2_measure_dispatch_mix.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.pg2_find_prefix_anchors.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, vp, C.c_int32, C.POINTER(C.c_int32)]
     return lib
 
 
@@ -56,6 +57,23 @@ def load_library(path=None):
             raise Pg2Error(abi.PG2_ERR_NO_DEVICE, "%s not built (run __graft_entry__.build()); no CPU fallback exists" % path)
         _libs[path] = _bind(C.CDLL(path))
     return _libs[path]
+
+
+def find_prefix_anchors(seq1, seq2, min_length, lib=None):
+    """pg2_find_prefix_anchors on two byte strings -> int32 array (n, 3) of (start_1, start_2, length), the reference's order
+    (Find_anchors::find_long_substrings, utils/find_anchors.cpp:35-127).  Host function of the C-ABI: needs no device."""
+    lib = lib or load_library()
+    cap = 1024
+    while True:
+        out = np.zeros((cap, 3), np.int32)
+        n = C.c_int32()
+        rc = lib.pg2_find_prefix_anchors(seq1, len(seq1), seq2, len(seq2), min_length, out.ctypes.data, cap, C.byref(n))
+        if rc == abi.PG2_ERR_CAPACITY:
+            cap = n.value
+            continue
+        if rc != abi.PG2_OK:
+            raise Pg2Error(rc, "pg2_find_prefix_anchors")
+        return out[: n.value].copy()
 
 
 RESULT_DTYPE = np.dtype([("score", "<f8"), ("cells", "<i8"), ("step_off", "<i8"), ("n_steps", "<i4"),

@@ -16,6 +16,7 @@
 #include "main/reads_aligner.h"
 #include "utils/check_version.h"
 #include "utils/exonerate_queries.h"
+#include "utils/find_anchors.h"
 
 using namespace std;
 using namespace ppa;
@@ -61,6 +62,13 @@ extern "C" Evol_model CAT(__wrap_, AMD_SYM)(Model_factory *self, double distance
     return ppa_b200::cached_alignment_model(self, distance, &CAT(__real_, AMD_SYM));
 }
 
+// Find_anchors::find_long_substrings (--use-prefix-anchors): same hits, linear hit thinning
+#define FLS_SYM _ZN3ppa12Find_anchors20find_long_substringsEPNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEES7_PSt6vectorINS_13Substring_hitESaIS9_EEi
+extern "C" void CAT(__real_, FLS_SYM)(Find_anchors *self, std::string *s1, std::string *s2, std::vector<Substring_hit> *hits, int min_length);
+extern "C" void CAT(__wrap_, FLS_SYM)(Find_anchors *self, std::string *s1, std::string *s2, std::vector<Substring_hit> *hits, int min_length) {
+    ppa_b200::find_long_substrings(self, s1, s2, hits, min_length, &CAT(__real_, FLS_SYM));
+}
+
 namespace {
 struct Stats_at_exit {
     ~Stats_at_exit() {
@@ -71,9 +79,10 @@ struct Stats_at_exit {
             if (f) {
                 fprintf(f, "{\"jobs\": %lld, \"cells\": %lld, \"batches\": %lld, \"fill_ms\": %.6f, \"traceback_ms\": %.6f, "
                            "\"wave_batches\": %lld, \"prefetch_batches\": %lld, \"cache_hits\": %lld, \"sharded_batches\": %lld, "
-                           "\"model_cache_hits\": %lld}\n",
+                           "\"model_cache_hits\": %lld, \"host_ms\": {\"stage\": %.3f, \"engine_calls\": %.3f, \"expand_path\": %.3f, "
+                           "\"build_ancestral_sequence\": %.3f, \"alignment_model\": %.3f, \"prefix_anchors\": %.3f}, \"anchor_calls\": %lld}\n",
                         t.jobs, t.cells, t.batches, t.fill_ms, t.traceback_ms, t.wave_batches, t.prefetch_batches, t.cache_hits, t.sharded_batches,
-                        t.model_cache_hits);
+                        t.model_cache_hits, t.host_stage_ms, t.host_engine_ms, t.host_expand_ms, t.host_build_ms, t.host_model_ms, t.host_anchor_ms, t.anchor_calls);
                 fclose(f);
             }
         }

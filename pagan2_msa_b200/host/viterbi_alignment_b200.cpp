@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <memory>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -25,6 +27,7 @@
 #include "main/node.h"
 #include "main/reads_aligner.h"
 #include "utils/fasta_reader.h"
+#include "utils/find_anchors.h"
 #include "utils/log_output.h"
 #include "utils/model_factory.h"
 #include "utils/settings_handle.h"
@@ -110,6 +113,15 @@ struct Pending {
 // The engine: one pg2_ctx per device named in PAGAN2_B200_DEVICES ("0-7", "0,2,3"; default PAGAN2_B200_DEVICE or 0), model
 // handles cached by what determines the table (alphabet, distance and the five scalars; Model_factory::alignment_model is
 // a pure function of the distance, model_factory.cpp:1871).
+// host wall time of the mirror's own steps, summed over threads (nanoseconds; PAGAN2_B200_STATS)
+std::atomic<long long> g_ns_stage(0), g_ns_engine(0), g_ns_expand(0), g_ns_build(0), g_ns_model(0), g_ns_anchor(0), g_anchor_calls(0);
+struct Scoped_ns {
+    std::atomic<long long> &acc;
+    std::chrono::steady_clock::time_point t0;
+    explicit Scoped_ns(std::atomic<long long> &a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~Scoped_ns() { acc += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 struct Engine {
     std::mutex mutex;  // one launch batch at a time: a pg2_ctx is not thread-safe, the reference's worker threads share the devices
     std::vector<int> devices;
@@ -187,6 +199,7 @@ struct Engine {
     // With several devices the batch is cut by contiguous index range, balanced by cell count; every device runs its
     // share on its own context and host thread, and the results meet in host memory.
     void device_align(const std::vector<Pending *> &batch, const std::vector<Model_entry *> &me) {
+        Scoped_ns timed(g_ns_engine);
         ensure();
         const size_t n = batch.size();
         if (!n) return;
@@ -331,6 +344,7 @@ uint32_t job_flags(Viterbi_alignment *va) {
 
 // settings, packing, band: everything of one alignment that needs no device
 void stage(Pending &p) {
+    Scoped_ns timed(g_ns_stage);
     prepare(p.job);
     Viterbi_alignment *va = p.job.va;
     if (!p.left) { pack_sequence(p.job.left, &p.left_store); p.left = &p.left_store; }
@@ -365,6 +379,7 @@ void finish(Pending &p, const pg2_model_desc &desc) {
     std::vector<pg2_step> out(cap);
     std::vector<int32_t> used_l(cap), used_r(cap);
     int32_t n = 0, nl = 0, nr = 0;
+    std::unique_ptr<Scoped_ns> timed(new Scoped_ns(g_ns_expand));
     int rc = pg2_expand_path(&job, &desc, &p.res, p.steps.data(), out.data(), &n, used_l.data(), &nl, used_r.data(), &nr);
     if (rc != PG2_OK) {
         Log_output::write_out("Viterbi_alignment: incorrect backward pointer (device path could not be expanded)\n", 0);
@@ -395,6 +410,7 @@ void finish(Pending &p, const pg2_model_desc &desc) {
         va->path[last_real].mp.full_score = 1.0;
     }
     Log_output::write_out("Viterbi_alignment: path found", 3);
+    timed.reset(new Scoped_ns(g_ns_build));
     va->ancestral_sequence = new Sequence(va->path.size(), va->model->get_data_type());
     va->build_ancestral_sequence(va->ancestral_sequence, &va->path, j.is_reads_sequence);
     Log_output::write_out("Viterbi_alignment: sequence built", 3);
@@ -650,7 +666,17 @@ namespace ppa_b200 {
 
 void set_device(int device) { engine().default_device = device; }
 
-Totals totals() { return engine().totals; }
+Totals totals() {
+    Totals t = engine().totals;
+    t.host_stage_ms = g_ns_stage.load() * 1e-6;
+    t.host_engine_ms = g_ns_engine.load() * 1e-6;
+    t.host_expand_ms = g_ns_expand.load() * 1e-6;
+    t.host_build_ms = g_ns_build.load() * 1e-6;
+    t.host_model_ms = g_ns_model.load() * 1e-6;
+    t.host_anchor_ms = g_ns_anchor.load() * 1e-6;
+    t.anchor_calls = g_anchor_calls.load();
+    return t;
+}
 
 void Alignment_batch::add(Viterbi_alignment *va, Sequence *left, Sequence *right, Evol_model *model, float l_branch_length,
                           float r_branch_length, bool is_reads_sequence) {
@@ -846,6 +872,7 @@ void copy_model(const Evol_model &src, Evol_model &dst) {
 static Evol_model clone_cached_model(Model_factory *mf, double distance, Evol_model (*build)(Model_factory *, double));
 
 Evol_model cached_alignment_model(Model_factory *mf, double distance, Evol_model (*build)(Model_factory *, double)) {
+    Scoped_ns timed(g_ns_model);
     static const bool off = getenv("PAGAN2_B200_NO_MODEL_CACHE") && atoi(getenv("PAGAN2_B200_NO_MODEL_CACHE"));
     if (off) return build(mf, distance);
     return clone_cached_model(mf, distance, build);
@@ -876,6 +903,40 @@ static Evol_model clone_cached_model(Model_factory *mf, double distance, Evol_mo
     Evol_model out(src.data_type, src.distance);
     copy_model(src, out);
     return out;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Prefix anchors (utils/find_anchors.cpp:35-127)
+// ------------------------------------------------------------------------------------------------------------------
+void find_long_substrings(Find_anchors *fa, std::string *seq1, std::string *seq2, std::vector<Substring_hit> *hits, int min_length,
+                          void (*reference_fn)(Find_anchors *, std::string *, std::string *, std::vector<Substring_hit> *, int)) {
+    Scoped_ns timed(g_ns_anchor);
+    g_anchor_calls++;
+    static const bool use_reference = getenv("PAGAN2_B200_REF_ANCHORS") && atoi(getenv("PAGAN2_B200_REF_ANCHORS"));
+    if (use_reference || !hits->empty()) { reference_fn(fa, seq1, seq2, hits, min_length); return; }
+    fa->len1 = (int)seq1->length();
+    fa->len2 = (int)seq2->length();
+    std::vector<pg2_anchor_hit> found((size_t)std::max(1024, std::min(fa->len1, fa->len2) / 16));
+    int32_t n = 0;
+    int rc = pg2_find_prefix_anchors(seq1->data(), fa->len1, seq2->data(), fa->len2, min_length, found.data(), (int32_t)found.size(), &n);
+    if (rc == PG2_ERR_CAPACITY) {
+        found.resize((size_t)n);
+        rc = pg2_find_prefix_anchors(seq1->data(), fa->len1, seq2->data(), fa->len2, min_length, found.data(), (int32_t)found.size(), &n);
+    }
+    if (rc != PG2_OK) {
+        Log_output::write_out("pagan2_b200: pg2_find_prefix_anchors failed (" + std::to_string(rc) + ")\n", 0);
+        exit(1);
+    }
+    hits->reserve((size_t)n);
+    for (int32_t k = 0; k < n; k++) {
+        Substring_hit s;  // (both strands plus by construction, substring_hit.h:40)
+        s.start_site_1 = found[(size_t)k].start_1;
+        s.start_site_2 = found[(size_t)k].start_2;
+        s.length = found[(size_t)k].length;
+        s.score = found[(size_t)k].length;
+        hits->push_back(s);
+    }
 }
 
 }  // namespace ppa_b200

@@ -100,6 +100,12 @@ void placement_end();
 // is the reference's own function; a later call for the same distance gets a deep copy of what it returned.
 ppa::Evol_model cached_alignment_model(ppa::Model_factory *mf, double distance, ppa::Evol_model (*build)(ppa::Model_factory *, double));
 
+// Find_anchors::find_long_substrings (utils/find_anchors.cpp:35-127) over pg2_find_prefix_anchors: the same
+// hits in the same order, without the reference's quadratic erase loop.  `reference_fn` is the reference's own function; it is
+// called instead when PAGAN2_B200_REF_ANCHORS is set or the hit vector is not empty on entry.
+void find_long_substrings(ppa::Find_anchors *fa, std::string *seq1, std::string *seq2, std::vector<ppa::Substring_hit> *hits, int min_length,
+                          void (*reference_fn)(ppa::Find_anchors *, std::string *, std::string *, std::vector<ppa::Substring_hit> *, int));
+
 // Device-side totals since process start (for the drop-in binary's stats file, PAGAN2_B200_STATS).
 struct Totals {
     long long jobs, cells, batches;
@@ -109,6 +115,12 @@ struct Totals {
     long long cache_hits;        // align() calls served from a prefetched batch
     long long sharded_batches;   // launch batches cut over more than one device
     long long model_cache_hits;  // Model_factory::alignment_model calls answered with a copy of an earlier model
+    // host wall time spent inside the host mirror, summed over the calling threads (ms): settings + graph packing, the engine calls
+    // (packing of the launch batch, upload, kernels, copy back -- the caller waits), path expansion + edge marks, the reference's own
+    // build_ancestral_sequence, and Model_factory::alignment_model (builds and copies)
+    double host_stage_ms, host_engine_ms, host_expand_ms, host_build_ms, host_model_ms;
+    double host_anchor_ms;       // find_long_substrings
+    long long anchor_calls;
 };
 Totals totals();
 

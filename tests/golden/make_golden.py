@@ -164,9 +164,28 @@ FIXTURES = [("prog_dna", progressive_dna), ("place_dna", placement_dna), ("pileu
             ("c1_full", c1_full), ("c3_full", c3_full), ("c4_full", c4_full), ("c5_full", c5_full)]
 
 
+def prefix_anchor_hits():
+    """prefix_anchors.json: the hits of the reference's Find_anchors::find_long_substrings (utils/find_anchors.cpp:35-127) for the
+    seeded string pairs of tests/test_anchors.py:cases()."""
+    import json
+
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import test_anchors
+
+    out = []
+    for a, b, k in test_anchors.cases():
+        hits = oracle_lib.ref_prefix_anchors(a, b, k)
+        out.append({"len1": len(a), "len2": len(b), "min_length": k, "hits": hits.tolist()})
+    with open(os.path.join(HERE, "prefix_anchors.json"), "w") as f:
+        json.dump(out, f)
+    print("prefix_anchors.json: %d pairs, %d hits" % (len(out), sum(len(o["hits"]) for o in out)))
+
+
 def main():
     oracle_lib.build_ref()
     only = sys.argv[1:]
+    if not only or "prefix_anchors" in only:
+        prefix_anchor_hits()
     for name, fn in FIXTURES:
         if only and name not in only:
             continue

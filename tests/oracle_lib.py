@@ -88,6 +88,9 @@ def ref_lib():
                                               C.POINTER(C.c_double), i32p, C.POINTER(C.c_double), C.c_int, i32p]
         lib.pagan2_ref_last_used.restype = C.c_int
         lib.pagan2_ref_last_used.argtypes = [C.c_int, i32p, C.c_int]
+        if hasattr(lib, "pagan2_ref_prefix_anchors"):
+            lib.pagan2_ref_prefix_anchors.restype = C.c_int
+            lib.pagan2_ref_prefix_anchors.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, i32p, C.c_int]
         _ref = lib
     return _ref
 
@@ -113,6 +116,18 @@ def ref_align_flat(job):
     if rc != 0:
         raise RuntimeError("reference path longer than capacity")
     return score.value, path[: n.value * 6].reshape(-1, 6).copy(), ps[: n.value].copy()
+
+
+def ref_prefix_anchors(seq1, seq2, min_length):
+    """The REFERENCE's Find_anchors::find_long_substrings on two byte strings -> int32 (n, 3): start_1, start_2, length."""
+    lib = ref_lib()
+    cap = 4096
+    while True:
+        out = np.zeros(cap * 3, np.int32)
+        n = lib.pagan2_ref_prefix_anchors(seq1, len(seq1), seq2, len(seq2), min_length, abi._ptr(out, C.c_int32), cap)
+        if n <= cap:
+            return out[: n * 3].reshape(-1, 3).copy()
+        cap = n
 
 
 def ref_last_used():
