@@ -249,6 +249,15 @@ typedef struct pg2_anchor_hit {
 int pg2_find_prefix_anchors(const char *seq1, int32_t len1, const char *seq2, int32_t len2, int32_t min_length,
                             pg2_anchor_hit *hits, int32_t cap, int32_t *n_hits);
 
+/* Replaces Find_anchors::define_tunnel (src/utils/find_anchors.cpp:320-435): hits -> the anchor band.  str1 / str2 are the
+ * sequence strings WITH the gap characters of skipped sites ('-', Sequence::get_sequence_string(true)); the hits count
+ * characters of the gapless strings.  upper / lower receive len1 + 1 values each: row i may use columns upper[i] .. lower[i]
+ * (what Viterbi_alignment keeps in upper_bound / lower_bound, viterbi_alignment.h:43-44, and passes on as pg2_job.upper /
+ * lower).  `width` = --anchors-offset.  The same values as the reference, in linear time (the reference builds the lower
+ * bounds by inserting at the front of a vector).  Host code. */
+int pg2_anchor_band(const pg2_anchor_hit *hits, int32_t n_hits, const char *str1, int32_t len1, const char *str2, int32_t len2,
+                    int32_t width, int32_t *upper, int32_t *lower);
+
 #ifdef __cplusplus
 }
 #endif

@@ -376,13 +376,8 @@ Sequence *unflatten(int n, const int *state, const int *off, const int *start, c
     return s;
 }
 
-} // namespace
-
-extern "C" int pagan2_ref_align_flat(int fas, const float *table, const float *scalars,
-                                     int ln, const int *lstate, const int *loff, const int *lstart, const float *llogw, const int *leidx,
-                                     int rn, const int *rstate, const int *roff, const int *rstart, const float *rlogw, const int *reidx,
-                                     const int *upper, const int *lower, int flags,
-                                     double *score_out, int *path_out, double *path_score_out, int path_cap, int *path_len_out) {
+// the reference's option table with its defaults (library callers have no command line)
+void flat_settings() {
     static bool inited = false;
     if (!inited) {
         const char *argv[] = {"pagan2_ref", "--silent"};
@@ -390,6 +385,16 @@ extern "C" int pagan2_ref_align_flat(int fas, const float *table, const float *s
         g_flat_mf = new Model_factory(Model_factory::dna);
         inited = true;
     }
+}
+
+} // namespace
+
+extern "C" int pagan2_ref_align_flat(int fas, const float *table, const float *scalars,
+                                     int ln, const int *lstate, const int *loff, const int *lstart, const float *llogw, const int *leidx,
+                                     int rn, const int *rstate, const int *roff, const int *rstart, const float *rlogw, const int *reidx,
+                                     const int *upper, const int *lower, int flags,
+                                     double *score_out, int *path_out, double *path_score_out, int path_cap, int *path_len_out) {
+    flat_settings();
     if (flags & 1) Settings_handle::st.vm.set("no-terminal-edges", "", false);
     else Settings_handle::st.vm.erase("no-terminal-edges");
     if (flags & 2) Settings_handle::st.vm.erase("no-reduced-terminal-penalties");
@@ -464,4 +469,29 @@ extern "C" int pagan2_ref_prefix_anchors(const char *seq1, int len1, const char 
         out[3 * k + 2] = hits[k].length;
     }
     return (int)hits.size();
+}
+
+// --------------------------------------------------------------------------------------------
+// pagan2_ref_anchor_band(): the reference's own Find_anchors::define_tunnel (find_anchors.cpp:320-489) -- hits -> the
+// per-row band bounds -- with --anchors-offset = width.  upper / lower receive len1 + 1 values each.
+// --------------------------------------------------------------------------------------------
+extern "C" int pagan2_ref_anchor_band(const int *hits, int n_hits, const char *str1, int len1, const char *str2, int len2, int width,
+                                      int *upper, int *lower) {
+    flat_settings();
+    Settings_handle::st.vm.erase("anchors-offset");
+    Settings_handle::st.vm.set("anchors-offset", std::to_string(width), false);
+    std::vector<Substring_hit> h((size_t)n_hits);
+    for (int k = 0; k < n_hits; k++) {
+        h[k].start_site_1 = hits[3 * k];
+        h[k].start_site_2 = hits[3 * k + 1];
+        h[k].length = hits[3 * k + 2];
+        h[k].score = hits[3 * k + 2];
+    }
+    std::string s1(str1, (size_t)len1), s2(str2, (size_t)len2);
+    std::vector<int> ub, lb;
+    Find_anchors fa;
+    fa.define_tunnel(&h, &ub, &lb, &s1, &s2);
+    if ((int)ub.size() != len1 + 1 || (int)lb.size() != len1 + 1) return -1;
+    for (int i = 0; i <= len1; i++) { upper[i] = ub[i]; lower[i] = lb[i]; }
+    return 0;
 }

@@ -88,3 +88,60 @@ extern "C" int pg2_find_prefix_anchors(const char *seq1, int32_t len1, const cha
     for (size_t k = 0; k < kept; k++) hits[k] = found[k];
     return PG2_OK;
 }
+
+// Hits -> anchor band (Find_anchors::define_tunnel, src/utils/find_anchors.cpp:320-435): per DP row i of sequence 1 (0 ..
+// len1, gaps of the sequence strings counted) the inclusive column range [upper[i], lower[i]] the alignment may use -- `width`
+// columns around the anchored diagonals, widening to the full rectangle between anchors.  The same two sweeps as the reference;
+// the lower bounds are written in place where the reference inserts every value at the FRONT of its vector (:419, quadratic:
+// 2 s per 200 kb alignment).
+extern "C" int pg2_anchor_band(const pg2_anchor_hit *hits, int32_t n_hits, const char *str1, int32_t len1, const char *str2, int32_t len2,
+                               int32_t width, int32_t *upper, int32_t *lower) {
+    if (n_hits < 0 || len1 < 0 || len2 < 0 || width < 0 || (n_hits > 0 && !hits) || !str1 || !str2 || !upper || !lower) return PG2_ERR_INVALID;
+    // positions of the characters in the gapped strings (the hits count characters, the band counts sites; :329-338)
+    std::vector<int32_t> index1, index2;
+    index1.reserve((size_t)len1);
+    index2.reserve((size_t)len2);
+    for (int32_t i = 0; i < len1; i++) if (str1[i] != '-') index1.push_back(i + 1);
+    for (int32_t i = 0; i < len2; i++) if (str2[i] != '-') index2.push_back(i + 1);
+    std::vector<int32_t> diagonals((size_t)len1 + 1, -1);
+    for (int32_t h = 0; h < n_hits; h++) {
+        const pg2_anchor_hit &hit = hits[h];
+        if (hit.start_1 < 0 || hit.start_2 < 0 || hit.length < 0 || (size_t)hit.start_1 + (size_t)hit.length > index1.size() ||
+            (size_t)hit.start_2 + (size_t)hit.length > index2.size())
+            return PG2_ERR_INVALID;  // (the reference's vector::at would throw)
+        for (int32_t i = 0; i < hit.length; i++) diagonals[(size_t)index1[(size_t)(hit.start_1 + i)]] = index2[(size_t)(hit.start_2 + i)];
+        const size_t after = (size_t)hit.start_1 + (size_t)hit.length;
+        if (after < index1.size() && index1[after] < (int32_t)diagonals.size()) diagonals[(size_t)index1[after]] = -2;  // :354-355
+    }
+    // upper bounds, top down (:360-394)
+    {
+        int32_t y1 = 0, y2 = 0, prev_y = 0, m_count = 0;
+        for (int32_t i = 0; i <= len1; i++) {
+            if (i >= width && diagonals[(size_t)(i - width)] >= 0) y1 = diagonals[(size_t)(i - width)];
+            if (diagonals[(size_t)i] >= 0) y2 = diagonals[(size_t)i] - width;
+            const bool run = diagonals[(size_t)i] >= 0 && i > 0 && diagonals[(size_t)(i - 1)] + 1 == diagonals[(size_t)i];
+            if (run) m_count++;
+            else if (diagonals[(size_t)i] == -2) m_count = 0;
+            int32_t y = std::max(std::min(y1, y2), 0);
+            if (run && m_count >= width) prev_y = y;
+            y = std::max(std::min(y, prev_y), 0);
+            upper[i] = y;
+        }
+    }
+    // lower bounds, bottom up (:396-420)
+    {
+        int32_t y1 = len2, y2 = len2, prev_y = len2, m_count = 0;
+        for (int32_t i = len1; i >= 0; i--) {
+            if (i <= len1 - width && diagonals[(size_t)(i + width)] >= 0) y1 = diagonals[(size_t)(i + width)];
+            if (diagonals[(size_t)i] >= 0) y2 = diagonals[(size_t)i] + width;
+            const bool run = diagonals[(size_t)i] >= 0 && i < len1 && diagonals[(size_t)(i + 1)] - 1 == diagonals[(size_t)i];
+            if (run) m_count++;
+            else if (diagonals[(size_t)i] == -2) m_count = 0;
+            int32_t y = std::min(std::max(y1, y2), len2);
+            if (run && m_count >= width) prev_y = y;
+            y = std::min(std::max(y, prev_y), len2);
+            lower[i] = y;
+        }
+    }
+    return PG2_OK;
+}

@@ -44,6 +44,7 @@ def _bind(lib):
     lib.pg2_measure_fp64_issue.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.pg2_measure_dispatch_mix.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.pg2_find_prefix_anchors.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, vp, C.c_int32, C.POINTER(C.c_int32)]
+    lib.pg2_anchor_band.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, vp, vp]
     return lib
 
 
@@ -74,6 +75,19 @@ def find_prefix_anchors(seq1, seq2, min_length, lib=None):
         if rc != abi.PG2_OK:
             raise Pg2Error(rc, "pg2_find_prefix_anchors")
         return out[: n.value].copy()
+
+
+def anchor_band(hits, str1, str2, width, lib=None):
+    """pg2_anchor_band: (n, 3) int32 hits + the two gapped sequence strings -> (upper, lower), len(str1) + 1 values each
+    (Find_anchors::define_tunnel, utils/find_anchors.cpp:320-435).  Host function of the C-ABI."""
+    lib = lib or load_library()
+    hits = np.ascontiguousarray(hits, np.int32).reshape(-1, 3)
+    upper = np.zeros(len(str1) + 1, np.int32)
+    lower = np.zeros(len(str1) + 1, np.int32)
+    rc = lib.pg2_anchor_band(hits.ctypes.data, len(hits), str1, len(str1), str2, len(str2), width, upper.ctypes.data, lower.ctypes.data)
+    if rc != abi.PG2_OK:
+        raise Pg2Error(rc, "pg2_anchor_band")
+    return upper, lower
 
 
 RESULT_DTYPE = np.dtype([("score", "<f8"), ("cells", "<i8"), ("step_off", "<i8"), ("n_steps", "<i4"),

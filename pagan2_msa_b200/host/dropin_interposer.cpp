@@ -69,6 +69,15 @@ extern "C" void CAT(__wrap_, FLS_SYM)(Find_anchors *self, std::string *s1, std::
     ppa_b200::find_long_substrings(self, s1, s2, hits, min_length, &CAT(__real_, FLS_SYM));
 }
 
+// Find_anchors::define_tunnel(hits, upper, lower, str1, str2): the band from the hits, linear time
+#define FDT_SYM _ZN3ppa12Find_anchors13define_tunnelEPSt6vectorINS_13Substring_hitESaIS2_EEPS1_IiSaIiEES8_PNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEESF_
+extern "C" void CAT(__real_, FDT_SYM)(Find_anchors *self, std::vector<Substring_hit> *hits, std::vector<int> *ub, std::vector<int> *lb, std::string *s1,
+                                     std::string *s2);
+extern "C" void CAT(__wrap_, FDT_SYM)(Find_anchors *self, std::vector<Substring_hit> *hits, std::vector<int> *ub, std::vector<int> *lb, std::string *s1,
+                                     std::string *s2) {
+    ppa_b200::define_tunnel(self, hits, ub, lb, s1, s2, &CAT(__real_, FDT_SYM));
+}
+
 namespace {
 struct Stats_at_exit {
     ~Stats_at_exit() {

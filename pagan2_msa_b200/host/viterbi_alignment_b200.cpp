@@ -939,4 +939,28 @@ void find_long_substrings(Find_anchors *fa, std::string *seq1, std::string *seq2
     }
 }
 
+
+void define_tunnel(Find_anchors *fa, std::vector<Substring_hit> *hits, std::vector<int> *upper_bound, std::vector<int> *lower_bound,
+                   std::string *str1, std::string *str2,
+                   void (*reference_fn)(Find_anchors *, std::vector<Substring_hit> *, std::vector<int> *, std::vector<int> *, std::string *,
+                                        std::string *)) {
+    Scoped_ns timed(g_ns_anchor);
+    static const bool use_reference = getenv("PAGAN2_B200_REF_ANCHORS") && atoi(getenv("PAGAN2_B200_REF_ANCHORS"));
+    if (use_reference || Settings_handle::st.is("plot-anchors-for-R")) { reference_fn(fa, hits, upper_bound, lower_bound, str1, str2); return; }
+    const int width = Settings_handle::st.get("anchors-offset").as<int>();
+    std::vector<pg2_anchor_hit> h(hits->size());
+    for (size_t k = 0; k < hits->size(); k++) {
+        h[k].start_1 = hits->at(k).start_site_1;
+        h[k].start_2 = hits->at(k).start_site_2;
+        h[k].length = hits->at(k).length;
+    }
+    const int len1 = (int)str1->length();
+    std::vector<int32_t> up((size_t)len1 + 1), lo((size_t)len1 + 1);
+    int rc = pg2_anchor_band(h.data(), (int32_t)h.size(), str1->data(), len1, str2->data(), (int)str2->length(), width, up.data(), lo.data());
+    if (rc != PG2_OK) { reference_fn(fa, hits, upper_bound, lower_bound, str1, str2); return; }  // (out-of-range hits: the reference throws)
+    // the reference appends the upper bounds and puts every lower bound in FRONT of what the vector holds (:391, :419)
+    upper_bound->insert(upper_bound->end(), up.begin(), up.end());
+    lower_bound->insert(lower_bound->begin(), lo.begin(), lo.end());
+}
+
 }  // namespace ppa_b200

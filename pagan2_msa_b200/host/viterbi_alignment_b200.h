@@ -106,6 +106,12 @@ ppa::Evol_model cached_alignment_model(ppa::Model_factory *mf, double distance, 
 void find_long_substrings(ppa::Find_anchors *fa, std::string *seq1, std::string *seq2, std::vector<ppa::Substring_hit> *hits, int min_length,
                           void (*reference_fn)(ppa::Find_anchors *, std::string *, std::string *, std::vector<ppa::Substring_hit> *, int));
 
+// Find_anchors::define_tunnel (utils/find_anchors.cpp:320-435) over pg2_anchor_band: the same band in linear time.
+void define_tunnel(ppa::Find_anchors *fa, std::vector<ppa::Substring_hit> *hits, std::vector<int> *upper_bound, std::vector<int> *lower_bound,
+                   std::string *str1, std::string *str2,
+                   void (*reference_fn)(ppa::Find_anchors *, std::vector<ppa::Substring_hit> *, std::vector<int> *, std::vector<int> *, std::string *,
+                                        std::string *));
+
 // Device-side totals since process start (for the drop-in binary's stats file, PAGAN2_B200_STATS).
 struct Totals {
     long long jobs, cells, batches;

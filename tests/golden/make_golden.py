@@ -179,6 +179,14 @@ def prefix_anchor_hits():
     with open(os.path.join(HERE, "prefix_anchors.json"), "w") as f:
         json.dump(out, f)
     print("prefix_anchors.json: %d pairs, %d hits" % (len(out), sum(len(o["hits"]) for o in out)))
+    # anchor_bands.json: the bands of the reference's Find_anchors::define_tunnel (:320-435) for test_anchors.py:band_cases()
+    out = []
+    for hits, s1, s2, width in test_anchors.band_cases():
+        up, lo = oracle_lib.ref_anchor_band(hits, s1, s2, width)
+        out.append({"len1": len(s1), "len2": len(s2), "width": width, "upper": up.tolist(), "lower": lo.tolist()})
+    with open(os.path.join(HERE, "anchor_bands.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("anchor_bands.json: %d bands" % len(out))
 
 
 def main():

@@ -91,6 +91,8 @@ def ref_lib():
         if hasattr(lib, "pagan2_ref_prefix_anchors"):
             lib.pagan2_ref_prefix_anchors.restype = C.c_int
             lib.pagan2_ref_prefix_anchors.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, i32p, C.c_int]
+            lib.pagan2_ref_anchor_band.restype = C.c_int
+            lib.pagan2_ref_anchor_band.argtypes = [i32p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, i32p, i32p]
         _ref = lib
     return _ref
 
@@ -128,6 +130,19 @@ def ref_prefix_anchors(seq1, seq2, min_length):
         if n <= cap:
             return out[: n * 3].reshape(-1, 3).copy()
         cap = n
+
+
+def ref_anchor_band(hits, str1, str2, width):
+    """The REFERENCE's Find_anchors::define_tunnel: hits (n, 3) + gapped strings -> (upper, lower)."""
+    lib = ref_lib()
+    hits = np.ascontiguousarray(hits, np.int32).reshape(-1)
+    upper = np.zeros(len(str1) + 1, np.int32)
+    lower = np.zeros(len(str1) + 1, np.int32)
+    rc = lib.pagan2_ref_anchor_band(abi._ptr(hits, C.c_int32) if len(hits) else None, len(hits) // 3, str1, len(str1), str2, len(str2), width,
+                                    abi._ptr(upper, C.c_int32), abi._ptr(lower, C.c_int32))
+    if rc != 0:
+        raise RuntimeError("reference define_tunnel returned vectors of unexpected length")
+    return upper, lower
 
 
 def ref_last_used():

@@ -87,3 +87,62 @@ def test_200kb_pair_matches_live_reference_and_is_fast():
     assert len(got) > 500
     print("200 kb pair: %d hits, %.2f s here, %.2f s in the reference" % (len(got), t1 - t0, t2 - t1))
     assert (t1 - t0) < (t2 - t1)
+
+
+def gapped(rng, s, p):
+    """Sequence string with the '-' characters of skipped sites (Sequence::get_sequence_string(true))."""
+    out = bytearray()
+    for c in s:
+        while rng.random() < p:
+            out.append(ord("-"))
+        out.append(c)
+    return bytes(out)
+
+
+def band_cases():
+    rng = np.random.default_rng(77)
+    out = []
+    for n, sub, indel, k, width, pgap in ((400, 0.03, 0.004, 12, 15, 0.0), (3000, 0.02, 0.001, 20, 15, 0.02), (3000, 0.02, 0.001, 20, 5, 0.0),
+                                          (8000, 0.05, 0.002, 30, 15, 0.01), (200, 0.3, 0.02, 30, 15, 0.0), (50, 0.0, 0.0, 10, 80, 0.0),
+                                          (1000, 0.01, 0.0, 25, 0, 0.0)):
+        a, b = related_pair(rng, n, sub, indel)
+        hits = engine.find_prefix_anchors(a, b, k)
+        # what define_tunnel gets: the hits that survive check_hits_order_conflict are a subset in start order; a sorted copy
+        # and the raw list are both valid inputs of the function
+        out.append((hits, gapped(rng, a, pgap), gapped(rng, b, pgap), width))
+        out.append((hits[np.argsort(hits[:, 0], kind="stable")] if len(hits) else hits, gapped(rng, a, pgap), gapped(rng, b, pgap), width))
+    return out
+
+
+@pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built")
+def test_band_matches_live_reference():
+    for hits, s1, s2, width in band_cases():
+        up, lo = engine.anchor_band(hits, s1, s2, width)
+        rup, rlo = oracle_lib.ref_anchor_band(hits, s1, s2, width)
+        assert up.tolist() == rup.tolist() and lo.tolist() == rlo.tolist(), (len(s1), len(s2), width, len(hits))
+
+
+def test_band_matches_committed_reference_bands():
+    want = json.load(open(GOLDEN.replace("prefix_anchors", "anchor_bands")))
+    assert len(want) == len(band_cases())
+    for (hits, s1, s2, width), w in zip(band_cases(), want):
+        up, lo = engine.anchor_band(hits, s1, s2, width)
+        assert up.tolist() == w["upper"] and lo.tolist() == w["lower"]
+
+
+@pytest.mark.skipif(not oracle_lib.ref_available(), reason="oracle/_ref not built")
+def test_band_200kb_matches_live_reference_and_is_fast():
+    import time
+
+    rng = np.random.default_rng(8)
+    a, b = related_pair(rng, 200000, 0.01, 0.0005)
+    hits = engine.find_prefix_anchors(a, b, 30)
+    hits = hits[np.argsort(hits[:, 0], kind="stable")]
+    t0 = time.perf_counter()
+    up, lo = engine.anchor_band(hits, a, b, 15)
+    t1 = time.perf_counter()
+    rup, rlo = oracle_lib.ref_anchor_band(hits, a, b, 15)
+    t2 = time.perf_counter()
+    assert up.tolist() == rup.tolist() and lo.tolist() == rlo.tolist()
+    print("200 kb band: %.3f s here, %.2f s in the reference" % (t1 - t0, t2 - t1))
+    assert (t1 - t0) < (t2 - t1)
