@@ -576,7 +576,7 @@ def main():
                                      "fill launches in the committed ncu capture"}},
             "fill_ms_per_step": ms_fill, "traceback_ms_per_step": tb_ms / args.steps, "wall_ms_per_step": ms_wall,
             "jobs_ok": ok, "jobs": len(jobs),
-            "kernels": {"lanes": stats["jobs_lanes"], "strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"], "pstrip": stats["jobs_pstrip"]},
+            "kernels": {"lanes": stats["jobs_lanes"], "strip": stats["jobs_strip"], "wavefront": stats["jobs_wavefront"], "pstrip": stats["jobs_pstrip"], "band": stats["jobs_band"]},
         }
         # strong scaling: --reads alignments in TOTAL over the ranks (BASELINE configs[1] is one 100k-read job); at N=1 it is
         # the main line itself

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PG2_ABI_VERSION 2
+#define PG2_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -209,6 +209,8 @@ typedef struct pg2_stats {
     int32_t jobs_strip_groups;
     int32_t jobs_lanes;        /* jobs the lane-per-alignment kernel took (shared row graph) */
     int32_t jobs_pstrip;       /* jobs the pipelined-strip kernel took (CTA per alignment: general x general, banded, small waves) */
+    int32_t jobs_band;         /* jobs the band kernel took (warp per anchored alignment of two plain chains) */
+    int32_t reserved0;
 } pg2_stats;
 int pg2_get_stats(pg2_ctx *ctx, pg2_stats *out);
 

@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-PG2_ABI_VERSION = 2
+PG2_ABI_VERSION = 3
 
 PG2_OK, PG2_ERR_INVALID, PG2_ERR_NO_DEVICE, PG2_ERR_CUDA, PG2_ERR_NOMEM, PG2_ERR_UNSUPPORTED, PG2_ERR_CAPACITY = range(7)
 PG2_JOB_OK, PG2_JOB_NO_PATH, PG2_JOB_BAD_BAND, PG2_JOB_BAD_GRAPH, PG2_JOB_BROKEN_PATH = range(5)
@@ -113,6 +113,8 @@ class Stats(C.Structure):
         ("jobs_strip_groups", C.c_int32),
         ("jobs_lanes", C.c_int32),
         ("jobs_pstrip", C.c_int32),
+        ("jobs_band", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

@@ -68,7 +68,7 @@ struct DevJob {
     int model;           // index into the DevModel array
     unsigned flags;
     int banded;
-    short kernel;        // 0 wavefront, 1 strip, 2 lanes, 3 pipelined strips
+    short kernel;        // 0 wavefront, 1 strip, 2 lanes, 3 pipelined strips, 4 band (warp per banded chain x chain job)
     short strip_general; // strip kernel: 1 = left graph needs the general row body, 0 = plain unit-weight chain
     long long band_base; // into d_blo / d_bhi (lx entries)
     long long diag_base; // into d_dlo / d_doff (lx+ly-1 entries)
@@ -84,7 +84,14 @@ struct DevJob {
     int n_blocks;        // pipelined-strip kernel: column blocks of the job
     int blk_base;        // pipelined-strip kernel: into d_vlast, PB_INTS ints per block
     int ps_ring;         // pipelined-strip kernel: virtual rows of the job's tallest block
+    int n_seg;           // band kernel: walk segments (BAND_SEG diagonals each)
+    long long b4_base;   // band kernel: the job's geometry record in d_band4 (pg2_band.cu: band_geo_off / band_roff_off / band_seg_off)
+    long long cand_base; // band kernel: the job's walk candidates (int4 records)
+    long long act_base;  // band kernel: per segment, the candidate the path enters it with and its word offset
 };
+
+constexpr int BAND_SEG = 256;       // diagonals per walk segment of the band kernel
+constexpr int BAND_MAX_DIAG = 400;  // longest anti-diagonal the band kernel's row ring takes (pg2_band.cu: BAND_R)
 
 // Lane kernel work item: up to 32 alignments that share the LEFT (row) graph, model and flags; every right
 // graph is a plain chain.  One warp takes one task, one alignment per lane.

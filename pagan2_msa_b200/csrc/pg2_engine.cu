@@ -50,6 +50,10 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
                       const int4 *d_vrow, const int *d_vlast, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv,
                       int max_lx, int max_slots, int *queue, int n_ctas, cudaStream_t stream);
 int lane_ctas_per_sm();
+void launch_band_fill(bool smalltab, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
+                      const int *d_state, const int *d_band4, unsigned *ptrs, DevResult *results, cudaStream_t stream);
+void launch_band_traceback(int n_jobs, int max_seg, const int *job_ids, const DevJob *jobs, const int *d_band4, const unsigned *ptrs,
+                           DevResult *results, int4 *cand, int2 *act, unsigned short *steps, cudaStream_t stream);
 bool strip_eligible(int lx, int ly, bool banded, int l_simple, int r_simple, int l_maxdeg, int r_maxdeg, int fas);
 void launch_traceback(int n_jobs, int n_wave, int n_ps, const int *job_ids, const DevJob *jobs, const DevGraph *graphs, const int *d_vlast, const int *d_off,
                       const int *d_estart, const int *d_blo, const int *d_bhi, const int *d_dlo, const long long *d_doff,
@@ -153,6 +157,7 @@ struct pg2_batch {
     std::vector<LaneTask> tasks;  // lane kernel work items, group by group
     long long total_steps = 0;
     long long total_cells = 0;
+    long long n_bcand = 0, n_bact = 0;  // band kernel: walk candidate records / segment records of the batch
     long long h2d_bytes = 0;
     size_t n_off_total = 0, n_edge_total = 0;  // device sizes of d_off / d_estart (staged explicit graphs + implicit chains)
     bool uploaded = false, ran = false, fetch_enqueued = false;
@@ -174,6 +179,7 @@ struct pg2_ctx {
     bool no_lanes = false;         // PG2_NO_LANES=1: keep shared-target jobs on the warp-per-alignment strip kernel (tests)
     bool no_pstrip = false;        // PG2_NO_PSTRIP=1: never use the pipelined-strip kernel (tests: the older kernels stay covered)
     bool pstrip_banded_chains = false;
+    bool no_band = false;          // PG2_NO_BAND=1: banded chain x chain jobs stay on the wavefront kernel's chain path (tests)
     int pstrip_cluster_max = 8;     // CTAs (SMs) one pipelined-strip alignment may be spread over (PG2_PSTRIP_CLUSTER; 1 = one CTA per job)  // PG2_PSTRIP_BANDED_CHAINS=1: banded chain x chain jobs too (tests)
     int pstrip_max_jobs = 600;     // strip-eligible jobs of a batch go to the pipelined-strip kernel when there are at most this
                                    // many of them (a warp per alignment cannot fill the chip; PG2_PSTRIP_MAX_JOBS)
@@ -182,6 +188,10 @@ struct pg2_ctx {
     PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_vrow, h_vlast;
     PinVec<float> h_elogw;
     PinVec<long long> h_doff;
+    PinVec<int> h_band4;           // band kernel: per job diagonal geometry, row pointer offsets, walk segment table (pg2_band.cu)
+    DevBuf<int> d_band4;
+    DevBuf<int4> d_bcand;          // band kernel: walk candidates of every segment
+    DevBuf<int2> d_bact;           // band kernel: the candidates the paths go through
     DevBuf<int> d_state, d_off, d_estart, d_blo, d_bhi, d_dlo, d_order, d_graph_status, d_vrow, d_vlast, d_queue;
     DevBuf<double4> d_saved, d_bcol;
     DevBuf<double> d_lane_scratch;
@@ -256,6 +266,8 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
     c->no_pstrip = nps && atoi(nps) != 0;
     const char *pbc = getenv("PG2_PSTRIP_BANDED_CHAINS");
     c->pstrip_banded_chains = pbc && atoi(pbc) != 0;
+    const char *nb = getenv("PG2_NO_BAND");
+    c->no_band = nb && atoi(nb) != 0;
     const char *pcl = getenv("PG2_PSTRIP_CLUSTER");
     if (pcl && atoi(pcl) >= 1 && atoi(pcl) <= 8) c->pstrip_cluster_max = atoi(pcl);
     const char *pmj = getenv("PG2_PSTRIP_MAX_JOBS");
@@ -277,6 +289,7 @@ extern "C" void pg2_ctx_destroy(pg2_ctx *c) {
     if (!c->borrowed_models)
         for (auto &m : c->models) if (m.live && m.d_table) cudaFree(m.d_table);
     c->h_state.release(); c->h_off.release(); c->h_estart.release(); c->h_blo.release(); c->h_bhi.release(); c->h_dlo.release();
+    c->h_band4.release(); c->d_band4.release(); c->d_bcand.release(); c->d_bact.release();
     c->h_elogw.release(); c->h_doff.release(); c->h_results.release(); c->h_models.release(); c->h_vrow.release(); c->h_vlast.release();
     c->d_vrow.release(); c->d_vlast.release(); c->d_queue.release(); c->d_saved.release(); c->d_bcol.release();
     c->d_state.release(); c->d_off.release(); c->d_estart.release(); c->d_blo.release(); c->d_bhi.release(); c->d_dlo.release();
@@ -567,14 +580,14 @@ static int build_row_program(pg2_ctx *c, DevGraph &dg) {
     return PG2_OK;
 }
 
-// clipped band + anti-diagonal geometry of one banded job (host, O(lx+ly))
-static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t *lower) {
+// clipped band + anti-diagonal geometry of one banded job (host, O(lx+ly)).  want4: the job may go to the band kernel
+// (plain unit-weight chains on both sides): its geometry record is written instead of the wavefront kernel's, unless the
+// longest diagonal is beyond what the band kernel takes.  Sets J.kernel = 4 when it did.
+static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t *lower, bool want4) {
     const int lx = J.lx, ly = J.ly, nd = lx + ly - 1;
     J.band_base = (long long)c->h_blo.n;
-    J.diag_base = (long long)c->h_dlo.n;
-    int *blo = c->h_blo.extend(lx), *bhi = c->h_bhi.extend(lx), *dlo = c->h_dlo.extend(nd + 1);
-    long long *doff = c->h_doff.extend(nd + 1);
-    if (!blo || !bhi || !dlo || !doff) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+    int *blo = c->h_blo.extend(lx), *bhi = c->h_bhi.extend(lx);
+    if (!blo || !bhi) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
     bool ok = true;
     for (int i = 0; i < lx; i++) {
         blo[i] = upper[i] > 0 ? upper[i] : 0;                  // tunnel_matrix.h:194
@@ -583,6 +596,51 @@ static int pack_band(pg2_ctx *c, DevJob &J, const int32_t *upper, const int32_t 
         if (i && (blo[i] < blo[i - 1] || bhi[i] < bhi[i - 1])) ok = false;
     }
     if (blo[0] > 0) ok = false;
+    if (want4 && ok) {
+        // band kernel record: first / last row of every diagonal (two closing entries: "no row"), row pointer offsets,
+        // candidate offsets of the walk segments
+        const int n_seg = (nd + BAND_SEG - 1) / BAND_SEG;
+        const size_t mark = c->h_band4.n;
+        if (mark & 1) { if (!c->h_band4.extend(1)) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed"); }  // geometry pairs are copied 8 bytes at a time
+        J.b4_base = (long long)c->h_band4.n;
+        int *geo = c->h_band4.extend((size_t)2 * (nd + 2) + lx + n_seg + 1);
+        if (!geo) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
+        int *roff = geo + 2 * (nd + 2), *seg = roff + lx;
+        long long cells = 0;
+        int max_diag = 1, first = 0, last = -1;
+        for (int s = 0; s < nd; s++) {
+            while (last + 1 < lx && blo[last + 1] + (last + 1) <= s) ++last;
+            while (first < lx && bhi[first] + first < s) ++first;
+            geo[2 * s] = first;
+            geo[2 * s + 1] = last;
+            if (last >= first) { cells += last - first + 1; max_diag = std::max(max_diag, last - first + 1); }
+        }
+        for (int s = nd; s < nd + 2; s++) { geo[2 * s] = lx; geo[2 * s + 1] = lx - 1; }
+        long long bytes = 0;
+        for (int i = 0; i < lx; i++) { roff[i] = (int)(bytes - blo[i]); bytes += bhi[i] - blo[i] + 1; }
+        if (max_diag <= BAND_MAX_DIAG && bytes < 0x7fff0000LL) {
+            long long cand = 0;
+            for (int k = 0; k < n_seg; k++) {
+                seg[k] = (int)cand;
+                const int top = (k + 1) * BAND_SEG - 1;
+                if (k == n_seg - 1) cand += 1;  // the top segment is entered by the end pointer alone
+                else cand += 3LL * (std::max(geo[2 * top + 1] - geo[2 * top] + 1, 0) + std::max(geo[2 * top - 1] - geo[2 * top - 2] + 1, 0));
+            }
+            seg[n_seg] = (int)cand;
+            J.kernel = 4;
+            J.n_seg = n_seg;
+            J.cells = cells;
+            J.max_diag = max_diag;
+            J.ptr_cells = 3 * ((bytes + 3) / 4);  // three planes (X, Y, M) of one byte per cell
+            J.diag_base = -1;
+            return PG2_OK;
+        }
+        c->h_band4.n = mark;  // too wide for the band kernel: the wavefront kernel's record instead
+    }
+    J.diag_base = (long long)c->h_dlo.n;
+    int *dlo = c->h_dlo.extend(nd + 1);
+    long long *doff = c->h_doff.extend(nd + 1);
+    if (!dlo || !doff) return fail(PG2_ERR_NOMEM, "pinned staging allocation failed");
     long long cells = 0;
     int max_diag = 1;
     if (ok) {
@@ -820,7 +878,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     b->n_jobs = n_jobs;
     b->jobs.resize(n_jobs);
     c->h_state.clear(); c->h_off.clear(); c->h_estart.clear(); c->h_elogw.clear(); c->h_vrow.clear(); c->h_vlast.clear();
-    c->h_blo.clear(); c->h_bhi.clear(); c->h_dlo.clear(); c->h_doff.clear();
+    c->h_blo.clear(); c->h_bhi.clear(); c->h_dlo.clear(); c->h_doff.clear(); c->h_band4.clear();
     GraphTable seen((size_t)n_jobs * 2);
     b->graphs.reserve((size_t)n_jobs + 16);
     std::vector<const pg2_graph *> sources;
@@ -923,15 +981,17 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         J.flags = j.flags;
         J.banded = j.upper != nullptr;
         J.band_base = J.diag_base = -1;
+        DevGraph &GL = b->graphs[J.left];
+        const DevGraph &GR = b->graphs[J.right];
         if (J.banded) {
-            rc = pack_band(c, J, j.upper, j.lower);
+            // anchored alignments of two plain unit-weight chains (leaf x leaf): the band kernel, one warp per job
+            const bool want4 = !c->force_wavefront && !c->no_band && !c->pstrip_banded_chains && GL.simple && GR.simple && GL.zero_w && GR.zero_w;
+            rc = pack_band(c, J, j.upper, j.lower, want4);
             if (rc != PG2_OK) { delete b; return rc; }
         } else {
             J.cells = (long long)J.lx * J.ly;
         }
-        DevGraph &GL = b->graphs[J.left];
-        const DevGraph &GR = b->graphs[J.right];
-        J.kernel = strip_eligible(J.lx, J.ly, J.banded != 0, GL.simple, GR.simple, GL.max_indeg, GR.max_indeg, c->models[j.model].fas) ? 1 : 0;
+        if (J.kernel != 4) J.kernel = strip_eligible(J.lx, J.ly, J.banded != 0, GL.simple, GR.simple, GL.max_indeg, GR.max_indeg, c->models[j.model].fas) ? 1 : 0;
         if (c->force_wavefront) J.kernel = 0;
         if (J.kernel == 1) {
             rc = build_row_program(c, GL);
@@ -942,7 +1002,15 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         J.strip_k = J.kernel == 1 ? pick_k : 0;
         J.strip_general = (J.kernel == 1 && !(GL.simple && GL.zero_w)) ? 1 : 0;
         if (J.kernel == 1 && c->models[j.model].fas <= STRIP_SMALL_FAS) J.strip_general |= 2;  // bit 1: shared-table variant
-        J.ptr_cells = J.kernel == 1 ? strip_cells(GL.n_vrows, J.ly, J.strip_k) : J.cells;
+        if (J.kernel == 4) J.strip_general = c->models[j.model].fas <= STRIP_SMALL_FAS ? 2 : 0;  // bit 1: shared-table variant
+        else J.ptr_cells = J.kernel == 1 ? strip_cells(GL.n_vrows, J.ly, J.strip_k) : J.cells;
+        if (J.kernel == 4) {
+            const int *seg = c->h_band4.p + J.b4_base + 2LL * (J.lx + J.ly - 1 + 2) + J.lx;
+            J.cand_base = b->n_bcand;
+            J.act_base = b->n_bact;
+            b->n_bcand += seg[J.n_seg];
+            b->n_bact += J.n_seg;
+        }
         J.step_base = step_base;
         J.step_cap = j.left.n_sites + j.right.n_sites;
         step_base += J.step_cap;
@@ -1119,7 +1187,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         g.max_diag = 1;
         g.max_slots = 0;
         g.max_lx = 1;
-        size_t per_cell = g.kernel == 0 ? 36 : (g.kernel == 3 ? 4 : 2);
+        size_t per_cell = g.kernel == 0 ? 36 : (g.kernel >= 3 ? 4 : 2);
         while (pos < b->order.size()) {
             DevJob &J = b->jobs[b->order[pos]];
             if (J.kernel != g.kernel || J.strip_k != g.strip_k || J.strip_general != g.strip_general) break;
@@ -1148,10 +1216,10 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
         size_t bytes = 0;
         long long off16 = 0, off32 = 0, offps = 0;
         for (auto &g : b->groups) {
-            const size_t need = (size_t)g.cells * (g.kernel == 0 ? 36 : (g.kernel == 3 ? 4 : 2));
+            const size_t need = (size_t)g.cells * (g.kernel == 0 ? 36 : (g.kernel >= 3 ? 4 : 2));
             if (bytes > 0 && bytes + need > c->scratch_bytes) { phase++; bytes = 0; off16 = off32 = offps = 0; }
             g.phase = phase;
-            long long &off = g.kernel == 0 ? off32 : (g.kernel == 3 ? offps : off16);
+            long long &off = g.kernel == 0 ? off32 : (g.kernel >= 3 ? offps : off16);  // the band kernel's bytes share the pipelined strips' word buffer
             g.ptr_off = off;
             off += g.cells;
             bytes += need;
@@ -1178,6 +1246,7 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     ENS(c->d_vrow, c->h_vrow.n + 4); ENS(c->d_vlast, c->h_vlast.n + 1); ENS(c->d_queue, 4);
     ENS(c->d_state, c->h_state.n + 1); ENS(c->d_off, b->n_off_total + 1); ENS(c->d_estart, b->n_edge_total + 1); ENS(c->d_elogw, b->n_edge_total + 1);
     ENS(c->d_blo, c->h_blo.n + 1); ENS(c->d_bhi, c->h_bhi.n + 1); ENS(c->d_dlo, c->h_dlo.n + 1); ENS(c->d_doff, c->h_doff.n + 1);
+    ENS(c->d_band4, c->h_band4.n + 2); ENS(c->d_bcand, (size_t)b->n_bcand + 1); ENS(c->d_bact, (size_t)b->n_bact + 1);
     ENS(c->d_jobs, b->jobs.size() + 1); ENS(c->d_graphs, b->graphs.size() + 1); ENS(c->d_order, b->order.size() + 1);
     ENS(c->d_graph_status, b->graphs.size() + 1); ENS(c->d_results, b->jobs.size() + 1); ENS(c->d_steps, (size_t)b->total_steps + 1);
     ENS(c->d_steps_compact, (size_t)b->total_steps + 1); ENS(c->d_step_scan, b->jobs.size() / 256 + 4);
@@ -1195,6 +1264,7 @@ static int upload_batch(pg2_ctx *c, pg2_batch *b) {
     H2D(c->d_bhi, c->h_bhi.p, c->h_bhi.n, int);
     H2D(c->d_dlo, c->h_dlo.p, c->h_dlo.n, int);
     H2D(c->d_doff, c->h_doff.p, c->h_doff.n, long long);
+    H2D(c->d_band4, c->h_band4.p, c->h_band4.n, int);
     H2D(c->d_jobs, b->jobs.data(), b->jobs.size(), DevJob);
     H2D(c->d_graphs, b->graphs.data(), b->graphs.size(), DevGraph);
     H2D(c->d_order, b->order.data(), b->order.size(), int);
@@ -1240,7 +1310,7 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
     // scratch for the largest phase of each buffer class (strip and lane groups share d_ptr16)
     long long max_w = 0, max_s = 0, max_ps = 0;
     for (auto &g : b->groups) {
-        long long &m = g.kernel == 0 ? max_w : (g.kernel == 3 ? max_ps : max_s);
+        long long &m = g.kernel == 0 ? max_w : (g.kernel >= 3 ? max_ps : max_s);
         m = std::max(m, g.ptr_off + g.cells);
     }
     if (max_ps > 0 && (rc = c->d_ptrps.ensure((size_t)max_ps)) != PG2_OK) return fail(rc, "pointer buffer allocation failed");
@@ -1308,7 +1378,7 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                     c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, c->stream);
     st.fill_ms = st.traceback_ms = 0;
     st.fill_launches = st.traceback_launches = 0;
-    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = st.jobs_pstrip = 0;
+    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = st.jobs_pstrip = st.jobs_band = 0;
     st.jobs_strip_groups = 0;
     st.cells = b->total_cells;
     st.traceback_bytes = 0;
@@ -1332,6 +1402,11 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                                    reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_vlast.p, c->d_blo.p, c->d_bhi.p, c->d_ptrps.p,
                                    c->d_results.p, c->d_ps_scratch.p, g.max_lx, g.ps_ring, g.max_slots, g.ps_park, c->d_queue.p, c->stream);
                 st.jobs_pstrip += g.count;
+                st.traceback_bytes += g.cells * 4;
+            } else if (g.kernel == 4) {
+                launch_band_fill((g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_band4.p,
+                                 c->d_ptrps.p, c->d_results.p, c->stream);
+                st.jobs_band += g.count;
                 st.traceback_bytes += g.cells * 4;
             } else if (g.kernel == 0) {
                 int threads = g.max_diag <= 32 ? 32 : g.max_diag <= 64 ? 64 : g.max_diag <= 128 ? 128 : g.max_diag <= 256 ? 256
@@ -1370,6 +1445,14 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
         launch_traceback(phase_jobs, phase_wave_jobs, phase_ps_jobs, c->d_order.p + b->groups[gi].first, c->d_jobs.p, c->d_graphs.p, c->d_vlast.p,
                          c->d_off.p, c->d_estart.p, c->d_blo.p, c->d_bhi.p, c->d_dlo.p, c->d_doff.p, c->d_ptr32.p, c->d_ptr16.p, c->d_ptrps.p,
                          c->d_steps.p, c->d_results.p, tb_stream);
+        for (size_t k = gi; k < ge; k++) {
+            const Group &g = b->groups[k];
+            if (g.kernel != 4) continue;
+            int max_seg = 0;
+            for (int q = g.first; q < g.first + g.count; q++) max_seg = std::max(max_seg, b->jobs[b->order[q]].n_seg);
+            launch_band_traceback(g.count, max_seg, c->d_order.p + g.first, c->d_jobs.p, c->d_band4.p, c->d_ptrps.p, c->d_results.p,
+                                  c->d_bcand.p, c->d_bact.p, c->d_steps.p, tb_stream);
+        }
         CU(cudaEventRecord(c->ev[4], tb_stream));
         if (tb_stream != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev[4], 0));
         if (!async) {
@@ -1690,7 +1773,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
             const pg2_stats &st = f.ctx->stats;
             agg.h2d_bytes += st.h2d_bytes; agg.d2h_bytes += st.d2h_bytes; agg.cells += st.cells; agg.traceback_bytes += st.traceback_bytes;
             agg.fill_launches += st.fill_launches; agg.traceback_launches += st.traceback_launches; agg.kernel_launches += st.kernel_launches;
-            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes; agg.jobs_pstrip += st.jobs_pstrip;
+            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes; agg.jobs_pstrip += st.jobs_pstrip; agg.jobs_band += st.jobs_band;
             agg.jobs_strip_groups += st.jobs_strip_groups; agg.d2h_ms += st.d2h_ms;
         }
         pg2_batch_destroy(f.ctx, f.batch);

@@ -399,7 +399,7 @@ __global__ void traceback_kernel(int n_jobs, const int *job_ids, const DevJob *j
                                  DevResult *results) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
-    if (jobs[job_ids[t]].kernel == 0 || jobs[job_ids[t]].kernel == 3) return;  // traceback_wave_kernel / traceback_pstrip_kernel
+    if (jobs[job_ids[t]].kernel == 0 || jobs[job_ids[t]].kernel >= 3) return;  // traceback_wave_kernel / traceback_pstrip_kernel / the band kernel's walk
     traceback_one(job_ids[t], jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
 }
 #endif
@@ -643,6 +643,7 @@ void launch_traceback(int n_jobs, int n_wave, int n_ps, const int *job_ids, cons
             res->status = st.s.status;
             continue;
         }
+        if (J.kernel == 4) continue;  // launch_band_traceback (pg2_band.cu)
         if (J.kernel != 0) {
             traceback_one(jid, jobs, graphs, d_vlast, d_off, d_estart, d_blo, d_bhi, d_dlo, d_doff, ptr32, ptr16, steps, results);
             continue;

@@ -25,6 +25,8 @@ static inline double2 make_double2(double x, double y) { double2 r = {x, y}; ret
 static inline double4 make_double4(double x, double y, double z, double w) { double4 r = {x, y, z, w}; return r; }
 struct uint3 { unsigned x, y, z; };
 struct uint4 { unsigned x, y, z, w; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 r = {x, y}; return r; }
 struct int4 { int x, y, z, w; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
 

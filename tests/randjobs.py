@@ -116,3 +116,45 @@ def random_shared_target_jobs(rng, n_jobs, fas=15, plain_left=False, weights=Non
             right.logw[:] = np.log(rng.uniform(0.2, 1.0, size=right.logw.shape[0]).astype(np.float32))
         jobs.append(FlatJob(left, right, model, flags))
     return jobs
+
+
+def random_anchor_band_job(rng, n, fas=15, width=(3, 12), bulge=0, p_indel=0.02, disconnect=False):
+    """Anchored leaf x leaf shape: two plain unit-weight chains of ~n sites (the second a copy with substitutions and
+    indels), a monotone band of varying half-width around the true path; `bulge` adds stretches where the band is that
+    much wider (gaps between anchors), `disconnect` cuts the band in two (no path: PG2_JOB_NO_PATH)."""
+    a = rng.integers(0, min(fas, 4), size=n).astype(np.int32)
+    b, col = [], []
+    for x in a:
+        r = rng.random()
+        if r < p_indel:  # deletion in b
+            col.append(max(len(b) - 1, 0))
+            continue
+        if r < 2 * p_indel:  # insertion in b
+            b.extend(rng.integers(0, min(fas, 4), size=int(rng.integers(1, 6))).tolist())
+        col.append(len(b))
+        b.append(int(x) if rng.random() > 0.05 else int(rng.integers(0, min(fas, 4))))
+    if not b:
+        b = [0]
+    left, right = FlatGraph.chain(a), FlatGraph.chain(np.array(b, np.int32))
+    lx, ly = left.n_sites - 1, right.n_sites - 1
+    c = np.concatenate([[0], np.array(col, np.int64) + 1])[:lx]
+    w_lo = rng.integers(width[0], width[1] + 1, size=lx)
+    w_hi = rng.integers(width[0], width[1] + 1, size=lx)
+    if bulge:
+        for _ in range(max(1, lx // 300)):
+            s0 = int(rng.integers(0, lx))
+            w_hi[s0:s0 + int(rng.integers(5, 60))] += int(rng.integers(1, bulge + 1))
+            s0 = int(rng.integers(0, lx))
+            w_lo[s0:s0 + int(rng.integers(5, 60))] += int(rng.integers(1, bulge + 1))
+    upper = np.maximum.accumulate(c - w_lo)
+    lower = np.maximum.accumulate(c + w_hi)
+    upper[0] = min(upper[0], 0)
+    lower[-1] = max(lower[-1], ly + 3)
+    job = FlatJob(left, right, random_model(rng, fas, rng.random() < 0.3), int(rng.integers(0, 4)))
+    if disconnect and lx > 8:
+        k = lx // 2
+        upper[k:] = np.maximum(upper[k:], lower[k - 1] + 2)  # rows k.. start right of where row k-1 ends
+        lower[k:] = np.maximum(lower[k:], upper[k:] + 1)
+        lower = np.maximum.accumulate(lower)
+    job.upper, job.lower = upper.astype(np.int32), lower.astype(np.int32)
+    return job

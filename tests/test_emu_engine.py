@@ -23,19 +23,20 @@ def emu_lib():
     return EMU_LIB
 
 
-def make_engine(lib, force_wavefront, no_lanes=False, no_pstrip=False, pstrip_k=None):
+def make_engine(lib, force_wavefront, no_lanes=False, no_pstrip=False, pstrip_k=None, no_band=False):
     """no_pstrip: keep the pipelined-strip kernel out, so that the warp-per-alignment strip kernel and the general
     wavefront kernel (its fallback) stay covered; pstrip_k=4 forces the wider strips."""
     os.environ["PG2_FORCE_WAVEFRONT"] = "1" if force_wavefront else "0"
     os.environ["PG2_NO_LANES"] = "1" if no_lanes else "0"
     os.environ["PG2_NO_PSTRIP"] = "1" if no_pstrip else "0"
+    os.environ["PG2_NO_BAND"] = "1" if no_band else "0"
     if pstrip_k:
         os.environ["PG2_PSTRIP_K"] = str(pstrip_k)
         os.environ["PG2_PSTRIP_BANDED_CHAINS"] = "1"  # (by default banded chain x chain jobs stay on the wavefront kernel)
     try:
         return engine.Engine(0, lib)
     finally:
-        for name in ("PG2_FORCE_WAVEFRONT", "PG2_NO_LANES", "PG2_NO_PSTRIP", "PG2_PSTRIP_K", "PG2_PSTRIP_BANDED_CHAINS"):
+        for name in ("PG2_FORCE_WAVEFRONT", "PG2_NO_LANES", "PG2_NO_PSTRIP", "PG2_PSTRIP_K", "PG2_PSTRIP_BANDED_CHAINS", "PG2_NO_BAND"):
             os.environ.pop(name, None)
 
 
@@ -216,7 +217,7 @@ def test_pipelined_align_batch_matches_single_shot(emu_lib, chunks):
         with make_engine(emu_lib, False) as eng:
             res = enginecheck.check_batch(eng, jobs)
             assert (res["kernel"] == 2).sum() >= 4 * 32
-            assert sum(eng.stats()[k] for k in ("jobs_lanes", "jobs_strip", "jobs_wavefront", "jobs_pstrip")) == len(jobs)
+            assert sum(eng.stats()[k] for k in ("jobs_lanes", "jobs_strip", "jobs_wavefront", "jobs_pstrip", "jobs_band")) == len(jobs)
             # twice on the same engine: the sibling context and its buffers are reused
             enginecheck.check_batch(eng, jobs[::-1])
     finally:
@@ -312,3 +313,32 @@ def test_reference_streams_at_baseline_size(emu_lib, golden, name):
     with make_engine(emu_lib, False) as eng:
         res = enginecheck.check_batch(eng, jobs)
     assert (res["kernel"] == 3).sum() >= len(jobs) - 2
+
+
+BAND_SHAPES = [(1, {}), (2, {}), (5, {}), (40, {}), (300, {}), (700, dict(bulge=40)), (1500, dict(bulge=120, width=(8, 30))),
+               (900, dict(fas=211)), (600, dict(disconnect=True)), (1200, dict(bulge=300, width=(10, 40)))]
+
+
+def band_jobs(seed, reps=2):
+    rng = np.random.default_rng(seed)
+    jobs = [enginecheck.expect_from_oracle(randjobs.random_anchor_band_job(rng, n, **kw)) for n, kw in BAND_SHAPES for _ in range(reps)]
+    # wider than the band kernel's row ring: the wavefront kernel keeps the job
+    wide = randjobs.random_anchor_band_job(rng, 600)
+    wide.upper = np.zeros_like(wide.upper)
+    wide.lower = np.full_like(wide.lower, wide.right.n_sites + 2)
+    jobs.append(enginecheck.expect_from_oracle(wide))
+    return jobs
+
+
+def test_band_kernel_vs_oracle(emu_lib):
+    """Anchored leaf x leaf jobs through the band kernel (one warp per job, rings indexed by row, M one diagonal ahead) and
+    its segmented walk: one-site graphs, several 32-step chunks and walk segments, diagonals longer than a warp (several
+    passes per step), the table outside shared memory (fas 211), a band cut in two (no path), every flag combination."""
+    jobs = band_jobs(301)
+    with make_engine(emu_lib, False) as eng:
+        res = enginecheck.check_batch(eng, jobs)
+        assert (res["kernel"][:-1] == 4).all() and res["kernel"][-1] == 0
+        assert eng.stats()["jobs_band"] == len(jobs) - 1
+    with make_engine(emu_lib, False, no_band=True) as eng:  # the same jobs on the wavefront kernel's chain path
+        res = enginecheck.check_batch(eng, jobs)
+        assert (res["kernel"] == 0).all()

@@ -46,7 +46,7 @@ def eng_wave():
 def eng_old():
     """Without the pipelined-strip kernel: the warp-per-alignment strip kernel and the general wavefront kernel (the
     fallback for graphs outside the pipelined-strip kernel's limits) stay covered."""
-    e = engine_with(PG2_NO_PSTRIP=1)
+    e = engine_with(PG2_NO_PSTRIP=1, PG2_NO_BAND=1)
     yield e
     e.close()
 
@@ -172,7 +172,7 @@ def test_random_jobs_vs_oracle(eng, eng_old, eng_ps4, kind, seed):
     jobs = [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for _ in range(300)]
     res = enginecheck.check_batch(eng, jobs)
     if kind == "banded_chain":
-        assert (res["kernel"] == 0).all()  # plain chains inside a band: the wavefront kernel's chain path
+        assert (res["kernel"] == 4).all()  # plain unit-weight chains inside a band: the band kernel
     else:
         assert (res["kernel"] == 3).mean() > 0.9
     res = enginecheck.check_batch(eng_ps4, jobs)
@@ -362,3 +362,16 @@ def test_pipelined_call_equals_resident_batch_at_scale(eng, golden):
         job = enginecheck.expect_from_oracle(jobs[k])
         st, _, _ = eng.expand(job, rb[k], sb, compact=True)
         assert oracle_lib.steps_equal(st, job.expected_path, job.expected_path_score) == []
+
+
+def test_band_kernel_vs_oracle(eng, eng_old):
+    """Anchored leaf x leaf jobs through the band kernel and its segmented walk (see tests/test_emu_engine.py for the shapes),
+    and the same jobs on the wavefront kernel's chain path."""
+    import test_emu_engine
+
+    jobs = test_emu_engine.band_jobs(401, reps=6)
+    res = enginecheck.check_batch(eng, jobs)
+    assert (res["kernel"][:-1] == 4).all() and res["kernel"][-1] == 0
+    assert eng.stats()["jobs_band"] == len(jobs) - 1
+    res = enginecheck.check_batch(eng_old, jobs)
+    assert (res["kernel"] == 0).all()

@@ -19,7 +19,7 @@ import randjobs  # noqa: E402
 import test_gpu_fullsize as fs  # noqa: E402
 from pagan2_msa_b200 import abi, engine, jobio, synth  # noqa: E402
 
-KERNEL = {0: "wavefront", 1: "strip", 2: "lanes", 3: "pstrip"}
+KERNEL = {0: "wavefront", 1: "strip", 2: "lanes", 3: "pstrip", 4: "band"}
 
 
 def golden(name):
