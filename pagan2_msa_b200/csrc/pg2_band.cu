@@ -76,6 +76,29 @@ __device__ __forceinline__ void band_cand(double s, unsigned code, double &best,
     best = p ? s : best;
     ptr = p ? code : ptr;
 }
+// The first-wins maximum of three candidates in their order (c1, c2, c3), two selects deep instead of three: the later
+// two are folded first (a tie keeps c2), the result replaces c1 only when strictly greater (a tie keeps c1) -- the same
+// winner as the sequential scan; no candidate above -inf leaves the cell without a pointer.  The candidates must not be NaN
+// (a NaN never wins the reference's `>`, but it would get through the fold): the reference's tables hold NaN for state pairs
+// it never scores, band_ls() turns them into -inf, which never wins either.
+__device__ __forceinline__ double band_max3(double c1, double c2, double c3, unsigned p1, unsigned p2, unsigned p3, unsigned &ptr) {
+    const bool q = c3 > c2;
+    const double g = q ? c3 : c2;
+    const unsigned pg = q ? p3 : p2;
+    const bool w = g > c1;
+    const double best = w ? g : c1;
+    ptr = w ? pg : p1;
+    ptr = (best == neg_inf()) ? (unsigned)NO_MAT : ptr;
+    return best;
+}
+// a pointer byte, written when the cell lies inside the band (a predicated store: no branch in the step)
+__device__ __forceinline__ void band_store_ptr(unsigned char *plane, int off, unsigned p, bool v) {
+#ifdef PG2_HOST_EMU
+    if (v) plane[off] = (unsigned char)p;
+#else
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u8 [%0], %1;\n\t}" ::"l"(plane + off), "r"(p), "r"((unsigned)v) : "memory");
+#endif
+}
 
 // One row of step s, one matrix.  The step writes the rows [lo0 - 1, hi0 + 3] of every ring slot: the computed value where
 // the cell lies inside the band -- X, Y of cell (i, s - i) for lo0 <= i <= hi0, M of cell (i, s + 1 - i) for lo1 <= i <= hi1
@@ -89,60 +112,55 @@ __device__ __forceinline__ void band_cand(double s, unsigned code, double &best,
 template <bool BOUNDARY>
 __device__ __forceinline__ void band_x_cell(const BandSm &sm, const BandConst &k, const BandStep &t, int i, unsigned char *PX) {
     const int r = i & BAND_RM, ru = (i - 1) & BAND_RM, j = t.s - i;
+    const int off = sm.rroff[r] + j;
     const double a = sm.x[t.b1 + ru], b = sm.y[t.b1 + ru], c = sm.m[t.b2 + ru];
     double extx = k.ext, pen = k.open;
     if (BOUNDARY) {
         if (k.term && (j == 0 || j == k.ly - 1)) extx = k.end_ext;  // terminal gap extension (:864-868)
         if (k.reduced && i == 1) pen = 0.0;                         // get_log_gap_open_penalty (basic_alignment.h:490-513)
     }
-    double best = neg_inf();
-    unsigned p = NO_MAT;
-    band_cand(__dadd_rn(a, extx), X_MAT, best, p);
-    band_cand(__dadd_rn(b, k.open), Y_MAT, best, p);
-    band_cand(__dadd_rn(__dadd_rn(c, k.lng), pen), M_MAT, best, p);
+    unsigned p;
+    const double best = band_max3(__dadd_rn(a, extx), __dadd_rn(b, k.open), __dadd_rn(__dadd_rn(c, k.lng), pen), X_MAT, Y_MAT, M_MAT, p);
     const bool v = i >= t.lo0 && i <= t.hi0;
     sm.x[t.b0 + r] = v ? best : neg_inf();
-    if (v) PX[(long long)sm.rroff[r] + j] = (unsigned char)p;
+    band_store_ptr(PX, off, p, v);
 }
 // Y of (i, j): ext, double, open out of (i, j-1)
 template <bool BOUNDARY>
 __device__ __forceinline__ void band_y_cell(const BandSm &sm, const BandConst &k, const BandStep &t, int i, unsigned char *PY) {
     const int r = i & BAND_RM, j = t.s - i;
+    const int off = sm.rroff[r] + j;
     const double a = sm.y[t.b1 + r], b = sm.x[t.b1 + r], c = sm.m[t.b2 + r];
     double exty = k.ext, pen = k.open;
     if (BOUNDARY) {
         if (k.term && (i == 0 || i == k.lx - 1)) exty = k.end_ext;  // (:875-879)
         if (k.reduced && j == 1) pen = 0.0;
     }
-    double best = neg_inf();
-    unsigned p = NO_MAT;
-    band_cand(__dadd_rn(a, exty), Y_MAT, best, p);
-    band_cand(__dadd_rn(b, k.open), X_MAT, best, p);
-    band_cand(__dadd_rn(__dadd_rn(c, k.lng), pen), M_MAT, best, p);
+    unsigned p;
+    const double best = band_max3(__dadd_rn(a, exty), __dadd_rn(b, k.open), __dadd_rn(__dadd_rn(c, k.lng), pen), Y_MAT, X_MAT, M_MAT, p);
     const bool v = i >= t.lo0 && i <= t.hi0;
     sm.y[t.b0 + r] = v ? best : neg_inf();
-    if (v) PY[(long long)sm.rroff[r] + j] = (unsigned char)p;
+    band_store_ptr(PY, off, p, v);
 }
+__device__ __forceinline__ double band_ls(float v) { return v != v ? neg_inf() : (double)v; }
 // the substitution terms of cell (i, s + 1 - i)
 template <bool SMALLTAB>
 __device__ __forceinline__ double2 band_subst(const BandSm &sm, const BandConst &k, int s, int i) {
     const int sl = sm.rstate[i & BAND_RM], sr = sm.cstate[(s + 1 - i) & BAND_CM];
     if (SMALLTAB) return sm.stab[sl + sr * k.fas];
-    const double ls = (double)__ldg(k.table + (size_t)sl + (size_t)sr * (size_t)k.fas);
+    const double ls = band_ls(__ldg(k.table + (size_t)sl + (size_t)sr * (size_t)k.fas));
     return make_double2(__dadd_rn(k.lng2, ls), __dadd_rn(k.lng, ls));
 }
 // M of (i, j+1): from M, X, Y of (i-1, j)   (:2029-2112)
 __device__ __forceinline__ void band_m_cell(const BandSm &sm, const BandStep &t, int i, double2 sub, unsigned char *PM) {
     const int r = i & BAND_RM, ru = (i - 1) & BAND_RM, j = t.s - i;
+    const int off = sm.rroff[r] + j + 1;
     const double a = sm.m[t.b2 + ru], b = sm.x[t.b1 + ru], c = sm.y[t.b1 + ru];
-    double best = neg_inf();
-    unsigned p = NO_MAT;
-    band_cand(__dadd_rn(a, sub.x), M_MAT, best, p);
-    band_cand(__dadd_rn(b, sub.y), X_MAT, best, p);
-    band_cand(__dadd_rn(c, sub.y), Y_MAT, best, p);
+    unsigned p;
+    const double best = band_max3(__dadd_rn(a, sub.x), __dadd_rn(b, sub.y), __dadd_rn(c, sub.y), M_MAT, X_MAT, Y_MAT, p);
     const bool v = i >= t.lo1 && i <= t.hi1;
     sm.m[t.b0 + r] = v ? best : neg_inf();
-    if (v) PM[(long long)sm.rroff[r] + j + 1] = (unsigned char)p;
+    band_store_ptr(PM, off, p, v);
 }
 
 // layout of a job's record in d_band4 (ints): [2 (nd + 2)] first / last row of every diagonal (+ two closing entries),
@@ -190,6 +208,43 @@ __device__ __forceinline__ void band_cp8(void *dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
+// The steps s_first .. s_last of one warp (ROLE 0 X, 1 Y, 2 M).  Straight-line code per step: the first pass of the warp over
+// the diagonal's rows, a rarely taken loop for diagonals longer than a warp, the CTA barrier, the ring rotation.  The
+// geometry of diagonal s + 2 is fetched at step s; the M warp fetches the substitution terms of its first pass one step ahead
+// (two dependent shared-memory loads that do not wait for the other warps' results).
+template <int ROLE, bool SMALLTAB, bool BOUNDARY>
+__device__ __forceinline__ void band_run_chunk(const BandSm &sm, const BandConst &k, int s_first, int s_last, int lane, int &b0, int &b1,
+                                               int &b2, unsigned char *PQ) {
+    BandStep t;
+    t.lo1 = sm.geo[2 * (s_first & BAND_GM)];
+    t.hi1 = sm.geo[2 * (s_first & BAND_GM) + 1];
+    int lo2 = sm.geo[2 * ((s_first + 1) & BAND_GM)], hi2 = sm.geo[2 * ((s_first + 1) & BAND_GM) + 1];
+    double2 sub_next = make_double2(0.0, 0.0);
+    if (ROLE == 2) sub_next = band_subst<SMALLTAB>(sm, k, s_first, t.lo1 - 1 + lane);
+    for (int s = s_first; s <= s_last; ++s) {
+        t.s = s; t.lo0 = t.lo1; t.hi0 = t.hi1; t.lo1 = lo2; t.hi1 = hi2;
+        lo2 = sm.geo[2 * ((s + 2) & BAND_GM)];
+        hi2 = sm.geo[2 * ((s + 2) & BAND_GM) + 1];
+        t.b0 = b0; t.b1 = b1; t.b2 = b2;
+        const int i0 = t.lo0 - 1 + lane;
+        if (ROLE == 2) {
+            const double2 sub = sub_next;
+            sub_next = band_subst<SMALLTAB>(sm, k, s + 1, t.lo1 - 1 + lane);
+            band_m_cell(sm, t, i0, sub, PQ);
+        } else if (ROLE == 0) band_x_cell<BOUNDARY>(sm, k, t, i0, PQ);
+        else band_y_cell<BOUNDARY>(sm, k, t, i0, PQ);
+        if (t.hi0 - t.lo0 + 4 >= 32) {  // rows lo0-1 .. hi0+3 do not fit one pass
+            for (int i = i0 + 32; i <= t.hi0 + 3 + lane; i += 32) {
+                if (ROLE == 2) band_m_cell(sm, t, i, band_subst<SMALLTAB>(sm, k, s, i), PQ);
+                else if (ROLE == 0) band_x_cell<BOUNDARY>(sm, k, t, i, PQ);
+                else band_y_cell<BOUNDARY>(sm, k, t, i, PQ);
+            }
+        }
+        __syncthreads();
+        const int freed = b2; b2 = b1; b1 = b0; b0 = freed;
+    }
+}
+
 template <bool SMALLTAB>
 __global__ void __launch_bounds__(BAND_THREADS, 1)
 band_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models, const int *d_state,
@@ -217,7 +272,7 @@ band_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
     for (int e = tid; e < BAND_C; e += BAND_THREADS) sm.cstate[e] = 0;
     if (SMALLTAB)
         for (int e = tid; e < m.fas * m.fas; e += BAND_THREADS) {
-            const double ls = (double)m.table[e];
+            const double ls = band_ls(m.table[e]);
             sm.stab[e] = make_double2(__dadd_rn(k.lng2, ls), __dadd_rn(k.lng, ls));
         }
     // diagonals 0 .. 63 of the geometry
@@ -230,56 +285,36 @@ band_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
     for (int s0 = 0; s0 < nd; s0 += 32) {
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
+        // staging, two chunks ahead: the geometry of diagonals s0+64 .., the rows up to hi(s0) + 68, the columns up to
+        // s0 + 66 - lo(s0) (a diagonal moves its row range by at most one row per step)
+        const int lo_s0 = sm.geo[2 * (s0 & BAND_GM)], hi_s0 = sm.geo[2 * (s0 & BAND_GM) + 1];
         {
-            // staging, two chunks ahead: the geometry of diagonals s0+64 .., the rows up to hi(s0) + 68, the columns up to
-            // s0 + 66 - lo(s0) (a diagonal moves its row range by at most one row per step)
-            const int lo_s0 = sm.geo[2 * (s0 & BAND_GM)], hi_s0 = sm.geo[2 * (s0 & BAND_GM) + 1];
             const int t = s0 + 64 + tid;
             if (tid < 32 && t < nd + 2) band_cp8(sm.geo + 2 * (t & BAND_GM), g_geo + 2 * t);
             const int row_target = hi_s0 + 68, col_target = s0 + 66 - lo_s0;
             for (; fr < row_target && fr < J.lx; fr += BAND_THREADS) {
                 const int i = fr + tid;
-                if (i < J.lx) { band_cp4(sm.rstate + (i & BAND_RM), l_state + i); band_cp4(sm.rroff + (i & BAND_RM), g_roff + i); }
+                // (the start sites carry no state of the alphabet: row 0 and column 0 keep the ring's 0 -- their M is -inf whatever the term)
+                if (i < J.lx) { if (i > 0) band_cp4(sm.rstate + (i & BAND_RM), l_state + i); band_cp4(sm.rroff + (i & BAND_RM), g_roff + i); }
             }
-            for (; fc < col_target && fc <= J.ly; fc += BAND_THREADS) {
+            for (; fc < col_target && fc < J.ly; fc += BAND_THREADS) {
                 const int j = fc + tid;
-                if (j <= J.ly) band_cp4(sm.cstate + (j & BAND_CM), r_state + j);
+                if (j > 0 && j < J.ly) band_cp4(sm.cstate + (j & BAND_CM), r_state + j);
             }
             if (s0 == 0) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncthreads(); }
         }
         const int s_first = s0 > 0 ? s0 : 1, s_last = min(s0 + 31, nd - 1);
-        BandStep t;
-        t.lo1 = sm.geo[2 * (s_first & BAND_GM)];
-        t.hi1 = sm.geo[2 * (s_first & BAND_GM) + 1];
-        // M warp: the substitution terms of the step's first pass are fetched one step ahead (two dependent shared-memory
-        // loads that do not wait for the other warps' results)
-        double2 sub_next = make_double2(0.0, 0.0);
-        if (role == 2) sub_next = band_subst<SMALLTAB>(sm, k, s_first, t.lo1 - 1 + lane);
-        for (int s = s_first; s <= s_last; ++s) {
-            t.s = s; t.lo0 = t.lo1; t.hi0 = t.hi1;
-            t.lo1 = sm.geo[2 * ((s + 1) & BAND_GM)];
-            t.hi1 = sm.geo[2 * ((s + 1) & BAND_GM) + 1];
-            t.b0 = b0; t.b1 = b1; t.b2 = b2;
-            const int i0 = t.lo0 - 1 + lane, i_end = t.hi0 + 3;
-            if (role == 2) {
-                const double2 sub = sub_next;
-                sub_next = band_subst<SMALLTAB>(sm, k, s + 1, t.lo1 - 1 + lane);
-                band_m_cell(sm, t, i0, sub, PQ);
-                for (int i = i0 + 32; i <= i_end + lane; i += 32) band_m_cell(sm, t, i, band_subst<SMALLTAB>(sm, k, s, i), PQ);
-            } else {
-                // a step that touches row 0 / 1 / lx-1 or column 0 / 1 / ly-1 takes the body with the terminal terms
-                const bool bnd = t.lo0 <= 1 || t.hi0 >= J.lx - 1 || s - t.hi0 <= 1 || s - t.lo0 >= J.ly - 1;
-                if (role == 0) {
-                    if (bnd) for (int i = i0; i <= i_end + lane; i += 32) band_x_cell<true>(sm, k, t, i, PQ);
-                    else     for (int i = i0; i <= i_end + lane; i += 32) band_x_cell<false>(sm, k, t, i, PQ);
-                } else {
-                    if (bnd) for (int i = i0; i <= i_end + lane; i += 32) band_y_cell<true>(sm, k, t, i, PQ);
-                    else     for (int i = i0; i <= i_end + lane; i += 32) band_y_cell<false>(sm, k, t, i, PQ);
-                }
-            }
-            __syncthreads();
-            const int freed = b2; b2 = b1; b1 = b0; b0 = freed;
-        }
+        // a chunk that may touch row 0 / 1 / lx-1 or column 0 / 1 / ly-1 takes the bodies with the terminal terms (the row and
+        // column ranges of a diagonal only move forward: the chunk's first and last step bound them)
+        const int hi_end = sm.geo[2 * ((s_last + 1) & BAND_GM) + 1];
+        const bool bnd = lo_s0 <= 1 || hi_end >= J.lx - 2 || s0 - hi_s0 <= 1 || s_last + 1 - lo_s0 >= J.ly - 2;
+        if (role == 0) {
+            if (bnd) band_run_chunk<0, SMALLTAB, true>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
+            else band_run_chunk<0, SMALLTAB, false>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
+        } else if (role == 1) {
+            if (bnd) band_run_chunk<1, SMALLTAB, true>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
+            else band_run_chunk<1, SMALLTAB, false>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
+        } else band_run_chunk<2, SMALLTAB, false>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
     }
     if (tid == 0) {
         // after the last step b1 is the slot of diagonal nd-1, b2 of diagonal nd-2 (which holds the M of nd-1)
@@ -331,7 +366,7 @@ void launch_band_fill(bool smalltab, int n_jobs, const DevJob *jobs, const int *
         const bool smalltab_job = m.fas <= STRIP_SMALL_FAS;
         if (smalltab_job)
             for (int e = 0; e < m.fas * m.fas; ++e) {
-                const double ls = (double)m.table[e];
+                const double ls = band_ls(m.table[e]);
                 sm.stab[e] = make_double2(__dadd_rn(k.lng2, ls), __dadd_rn(k.lng, ls));
             }
         band_init_corner(sm, J, g_geo, g_roff, P8);
@@ -341,8 +376,8 @@ void launch_band_fill(bool smalltab, int n_jobs, const DevJob *jobs, const int *
             t.s = s; t.lo0 = g_geo[2 * s]; t.hi0 = g_geo[2 * s + 1]; t.lo1 = g_geo[2 * (s + 1)]; t.hi1 = g_geo[2 * (s + 1) + 1];
             t.b0 = b0; t.b1 = b1; t.b2 = b2;
             // staged as far ahead as the kernel's chunks may reach (the ring sizes are part of what is tested)
-            for (; fr < J.lx && fr <= t.hi0 + 68 + 32 + BAND_THREADS; ++fr) { sm.rstate[fr & BAND_RM] = l_state[fr]; sm.rroff[fr & BAND_RM] = g_roff[fr]; }
-            for (; fc <= J.ly && fc <= s + 66 + 32 + BAND_THREADS - t.lo0; ++fc) sm.cstate[fc & BAND_CM] = r_state[fc];
+            for (; fr < J.lx && fr <= t.hi0 + 68 + 32 + BAND_THREADS; ++fr) { if (fr > 0) sm.rstate[fr & BAND_RM] = l_state[fr]; sm.rroff[fr & BAND_RM] = g_roff[fr]; }
+            for (; fc < J.ly && fc <= s + 66 + 32 + BAND_THREADS - t.lo0; ++fc) if (fc > 0) sm.cstate[fc & BAND_CM] = r_state[fc];
             const bool bnd = t.lo0 <= 1 || t.hi0 >= J.lx - 1 || s - t.hi0 <= 1 || s - t.lo0 >= J.ly - 1;
             const int i_end = t.hi0 + 3 + 31;  // the last pass of the kernel runs all its lanes
             for (int i = i_end; i >= t.lo0 - 1; --i) {
