@@ -27,9 +27,10 @@
 
 namespace pg2 {
 
-constexpr int BAND_R = 512;   // row ring: rows live around a diagonal, rows staged ahead (BAND_MAX_DIAG + 100 < BAND_R)
+constexpr int BAND_R = 512;   // row ring: rows live around a diagonal, rows staged ahead (BAND_MAX_DIAG + 2 BAND_CHUNK + 8 + BAND_THREADS < BAND_R)
 constexpr int BAND_C = 1024;  // column ring
-constexpr int BAND_G = 128;   // geometry ring: diagonals s0-32 .. s0+95
+constexpr int BAND_G = 256;   // geometry ring: diagonals s0-48 .. s0+159
+constexpr int BAND_CHUNK = 48;  // steps between two staging points; a multiple of 3, so that the ring slots of a step are constants
 constexpr int BAND_RM = BAND_R - 1, BAND_CM = BAND_C - 1, BAND_GM = BAND_G - 1;
 constexpr int BAND_THREADS = 96;  // one warp per matrix: X, Y, M
 
@@ -208,41 +209,51 @@ __device__ __forceinline__ void band_cp8(void *dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-// The steps s_first .. s_last of one warp (ROLE 0 X, 1 Y, 2 M).  Straight-line code per step: the first pass of the warp over
-// the diagonal's rows, a rarely taken loop for diagonals longer than a warp, the CTA barrier, the ring rotation.  The
-// geometry of diagonal s + 2 is fetched at step s; the M warp fetches the substitution terms of its first pass one step ahead
-// (two dependent shared-memory loads that do not wait for the other warps' results).
+// One step of one warp (ROLE 0 X, 1 Y, 2 M); B0, B1, B2: the ring slots of diagonals s, s-1, s-2 -- constants, the step
+// loop is unrolled three times.  Straight-line code: the first pass of the warp over the diagonal's rows, a rarely taken loop
+// for diagonals longer than a warp, the CTA barrier.  The geometry of diagonal s + 2 is fetched at step s; the M warp fetches
+// the substitution terms of its first pass one step ahead (two dependent shared-memory loads that do not wait for the other
+// warps' results).
+template <int ROLE, bool SMALLTAB, bool BOUNDARY, int B0, int B1, int B2>
+__device__ __forceinline__ void band_step(const BandSm &sm, const BandConst &k, BandStep &t, int s, int lane, int &lo2, int &hi2,
+                                          double2 &sub_next, unsigned char *PQ) {
+    t.s = s; t.lo0 = t.lo1; t.hi0 = t.hi1; t.lo1 = lo2; t.hi1 = hi2;
+    lo2 = sm.geo[2 * ((s + 2) & BAND_GM)];
+    hi2 = sm.geo[2 * ((s + 2) & BAND_GM) + 1];
+    t.b0 = B0 * BAND_R; t.b1 = B1 * BAND_R; t.b2 = B2 * BAND_R;
+    const int i0 = t.lo0 - 1 + lane;
+    if (ROLE == 2) {
+        const double2 sub = sub_next;
+        sub_next = band_subst<SMALLTAB>(sm, k, s + 1, t.lo1 - 1 + lane);
+        band_m_cell(sm, t, i0, sub, PQ);
+    } else if (ROLE == 0) band_x_cell<BOUNDARY>(sm, k, t, i0, PQ);
+    else band_y_cell<BOUNDARY>(sm, k, t, i0, PQ);
+    if (t.hi0 - t.lo0 + 4 >= 32) {  // rows lo0-1 .. hi0+3 do not fit one pass
+        for (int i = i0 + 32; i <= t.hi0 + 3 + lane; i += 32) {
+            if (ROLE == 2) band_m_cell(sm, t, i, band_subst<SMALLTAB>(sm, k, s, i), PQ);
+            else if (ROLE == 0) band_x_cell<BOUNDARY>(sm, k, t, i, PQ);
+            else band_y_cell<BOUNDARY>(sm, k, t, i, PQ);
+        }
+    }
+    __syncthreads();
+}
+// the steps s_first .. s_first + n - 1 of a chunk; s_first = 1 (mod 3): step s writes slot s % 3
 template <int ROLE, bool SMALLTAB, bool BOUNDARY>
-__device__ __forceinline__ void band_run_chunk(const BandSm &sm, const BandConst &k, int s_first, int s_last, int lane, int &b0, int &b1,
-                                               int &b2, unsigned char *PQ) {
+__device__ __forceinline__ void band_run_chunk(const BandSm &sm, const BandConst &k, int s_first, int n, int lane, unsigned char *PQ) {
     BandStep t;
     t.lo1 = sm.geo[2 * (s_first & BAND_GM)];
     t.hi1 = sm.geo[2 * (s_first & BAND_GM) + 1];
     int lo2 = sm.geo[2 * ((s_first + 1) & BAND_GM)], hi2 = sm.geo[2 * ((s_first + 1) & BAND_GM) + 1];
     double2 sub_next = make_double2(0.0, 0.0);
     if (ROLE == 2) sub_next = band_subst<SMALLTAB>(sm, k, s_first, t.lo1 - 1 + lane);
-    for (int s = s_first; s <= s_last; ++s) {
-        t.s = s; t.lo0 = t.lo1; t.hi0 = t.hi1; t.lo1 = lo2; t.hi1 = hi2;
-        lo2 = sm.geo[2 * ((s + 2) & BAND_GM)];
-        hi2 = sm.geo[2 * ((s + 2) & BAND_GM) + 1];
-        t.b0 = b0; t.b1 = b1; t.b2 = b2;
-        const int i0 = t.lo0 - 1 + lane;
-        if (ROLE == 2) {
-            const double2 sub = sub_next;
-            sub_next = band_subst<SMALLTAB>(sm, k, s + 1, t.lo1 - 1 + lane);
-            band_m_cell(sm, t, i0, sub, PQ);
-        } else if (ROLE == 0) band_x_cell<BOUNDARY>(sm, k, t, i0, PQ);
-        else band_y_cell<BOUNDARY>(sm, k, t, i0, PQ);
-        if (t.hi0 - t.lo0 + 4 >= 32) {  // rows lo0-1 .. hi0+3 do not fit one pass
-            for (int i = i0 + 32; i <= t.hi0 + 3 + lane; i += 32) {
-                if (ROLE == 2) band_m_cell(sm, t, i, band_subst<SMALLTAB>(sm, k, s, i), PQ);
-                else if (ROLE == 0) band_x_cell<BOUNDARY>(sm, k, t, i, PQ);
-                else band_y_cell<BOUNDARY>(sm, k, t, i, PQ);
-            }
-        }
-        __syncthreads();
-        const int freed = b2; b2 = b1; b1 = b0; b0 = freed;
+    int s = s_first;
+    for (; n >= 3; n -= 3, s += 3) {
+        band_step<ROLE, SMALLTAB, BOUNDARY, 1, 0, 2>(sm, k, t, s, lane, lo2, hi2, sub_next, PQ);
+        band_step<ROLE, SMALLTAB, BOUNDARY, 2, 1, 0>(sm, k, t, s + 1, lane, lo2, hi2, sub_next, PQ);
+        band_step<ROLE, SMALLTAB, BOUNDARY, 0, 2, 1>(sm, k, t, s + 2, lane, lo2, hi2, sub_next, PQ);
     }
+    if (n >= 1) band_step<ROLE, SMALLTAB, BOUNDARY, 1, 0, 2>(sm, k, t, s, lane, lo2, hi2, sub_next, PQ);
+    if (n >= 2) band_step<ROLE, SMALLTAB, BOUNDARY, 2, 1, 0>(sm, k, t, s + 1, lane, lo2, hi2, sub_next, PQ);
 }
 
 template <bool SMALLTAB>
@@ -275,23 +286,23 @@ band_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
             const double ls = band_ls(m.table[e]);
             sm.stab[e] = make_double2(__dadd_rn(k.lng2, ls), __dadd_rn(k.lng, ls));
         }
-    // diagonals 0 .. 63 of the geometry
-    if (tid < 64 && tid < nd + 2) band_cp8(sm.geo + 2 * (tid & BAND_GM), g_geo + 2 * tid);
+    // the geometry of diagonals 0 .. 2 BAND_CHUNK + 15
+    for (int t = tid; t < 2 * BAND_CHUNK + 16 && t < nd + 2; t += BAND_THREADS) band_cp8(sm.geo + 2 * (t & BAND_GM), g_geo + 2 * t);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (tid == 0) band_init_corner(sm, J, g_geo, g_roff, P8);
     int fr = 0, fc = 0;  // rows / columns staged so far
-    int b0 = BAND_R, b1 = 0, b2 = 2 * BAND_R;  // step 1 writes slot 1, diagonal 0 is slot 0, "diagonal -1" slot 2
-    for (int s0 = 0; s0 < nd; s0 += 32) {
+    // chunk c: steps s0 + 1 .. s0 + BAND_CHUNK, s0 = c BAND_CHUNK (the last step is nd - 1)
+    for (int s0 = 0; s0 + 1 < nd; s0 += BAND_CHUNK) {
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
-        // staging, two chunks ahead: the geometry of diagonals s0+64 .., the rows up to hi(s0) + 68, the columns up to
-        // s0 + 66 - lo(s0) (a diagonal moves its row range by at most one row per step)
+        // staging, two chunks ahead: the geometry of diagonals s0 + 2 CHUNK + 16 .., the rows up to hi(s0) + 2 CHUNK + 8, the
+        // columns up to s0 + 2 CHUNK + 8 - lo(s0) (a diagonal moves its row range by at most one row per step)
         const int lo_s0 = sm.geo[2 * (s0 & BAND_GM)], hi_s0 = sm.geo[2 * (s0 & BAND_GM) + 1];
         {
-            const int t = s0 + 64 + tid;
-            if (tid < 32 && t < nd + 2) band_cp8(sm.geo + 2 * (t & BAND_GM), g_geo + 2 * t);
-            const int row_target = hi_s0 + 68, col_target = s0 + 66 - lo_s0;
+            const int t = s0 + 2 * BAND_CHUNK + 16 + tid;
+            if (tid < BAND_CHUNK && t < nd + 2) band_cp8(sm.geo + 2 * (t & BAND_GM), g_geo + 2 * t);
+            const int row_target = hi_s0 + 2 * BAND_CHUNK + 8, col_target = s0 + 2 * BAND_CHUNK + 8 - lo_s0;
             for (; fr < row_target && fr < J.lx; fr += BAND_THREADS) {
                 const int i = fr + tid;
                 // (the start sites carry no state of the alphabet: row 0 and column 0 keep the ring's 0 -- their M is -inf whatever the term)
@@ -303,21 +314,22 @@ band_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
             }
             if (s0 == 0) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncthreads(); }
         }
-        const int s_first = s0 > 0 ? s0 : 1, s_last = min(s0 + 31, nd - 1);
+        const int s_first = s0 + 1, n = min(BAND_CHUNK, nd - 1 - s0), s_last = s0 + n;
         // a chunk that may touch row 0 / 1 / lx-1 or column 0 / 1 / ly-1 takes the bodies with the terminal terms (the row and
         // column ranges of a diagonal only move forward: the chunk's first and last step bound them)
         const int hi_end = sm.geo[2 * ((s_last + 1) & BAND_GM) + 1];
         const bool bnd = lo_s0 <= 1 || hi_end >= J.lx - 2 || s0 - hi_s0 <= 1 || s_last + 1 - lo_s0 >= J.ly - 2;
         if (role == 0) {
-            if (bnd) band_run_chunk<0, SMALLTAB, true>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
-            else band_run_chunk<0, SMALLTAB, false>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
+            if (bnd) band_run_chunk<0, SMALLTAB, true>(sm, k, s_first, n, lane, PQ);
+            else band_run_chunk<0, SMALLTAB, false>(sm, k, s_first, n, lane, PQ);
         } else if (role == 1) {
-            if (bnd) band_run_chunk<1, SMALLTAB, true>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
-            else band_run_chunk<1, SMALLTAB, false>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
-        } else band_run_chunk<2, SMALLTAB, false>(sm, k, s_first, s_last, lane, b0, b1, b2, PQ);
+            if (bnd) band_run_chunk<1, SMALLTAB, true>(sm, k, s_first, n, lane, PQ);
+            else band_run_chunk<1, SMALLTAB, false>(sm, k, s_first, n, lane, PQ);
+        } else band_run_chunk<2, SMALLTAB, false>(sm, k, s_first, n, lane, PQ);
     }
     if (tid == 0) {
-        // after the last step b1 is the slot of diagonal nd-1, b2 of diagonal nd-2 (which holds the M of nd-1)
+        // diagonal nd-1 sits in slot (nd-1) % 3, diagonal nd-2 (which holds the M of nd-1) in slot (nd-2) % 3; "diagonal -1" in slot 2
+        const int b1 = ((nd - 1) % 3) * BAND_R, b2 = ((nd + 1) % 3) * BAND_R;
         const int r = (J.lx - 1) & BAND_RM;
         const int lo = g_geo[2 * (nd - 1)], hi = g_geo[2 * (nd - 1) + 1];
         double X = ninf, Y = ninf, M = ninf;
@@ -376,8 +388,8 @@ void launch_band_fill(bool smalltab, int n_jobs, const DevJob *jobs, const int *
             t.s = s; t.lo0 = g_geo[2 * s]; t.hi0 = g_geo[2 * s + 1]; t.lo1 = g_geo[2 * (s + 1)]; t.hi1 = g_geo[2 * (s + 1) + 1];
             t.b0 = b0; t.b1 = b1; t.b2 = b2;
             // staged as far ahead as the kernel's chunks may reach (the ring sizes are part of what is tested)
-            for (; fr < J.lx && fr <= t.hi0 + 68 + 32 + BAND_THREADS; ++fr) { if (fr > 0) sm.rstate[fr & BAND_RM] = l_state[fr]; sm.rroff[fr & BAND_RM] = g_roff[fr]; }
-            for (; fc < J.ly && fc <= s + 66 + 32 + BAND_THREADS - t.lo0; ++fc) if (fc > 0) sm.cstate[fc & BAND_CM] = r_state[fc];
+            for (; fr < J.lx && fr <= t.hi0 + 2 * BAND_CHUNK + 8 + BAND_THREADS; ++fr) { if (fr > 0) sm.rstate[fr & BAND_RM] = l_state[fr]; sm.rroff[fr & BAND_RM] = g_roff[fr]; }
+            for (; fc < J.ly && fc <= s + 2 * BAND_CHUNK + 8 + BAND_THREADS - t.lo0; ++fc) if (fc > 0) sm.cstate[fc & BAND_CM] = r_state[fc];
             const bool bnd = t.lo0 <= 1 || t.hi0 >= J.lx - 1 || s - t.hi0 <= 1 || s - t.lo0 >= J.ly - 1;
             const int i_end = t.hi0 + 3 + 31;  // the last pass of the kernel runs all its lanes
             for (int i = i_end; i >= t.lo0 - 1; --i) {

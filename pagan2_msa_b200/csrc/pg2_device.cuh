@@ -91,7 +91,7 @@ struct DevJob {
 };
 
 constexpr int BAND_SEG = 256;       // diagonals per walk segment of the band kernel
-constexpr int BAND_MAX_DIAG = 400;  // longest anti-diagonal the band kernel's row ring takes (pg2_band.cu: BAND_R)
+constexpr int BAND_MAX_DIAG = 300;  // longest anti-diagonal the band kernel's row ring takes (pg2_band.cu: BAND_R, staging reach)
 
 // Lane kernel work item: up to 32 alignments that share the LEFT (row) graph, model and flags; every right
 // graph is a plain chain.  One warp takes one task, one alignment per lane.

@@ -33,7 +33,7 @@ void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_c
 void launch_expand_implicit(int n_graphs, const DevGraph *graphs, int *d_off, int *d_estart, float *d_elogw, cudaStream_t stream);
 void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
                      const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
-                     DevResult *results, cudaStream_t stream);
+                     DevResult *results, bool few_long, cudaStream_t stream);
 void launch_compact_steps(int n_jobs, const DevJob *jobs, const DevResult *results, long long *block_scratch, long long *total,
                           const unsigned short *steps_in, unsigned short *steps_out, cudaStream_t stream);
 void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
@@ -158,6 +158,7 @@ struct pg2_batch {
     long long total_steps = 0;
     long long total_cells = 0;
     long long n_bcand = 0, n_bact = 0;  // band kernel: walk candidate records / segment records of the batch
+    bool few_long = false;              // at most a few thousand graphs, some of them long: validation takes a CTA per graph
     long long h2d_bytes = 0;
     size_t n_off_total = 0, n_edge_total = 0;  // device sizes of d_off / d_estart (staged explicit graphs + implicit chains)
     bool uploaded = false, ran = false, fetch_enqueued = false;
@@ -1018,6 +1019,11 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     }
     b->total_steps = step_base;
     b->n_graphs = (int)b->graphs.size();
+    if (b->graphs.size() <= 4096 && n_jobs <= 4096) {
+        int longest = 0;
+        for (const DevGraph &g : b->graphs) longest = std::max(longest, g.n_sites);
+        b->few_long = longest >= 2048;
+    }
 
     timer.lap("5 bands, kernels, row programs");
     // ---- lane kernel tasks: strip-eligible jobs that share the row graph, model and flags, 32 per warp ----
@@ -1375,7 +1381,7 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
 
     CU(cudaEventRecord(c->ev[7], c->stream));
     launch_validate(b->n_graphs, b->n_jobs, c->d_graphs.p, c->d_jobs.p, c->d_models.p, c->d_state.p, c->d_off.p, c->d_estart.p,
-                    c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, c->stream);
+                    c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, b->few_long, c->stream);
     st.fill_ms = st.traceback_ms = 0;
     st.fill_launches = st.traceback_launches = 0;
     st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = st.jobs_pstrip = st.jobs_band = 0;

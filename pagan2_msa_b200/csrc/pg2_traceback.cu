@@ -562,11 +562,51 @@ void launch_expand_implicit(int n_graphs, const DevGraph *graphs, int *d_off, in
 #endif
 }
 
+#ifndef PG2_HOST_EMU
+// the same checks with a whole CTA per graph / job: a launch batch of a few long graphs (a guide-tree wave of 200 kb
+// sequences) would otherwise wait for one warp per graph to stride over 200 000 sites (6.6 + 3 ms per 16 alignments)
+__global__ void __launch_bounds__(256) validate_graphs_cta_kernel(int n_graphs, DevGraph *graphs, const int *d_state, const int *d_off,
+                                                                  const int *d_estart, int *graph_status) {
+    __shared__ int s_maxdeg;
+    const int g = blockIdx.x;
+    if (threadIdx.x == 0) s_maxdeg = 0;
+    __syncthreads();
+    int bad, maxdeg, simple;
+    check_graph_lane(graphs[g], d_off, d_estart, threadIdx.x, blockDim.x, bad, maxdeg, simple);
+    atomicMax(&s_maxdeg, maxdeg);
+    bad = __syncthreads_or(bad);
+    simple = __syncthreads_and(simple);
+    if (threadIdx.x == 0) finish_graph(graphs, graph_status, g, bad, s_maxdeg, simple);
+}
+__global__ void __launch_bounds__(256) validate_jobs_cta_kernel(int n_jobs, const DevJob *jobs, const DevGraph *graphs, const DevModel *models,
+                                                                const int *graph_status, const int *d_state, const int *d_blo,
+                                                                const int *d_bhi, DevResult *results) {
+    const int jid = blockIdx.x;
+    const DevJob J = jobs[jid];
+    int status = JOB_OK;
+    const int gs_l = graph_status[J.left], gs_r = graph_status[J.right];
+    if (gs_l != JOB_OK) status = gs_l;
+    else if (gs_r != JOB_OK) status = gs_r;
+    const int bad_state = __syncthreads_or(status == JOB_OK ? check_states_lane(J, graphs, models, d_state, threadIdx.x, blockDim.x) : 0);
+    if (status == JOB_OK && bad_state) status = JOB_BAD_GRAPH;
+    const int bad_band = __syncthreads_or((status == JOB_OK && J.banded) ? check_band_lane(J, d_blo, d_bhi, threadIdx.x, blockDim.x) : 0);
+    if (status == JOB_OK && bad_band) status = JOB_BAD_BAND;
+    if (threadIdx.x == 0) finish_job(results, jid, status);
+}
+#endif
+
+// few_long: the batch holds at most a few thousand graphs and some of them are long -- a CTA per graph / job
 void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
                      const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
-                     DevResult *results, cudaStream_t stream) {
+                     DevResult *results, bool few_long, cudaStream_t stream) {
 #ifndef PG2_HOST_EMU
     const int warps = 8;
+    if (few_long) {
+        if (n_graphs > 0) validate_graphs_cta_kernel<<<n_graphs, 256, 0, stream>>>(n_graphs, graphs, d_state, d_off, d_estart, graph_status);
+        if (n_jobs > 0)
+            validate_jobs_cta_kernel<<<n_jobs, 256, 0, stream>>>(n_jobs, jobs, graphs, models, graph_status, d_state, d_blo, d_bhi, results);
+        return;
+    }
     if (n_graphs > 0)
         validate_graphs_kernel<<<(n_graphs + warps - 1) / warps, warps * 32, 0, stream>>>(n_graphs, graphs, d_state, d_off, d_estart,
                                                                                          graph_status);
