@@ -23,14 +23,16 @@ def eng():
 
 @pytest.fixture(scope="module")
 def eng_old():
-    """Without the pipelined-strip kernel (strip + wavefront kernels only)."""
+    """Without the pipelined-strip and band kernels (strip + wavefront kernels only)."""
     import os
 
     os.environ["PG2_NO_PSTRIP"] = "1"
+    os.environ["PG2_NO_BAND"] = "1"
     try:
         e = engine.Engine(0)
     finally:
         os.environ.pop("PG2_NO_PSTRIP", None)
+        os.environ.pop("PG2_NO_BAND", None)
     yield e
     e.close()
 
@@ -75,7 +77,8 @@ def indel_copy(a, rng, sub, n_indels, max_len):
 
 
 def test_config5_anchored_200kb(eng, eng_old, eng_ps, golden):
-    """configs[4]: one 200 kb x 200 kb alignment inside an anchor band (banded wavefront kernel, 10 M in-band cells)."""
+    """configs[4]: one 200 kb x 200 kb alignment inside an anchor band (10 M in-band cells): the band kernel, the pipelined
+    strips, and the wavefront kernel's chain path."""
     rng = np.random.default_rng(5005)
     model = golden["anchored"][0].model
     a = rng.integers(0, 4, size=200000).astype(np.int32)
@@ -92,7 +95,7 @@ def test_config5_anchored_200kb(eng, eng_old, eng_ps, golden):
     assert 9_000_000 < job.cells < 12_000_000
     job = enginecheck.expect_from_oracle(job)
     res = enginecheck.check_batch(eng, [job])
-    assert res["kernel"][0] == 0 and res["status"][0] == 0
+    assert res["kernel"][0] == 4 and res["status"][0] == 0
     res = enginecheck.check_batch(eng_ps, [job])
     assert res["kernel"][0] == 3 and res["status"][0] == 0
     res = enginecheck.check_batch(eng_old, [job])
