@@ -9,13 +9,13 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
-#include <memory>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -839,7 +839,7 @@ void placement_end() {
 namespace {
 struct Model_cache {
     std::mutex m;
-    std::map<std::pair<Model_factory *, uint64_t>, Evol_model *> models;
+    std::map<std::pair<Model_factory *, uint64_t>, std::shared_ptr<Evol_model>> models;
     size_t bytes = 0;
 } g_model_cache;
 
@@ -882,26 +882,30 @@ static Evol_model clone_cached_model(Model_factory *mf, double distance, Evol_mo
     uint64_t bits;
     memcpy(&bits, &distance, 8);
     const std::pair<Model_factory *, uint64_t> key(mf, bits);
-    std::lock_guard<std::mutex> lk(g_model_cache.m);
-    auto it = g_model_cache.models.find(key);
-    if (it == g_model_cache.models.end()) {
-        Evol_model built = build(mf, distance);  // (as the reference's callers take it)
-        Evol_model *master = new Evol_model(built.data_type, built.distance);
-        copy_model(built, *master);
-        const size_t b = model_bytes(*master);
-        if (g_model_cache.bytes + b > ((size_t)2 << 30)) {  // bounded: a tree of distinct branch lengths gains nothing from the cache
-            for (auto &kv : g_model_cache.models) delete kv.second;
-            g_model_cache.models.clear();
-            g_model_cache.bytes = 0;
+    // the lookup (and a first build) under the lock; the copy -- 71 MB of tables for codon models -- outside it, so that the
+    // host threads of a wave copy side by side (the master stays alive through the shared pointer if the cache is emptied)
+    std::shared_ptr<Evol_model> master;
+    {
+        std::lock_guard<std::mutex> lk(g_model_cache.m);
+        auto it = g_model_cache.models.find(key);
+        if (it == g_model_cache.models.end()) {
+            Evol_model built = build(mf, distance);  // (as the reference's callers take it)
+            master = std::make_shared<Evol_model>(built.data_type, built.distance);
+            copy_model(built, *master);
+            const size_t b = model_bytes(*master);
+            if (g_model_cache.bytes + b > ((size_t)2 << 30)) {  // bounded: a tree of distinct branch lengths gains nothing from the cache
+                g_model_cache.models.clear();
+                g_model_cache.bytes = 0;
+            }
+            g_model_cache.bytes += b;
+            g_model_cache.models.emplace(key, master);
+        } else {
+            master = it->second;
+            engine().totals.model_cache_hits++;
         }
-        g_model_cache.bytes += b;
-        it = g_model_cache.models.emplace(key, master).first;
-    } else {
-        engine().totals.model_cache_hits++;
     }
-    const Evol_model &src = *it->second;
-    Evol_model out(src.data_type, src.distance);
-    copy_model(src, out);
+    Evol_model out(master->data_type, master->distance);
+    copy_model(*master, out);
     return out;
 }
 
