@@ -19,14 +19,22 @@
 
 namespace pg2 {
 
-constexpr int WAVE_RING_MAX = 2816;  // longest diagonal the shared-memory ring takes: 9 doubles per cell, 198 KB
+constexpr int WAVE_RING_MAX = 2816;      // longest diagonal the shared-memory ring takes: 3 slots x 3 doubles per cell, 198 KB
+constexpr int WAVE_RING_DOUBLES = 25344;  // the ring's budget: 198 KB of doubles
+constexpr int WAVE_RING_DEPTH_MAX = 64;
 
-// scores of diagonals s, s-1, s-2 in shared memory: buf[slot][X,Y,M][cap]
+// scores of the last `depth` diagonals in shared memory: buf[slot][X,Y,M][cap].  Depth 3 serves the predecessors of plain
+// sites; a job with short diagonals gets as many slots as the budget holds (a 400-column read graph: 21), so that the
+// sources of multi-edge sites -- cell (p, q) with s - (p + q) < depth, i.e. every edge pair whose spans add up to less than
+// the depth -- come from shared memory as well instead of the L2-resident scratch (the pileup step on this kernel: 23.6 ->
+// 19.5 ms; what remains is the divergent edge-pair loops of one SM's warps).
 struct WaveRing {
     double *buf;         // nullptr: the diagonals of this job do not fit; every read goes to the global scratch
+    int *range;          // [depth][2] first / last row held by every slot (last < first: the slot holds no diagonal)
     int cap;             // cells per diagonal the ring holds
-    int s;               // diagonal being computed; cells on s-1 and s-2 are served from the ring
-    int off0, off1, off2;  // offsets (in doubles) of the ring slots of diagonals s, s-1, s-2; they rotate, nothing is recomputed
+    int depth, cur;      // slots; slot of the diagonal being computed (diagonal s - d sits d slots before it, cyclically)
+    int s;               // diagonal being computed
+    int off0, off1, off2;  // offsets (in doubles) of the ring slots of diagonals s, s-1, s-2
     int lo0, lo1, hi1, lo2, hi2;  // first row of diagonal s; row ranges of diagonals s-1 and s-2
     bool global_scores;  // false: both graphs are plain chains, the global scratch is never read
 };
@@ -70,6 +78,17 @@ __device__ __forceinline__ double4 load_cell(const WaveCtx &c, int p, int q) {
                 return make_double4(ninf, ninf, ninf, 0.0);
             }
             const double *b = c.ring.buf + (ds == 1 ? c.ring.off1 : c.ring.off2) + (p - lo);
+            return make_double4(b[0], b[c.ring.cap], b[2 * c.ring.cap], 0.0);
+        }
+        if (ds > 2 && ds < c.ring.depth) {  // an older diagonal the ring still holds
+            int slot = c.ring.cur - ds;
+            if (slot < 0) slot += c.ring.depth;
+            const int lo = c.ring.range[2 * slot], hi = c.ring.range[2 * slot + 1];
+            if (p < lo || p > hi) {
+                double ninf = neg_inf();
+                return make_double4(ninf, ninf, ninf, 0.0);
+            }
+            const double *b = c.ring.buf + slot * 3 * c.ring.cap + (p - lo);
             return make_double4(b[0], b[c.ring.cap], b[2 * c.ring.cap], 0.0);
         }
     }
@@ -195,14 +214,22 @@ __device__ __forceinline__ void make_wave_ctx(WaveCtx &c, const DevJob &J, const
     c.doff = c.banded ? d_doff + J.diag_base : nullptr;
     c.scores = scores + J.cell_base;
     c.ring.buf = nullptr;
+    c.ring.range = nullptr;
     c.ring.cap = 0;
+    c.ring.depth = 3;
+    c.ring.cur = 1;
     c.ring.global_scores = true;
     c.two_pass = false;
     c.chain_job = false;
 }
 
 // the ring holds this job's diagonals: serve near reads from it; plain chains on both sides never read the scratch
-__device__ __forceinline__ void wave_use_ring(WaveCtx &c, double *buf, int cap, const DevGraph &GL, const DevGraph &GR,
+// slots the ring of a launch group gets: as many as the budget holds, at least the three the plain predecessors need
+__host__ __device__ inline int wave_ring_depth(int cap) {
+    const int d = WAVE_RING_DOUBLES / (3 * (cap > 0 ? cap : 1));
+    return d < 3 ? 3 : (d > WAVE_RING_DEPTH_MAX ? WAVE_RING_DEPTH_MAX : d);
+}
+__device__ __forceinline__ void wave_use_ring(WaveCtx &c, double *buf, int *range, int cap, int depth, const DevGraph &GL, const DevGraph &GR,
                                               const int *d_vlast) {
     // two passes pay when the listed sites are a handful (plain leaves inside an anchor band): the general body's
     // latency is then off the diagonal's critical path; with a few per cent of listed sites the single pass is faster
@@ -215,24 +242,30 @@ __device__ __forceinline__ void wave_use_ring(WaveCtx &c, double *buf, int cap, 
         c.cur_l = c.cur_r = 0;
     }
     c.ring.buf = buf;
+    c.ring.range = range;
     c.ring.cap = cap;
+    c.ring.depth = depth;
     c.ring.global_scores = !(GL.simple && GR.simple);
     c.ring.lo1 = 0; c.ring.hi1 = 0;   // diagonal 0 is the start corner
     c.ring.lo2 = 0; c.ring.hi2 = -1;  // there is no diagonal -1
-    // the first diagonal computed is s = 1: it goes to slot 1, diagonal 0 sits in slot 0, slot 2 is free
-    c.ring.off0 = 3 * cap; c.ring.off1 = 0; c.ring.off2 = 6 * cap;
+    // the first diagonal computed is s = 1: it goes to slot 1, diagonal 0 sits in slot 0, "diagonal -1" in the last slot
+    c.ring.cur = 1;
+    c.ring.off0 = 3 * cap; c.ring.off1 = 0; c.ring.off2 = (depth - 1) * 3 * cap;
 }
-__device__ __forceinline__ void wave_ring_begin(WaveCtx &c, int s, int ilo) {
+// `writer`: the one thread that records the diagonal's row range for the reads of later diagonals (they see it after this
+// diagonal's barrier; the slot's previous tenant, diagonal s - depth, is out of every reader's reach)
+__device__ __forceinline__ void wave_ring_begin(WaveCtx &c, int s, int ilo, int ihi, bool writer) {
     c.ring.s = s;
     c.ring.lo0 = ilo;
+    if (writer && c.ring.range) { c.ring.range[2 * c.ring.cur] = ilo; c.ring.range[2 * c.ring.cur + 1] = ihi; }
 }
 __device__ __forceinline__ void wave_ring_end(WaveCtx &c, int ilo, int ihi) {
     c.ring.lo2 = c.ring.lo1; c.ring.hi2 = c.ring.hi1;
     c.ring.lo1 = ilo; c.ring.hi1 = ihi;
-    const int freed = c.ring.off2;  // the slot of diagonal s-2 takes diagonal s+1
+    c.ring.cur = c.ring.cur + 1 == c.ring.depth ? 0 : c.ring.cur + 1;
     c.ring.off2 = c.ring.off1;
     c.ring.off1 = c.ring.off0;
-    c.ring.off0 = freed;
+    c.ring.off0 = c.ring.cur * 3 * c.ring.cap;
 }
 
 // initialise_array_corner (:725-733)
@@ -241,7 +274,10 @@ __device__ __forceinline__ void wave_init(const WaveCtx &c, unsigned *P) {
     double2 *s0 = reinterpret_cast<double2 *>(c.scores);
     s0[0] = make_double2(ninf, ninf);
     s0[1] = make_double2(0.0, 0.0);
-    if (c.ring.buf) { c.ring.buf[0] = ninf; c.ring.buf[c.ring.cap] = ninf; c.ring.buf[2 * c.ring.cap] = 0.0; }  // slot 0 = diagonal 0
+    if (c.ring.buf) {  // slot 0 = diagonal 0; the other slots hold nothing yet
+        c.ring.buf[0] = ninf; c.ring.buf[c.ring.cap] = ninf; c.ring.buf[2 * c.ring.cap] = 0.0;
+        for (int d = 0; d < c.ring.depth; ++d) { c.ring.range[2 * d] = 0; c.ring.range[2 * d + 1] = d == 0 ? 0 : -1; }
+    }
     P[0] = cell_word(NO_MAT, NO_MAT, NO_MAT);
 }
 
@@ -418,7 +454,7 @@ __global__ void __launch_bounds__(1024, 1)
 wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models, const int *d_state,
                       const int *d_off, const int *d_estart, const float *d_elogw, const int *d_blo, const int *d_bhi,
                       const int *d_dlo, const long long *d_doff, const int *d_vlast, double4 *scores, unsigned *ptrs, DevResult *results,
-                      int ring_cap) {
+                      int ring_cap, int ring_depth) {
     extern __shared__ __align__(16) double wave_smem[];
     const int jid = job_ids[blockIdx.x];
     const DevJob &J = jobs[jid];
@@ -428,7 +464,7 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
     const DevModel m = models[J.model];
     WaveCtx c;
     make_wave_ctx(c, J, GL, GR, d_state, d_off, d_estart, d_elogw, d_blo, d_bhi, d_dlo, d_doff, scores);
-    if (ring_cap > 0) wave_use_ring(c, wave_smem, ring_cap, GL, GR, d_vlast);
+    if (ring_cap > 0) wave_use_ring(c, wave_smem, reinterpret_cast<int *>(wave_smem + (size_t)ring_depth * 3 * ring_cap), ring_cap, ring_depth, GL, GR, d_vlast);
     unsigned *P = ptrs + J.cell_base;
     const unsigned flags = J.flags;
     const float lng2 = __fmul_rn(2.0f, m.lng);  // 2*model->log_non_gap() stays float (:1364)
@@ -453,7 +489,7 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
                 const int s = s0 + d;
                 const int ilo = __shfl_sync(0xffffffffu, g_lo, d), ihi = __shfl_sync(0xffffffffu, g_hi, d);
                 const long long base = __shfl_sync(0xffffffffu, g_base, d);
-                wave_ring_begin(c, s, ilo);
+                wave_ring_begin(c, s, ilo, ihi, threadIdx.x == 0);
                 wave_chain_cell(c, m, flags, lng2, s, ilo, ihi, base, P, (int)threadIdx.x, track);
                 __syncthreads();
                 wave_ring_end(c, ilo, ihi);
@@ -464,12 +500,12 @@ wavefront_fill_kernel(const DevJob *jobs, const int *job_ids, const DevGraph *gr
         int ilo, ihi;
         long long base;
         diag_geometry(c, s, ilo, ihi, base);
-        wave_ring_begin(c, s, ilo);
+        wave_ring_begin(c, s, ilo, ihi, threadIdx.x == 0);
         wave_diagonal(c, m, flags, lng2, s, ilo, ihi, base, P, (int)threadIdx.x, (int)blockDim.x);
         __syncthreads();  // diagonal s is complete; the ring slot of diagonal s-2 may be overwritten
         wave_ring_end(c, ilo, ihi);
     }
-    wave_ring_begin(c, n_diag, 0);  // the end corner reads cells of the last two diagonals from the ring
+    wave_ring_begin(c, n_diag, 0, -1, false);  // the end corner reads the cells of the last diagonals from the ring
     if (threadIdx.x == 0) end_corner(c, m, res);
 }
 #endif
@@ -481,11 +517,12 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
     if (n_jobs <= 0) return;
     // ring of three diagonals x {X,Y,M} in shared memory when the group's longest diagonal fits
     const int ring_cap = max_diag <= WAVE_RING_MAX ? (max_diag > 0 ? max_diag : 1) : 0;
+    const int ring_depth = wave_ring_depth(ring_cap);
 #ifndef PG2_HOST_EMU
-    const int smem = ring_cap * 9 * (int)sizeof(double);
+    const int smem = ring_cap > 0 ? ring_cap * 3 * ring_depth * (int)sizeof(double) + 2 * ring_depth * (int)sizeof(int) : 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(wavefront_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     wavefront_fill_kernel<<<n_jobs, threads, smem, stream>>>(jobs, job_ids, graphs, models, d_state, d_off, d_estart, d_elogw, d_blo,
-                                                             d_bhi, d_dlo, d_doff, d_vlast, scores, ptrs, results, ring_cap);
+                                                             d_bhi, d_dlo, d_doff, d_vlast, scores, ptrs, results, ring_cap, ring_depth);
 #else
     // CPU test emulation: anti-diagonals in order, cells of one diagonal in any order
     (void)threads; (void)stream;
@@ -498,8 +535,9 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
         const DevModel m = models[J.model];
         WaveCtx c;
         make_wave_ctx(c, J, GL, GR, d_state, d_off, d_estart, d_elogw, d_blo, d_bhi, d_dlo, d_doff, scores);
-        std::vector<double> ring((size_t)ring_cap * 9 + 1);
-        if (ring_cap > 0) wave_use_ring(c, ring.data(), ring_cap, GL, GR, d_vlast);
+        std::vector<double> ring((size_t)ring_cap * 3 * ring_depth + 1);
+        std::vector<int> ring_range((size_t)2 * ring_depth);
+        if (ring_cap > 0) wave_use_ring(c, ring.data(), ring_range.data(), ring_cap, ring_depth, GL, GR, d_vlast);
         unsigned *P = ptrs + J.cell_base;
         const float lng2 = __fmul_rn(2.0f, m.lng);
         wave_init(c, P);
@@ -515,7 +553,7 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
                 int ilo, ihi;
                 long long base;
                 diag_geometry(c, s, ilo, ihi, base);
-                wave_ring_begin(c, s, ilo);
+                wave_ring_begin(c, s, ilo, ihi, true);
                 for (int tid = emu_threads - 1; tid >= 0; --tid) wave_chain_cell(c, m, J.flags, lng2, s, ilo, ihi, base, P, tid, track[(size_t)tid]);
                 wave_ring_end(c, ilo, ihi);
             }
@@ -524,12 +562,12 @@ void launch_wavefront_fill(int n_jobs, int threads, const DevJob *jobs, const in
             int ilo, ihi;
             long long base;
             diag_geometry(c, s, ilo, ihi, base);
-            wave_ring_begin(c, s, ilo);
+            wave_ring_begin(c, s, ilo, ihi, true);
             // a handful of emulated threads, last first: the shares of a diagonal are independent of each other
             for (int tid = 4; tid >= 0; --tid) wave_diagonal(c, m, J.flags, lng2, s, ilo, ihi, base, P, tid, 5);
             wave_ring_end(c, ilo, ihi);
         }
-        wave_ring_begin(c, n_diag, 0);
+        wave_ring_begin(c, n_diag, 0, -1, false);
         end_corner(c, m, res);
     }
 #endif
