@@ -210,7 +210,7 @@ typedef struct pg2_stats {
     int32_t jobs_lanes;        /* jobs the lane-per-alignment kernel took (shared row graph) */
     int32_t jobs_pstrip;       /* jobs the pipelined-strip kernel took (CTA per alignment: general x general, banded, small waves) */
     int32_t jobs_band;         /* jobs the band kernel took (warp per anchored alignment of two plain chains) */
-    int32_t reserved0;
+    int32_t jobs_pstrip_ring;  /* ... of the pipelined-strip jobs, those that ran with the shared-memory row ring */
 } pg2_stats;
 int pg2_get_stats(pg2_ctx *ctx, pg2_stats *out);
 

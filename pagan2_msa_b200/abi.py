@@ -114,7 +114,7 @@ class Stats(C.Structure):
         ("jobs_lanes", C.c_int32),
         ("jobs_pstrip", C.c_int32),
         ("jobs_band", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("jobs_pstrip_ring", C.c_int32),
     ]
 
 

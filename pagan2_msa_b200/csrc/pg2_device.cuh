@@ -54,6 +54,8 @@ struct DevGraph {
     int cp_n_blocks;
     int cp_k;        // columns per lane the program was cut for (0: the graph cannot be a pstrip column graph)
     int cp_park;     // parked columns of the block that has most of them (sizes the kernel's shared-memory history)
+    int max_span;    // longest edge into a DP site (site - start site); 1 for plain chains (host, classify_graph)
+    int n_extra;     // backward edges beyond one per site (host, classify_graph): how far the graph is from a chain
 };
 
 struct DevModel {

@@ -24,12 +24,12 @@
 #include "pg2_pstrip_geom.cuh"
 
 namespace pg2 {
-int pstrip_warps(int n_blocks, int park_cap, bool smalltab);
+int pstrip_warps(int n_blocks, int park_cap, bool smalltab, int rr);
 long long pstrip_cta_double4(int K, int nw, int max_lx, int ring, int max_slots);
 void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_clusters, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                         const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                         const int4 *d_vrow, const int *d_vlast, const int *d_blo, const int *d_bhi, unsigned *ptrs, DevResult *results,
-                        double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int *queue, cudaStream_t stream);
+                        double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int rr, int *queue, cudaStream_t stream);
 void launch_expand_implicit(int n_graphs, const DevGraph *graphs, int *d_off, int *d_estart, float *d_elogw, cudaStream_t stream);
 void launch_validate(int n_graphs, int n_jobs, DevGraph *graphs, const DevJob *jobs, const DevModel *models, const int *d_state,
                      const int *d_off, const int *d_estart, const int *d_blo, const int *d_bhi, int *graph_status,
@@ -131,6 +131,12 @@ struct ModelRec {
     DevModel dev;
 };
 
+// pipelined strips: rows of the shared-memory row ring a launch group runs with (bits 2-3 of strip_general; 0: parked rows)
+static inline int ps_ring_rows(int strip_general) {
+    const int tier = (strip_general >> 2) & 7;
+    return tier == 0 ? 0 : (4 << tier);  // 8, 16, 32, 64, 128
+}
+
 struct Group {
     int kernel;        // 0 wavefront, 1 strip, 2 lanes
     int variant = 0;   // lane kernel: template variant shared by the group's tasks
@@ -180,6 +186,8 @@ struct pg2_ctx {
     bool no_lanes = false;         // PG2_NO_LANES=1: keep shared-target jobs on the warp-per-alignment strip kernel (tests)
     bool no_pstrip = false;        // PG2_NO_PSTRIP=1: never use the pipelined-strip kernel (tests: the older kernels stay covered)
     bool pstrip_banded_chains = false;
+    bool force_psring = false;     // PG2_FORCE_PSRING=1: the row-ring step for every eligible job, chains too (tests)
+    bool no_psring = false;        // PG2_NO_PSRING=1: the pipelined strips keep parked rows in global memory (the older step body; tests)
     bool no_band = false;          // PG2_NO_BAND=1: banded chain x chain jobs stay on the wavefront kernel's chain path (tests)
     int pstrip_cluster_max = 8;     // CTAs (SMs) one pipelined-strip alignment may be spread over (PG2_PSTRIP_CLUSTER; 1 = one CTA per job)  // PG2_PSTRIP_BANDED_CHAINS=1: banded chain x chain jobs too (tests)
     int pstrip_max_jobs = 600;     // strip-eligible jobs of a batch go to the pipelined-strip kernel when there are at most this
@@ -267,6 +275,10 @@ extern "C" int pg2_ctx_create(int device, pg2_ctx **out) {
     c->no_pstrip = nps && atoi(nps) != 0;
     const char *pbc = getenv("PG2_PSTRIP_BANDED_CHAINS");
     c->pstrip_banded_chains = pbc && atoi(pbc) != 0;
+    const char *npr = getenv("PG2_NO_PSRING");
+    c->no_psring = npr && atoi(npr) != 0;
+    const char *fpr = getenv("PG2_FORCE_PSRING");
+    c->force_psring = fpr && atoi(fpr) != 0;
     const char *nb = getenv("PG2_NO_BAND");
     c->no_band = nb && atoi(nb) != 0;
     const char *pcl = getenv("PG2_PSTRIP_CLUSTER");
@@ -410,6 +422,8 @@ static void classify_graph(DevGraph &dg, const pg2_graph &g) {
     const int n_edges = g.n_edges;
     const int *po = g.bwd_off, *pe = g.edge_start;
     const float *pw = g.edge_logw;
+    dg.max_span = 1;
+    dg.n_extra = 0;
     if (!po) {  // compact form: the caller states that the graph is a plain unit-weight chain
         dg.max_indeg = 1;
         dg.simple = 1;
@@ -435,15 +449,21 @@ static void classify_graph(DevGraph &dg, const pg2_graph &g) {
             return;
         }
     }
-    int simple = 1, maxdeg = 0;
+    int simple = 1, maxdeg = 0, maxspan = 1;
     for (int s = 0; s < g.n_sites; s++) {
         int k0 = po[s], k1 = po[s + 1];
         if (k1 < k0 || k1 > n_edges || k0 < 0) { simple = 0; maxdeg = -1; break; }  // malformed: the device flags it
         int deg = k1 - k0;
         if (deg > maxdeg) maxdeg = deg;
-        if (s > 0 && (deg != 1 || pe[k0] != s - 1)) simple = 0;
+        if (s > 0 && (deg != 1 || pe[k0] != s - 1)) {
+            simple = 0;
+            if (s < g.n_sites - 1)  // (the stop site is no DP site: the end corner reads its sources from the end columns)
+                for (int k = k0; k < k1; k++) maxspan = std::max(maxspan, s - pe[k]);
+        }
         if (s == 0 && deg != 0) simple = 0;
     }
+    dg.max_span = maxspan;
+    dg.n_extra = std::max(0, n_edges - (g.n_sites - 1));
     dg.max_indeg = maxdeg;
     dg.simple = simple;
     dg.zero_w = 1;
@@ -849,6 +869,18 @@ static int try_pstrip(pg2_ctx *c, pg2_batch *b, DevJob &J) {
     J.kernel = 3;
     J.strip_k = K;
     J.strip_general = c->models[J.model].fas <= STRIP_SMALL_FAS ? 2 : 0;
+    // the row-ring step (pg2_pstrip.cu: ps_step_ring): the block's last 8 .. 128 rows in shared memory.  The ring must outlast
+    // the longest left edge plus the lanes the longest right edge reaches back (a lane is one virtual row ahead of the next)
+    // It pays where the graphs are general enough (measured: C1 / C4 ancestors with 5-10 % extra edges 7.1 -> 5.2 ms, the pileup
+    // step 15.4 -> 8.2 ms); on chains and near-chains (leaf pairs, 200 kb ancestors with 0.2 % extra edges) the register-resident
+    // row of ps_step is 10-25 % faster.
+    const bool general_enough = (long long)GL.n_extra * 100 >= GL.n_sites || (long long)GR.n_extra * 100 >= GR.n_sites;
+    if (K == 2 && !c->no_psring && (general_enough || c->force_psring)) {
+        const int need = GL.max_span + (GR.max_span + K - 1) / K + 4;
+        // tiers of 8, 16, 32, 64, 128 rows in bits 2-4 (128: one warp per CTA, 204 KB of ring -- the pileup root's longest edges)
+        for (int tier = 3; tier <= 5; tier++)  // (no tier below 32 rows: a smaller ring is no faster, and launch groups split by tier)
+            if (need <= (4 << tier)) { J.strip_general |= tier << 2; break; }
+    }
     J.n_blocks = nb;
     J.blk_base = blk_base;
     J.ps_ring = tallest;
@@ -1208,7 +1240,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
                 while (g.ps_ring < J.ps_ring) g.ps_ring <<= 1;
                 g.ps_park = std::max(g.ps_park, b->graphs[J.right].cp_park);
                 g.ps_blocks = std::max(g.ps_blocks, J.n_blocks);
-                g.ps_nw = pstrip_warps(g.ps_blocks, g.ps_park, (g.strip_general & 2) != 0);
+                g.ps_nw = pstrip_warps(g.ps_blocks, g.ps_park, (g.strip_general & 2) != 0, ps_ring_rows(g.strip_general));
             }
             g.count++;
             pos++;
@@ -1384,7 +1416,7 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                     c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, b->few_long, c->stream);
     st.fill_ms = st.traceback_ms = 0;
     st.fill_launches = st.traceback_launches = 0;
-    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = st.jobs_pstrip = st.jobs_band = 0;
+    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = st.jobs_pstrip = st.jobs_band = st.jobs_pstrip_ring = 0;
     st.jobs_strip_groups = 0;
     st.cells = b->total_cells;
     st.traceback_bytes = 0;
@@ -1406,8 +1438,10 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                 launch_pstrip_fill(g.strip_k, (g.strip_general & 2) != 0, sh.nw, sh.G, g.count, sh.clusters, c->d_jobs.p, ids, c->d_graphs.p,
                                    c->d_models.p, c->d_state.p, c->d_off.p, c->d_estart.p, c->d_elogw.p,
                                    reinterpret_cast<const int4 *>(c->d_vrow.p), c->d_vlast.p, c->d_blo.p, c->d_bhi.p, c->d_ptrps.p,
-                                   c->d_results.p, c->d_ps_scratch.p, g.max_lx, g.ps_ring, g.max_slots, g.ps_park, c->d_queue.p, c->stream);
+                                   c->d_results.p, c->d_ps_scratch.p, g.max_lx, g.ps_ring, g.max_slots, g.ps_park, ps_ring_rows(g.strip_general),
+                                   c->d_queue.p, c->stream);
                 st.jobs_pstrip += g.count;
+                if (g.strip_k == 2 && ps_ring_rows(g.strip_general) > 0) st.jobs_pstrip_ring += g.count;
                 st.traceback_bytes += g.cells * 4;
             } else if (g.kernel == 4) {
                 launch_band_fill((g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_band4.p,
@@ -1779,7 +1813,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
             const pg2_stats &st = f.ctx->stats;
             agg.h2d_bytes += st.h2d_bytes; agg.d2h_bytes += st.d2h_bytes; agg.cells += st.cells; agg.traceback_bytes += st.traceback_bytes;
             agg.fill_launches += st.fill_launches; agg.traceback_launches += st.traceback_launches; agg.kernel_launches += st.kernel_launches;
-            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes; agg.jobs_pstrip += st.jobs_pstrip; agg.jobs_band += st.jobs_band;
+            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes; agg.jobs_pstrip += st.jobs_pstrip; agg.jobs_band += st.jobs_band; agg.jobs_pstrip_ring += st.jobs_pstrip_ring;
             agg.jobs_strip_groups += st.jobs_strip_groups; agg.d2h_ms += st.d2h_ms;
         }
         pg2_batch_destroy(f.ctx, f.batch);

@@ -59,6 +59,10 @@ struct PsCtx {
     int park_cap;        // history slots per block (the launch group's largest block need)
     double4 *endstore;   // [PS_MAX_END][lx]
     int saved_stride;    // 1 + 32*K
+    // row ring (ps_step_ring): the last rr rows of the block in shared memory, [rr + 1][X,Y,M][K][33] doubles; entry l + 1 of a
+    // [k] line is lane l's column k, entry 0 of line K - 1 the column left of the block; row rr is the "no row" of -inf
+    double *rowring;
+    int rr;              // ring rows (a power of two), 0: the kernel runs ps_step (parked rows in global memory, column history)
 };
 
 // the three scalars every candidate needs, in registers (everything else of PsCtx is read from shared memory on demand)
@@ -298,6 +302,145 @@ __device__ __forceinline__ bool ps_step(const PsCtx &c, const PsHot &h3, PsLane<
     return true;
 }
 
+// ---- ps_step_ring: the same virtual row with every source row in shared memory -------------------------------------------
+// ps_step keeps the row above in registers and fetches any other source row (a long-span edge) from a parked copy in global
+// memory; the lanes of a warp are on 32 different rows, so on ancestor graphs almost every step runs the swap code for a few
+// lanes and the general-column loops for a few others (ncu, 1.2 k x 1.2 k root: 11.7 of 32 threads per instruction, 1 150
+// instructions per step).  Here the block keeps its last rr rows in a shared-memory ring: EVERY source cell -- (p, j) for X,
+// (p, j - 1) or (p, pr) for M, (i, pr) for the Y of a general column -- is one shared-memory load at an address computed from the
+// row program entry, whatever the edge; there is no swap, no parked row, no column history and no branch on the kind of row.
+// Hazards: lane l reads columns of lanes l' <= l; lane l' is l - l' virtual rows ahead and overwrites ring row (i' & (rr - 1)) as
+// it completes site i', so rr must exceed the longest left span plus the lane distance of the longest right span plus 2 (the
+// engine picks rr per launch group, try_pstrip).
+template <int K> __device__ __forceinline__ int ps_rr_index(int row, int mat, int k, int l1) { return ((row * 3 + mat) * K + k) * 33 + l1; }
+
+template <int K, bool SMALLTAB>
+__device__ __forceinline__ bool ps_step_ring(const PsCtx &c, const PsHot &h3, PsLane<K> &st, PsAcc<K> &acc, int lane, int4 vr,
+                                             double rX, double rY, double rM, unsigned *out) {
+    const double ninf = neg_inf();
+    const int info = vr.x, i = vr.z;
+    const int sl = info & VR_STATE_MASK;
+    const bool first = (info & VR_FIRST) != 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        acc.nX[k] = first ? ninf : acc.nX[k];
+        acc.nM[k] = first ? ninf : acc.nM[k];
+        acc.pX[k] = first ? (unsigned)NO_MAT : acc.pX[k];
+        acc.pM[k] = first ? (unsigned)NO_MAT : acc.pM[k];
+    }
+    const bool edge = !(info & VR_NOEDGE);
+    int p = i - 1;
+    if (edge && !(info & VR_REG)) p = c.l_estart[vr.y];
+    // a row above the block's first row lies outside the band for every column of the block (and for c0 - 1): the "no row"
+    const bool pvalid = edge && p >= c.i0;
+    const int rp = pvalid ? (p & (c.rr - 1)) : c.rr;
+    const double pen = ((h3.flags & PH_REDUCED) && p == 0) ? 0.0 : h3.open;  // get_log_gap_open_penalty (basic_alignment.h:490-513)
+    const double wl = (info & VR_ZERO_W) ? 0.0 : (double)c.l_elogw[edge ? vr.y : 0];
+    const unsigned lord = ((unsigned)vr.w >> 16) << 2;
+    const double *R = c.rowring;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        // X: ext, double, open out of (p, j) (:2116-2211)
+        const double sX = R[ps_rr_index<K>(rp, 0, k, lane + 1)], sY = R[ps_rr_index<K>(rp, 1, k, lane + 1)], sM = R[ps_rr_index<K>(rp, 2, k, lane + 1)];
+        ps_cand(__dadd_rn(sX, st.extX[k]), X_MAT | lord, acc.nX[k], acc.pX[k]);
+        ps_cand(__dadd_rn(sY, h3.open), Y_MAT | lord, acc.nX[k], acc.pX[k]);
+        ps_cand(__dadd_rn(__dadd_rn(sM, h3.lng), pen), M_MAT | lord, acc.nX[k], acc.pX[k]);
+        // M: from M, X, Y of (p, pr) for every backward edge pr -> j (:1353-1436, :2029-2112)
+        double mlog, xlog;
+        ps_subst<SMALLTAB>(c, h3, sl, st.colbase[k], mlog, xlog);
+        if (!(st.cinfo[k] & PC_GENERAL)) {
+            const int kk = k ? k - 1 : K - 1, l1 = k ? lane + 1 : lane;  // column j - 1: the lane's own, or the last one of the lane before
+            const double qX = R[ps_rr_index<K>(rp, 0, kk, l1)], qY = R[ps_rr_index<K>(rp, 1, kk, l1)], qM = R[ps_rr_index<K>(rp, 2, kk, l1)];
+            double a = __dadd_rn(qM, mlog), b = __dadd_rn(qX, xlog), d = __dadd_rn(qY, xlog);
+            if (h3.flags & PH_WEIGHTS) {
+                a = __dadd_rn(__dadd_rn(a, wl), st.wr[k]);
+                b = __dadd_rn(__dadd_rn(b, wl), st.wr[k]);
+                d = __dadd_rn(__dadd_rn(d, wl), st.wr[k]);
+            }
+            ps_cand(a, M_MAT | lord, acc.nM[k], acc.pM[k]);
+            ps_cand(b, X_MAT | lord, acc.nM[k], acc.pM[k]);
+            ps_cand(d, Y_MAT | lord, acc.nM[k], acc.pM[k]);
+        } else if (st.cinfo[k] >= 0 && edge) {
+            const int j = st.j0 + k, kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
+            for (int kr = kr0; kr < kr1; ++kr) {
+                const int cc = c.r_estart[kr] - c.c0;  // >= 0: blocks start at cut points of the column graph
+                const int kk = cc % K, l1 = cc / K + 1;
+                const double vx = R[ps_rr_index<K>(rp, 0, kk, l1)], vy = R[ps_rr_index<K>(rp, 1, kk, l1)], vm = R[ps_rr_index<K>(rp, 2, kk, l1)];
+                const double wrk = (double)c.r_elogw[kr];
+                const unsigned code = lord | ((unsigned)(kr - kr0) << 8);
+                ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vm, mlog), wl), wrk), M_MAT | code, acc.nM[k], acc.pM[k]);
+                ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vx, xlog), wl), wrk), X_MAT | code, acc.nM[k], acc.pM[k]);
+                ps_cand(__dadd_rn(__dadd_rn(__dadd_rn(vy, xlog), wl), wrk), Y_MAT | code, acc.nM[k], acc.pM[k]);
+            }
+        }
+    }
+    if (!(info & VR_LAST)) return false;
+
+    // ---- the site's last virtual row: Y chain along the strip, band mask, pointer words, the row goes into the ring ----
+    if (st.j0 == 0) {  // DP column 0 has no M; (0,0) is the start corner (:725-733, :956-969)
+        acc.nM[0] = (i == 0) ? 0.0 : ninf;
+        acc.pM[0] = NO_MAT;
+    }
+    const double extY = ((h3.flags & PH_TERM) && (i == 0 || i == h3.lx1)) ? c.end_ext : h3.ext;
+    int blo = 0, bhi = 0x7fffffff;
+    if (h3.flags & PH_BANDED) { blo = c.blo[i]; bhi = c.bhi[i]; }
+    const unsigned plain_row = ((info & VR_FAST) == VR_FAST && edge) ? PSW_PLAIN_ROW : 0u;
+    const int ri = i & (c.rr - 1);
+    double *W = c.rowring;
+    if (lane == 0) {  // the column left of the block, row i (rX, rY, rM: the boundary entry lane 0 fetched)
+        W[ps_rr_index<K>(ri, 0, K - 1, 0)] = rX; W[ps_rr_index<K>(ri, 1, K - 1, 0)] = rY; W[ps_rr_index<K>(ri, 2, K - 1, 0)] = rM;
+    }
+    // cell (i, j0 - 1): the lane to the left completed row i one step ago and left it in the ring -- no shuffle
+    rX = W[ps_rr_index<K>(ri, 0, K - 1, lane)]; rY = W[ps_rr_index<K>(ri, 1, K - 1, lane)]; rM = W[ps_rr_index<K>(ri, 2, K - 1, lane)];
+    double lXo = __dadd_rn(rX, h3.open), lMo = __dadd_rn(__dadd_rn(rM, h3.lng), h3.open), lY = rY;
+    if (st.j0 == 1 && i == 0 && (h3.flags & PH_REDUCED)) lMo = __dadd_rn(__dadd_rn(rM, h3.lng), 0.0);  // the neighbour is the start corner
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = st.j0 + k;
+        double ny;
+        unsigned py, plain_col = 0;
+        if (!(st.cinfo[k] & PC_GENERAL)) {
+            const bool p2 = lMo > lXo;
+            const double g = p2 ? lMo : lXo;
+            const double a = __dadd_rn(lY, extY);
+            const bool p1 = g > a;
+            ny = p1 ? g : a;
+            py = p1 ? (p2 ? (unsigned)M_MAT : (unsigned)X_MAT) : (unsigned)Y_MAT;
+            py = (ny == ninf) ? (unsigned)NO_MAT : py;  // no candidate: the cell keeps no pointer (it is never walked)
+            plain_col = j > 0 ? PSW_PLAIN_COL : 0u;
+        } else {
+            ny = ninf;
+            py = NO_MAT;
+            if (st.cinfo[k] >= 0) {
+                // Y of a general column: every backward edge pr -> j, sources (i, pr) from the ring (written by this lane a
+                // moment ago or by a lane to the left on an earlier step)
+                const int kr0 = c.r_off[j], kr1 = c.r_off[j + 1];
+                for (int kr = kr0; kr < kr1; ++kr) {
+                    const int pr = c.r_estart[kr], cc = pr - c.c0;
+                    const int kk = cc % K, l1 = cc / K + 1;
+                    const double vx = W[ps_rr_index<K>(ri, 0, kk, l1)], vy = W[ps_rr_index<K>(ri, 1, kk, l1)], vm = W[ps_rr_index<K>(ri, 2, kk, l1)];
+                    const double penY = ((h3.flags & PH_REDUCED) && pr == 0) ? 0.0 : h3.open;
+                    const unsigned ord = (unsigned)(kr - kr0) << 2;
+                    ps_cand(__dadd_rn(vy, extY), Y_MAT | ord, ny, py);
+                    ps_cand(__dadd_rn(vx, h3.open), X_MAT | ord, ny, py);
+                    ps_cand(__dadd_rn(__dadd_rn(vm, h3.lng), penY), M_MAT | ord, ny, py);
+                }
+            }
+        }
+        double nx = acc.nX[k], nm = acc.nM[k];
+        if (j < blo || j > bhi) { nx = ninf; ny = ninf; nm = ninf; }  // Tunnel_slice::at: -inf outside the band
+        double nmo = __dadd_rn(__dadd_rn(nm, h3.lng), h3.open);
+        if (j == 0 && i == 0 && (h3.flags & PH_REDUCED)) nmo = __dadd_rn(__dadd_rn(nm, h3.lng), 0.0);  // the start corner's gap moves
+        out[k] = cell_word(acc.pX[k], py, acc.pM[k]) | plain_row | plain_col;
+        st.X[k] = nx; st.Y[k] = ny; st.M[k] = nm;
+        W[ps_rr_index<K>(ri, 0, k, lane + 1)] = nx; W[ps_rr_index<K>(ri, 1, k, lane + 1)] = ny; W[ps_rr_index<K>(ri, 2, k, lane + 1)] = nm;
+        if (st.cinfo[k] >= 0 && (st.cinfo[k] & PC_ENDCOL) && (info & VR_ENDPRED))
+            c.endstore[(long long)((st.cinfo[k] >> PC_END_SHIFT) & 3) * c.lx + i] = make_double4(nx, ny, nm, 0.0);
+        lXo = __dadd_rn(nx, h3.open); lMo = nmo; lY = ny;
+    }
+    return true;
+}
+
 // per-lane constants of one block
 template <int K>
 __device__ __forceinline__ void ps_init_lane(const PsCtx &c, PsLane<K> &st, int lane) {
@@ -419,12 +562,12 @@ __device__ __forceinline__ void ps_store_release(int *p, int v, bool wide) {
     else asm volatile("st.release.cta.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int K, bool SMALLTAB>
+template <int K, bool SMALLTAB, bool RING>
 __global__ void __launch_bounds__(PS_MAX_WARPS * 32, 1)
 pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models, const int *d_state,
                    const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow, const int *d_vlast, const int *d_blo,
                    const int *d_bhi, unsigned *ptrs, DevResult *results, double4 *scratch, long long cta_d4, long long end_d4, int ring,
-                   int max_slots, int park_cap, int *queue) {
+                   int max_slots, int park_cap, int rr, int *queue) {
     extern __shared__ __align__(16) unsigned char ps_smem[];
     // One alignment is swept by the warps of a whole thread-block CLUSTER: G CTAs of nw warps on G SMs (a guide-tree wave
     // holds a handful of alignments and 148 SMs; with 4 warps per CTA every warp has an SM sub-partition to itself).
@@ -436,7 +579,8 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
     const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NW = G * nw, gw = w * G + rank;
     double *hist_all = reinterpret_cast<double *>(ps_smem);
-    const int hist_doubles = PS_HIST * park_cap * 3;
+    // per warp: the parked-column history (ps_step) or the row ring (ps_step_ring)
+    const int hist_doubles = RING ? (rr + 1) * 3 * K * 33 : PS_HIST * park_cap * 3;
     double2 *s_tab = reinterpret_cast<double2 *>(hist_all + (size_t)nw * hist_doubles);
     __shared__ int s_job;
     // the warp-uniform constants live in shared memory, one copy per warp (the block fields differ): in registers they
@@ -444,6 +588,9 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
     __shared__ PsCtx s_ctx[PS_MAX_WARPS];
     // boundary column entries on their way in (cp.async, PS_PREFETCH steps ahead), a ring of 8 per warp: {X, Y, M, -}
     __shared__ __align__(16) double s_bnd[PS_MAX_WARPS][8][4];
+    // ps_step: the strip's last column on its way to the next lane.  (A __shfl_up_sync here sits in a loop whose trip count
+    // comes from memory; ptxas wraps every such shuffle in a WARPSYNC.COLLECTIVE call -- a fifth of the kernel's time, ncu.)
+    __shared__ double s_xch[PS_MAX_WARPS][3][33];
     const double ninf = neg_inf();
     const int ring_mask = ring - 1;
     double4 *cl_scratch = scratch + (long long)(blockIdx.x / G) * cta_d4;  // one region per cluster
@@ -478,6 +625,8 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
         if (lane == 0) {
             ps_make_ctx(c, J, GL, GR, m, d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, d_blo, d_bhi);
             c.hist = hist_all + (size_t)w * hist_doubles;
+            c.rowring = c.hist;
+            c.rr = RING ? rr : 0;
             c.park_cap = park_cap;
             c.endstore = endstore;
             c.saved = my + 2LL * ring;
@@ -563,9 +712,12 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
             int4 vr_next = vr_idle;
             if (lane == 0 && v1 > v0) vr_next = __ldg(c.l_vrow + v0);
             for (int t = 0; t < n_steps; ++t) {
-                double rX = __shfl_up_sync(0xffffffffu, st.X[K - 1], 1);
-                double rY = __shfl_up_sync(0xffffffffu, st.Y[K - 1], 1);
-                double rM = __shfl_up_sync(0xffffffffu, st.M[K - 1], 1);
+                double rX = 0.0, rY = 0.0, rM = 0.0;
+                if (!RING) {  // (the row-ring step reads its left neighbour from the ring)
+                    s_xch[w][0][lane + 1] = st.X[K - 1]; s_xch[w][1][lane + 1] = st.Y[K - 1]; s_xch[w][2][lane + 1] = st.M[K - 1];
+                    __syncwarp();
+                    rX = s_xch[w][0][lane]; rY = s_xch[w][1][lane]; rM = s_xch[w][2][lane];
+                }
                 asm volatile("cp.async.wait_group %0;" ::"n"(PS_PREFETCH - 1) : "memory");
                 if (lane == 0) { const double *e = ringp + (t & 7) * 4; rX = e[0]; rY = e[1]; rM = e[2]; }
                 issue(v0 + t + PS_PREFETCH);
@@ -577,10 +729,11 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
                     vr_next = vr_idle;
                     if (vn >= v0 && vn < v1 && lane <= last_lane) vr_next = __ldg(c.l_vrow + vn);
                 }
-                const bool any_saved = __any_sync(0xffffffffu, active && !(vr.x & (VR_REG | VR_NOEDGE)));
+                const bool any_saved = RING ? false : __any_sync(0xffffffffu, active && !(vr.x & (VR_REG | VR_NOEDGE)));
                 if (active) {
                     unsigned wds[K];
-                    const bool done = ps_step<K, SMALLTAB>(c, h3, st, acc, lane, vr, any_saved, rX, rY, rM, wds);
+                    const bool done = RING ? ps_step_ring<K, SMALLTAB>(c, h3, st, acc, lane, vr, rX, rY, rM, wds)
+                                           : ps_step<K, SMALLTAB>(c, h3, st, acc, lane, vr, any_saved, rX, rY, rM, wds);
                     if (done) {
                         unsigned *dst = out + (long long)t * 32 * K;
                         if (K == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(wds[0], wds[1]);
@@ -589,7 +742,7 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
 #pragma unroll
                             for (int k = 0; k < K; ++k) dst[k] = wds[k];
                         }
-                        const int slot = (int)((unsigned)vr.x >> VR_SLOT_SHIFT) - 1;
+                        const int slot = RING ? -1 : (int)((unsigned)vr.x >> VR_SLOT_SHIFT) - 1;
                         if (slot >= 0) {  // park the row for long-span edges
                             double4 *row = c.saved + (long long)slot * c.saved_stride + (st.j0 - c.c0);
                             if (lane == 0) row[0] = make_double4(st.bX, st.bY, st.bM, 0.0);
@@ -619,13 +772,16 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
 #endif
 
 // smem of one CTA: the parked-column histories of its warps (+ the shared substitution table)
-static size_t ps_smem_bytes(int nw, int park_cap, bool smalltab) {
-    return (size_t)nw * PS_HIST * park_cap * 3 * sizeof(double) + (smalltab ? STRIP_SMALL_FAS * STRIP_SMALL_FAS * sizeof(double2) : 0);
+// (rr > 0: the row ring of ps_step_ring, K = 2)
+static size_t ps_smem_bytes(int nw, int park_cap, bool smalltab, int rr) {
+    const size_t per_warp = rr > 0 ? (size_t)(rr + 1) * 3 * 2 * 33 : (size_t)PS_HIST * park_cap * 3;
+    return (size_t)nw * per_warp * sizeof(double) + (smalltab ? STRIP_SMALL_FAS * STRIP_SMALL_FAS * sizeof(double2) : 0);
 }
-// warps per CTA: as many as the job has blocks, the kernel allows and the histories fit
-int pstrip_warps(int n_blocks, int park_cap, bool smalltab) {
+// warps per CTA: as many as the job has blocks, the kernel allows and the histories / row rings fit
+int pstrip_warps(int n_blocks, int park_cap, bool smalltab, int rr) {
     int nw = n_blocks < PS_MAX_WARPS ? n_blocks : PS_MAX_WARPS;
-    while (nw > 1 && ps_smem_bytes(nw, park_cap, smalltab) > (size_t)PS_SMEM_BUDGET) --nw;
+    const size_t budget = rr > 0 ? (size_t)224 * 1024 : (size_t)PS_SMEM_BUDGET;  // (two warps with 64-row rings: 210 KB)
+    while (nw > 1 && ps_smem_bytes(nw, park_cap, smalltab, rr) > budget) --nw;
     return nw < 1 ? 1 : nw;
 }
 
@@ -636,12 +792,14 @@ template <int K>
 static void ps_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &GR, const DevModel &m, const int *d_state, const int *d_off,
                            const int *d_estart, const float *d_elogw, const int4 *d_vrow, const int *d_vlast, const int *d_blo,
                            const int *d_bhi, unsigned *ptrs, DevResult *res, double4 *scratch, long long end_d4, int ring, int max_slots,
-                           int park_cap) {
+                           int park_cap, int rr) {
     const double ninf = neg_inf();
     PsCtx c;
     ps_make_ctx(c, J, GL, GR, m, d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, d_blo, d_bhi);
-    std::vector<double> hist((size_t)PS_HIST * park_cap * 3);
+    std::vector<double> hist(rr > 0 ? (size_t)(rr + 1) * 3 * K * 33 : (size_t)PS_HIST * park_cap * 3);
     c.hist = hist.data();
+    c.rowring = hist.data();
+    c.rr = rr;
     c.park_cap = park_cap;
     c.endstore = scratch;
     double4 *ringbuf[2] = {scratch + end_d4, scratch + end_d4 + ring};
@@ -705,12 +863,15 @@ static void ps_emulate_job(const DevJob &J, const DevGraph &GL, const DevGraph &
                 } else { rX = sx[l - 1]; rY = sy[l - 1]; rM = sm[l - 1]; }
                 unsigned wds[K];
                 bool done;
-                if (smalltab) done = ps_step<K, true>(c, h3, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
+                if (rr > 0) {
+                    if (smalltab) done = ps_step_ring<K, true>(c, h3, st[l], acc[l], l, vr[l], rX, rY, rM, wds);
+                    else done = ps_step_ring<K, false>(c, h3, st[l], acc[l], l, vr[l], rX, rY, rM, wds);
+                } else if (smalltab) done = ps_step<K, true>(c, h3, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
                 else done = ps_step<K, false>(c, h3, st[l], acc[l], l, vr[l], any_saved, rX, rY, rM, wds);
                 if (!done) continue;
                 unsigned *dst = P + ptr_off + ((long long)t * 32 + l) * K;
                 for (int k = 0; k < K; ++k) dst[k] = wds[k];
-                const int slot = (int)((unsigned)vr[l].x >> VR_SLOT_SHIFT) - 1;
+                const int slot = rr > 0 ? -1 : (int)((unsigned)vr[l].x >> VR_SLOT_SHIFT) - 1;
                 if (slot >= 0) {
                     double4 *row = c.saved + (long long)slot * c.saved_stride + (st[l].j0 - c.c0);
                     if (l == 0) row[0] = make_double4(st[l].bX, st[l].bY, st[l].bM, 0.0);
@@ -738,13 +899,14 @@ long long pstrip_cta_double4(int K, int nw, int max_lx, int ring, int max_slots)
 void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_clusters, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                         const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                         const int4 *d_vrow, const int *d_vlast, const int *d_blo, const int *d_bhi, unsigned *ptrs, DevResult *results,
-                        double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int *queue, cudaStream_t stream) {
+                        double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int rr, int *queue, cudaStream_t stream) {
     if (n_jobs <= 0) return;
+    if (K != 2) rr = 0;  // the row ring is built for K = 2
     const long long end_d4 = (long long)PS_MAX_END * max_lx;
     const long long cta_d4 = pstrip_cta_double4(K, nw * G, max_lx, ring, max_slots);
 #ifndef PG2_HOST_EMU
     cudaMemsetAsync(queue, 0, sizeof(int), stream);
-    const int smem = (int)ps_smem_bytes(nw, park_cap, smalltab);
+    const int smem = (int)ps_smem_bytes(nw, park_cap, smalltab, rr);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n_clusters * G));
     cfg.blockDim = dim3((unsigned)(nw * 32));
@@ -757,15 +919,16 @@ void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-#define PG2_PS_LAUNCH(KK, S)                                                                                                      \
+#define PG2_PS_LAUNCH(KK, S, RG)                                                                                                  \
     do {                                                                                                                          \
-        cudaFuncSetAttribute(pstrip_fill_kernel<KK, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
-        cudaLaunchKernelEx(&cfg, pstrip_fill_kernel<KK, S>, n_jobs, jobs, job_ids, graphs, models, d_state, d_off, d_estart,       \
+        cudaFuncSetAttribute(pstrip_fill_kernel<KK, S, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                   \
+        cudaLaunchKernelEx(&cfg, pstrip_fill_kernel<KK, S, RG>, n_jobs, jobs, job_ids, graphs, models, d_state, d_off, d_estart,   \
                            d_elogw, d_vrow, d_vlast, d_blo, d_bhi, ptrs, results, scratch, cta_d4, end_d4, ring, max_slots,       \
-                           park_cap, queue);                                                                                      \
+                           park_cap, rr, queue);                                                                                  \
     } while (0)
-    if (K == 2) { if (smalltab) PG2_PS_LAUNCH(2, true); else PG2_PS_LAUNCH(2, false); }
-    else { if (smalltab) PG2_PS_LAUNCH(4, true); else PG2_PS_LAUNCH(4, false); }
+    if (K == 2 && rr > 0) { if (smalltab) PG2_PS_LAUNCH(2, true, true); else PG2_PS_LAUNCH(2, false, true); }
+    else if (K == 2) { if (smalltab) PG2_PS_LAUNCH(2, true, false); else PG2_PS_LAUNCH(2, false, false); }
+    else { if (smalltab) PG2_PS_LAUNCH(4, true, false); else PG2_PS_LAUNCH(4, false, false); }
 #undef PG2_PS_LAUNCH
 #else
     (void)queue; (void)stream; (void)n_clusters; (void)nw; (void)G; (void)smalltab; (void)cta_d4;
@@ -775,9 +938,9 @@ void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_c
         DevResult *res = results + jid;
         if (res->status != JOB_OK) continue;
         if (K == 2) ps_emulate_job<2>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast,
-                                      d_blo, d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap);
+                                      d_blo, d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap, rr);
         else ps_emulate_job<4>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, d_blo,
-                               d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap);
+                               d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap, 0);
     }
 #endif
 }

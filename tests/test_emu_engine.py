@@ -23,20 +23,22 @@ def emu_lib():
     return EMU_LIB
 
 
-def make_engine(lib, force_wavefront, no_lanes=False, no_pstrip=False, pstrip_k=None, no_band=False):
+def make_engine(lib, force_wavefront, no_lanes=False, no_pstrip=False, pstrip_k=None, no_band=False, psring=None):
     """no_pstrip: keep the pipelined-strip kernel out, so that the warp-per-alignment strip kernel and the general
     wavefront kernel (its fallback) stay covered; pstrip_k=4 forces the wider strips."""
     os.environ["PG2_FORCE_WAVEFRONT"] = "1" if force_wavefront else "0"
     os.environ["PG2_NO_LANES"] = "1" if no_lanes else "0"
     os.environ["PG2_NO_PSTRIP"] = "1" if no_pstrip else "0"
     os.environ["PG2_NO_BAND"] = "1" if no_band else "0"
+    os.environ["PG2_FORCE_PSRING"] = "1" if psring is True else "0"  # the row-ring step for every eligible pipelined-strip job
+    os.environ["PG2_NO_PSRING"] = "1" if psring is False else "0"    # ... for none
     if pstrip_k:
         os.environ["PG2_PSTRIP_K"] = str(pstrip_k)
         os.environ["PG2_PSTRIP_BANDED_CHAINS"] = "1"  # (by default banded chain x chain jobs stay on the wavefront kernel)
     try:
         return engine.Engine(0, lib)
     finally:
-        for name in ("PG2_FORCE_WAVEFRONT", "PG2_NO_LANES", "PG2_NO_PSTRIP", "PG2_PSTRIP_K", "PG2_PSTRIP_BANDED_CHAINS", "PG2_NO_BAND"):
+        for name in ("PG2_FORCE_WAVEFRONT", "PG2_NO_LANES", "PG2_NO_PSTRIP", "PG2_PSTRIP_K", "PG2_PSTRIP_BANDED_CHAINS", "PG2_NO_BAND", "PG2_FORCE_PSRING", "PG2_NO_PSRING"):
             os.environ.pop(name, None)
 
 
@@ -342,3 +344,21 @@ def test_band_kernel_vs_oracle(emu_lib):
     with make_engine(emu_lib, False, no_band=True) as eng:  # the same jobs on the wavefront kernel's chain path
         res = enginecheck.check_batch(eng, jobs)
         assert (res["kernel"] == 0).all()
+
+
+@pytest.mark.parametrize("psring", [True, False])
+def test_pstrip_row_ring_and_register_rows(emu_lib, golden, psring):
+    """The two step bodies of the pipelined-strip kernel -- every source row from the shared-memory row ring (ps_step_ring) and
+    the row above in registers with parked rows in global memory (ps_step) -- on the reference's own job streams (ancestors,
+    pileup root with 63-site edges: the 128-row ring, 1892-state codons) and on random general / banded graphs."""
+    rng = np.random.default_rng(777)
+    jobs = golden["c1_full"][8:] + golden["c3_full"][-6:] + golden["c4_full"][-2:] + golden["pileup_hp"] + golden["prog_dna"]
+    jobs += [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for kind in ("general", "banded", "strip") for _ in range(25)]
+    with make_engine(emu_lib, False, no_lanes=True, psring=psring) as eng:
+        res = enginecheck.check_batch(eng, jobs)
+        st = eng.stats()
+    assert (res["kernel"] == 3).mean() > 0.9
+    if psring:
+        assert st["jobs_pstrip_ring"] >= 0.9 * st["jobs_pstrip"]
+    else:
+        assert st["jobs_pstrip_ring"] == 0

@@ -375,3 +375,20 @@ def test_band_kernel_vs_oracle(eng, eng_old):
     assert eng.stats()["jobs_band"] == len(jobs) - 1
     res = enginecheck.check_batch(eng_old, jobs)
     assert (res["kernel"] == 0).all()
+
+
+@pytest.mark.parametrize("psring", [1, 0])
+def test_pstrip_row_ring_and_register_rows(golden, psring):
+    """Both step bodies of the pipelined-strip kernel (row ring in shared memory / row above in registers) on the reference's
+    job streams at BASELINE sizes and on random general / banded graphs; see tests/test_emu_engine.py."""
+    rng = np.random.default_rng(778)
+    jobs = golden["c1_full"] + golden["c3_full"] + golden["c4_full"] + golden["c5_full"][2:] + golden["pileup_hp"] + golden["prog_dna"]
+    jobs += [enginecheck.expect_from_oracle(randjobs.random_job(rng, kind)) for kind in ("general", "banded", "strip") for _ in range(100)]
+    e = engine_with(PG2_NO_LANES=1, PG2_FORCE_PSRING=psring, PG2_NO_PSRING=1 - psring)
+    try:
+        res = enginecheck.check_batch(e, jobs)
+        st = e.stats()
+    finally:
+        e.close()
+    assert (res["kernel"] == 3).mean() > 0.9
+    assert (st["jobs_pstrip_ring"] >= 0.9 * st["jobs_pstrip"]) if psring else (st["jobs_pstrip_ring"] == 0)
