@@ -869,18 +869,6 @@ static int try_pstrip(pg2_ctx *c, pg2_batch *b, DevJob &J) {
     J.kernel = 3;
     J.strip_k = K;
     J.strip_general = c->models[J.model].fas <= STRIP_SMALL_FAS ? 2 : 0;
-    // the row-ring step (pg2_pstrip.cu: ps_step_ring): the block's last 8 .. 128 rows in shared memory.  The ring must outlast
-    // the longest left edge plus the lanes the longest right edge reaches back (a lane is one virtual row ahead of the next)
-    // It pays where the graphs are general enough (measured: C1 / C4 ancestors with 5-10 % extra edges 7.1 -> 5.2 ms, the pileup
-    // step 15.4 -> 8.2 ms); on chains and near-chains (leaf pairs, 200 kb ancestors with 0.2 % extra edges) the register-resident
-    // row of ps_step is 10-25 % faster.
-    const bool general_enough = (long long)GL.n_extra * 100 >= GL.n_sites || (long long)GR.n_extra * 100 >= GR.n_sites;
-    if (K == 2 && !c->no_psring && (general_enough || c->force_psring)) {
-        const int need = GL.max_span + (GR.max_span + K - 1) / K + 4;
-        // tiers of 8, 16, 32, 64, 128 rows in bits 2-4 (128: one warp per CTA, 204 KB of ring -- the pileup root's longest edges)
-        for (int tier = 3; tier <= 5; tier++)  // (no tier below 32 rows: a smaller ring is no faster, and launch groups split by tier)
-            if (need <= (4 << tier)) { J.strip_general |= tier << 2; break; }
-    }
     J.n_blocks = nb;
     J.blk_base = blk_base;
     J.ps_ring = tallest;
@@ -1192,6 +1180,35 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
                 if (rc == PG2_ERR_NOMEM) { delete b; return fail(rc, "pinned staging allocation failed"); }
             }
         }
+    }
+    // The row-ring step of the pipelined strips (pg2_pstrip.cu: ps_step_ring: the block's last 32, 64 or 128 rows in shared
+    // memory), decided for the whole launch batch so that its K = 2 jobs stay ONE launch group (a wave of leaf pairs and ancestor
+    // pairs in two launches runs one after the other).  It pays where the graphs are general enough (measured: C1 ancestors with
+    // 10 % extra edges 7.1 -> 5.2 ms, C4 root 5.6 -> 5.0, the pileup step 15.4 -> 8.2); on chains and near-chains (leaf pairs,
+    // ancestors with 0.2-2 % extra edges) the register-resident row of ps_step is 10-25 % faster.  The ring must outlast the
+    // longest left edge plus the lanes the longest right edge reaches back (a lane is one virtual row ahead of the next).  A
+    // 64-row ring leaves room for two warps per CTA, a 128-row ring for one: with a cluster of 8 CTAs that is 16 / 8 column
+    // blocks in flight, and a job with more blocks than that is better off with ps_step's four warps per CTA.
+    if (!c->no_psring) {
+        bool general = c->force_psring;
+        int need = 0, blocks = 0;
+        for (int t = 0; t < n_jobs; t++) {
+            const DevJob &J = b->jobs[t];
+            if (J.kernel != 3 || J.strip_k != 2) continue;
+            const DevGraph &GL = b->graphs[J.left], &GR = b->graphs[J.right];
+            if ((long long)GL.n_extra * 25 >= GL.n_sites || (long long)GR.n_extra * 25 >= GR.n_sites) general = true;  // 4 % extra edges
+            need = std::max(need, GL.max_span + (GR.max_span + 1) / 2 + 4);
+            blocks = std::max(blocks, J.n_blocks);
+        }
+        int tier = 0;
+        if (general && need > 0)
+            for (int q = 3; q <= 5; q++)
+                if (need <= (4 << q)) { if (q == 3 || c->force_psring || blocks <= (q == 4 ? 16 : 8)) tier = q; break; }
+        if (tier)
+            for (int t = 0; t < n_jobs; t++) {
+                DevJob &J = b->jobs[t];
+                if (J.kernel == 3 && J.strip_k == 2) J.strip_general |= tier << 2;
+            }
     }
     for (int t = 0; t < n_jobs; t++) {
         DevJob &J = b->jobs[t];
