@@ -24,7 +24,7 @@
 #include "pg2_pstrip_geom.cuh"
 
 namespace pg2 {
-int pstrip_warps(int n_blocks, int park_cap, bool smalltab, int rr);
+int pstrip_warps(int n_blocks, int park_cap, bool smalltab, int rr, int K);
 long long pstrip_cta_double4(int K, int nw, int max_lx, int ring, int max_slots);
 void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_clusters, const DevJob *jobs, const int *job_ids, const DevGraph *graphs,
                         const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
@@ -749,7 +749,15 @@ static int build_col_program(pg2_ctx *c, DevGraph &dg) {
         }
     }
     int K = maxspan <= (PS_HIST - 3) * 2 ? 2 : (maxspan <= (PS_HIST - 3) * 4 ? 4 : 0);
-    if (const char *fk = getenv("PG2_PSTRIP_K")) if (atoi(fk) == 4 && K == 2) K = 4;
+    // One column per lane for heavily general column graphs (454 / homopolymer read graphs: a third of the columns have two or
+    // three backward edges).  A step costs the warp the SUM over a lane's columns of the longest edge loop among the lanes, so
+    // half the columns per lane is half the step; the blocks are 32 columns wide, twice as many warps work on the alignment.
+    if (K == 2 && maxspan <= PS_HIST - 3 && (long long)dg.n_extra * 5 >= dg.n_sites && !c->no_psring) K = 1;
+    if (const char *fk = getenv("PG2_PSTRIP_K")) {
+        if (atoi(fk) == 4 && K <= 2) K = 4;
+        if (atoi(fk) == 2 && K == 1) K = 2;
+        if (atoi(fk) == 1 && K == 2 && maxspan <= PS_HIST - 3) K = 1;
+    }
     if (K == 0) return PG2_ERR_UNSUPPORTED;
     // columns the end corner reads: the predecessors of the stop site and the last DP column
     std::vector<int> endcols(1, cols - 1);
@@ -766,7 +774,7 @@ static int build_col_program(pg2_ctx *c, DevGraph &dg) {
         std::vector<char> cut((size_t)cols + 1, 0);
         int run = 0;
         for (int cc = 0; cc <= cols; cc++) { run += forbid[(size_t)cc]; cut[(size_t)cc] = run == 0; }
-        for (; K <= 4; K += 2) {
+        for (; K <= 4; K *= 2) {
             blocks.clear();
             int c0 = 0;
             while (c0 < cols) {
@@ -1190,25 +1198,32 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
     // 64-row ring leaves room for two warps per CTA, a 128-row ring for one: with a cluster of 8 CTAs that is 16 / 8 column
     // blocks in flight, and a job with more blocks than that is better off with ps_step's four warps per CTA.
     if (!c->no_psring) {
-        bool general = c->force_psring;
-        int need = 0, blocks = 0;
-        for (int t = 0; t < n_jobs; t++) {
-            const DevJob &J = b->jobs[t];
-            if (J.kernel != 3 || J.strip_k != 2) continue;
-            const DevGraph &GL = b->graphs[J.left], &GR = b->graphs[J.right];
-            if ((long long)GL.n_extra * 25 >= GL.n_sites || (long long)GR.n_extra * 25 >= GR.n_sites) general = true;  // 4 % extra edges
-            need = std::max(need, GL.max_span + (GR.max_span + 1) / 2 + 4);
-            blocks = std::max(blocks, J.n_blocks);
-        }
-        int tier = 0;
-        if (general && need > 0)
-            for (int q = 3; q <= 5; q++)
-                if (need <= (4 << q)) { if (q == 3 || c->force_psring || blocks <= (q == 4 ? 16 : 8)) tier = q; break; }
-        if (tier)
+        for (int K = 1; K <= 2; K++) {  // (jobs of different strip widths are different launch groups anyway)
+            bool general = c->force_psring;
+            int need = 0, blocks = 0;
             for (int t = 0; t < n_jobs; t++) {
-                DevJob &J = b->jobs[t];
-                if (J.kernel == 3 && J.strip_k == 2) J.strip_general |= tier << 2;
+                const DevJob &J = b->jobs[t];
+                if (J.kernel != 3 || J.strip_k != K) continue;
+                const DevGraph &GL = b->graphs[J.left], &GR = b->graphs[J.right];
+                if ((long long)GL.n_extra * 25 >= GL.n_sites || (long long)GR.n_extra * 25 >= GR.n_sites) general = true;  // 4 % extra edges
+                need = std::max(need, GL.max_span + (GR.max_span + K - 1) / K + 4);
+                blocks = std::max(blocks, J.n_blocks);
             }
+            int tier = 0;
+            if (general && need > 0)
+                for (int q = 3; q <= 5; q++)
+                    if (need <= (4 << q)) {
+                        const size_t ring_bytes = (size_t)((4 << q) + 1) * 3 * K * 33 * sizeof(double);
+                        const int warps = (int)std::min<size_t>(4, ((size_t)220 * 1024) / ring_bytes);  // per CTA; 8 CTAs per cluster
+                        if (warps >= 4 || c->force_psring || blocks <= 8 * warps) tier = q;
+                        break;
+                    }
+            if (tier)
+                for (int t = 0; t < n_jobs; t++) {
+                    DevJob &J = b->jobs[t];
+                    if (J.kernel == 3 && J.strip_k == K) J.strip_general |= tier << 2;
+                }
+        }
     }
     for (int t = 0; t < n_jobs; t++) {
         DevJob &J = b->jobs[t];
@@ -1257,7 +1272,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
                 while (g.ps_ring < J.ps_ring) g.ps_ring <<= 1;
                 g.ps_park = std::max(g.ps_park, b->graphs[J.right].cp_park);
                 g.ps_blocks = std::max(g.ps_blocks, J.n_blocks);
-                g.ps_nw = pstrip_warps(g.ps_blocks, g.ps_park, (g.strip_general & 2) != 0, ps_ring_rows(g.strip_general));
+                g.ps_nw = pstrip_warps(g.ps_blocks, g.ps_park, (g.strip_general & 2) != 0, ps_ring_rows(g.strip_general), g.strip_k);
             }
             g.count++;
             pos++;
@@ -1458,7 +1473,7 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                                    c->d_results.p, c->d_ps_scratch.p, g.max_lx, g.ps_ring, g.max_slots, g.ps_park, ps_ring_rows(g.strip_general),
                                    c->d_queue.p, c->stream);
                 st.jobs_pstrip += g.count;
-                if (g.strip_k == 2 && ps_ring_rows(g.strip_general) > 0) st.jobs_pstrip_ring += g.count;
+                if (g.strip_k <= 2 && ps_ring_rows(g.strip_general) > 0) st.jobs_pstrip_ring += g.count;
                 st.traceback_bytes += g.cells * 4;
             } else if (g.kernel == 4) {
                 launch_band_fill((g.strip_general & 2) != 0, g.count, c->d_jobs.p, ids, c->d_graphs.p, c->d_models.p, c->d_state.p, c->d_band4.p,

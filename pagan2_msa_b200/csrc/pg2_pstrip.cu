@@ -312,7 +312,13 @@ __device__ __forceinline__ bool ps_step(const PsCtx &c, const PsHot &h3, PsLane<
 // Hazards: lane l reads columns of lanes l' <= l; lane l' is l - l' virtual rows ahead and overwrites ring row (i' & (rr - 1)) as
 // it completes site i', so rr must exceed the longest left span plus the lane distance of the longest right span plus 2 (the
 // engine picks rr per launch group, try_pstrip).
-template <int K> __device__ __forceinline__ int ps_rr_index(int row, int mat, int k, int l1) { return ((row * 3 + mat) * K + k) * 33 + l1; }
+template <int K> __device__ __forceinline__ int ps_rr_index(int row, int mat, int k, int l1) {
+#ifdef PG2_HOST_EMU
+    // the CPU test build checks every ring address the step computes (rows 0 .. 128, the "no row" included)
+    if (row < 0 || row > 128 || mat < 0 || mat > 2 || k < 0 || k >= K || l1 < 0 || l1 > 32) abort();
+#endif
+    return ((row * 3 + mat) * K + k) * 33 + l1;
+}
 
 template <int K, bool SMALLTAB>
 __device__ __forceinline__ bool ps_step_ring(const PsCtx &c, const PsHot &h3, PsLane<K> &st, PsAcc<K> &acc, int lane, int4 vr,
@@ -580,7 +586,8 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
     const int NW = G * nw, gw = w * G + rank;
     double *hist_all = reinterpret_cast<double *>(ps_smem);
     // per warp: the parked-column history (ps_step) or the row ring (ps_step_ring)
-    const int hist_doubles = RING ? (rr + 1) * 3 * K * 33 : PS_HIST * park_cap * 3;
+    // (an even count: the double2 table behind the warps' regions is read 16 bytes at a time)
+    const int hist_doubles = ((RING ? (rr + 1) * 3 * K * 33 : PS_HIST * park_cap * 3) + 1) & ~1;
     double2 *s_tab = reinterpret_cast<double2 *>(hist_all + (size_t)nw * hist_doubles);
     __shared__ int s_job;
     // the warp-uniform constants live in shared memory, one copy per warp (the block fields differ): in registers they
@@ -772,16 +779,17 @@ pstrip_fill_kernel(int n_jobs, const DevJob *jobs, const int *job_ids, const Dev
 #endif
 
 // smem of one CTA: the parked-column histories of its warps (+ the shared substitution table)
-// (rr > 0: the row ring of ps_step_ring, K = 2)
-static size_t ps_smem_bytes(int nw, int park_cap, bool smalltab, int rr) {
-    const size_t per_warp = rr > 0 ? (size_t)(rr + 1) * 3 * 2 * 33 : (size_t)PS_HIST * park_cap * 3;
+// (rr > 0: the row ring of ps_step_ring, K = 1 or 2)
+static size_t ps_smem_bytes(int nw, int park_cap, bool smalltab, int rr, int K) {
+    const size_t per_warp = ((rr > 0 ? (size_t)(rr + 1) * 3 * K * 33 : (size_t)PS_HIST * park_cap * 3) + 1) & ~(size_t)1;
     return (size_t)nw * per_warp * sizeof(double) + (smalltab ? STRIP_SMALL_FAS * STRIP_SMALL_FAS * sizeof(double2) : 0);
 }
 // warps per CTA: as many as the job has blocks, the kernel allows and the histories / row rings fit
-int pstrip_warps(int n_blocks, int park_cap, bool smalltab, int rr) {
+int pstrip_warps(int n_blocks, int park_cap, bool smalltab, int rr, int K) {
     int nw = n_blocks < PS_MAX_WARPS ? n_blocks : PS_MAX_WARPS;
+    if (K > 2) rr = 0;
     const size_t budget = rr > 0 ? (size_t)224 * 1024 : (size_t)PS_SMEM_BUDGET;  // (two warps with 64-row rings: 210 KB)
-    while (nw > 1 && ps_smem_bytes(nw, park_cap, smalltab, rr) > budget) --nw;
+    while (nw > 1 && ps_smem_bytes(nw, park_cap, smalltab, rr, K) > budget) --nw;
     return nw < 1 ? 1 : nw;
 }
 
@@ -901,12 +909,12 @@ void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_c
                         const int4 *d_vrow, const int *d_vlast, const int *d_blo, const int *d_bhi, unsigned *ptrs, DevResult *results,
                         double4 *scratch, int max_lx, int ring, int max_slots, int park_cap, int rr, int *queue, cudaStream_t stream) {
     if (n_jobs <= 0) return;
-    if (K != 2) rr = 0;  // the row ring is built for K = 2
+    if (K > 2) rr = 0;  // the row ring is built for K = 1 and 2
     const long long end_d4 = (long long)PS_MAX_END * max_lx;
     const long long cta_d4 = pstrip_cta_double4(K, nw * G, max_lx, ring, max_slots);
 #ifndef PG2_HOST_EMU
     cudaMemsetAsync(queue, 0, sizeof(int), stream);
-    const int smem = (int)ps_smem_bytes(nw, park_cap, smalltab, rr);
+    const int smem = (int)ps_smem_bytes(nw, park_cap, smalltab, rr, K);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n_clusters * G));
     cfg.blockDim = dim3((unsigned)(nw * 32));
@@ -926,7 +934,9 @@ void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_c
                            d_elogw, d_vrow, d_vlast, d_blo, d_bhi, ptrs, results, scratch, cta_d4, end_d4, ring, max_slots,       \
                            park_cap, rr, queue);                                                                                  \
     } while (0)
-    if (K == 2 && rr > 0) { if (smalltab) PG2_PS_LAUNCH(2, true, true); else PG2_PS_LAUNCH(2, false, true); }
+    if (K == 1 && rr > 0) { if (smalltab) PG2_PS_LAUNCH(1, true, true); else PG2_PS_LAUNCH(1, false, true); }
+    else if (K == 1) { if (smalltab) PG2_PS_LAUNCH(1, true, false); else PG2_PS_LAUNCH(1, false, false); }
+    else if (K == 2 && rr > 0) { if (smalltab) PG2_PS_LAUNCH(2, true, true); else PG2_PS_LAUNCH(2, false, true); }
     else if (K == 2) { if (smalltab) PG2_PS_LAUNCH(2, true, false); else PG2_PS_LAUNCH(2, false, false); }
     else { if (smalltab) PG2_PS_LAUNCH(4, true, false); else PG2_PS_LAUNCH(4, false, false); }
 #undef PG2_PS_LAUNCH
@@ -937,7 +947,9 @@ void launch_pstrip_fill(int K, bool smalltab, int nw, int G, int n_jobs, int n_c
         const DevJob &J = jobs[jid];
         DevResult *res = results + jid;
         if (res->status != JOB_OK) continue;
-        if (K == 2) ps_emulate_job<2>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast,
+        if (K == 1) ps_emulate_job<1>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast,
+                                      d_blo, d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap, rr);
+        else if (K == 2) ps_emulate_job<2>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast,
                                       d_blo, d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap, rr);
         else ps_emulate_job<4>(J, graphs[J.left], graphs[J.right], models[J.model], d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, d_blo,
                                d_bhi, ptrs, res, scratch, end_d4, ring, max_slots, park_cap, 0);

@@ -527,7 +527,8 @@ __global__ void __launch_bounds__(64) traceback_pstrip_kernel(int n_jobs, const 
         if (done) break;
         const int nb = __shfl_sync(0xffffffffu, st.b, 0), nt = __shfl_sync(0xffffffffu, st.need_t, 0);
         __syncwarp();
-        if (tj.K == 2) ps_trace_load<2>(tj, W, nb, nt, lane);
+        if (tj.K == 1) ps_trace_load<1>(tj, W, nb, nt, lane);
+        else if (tj.K == 2) ps_trace_load<2>(tj, W, nb, nt, lane);
         else ps_trace_load<4>(tj, W, nb, nt, lane);
         if (lane == 0) { W.b = nb; W.t_hi = nt; }
         __syncwarp();
@@ -672,7 +673,8 @@ void launch_traceback(int n_jobs, int n_wave, int n_ps, const int *job_ids, cons
                 ps_trace_walk(J, tj, W, l_off, r_off, l_es, r_es, st);
                 if (st.s.done) break;
                 for (int lane = 0; lane < 32; ++lane) {
-                    if (tj.K == 2) ps_trace_load<2>(tj, W, st.b, st.need_t, lane);
+                    if (tj.K == 1) ps_trace_load<1>(tj, W, st.b, st.need_t, lane);
+                    else if (tj.K == 2) ps_trace_load<2>(tj, W, st.b, st.need_t, lane);
                     else ps_trace_load<4>(tj, W, st.b, st.need_t, lane);
                 }
                 W.b = st.b; W.t_hi = st.need_t;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""A small launch batch through every fill kernel and walk, for compute-sanitizer (memcheck / racecheck):
-    compute-sanitizer --tool racecheck python tools/sanitize_small.py
+"""A small launch batch through every fill kernel and walk, small enough to run under a memory checker where one is
+available (compute-sanitizer --tool memcheck python tools/sanitize_small.py; it is closed on the pool this was built on).
 Shared-target placement jobs (lane kernel), progressive / pileup / codon jobs (pipelined strips, both step bodies), anchored leaf
 pairs (band kernel + segmented walk), the general wavefront kernel; every result is compared with the oracle."""
 import os
