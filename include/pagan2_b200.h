@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PG2_ABI_VERSION 3
+#define PG2_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -211,6 +211,7 @@ typedef struct pg2_stats {
     int32_t jobs_pstrip;       /* jobs the pipelined-strip kernel took (CTA per alignment: general x general, banded, small waves) */
     int32_t jobs_band;         /* jobs the band kernel took (warp per anchored alignment of two plain chains) */
     int32_t jobs_pstrip_ring;  /* ... of the pipelined-strip jobs, those that ran with the shared-memory row ring */
+    int32_t jobs_lanes_wide;   /* ... of the lane-kernel jobs, those launched in the latency shape (one CTA of 10 warps per SM) */
 } pg2_stats;
 int pg2_get_stats(pg2_ctx *ctx, pg2_stats *out);
 

@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-PG2_ABI_VERSION = 3
+PG2_ABI_VERSION = 4
 
 PG2_OK, PG2_ERR_INVALID, PG2_ERR_NO_DEVICE, PG2_ERR_CUDA, PG2_ERR_NOMEM, PG2_ERR_UNSUPPORTED, PG2_ERR_CAPACITY = range(7)
 PG2_JOB_OK, PG2_JOB_NO_PATH, PG2_JOB_BAD_BAND, PG2_JOB_BAD_GRAPH, PG2_JOB_BROKEN_PATH = range(5)
@@ -115,6 +115,7 @@ class Stats(C.Structure):
         ("jobs_pstrip", C.c_int32),
         ("jobs_band", C.c_int32),
         ("jobs_pstrip_ring", C.c_int32),
+        ("jobs_lanes_wide", C.c_int32),
     ]
 
 

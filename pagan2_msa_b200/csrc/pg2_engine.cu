@@ -45,11 +45,11 @@ void launch_strip_fill(int K, bool general, bool smalltab, int n_jobs, const Dev
                        unsigned short *ptrs, DevResult *results, double4 *saved_all, long long saved_per_warp, double4 *bcol_all,
                        long long bcol_per_warp, int *queue, int n_warps, cudaStream_t stream);
 int strip_warps_per_sm();
-void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
+void launch_lane_fill(int variant, int W, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
                       const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
                       const int4 *d_vrow, const int *d_vlast, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv,
                       int max_lx, int max_slots, int *queue, int n_ctas, cudaStream_t stream);
-int lane_ctas_per_sm();
+int lane_ctas_per_sm(int W);
 void launch_band_fill(bool smalltab, int n_jobs, const DevJob *jobs, const int *job_ids, const DevGraph *graphs, const DevModel *models,
                       const int *d_state, const int *d_band4, unsigned *ptrs, DevResult *results, cudaStream_t stream);
 void launch_band_traceback(int n_jobs, int max_seg, const int *job_ids, const DevJob *jobs, const int *d_band4, const unsigned *ptrs,
@@ -148,6 +148,7 @@ struct Group {
     int max_diag;
     int max_slots, max_lx;  // strip kernel per-warp scratch: saved rows, boundary column
     int max_nv = 1;         // lane kernel: longest row program
+    int lane_w = LANE_W;    // lane kernel: warps per CTA (LANE_W: three CTAs per SM; LANE_W_WIDE: one, for launches that cannot fill the chip)
     int ps_ring = 1, ps_nw = 1;  // pipelined-strip kernel: boundary ring (virtual rows, power of two), warps per CTA
     int ps_park = 1, ps_blocks = 1;  // ... history slots per block, most blocks of a job
     int phase = 0;          // groups of one phase keep their pointer buffers side by side and share one traceback launch
@@ -193,6 +194,7 @@ struct pg2_ctx {
     int pstrip_max_jobs = 600;     // strip-eligible jobs of a batch go to the pipelined-strip kernel when there are at most this
                                    // many of them (a warp per alignment cannot fill the chip; PG2_PSTRIP_MAX_JOBS)
     size_t lane_scratch_bytes = (size_t)8 << 30;  // cap of the lane kernel's per-CTA wrap / end-column / parked-row scratch
+    int lane_wide_hint = -1;  // pipelined pg2_align_batch: the shape of the whole call's lane launches (1 wide, 0 narrow), decided once
     // staging (pinned) and device arrays of the current batch
     PinVec<int> h_state, h_off, h_estart, h_blo, h_bhi, h_dlo, h_vrow, h_vlast;
     PinVec<float> h_elogw;
@@ -1066,7 +1068,7 @@ extern "C" int pg2_batch_create(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs,
             const DevJob &J = b->jobs[t];
             if (J.kernel != 1) continue;
             const DevGraph &GL = b->graphs[J.left];
-            if ((size_t)lane_cta_doubles(GL.n_vrows, J.lx, GL.n_slots) * sizeof(double) > c->lane_scratch_bytes / 16) continue;
+            if ((size_t)lane_cta_doubles(GL.n_vrows, J.lx, GL.n_slots, LANE_W) * sizeof(double) > c->lane_scratch_bytes / 16) continue;
             std::vector<BucketRef> &refs = by_graph[J.left];
             int bi = -1;
             for (const BucketRef &r : refs) if (r.model == J.model && r.flags == (J.flags & 3u)) { bi = r.bucket; break; }
@@ -1394,15 +1396,37 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
 #else
     const int resident_warps = c->prop.multiProcessorCount * strip_warps_per_sm();
 #endif
-    const int lane_resident = c->prop.multiProcessorCount * lane_ctas_per_sm();
     auto lane_ctas = [&](const Group &g) {
-        const size_t per_cta = (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots) * sizeof(double);
+        const size_t lane_resident = (size_t)std::max(c->prop.multiProcessorCount, 1) * lane_ctas_per_sm(g.lane_w);
+        const size_t per_cta = (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots, g.lane_w) * sizeof(double);
         size_t fit = std::max<size_t>(c->lane_scratch_bytes / per_cta, 1);
-        return (int)std::min<size_t>(std::min<size_t>(fit, (size_t)lane_resident), (size_t)std::max(g.task_count, 1));
+        return (int)std::min<size_t>(std::min<size_t>(fit, lane_resident), (size_t)std::max(g.task_count, 1));
     };
+    // A lane launch that cannot keep the chip's CTA slots busy for long -- a shard of a strong-scaling run, the trial alignments of
+    // a few reads -- waits for its longest task (the root-most target of a placement tree has twice the sites of a leaf and a third
+    // of them with several edges: 22 ms against 7 ms for the others).  Such launches take the wide shape: one CTA of LANE_W_WIDE
+    // warps per SM, a task's strips in two rounds instead of five.  PG2_LANE_W = 4 / 10 forces a shape, PG2_LANE_WIDE_TASKS sets
+    // the limit (tasks per SM below which the wide shape is used).
+    {
+        const char *fw = getenv("PG2_LANE_W"), *ft = getenv("PG2_LANE_WIDE_TASKS");
+        const int forced = fw ? atoi(fw) : 0;
+        const int per_sm = (ft && atoi(ft) >= 0) ? atoi(ft) : LANE_WIDE_TASKS_PER_SM;
+        for (auto &g : b->groups) {
+            if (g.kernel != 2) continue;
+            int max_strips = 0;
+            for (int t = 0; t < g.task_count; t++) max_strips = std::max(max_strips, (b->tasks[(size_t)g.task_first + t].max_ly + LANE_K - 1) / LANE_K);
+            // (the chunks of a pipelined call share the chip: the call decides for all of them, by the tasks it holds in total)
+            bool wide = (c->lane_wide_hint >= 0 ? c->lane_wide_hint == 1 : g.task_count <= per_sm * std::max(c->prop.multiProcessorCount, 1)) &&
+                        max_strips > LANE_W;
+            if (forced == LANE_W) wide = false;
+            if (forced == LANE_W_WIDE) wide = true;
+            if (wide && (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots, LANE_W_WIDE) * sizeof(double) > c->lane_scratch_bytes) wide = false;
+            g.lane_w = wide ? LANE_W_WIDE : LANE_W;
+        }
+    }
     for (auto &g : b->groups)
         if (g.kernel == 2) {
-            size_t need = (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots) * lane_ctas(g);
+            size_t need = (size_t)lane_cta_doubles(g.max_nv, g.max_lx, g.max_slots, g.lane_w) * lane_ctas(g);
             if ((rc = c->d_lane_scratch.ensure(need)) != PG2_OK) return fail(rc, "lane scratch allocation failed");
         }
     // pipelined strips: one CLUSTER per job in flight.  A launch with few jobs (a guide-tree wave, a pileup step) spreads every
@@ -1448,7 +1472,7 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                     c->d_blo.p, c->d_bhi.p, c->d_graph_status.p, c->d_results.p, b->few_long, c->stream);
     st.fill_ms = st.traceback_ms = 0;
     st.fill_launches = st.traceback_launches = 0;
-    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = st.jobs_pstrip = st.jobs_band = st.jobs_pstrip_ring = 0;
+    st.jobs_wavefront = st.jobs_strip = st.jobs_lanes = st.jobs_pstrip = st.jobs_band = st.jobs_pstrip_ring = st.jobs_lanes_wide = 0;
     st.jobs_strip_groups = 0;
     st.cells = b->total_cells;
     st.traceback_bytes = 0;
@@ -1489,11 +1513,12 @@ static int batch_run_impl(pg2_ctx *c, pg2_batch *b, bool async) {
                 st.jobs_wavefront += g.count;
                 st.traceback_bytes += g.cells * 4;
             } else if (g.kernel == 2) {
-                launch_lane_fill(g.variant, g.task_count, c->d_tasks.p + g.task_first, c->d_jobs.p, c->d_graphs.p, c->d_models.p,
+                launch_lane_fill(g.variant, g.lane_w, g.task_count, c->d_tasks.p + g.task_first, c->d_jobs.p, c->d_graphs.p, c->d_models.p,
                                  c->d_state.p, c->d_off.p, c->d_estart.p, c->d_elogw.p, reinterpret_cast<const int4 *>(c->d_vrow.p),
                                  c->d_vlast.p, c->d_ptr16.p, c->d_results.p, c->d_lane_scratch.p, g.max_nv, g.max_lx, g.max_slots, c->d_queue.p,
                                  lane_ctas(g), c->stream);
                 st.jobs_lanes += g.count;
+                if (g.lane_w == LANE_W_WIDE) st.jobs_lanes_wide += g.count;
                 st.jobs_strip_groups++;
                 st.traceback_bytes += g.cells * 2;
             } else {
@@ -1701,6 +1726,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
     if (n_jobs < min_jobs || (np && atoi(np) != 0)) return align_batch_single(c, n_jobs, jobs, results, steps, step_cap);
     PackTimer timer;
     // group the jobs by left graph (first-appearance order), then cut into chunks by cell count
+    long long est_tasks = 0;  // lane tasks the call would form if every group went to the lane kernel
     std::vector<int> perm(n_jobs);
     std::vector<long long> cells_prefix((size_t)n_jobs + 1, 0);
     {
@@ -1757,6 +1783,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         }
         for (int t = 0; t < n_jobs; t++) perm[start[gid[t]]++] = t;
         for (int k = 0; k < n_jobs; k++) cells_prefix[k + 1] = cells_prefix[k] + cells[perm[k]];
+        for (int n : count) est_tasks += (n + 31) / 32;
     }
     const long long total = cells_prefix[n_jobs];
     int n_chunks = (int)std::min<long long>(8, std::max<long long>(2, total / 2500000000LL));
@@ -1803,6 +1830,14 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         ~BudgetGuard() { c->scratch_bytes = saved; }
     } budget_guard = {c, c->scratch_bytes};
     if (n_slots > 1) c->scratch_bytes = budget_guard.saved / PIPE_SLOTS;
+    // the lane launches of all chunks take one shape: the latency shape when the whole call cannot keep the chip's CTA slots busy
+    // for long (batch_run_impl)
+    bool wide_call;
+    {
+        const char *ft = getenv("PG2_LANE_WIDE_TASKS");
+        const int per_sm = (ft && atoi(ft) >= 0) ? atoi(ft) : LANE_WIDE_TASKS_PER_SM;
+        wide_call = est_tasks <= (long long)per_sm * std::max(c->prop.multiProcessorCount, 1);
+    }
     timer.lap("= group + chunk");
     // PG2_TIMING: device timeline of the chunks against one origin (tuning aid)
     cudaEvent_t origin = nullptr;
@@ -1845,7 +1880,7 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
             const pg2_stats &st = f.ctx->stats;
             agg.h2d_bytes += st.h2d_bytes; agg.d2h_bytes += st.d2h_bytes; agg.cells += st.cells; agg.traceback_bytes += st.traceback_bytes;
             agg.fill_launches += st.fill_launches; agg.traceback_launches += st.traceback_launches; agg.kernel_launches += st.kernel_launches;
-            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes; agg.jobs_pstrip += st.jobs_pstrip; agg.jobs_band += st.jobs_band; agg.jobs_pstrip_ring += st.jobs_pstrip_ring;
+            agg.jobs_wavefront += st.jobs_wavefront; agg.jobs_strip += st.jobs_strip; agg.jobs_lanes += st.jobs_lanes; agg.jobs_pstrip += st.jobs_pstrip; agg.jobs_band += st.jobs_band; agg.jobs_pstrip_ring += st.jobs_pstrip_ring; agg.jobs_lanes_wide += st.jobs_lanes_wide;
             agg.jobs_strip_groups += st.jobs_strip_groups; agg.d2h_ms += st.d2h_ms;
         }
         pg2_batch_destroy(f.ctx, f.batch);
@@ -1872,7 +1907,9 @@ extern "C" int pg2_align_batch(pg2_ctx *c, int32_t n_jobs, const pg2_job *jobs, 
         if (step_base + cap > step_cap) { rc = fail(PG2_ERR_CAPACITY, "step buffer too small"); break; }
         step_base += cap;
         rc = pg2_batch_create(f.ctx, f.hi - f.lo, chunk_jobs.data(), &f.batch);
+        f.ctx->lane_wide_hint = wide_call ? 1 : 0;
         if (rc == PG2_OK) rc = batch_run_impl(f.ctx, f.batch, true);
+        f.ctx->lane_wide_hint = -1;
         if (rc == PG2_OK) rc = fetch_enqueue(f.ctx, f.batch, step_cap - f.step_base);
         if (timer.on)
             fprintf(stderr, "pg2 chunk [%6d,%6d): enqueued at %6.2f ms (host)\n", f.lo, f.hi,

@@ -510,12 +510,12 @@ __device__ __forceinline__ void lane_make_geom(LaneGeom &g, bool active, int ly)
 struct LaneSched {
     int n_strips, rounds, n_blocks, period, items;
 };
-__device__ __forceinline__ LaneSched lane_schedule(int nv, int max_ly) {
+template <int W> __device__ __forceinline__ LaneSched lane_schedule(int nv, int max_ly) {
     LaneSched s;
     s.n_strips = (max_ly + LANE_K - 1) / LANE_K;
-    s.rounds = (s.n_strips + LANE_W - 1) / LANE_W;
+    s.rounds = (s.n_strips + W - 1) / W;
     s.n_blocks = (nv + LANE_B - 1) / LANE_B;
-    s.period = s.n_blocks > LANE_W + 1 ? s.n_blocks : LANE_W + 1;
+    s.period = s.n_blocks > W + 1 ? s.n_blocks : W + 1;
     s.items = s.rounds * s.period;
     return s;
 }
@@ -523,11 +523,12 @@ __device__ __forceinline__ LaneSched lane_schedule(int nv, int max_ly) {
 // shared-memory ring: channels 0 .. W-2 (warp c -> warp c+1) are LANE_D blocks deep, channel W-1 (the wrap
 // prefetch of warp 0) two blocks; one block = [LANE_B rows][X,Y,M][32 lanes] doubles
 constexpr int LANE_BLOCK_DOUBLES = LANE_B * 96;
-constexpr int LANE_RING_DOUBLES = ((LANE_W - 1) * LANE_D + 2) * LANE_BLOCK_DOUBLES;
-__device__ __forceinline__ int lane_ring_offset(int channel, int u) {
-    return channel < LANE_W - 1 ? (channel * LANE_D + u % LANE_D) * LANE_BLOCK_DOUBLES
-                                : ((LANE_W - 1) * LANE_D + (u & 1)) * LANE_BLOCK_DOUBLES;
-}
+template <int W> struct LaneRing {
+    static constexpr int doubles = ((W - 1) * LANE_D + 2) * LANE_BLOCK_DOUBLES;
+    __device__ __forceinline__ static int offset(int channel, int u) {
+        return channel < W - 1 ? (channel * LANE_D + u % LANE_D) * LANE_BLOCK_DOUBLES : ((W - 1) * LANE_D + (u & 1)) * LANE_BLOCK_DOUBLES;
+    }
+};
 
 #ifndef PG2_HOST_EMU
 // Progress counters (shared memory, one per pipeline stage).  A stage publishes "item u done" with a release
@@ -561,20 +562,25 @@ __device__ __forceinline__ void lane_publish(int *p, int value, int lane) {
     }
 }
 
-// CTAs placed on each SM so far (never reset: only its value modulo LANE_W is used)
+// CTAs placed on each SM so far (never reset: only its value modulo W is used)
 __device__ int g_lane_sm_rotation[256];
 
-template <int K, bool GENERAL, bool SMALLTAB, bool WR>
-__global__ void __launch_bounds__(LANE_W * 32, PG2_LANE_MINB)
+// W: warps per CTA = strips of one task in flight.  LANE_W (4, three CTAs per SM) is the throughput shape: a launch with more
+// tasks than the chip holds CTAs keeps twelve warps per SM busy whatever W is, and short pipelines waste less of a task's last
+// round.  LANE_W_WIDE (10, one CTA per SM) is the latency shape for launches that cannot fill the chip (a shard of a
+// strong-scaling run, the trial alignments of a few reads): a task's 19 strips take two rounds instead of five, so the longest
+// task -- what such a launch waits for -- ends 2.5 times sooner.
+template <int K, int W, bool GENERAL, bool SMALLTAB, bool WR>
+__global__ void __launch_bounds__(W * 32, (W == LANE_W ? PG2_LANE_MINB : 1))
 lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs, const DevModel *models,
                  const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow, const int *d_vlast,
                  unsigned short *ptrs, DevResult *results, double *scratch, long long wrap_doubles, long long endcol_doubles,
                  long long slot_doubles, int *queue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *ring = reinterpret_cast<double *>(smem_raw);
-    double2 *s_tab = reinterpret_cast<double2 *>(ring + LANE_RING_DOUBLES);
+    double2 *s_tab = reinterpret_cast<double2 *>(ring + LaneRing<W>::doubles);
     __shared__ int s_task;
-    __shared__ int s_progress[LANE_W];
+    __shared__ int s_progress[W];
     const int lane = threadIdx.x & 31;
     // pipeline stage of this warp.  Hardware warp k of every CTA lives on SM sub-partition k % 4; rotating the
     // stages by the CTA index puts one warp of each stage on every sub-partition (stage 0 carries the wrap
@@ -582,7 +588,7 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
 #if defined(PG2_LANE_NOROT)
     const int w = threadIdx.x >> 5;
 #elif !defined(PG2_LANE_ROT_SM)
-    const int w = ((threadIdx.x >> 5) + blockIdx.x) % LANE_W;
+    const int w = ((threadIdx.x >> 5) + blockIdx.x) % W;
 #else
     // (tuning variant, measured and not adopted: the rotation counted per SM instead of taken from the CTA index, for the case
     // that several launches share the chip -- e2e 70.0 vs 69.4 ms, resident fill 55.2 vs 54.1 ms: the stage index stops being
@@ -594,10 +600,9 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
         s_rot = atomicAdd(&g_lane_sm_rotation[smid & 255u], 1);
     }
     __syncthreads();
-    const int w = ((threadIdx.x >> 5) + s_rot) & (LANE_W - 1);
-    static_assert((LANE_W & (LANE_W - 1)) == 0, "stage rotation assumes a power-of-two warp count");
+    const int w = ((threadIdx.x >> 5) + s_rot) % W;
 #endif
-    double *wrap = scratch + (long long)blockIdx.x * (wrap_doubles + endcol_doubles + LANE_W * slot_doubles);
+    double *wrap = scratch + (long long)blockIdx.x * (wrap_doubles + endcol_doubles + W * slot_doubles);
     double *endcol = wrap + wrap_doubles;
     double *slots = endcol + endcol_doubles + (long long)w * slot_doubles + lane;
     int *progress = s_progress;
@@ -606,7 +611,7 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
     for (;;) {
         __syncthreads();  // the previous task's end corners are done with endcol; s_task / s_progress may be rewritten
         if (threadIdx.x == 0) s_task = atomicAdd(queue, 1);
-        if (threadIdx.x < LANE_W) s_progress[threadIdx.x] = 0;
+        if (threadIdx.x < W) s_progress[threadIdx.x] = 0;
         __syncthreads();
         const int q = s_task;
         if (q >= n_tasks) break;
@@ -638,7 +643,7 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
         const int *r_state = d_state + GR.state_base;
         const float *r_elogw = d_elogw + GR.edge_base;
         uint4 *ptr = reinterpret_cast<uint4 *>(ptrs + T.ptr_base) + lane;
-        const LaneSched sch = lane_schedule(c.nv, T.max_ly);
+        const LaneSched sch = lane_schedule<W>(c.nv, T.max_ly);
         LState<K> st;
         lane_strip_init<K, WR, SMALLTAB>(c, st, g, 0, r_state, r_elogw);
 
@@ -652,7 +657,7 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
 #endif
         int plain_n = __ldg(c.l_vplain);  // the next item's row mask, fetched one item ahead
         for (int u = 0; u < sch.items; ++u) {
-            const int r = u / sch.period, b = u - r * sch.period, s = r * LANE_W + w;
+            const int r = u / sch.period, b = u - r * sch.period, s = r * W + w;
             const unsigned plain = (unsigned)plain_n;
             {
                 const int b1 = (b + 1 == sch.period) ? 0 : b + 1;
@@ -663,9 +668,9 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
                 // the copy lands while this item is being computed
                 const int u1 = u + 1, r1 = u1 / sch.period, b1 = u1 - r1 * sch.period;
                 if (r1 >= 1 && r1 < sch.rounds && b1 < sch.n_blocks) {
-                    lane_wait(progress + LANE_W - 1, u1 - sch.period + 1);
+                    lane_wait(progress + W - 1, u1 - sch.period + 1);
                     const int v0 = b1 * LANE_B, v1 = min(v0 + LANE_B, c.nv);
-                    double *dst = ring + lane_ring_offset(LANE_W - 1, u1) + lane;
+                    double *dst = ring + LaneRing<W>::offset(W - 1, u1) + lane;
                     const double *src = wrap + (long long)v0 * 96 + lane;
                     for (int e = 0; e < (v1 - v0) * 3; ++e) {
                         const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e * 32);
@@ -676,12 +681,12 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
             if (s < sch.n_strips && b < sch.n_blocks) {
                 const bool has_next = s + 1 < sch.n_strips;
                 { PG2_T0; if (w > 0) lane_wait(progress + w - 1, u + 1); PG2_T1(t_in); }        // input block published
-                { PG2_T0; if (has_next && w < LANE_W - 1) lane_wait(progress + w + 1, u - LANE_D + 1); PG2_T1(t_out); }  // output slot drained
+                { PG2_T0; if (has_next && w < W - 1) lane_wait(progress + w + 1, u - LANE_D + 1); PG2_T1(t_out); }  // output slot drained
                 if (b == 0) lane_strip_init<K, WR, SMALLTAB>(c, st, g, s * K, r_state, r_elogw);
                 const int v0 = b * LANE_B, v1 = min(v0 + LANE_B, c.nv);
-                const double *ring_in = ring + lane_ring_offset((w + LANE_W - 1) % LANE_W, u) + lane;
-                double *ring_out = (has_next && w != LANE_W - 1) ? ring + lane_ring_offset(w, u) + lane : nullptr;
-                double *wrap_out = (has_next && w == LANE_W - 1) ? wrap + lane : nullptr;
+                const double *ring_in = ring + LaneRing<W>::offset((w + W - 1) % W, u) + lane;
+                double *ring_out = (has_next && w != W - 1) ? ring + LaneRing<W>::offset(w, u) + lane : nullptr;
+                double *wrap_out = (has_next && w == W - 1) ? wrap + lane : nullptr;
                 { PG2_T0; lane_block<K, GENERAL, SMALLTAB, WR>(c, st, g, s, v0, v1, plain, ring_in, ring_out, wrap_out, slots, endcol + lane, ptr); PG2_T1(t_blk); }
             }
             { PG2_T0; if (w == 0) asm volatile("cp.async.wait_all;" ::: "memory"); PG2_T1(t_pre); }
@@ -698,46 +703,21 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
 }
 #endif
 
-int lane_ctas_per_sm() { return PG2_LANE_MINB; }
+// CTAs of one SM: three of LANE_W warps, one of LANE_W_WIDE
+int lane_ctas_per_sm(int W) { return W == LANE_W ? PG2_LANE_MINB : 1; }
 
-// Launches one group of lane tasks that share the kernel variant.  `scratch`: n_ctas * lane_cta_doubles doubles.
-void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
-                      const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
-                      const int4 *d_vrow, const int *d_vlast, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv,
-                      int max_lx, int max_slots, int *queue, int n_ctas, cudaStream_t stream) {
-    if (n_tasks <= 0) return;
+#ifdef PG2_HOST_EMU
+// CPU test emulation of ONE CTA: the same items and block bodies; warp w runs item t - w at step t, warps and
+// lanes one after the other -- one of the interleavings the progress counters admit (a producer's ring slot
+// is read one step after it was written and rewritten LANE_D steps later).
+template <int W>
+static void lane_emulate(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs, const DevModel *models,
+                         const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
+                         const int *d_vlast, unsigned short *ptrs, DevResult *results, double *scratch, long long wrap_doubles,
+                         long long endcol_doubles, long long slot_doubles) {
     constexpr int K = LANE_K;
-    const long long wrap_doubles = (long long)max_nv * 96, endcol_doubles = (long long)max_lx * 96;
-    const long long slot_doubles = (long long)(max_slots + 2) * LANE_SLOT_DOUBLES;
-#ifndef PG2_HOST_EMU
-    cudaMemsetAsync(queue, 0, sizeof(int), stream);
-    const int smem = LANE_RING_DOUBLES * (int)sizeof(double) + ((variant & 2) ? STRIP_SMALL_FAS * STRIP_SMALL_FAS * (int)sizeof(double2) : 0);
-#define PG2_LANE_LAUNCH(G, S, W)                                                                                                  \
-    do {                                                                                                                          \
-        cudaFuncSetAttribute(lane_fill_kernel<K, G, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                    \
-        lane_fill_kernel<K, G, S, W><<<n_ctas, LANE_W * 32, smem, stream>>>(n_tasks, tasks, jobs, graphs, models, d_state, d_off, \
-                                                                            d_estart, d_elogw, d_vrow, d_vlast, ptrs, results,    \
-                                                                            scratch,                                              \
-                                                                            wrap_doubles, endcol_doubles, slot_doubles, queue);   \
-    } while (0)
-    switch (variant & 7) {
-        case 0: PG2_LANE_LAUNCH(false, false, false); break;
-        case 1: PG2_LANE_LAUNCH(true, false, false); break;
-        case 2: PG2_LANE_LAUNCH(false, true, false); break;
-        case 3: PG2_LANE_LAUNCH(true, true, false); break;
-        case 4: PG2_LANE_LAUNCH(false, false, true); break;
-        case 5: PG2_LANE_LAUNCH(true, false, true); break;
-        case 6: PG2_LANE_LAUNCH(false, true, true); break;
-        case 7: PG2_LANE_LAUNCH(true, true, true); break;
-    }
-#undef PG2_LANE_LAUNCH
-#else
-    // CPU test emulation of ONE CTA: the same items and block bodies; warp w runs item t - w at step t, warps and
-    // lanes one after the other -- one of the interleavings the progress counters admit (a producer's ring slot
-    // is read one step after it was written and rewritten LANE_D steps later).
-    (void)queue; (void)n_ctas; (void)stream;
     double *wrap = scratch, *endcol = wrap + wrap_doubles, *slots0 = endcol + endcol_doubles;
-    std::vector<double> ring((size_t)LANE_RING_DOUBLES);
+    std::vector<double> ring((size_t)LaneRing<W>::doubles);
     for (int q = 0; q < n_tasks; ++q) {
         const LaneTask &T = tasks[q];
         const DevGraph GL = graphs[T.left];
@@ -753,8 +733,8 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
             }
             c.stab = tab.data();
         }
-        const LaneSched sch = lane_schedule(c.nv, T.max_ly);
-        std::vector<LState<K> > st((size_t)LANE_W * 32);
+        const LaneSched sch = lane_schedule<W>(c.nv, T.max_ly);
+        std::vector<LState<K> > st((size_t)W * 32);
         LaneGeom geom[32];
         const int *r_state[32];
         const float *r_elogw[32];
@@ -769,11 +749,11 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
             r_state[lane] = d_state + GR.state_base;
             r_elogw[lane] = d_elogw + GR.edge_base;
         }
-        for (int t = 0; t < sch.items + LANE_W - 1; ++t) {
-            for (int w = 0; w < LANE_W; ++w) {
+        for (int t = 0; t < sch.items + W - 1; ++t) {
+            for (int w = 0; w < W; ++w) {
                 const int u = t - w;
                 if (u < 0 || u >= sch.items) continue;
-                const int r = u / sch.period, b = u - r * sch.period, s = r * LANE_W + w;
+                const int r = u / sch.period, b = u - r * sch.period, s = r * W + w;
                 if (s < sch.n_strips && b < sch.n_blocks) {
                     const int v0 = b * LANE_B, v1 = v0 + LANE_B < c.nv ? v0 + LANE_B : c.nv;
                     const bool has_next = s + 1 < sch.n_strips;
@@ -783,9 +763,9 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
     do {                                                                                                               \
         if (b == 0) lane_strip_init<K, WRV, SM>(c, S, geom[lane], s * K, r_state[lane], r_elogw[lane]);                \
         lane_block<K, G, SM, WRV>(c, S, geom[lane], s, v0, v1, (unsigned)c.l_vplain[b],                                                    \
-                                  ring.data() + lane_ring_offset((w + LANE_W - 1) % LANE_W, u) + lane,                 \
-                                  (has_next && w != LANE_W - 1) ? ring.data() + lane_ring_offset(w, u) + lane : nullptr, \
-                                  (has_next && w == LANE_W - 1) ? wrap + lane : nullptr,                               \
+                                  ring.data() + LaneRing<W>::offset((w + W - 1) % W, u) + lane,                 \
+                                  (has_next && w != W - 1) ? ring.data() + LaneRing<W>::offset(w, u) + lane : nullptr, \
+                                  (has_next && w == W - 1) ? wrap + lane : nullptr,                               \
                                   slots0 + (long long)w * slot_doubles + lane, endcol + lane,                          \
                                   reinterpret_cast<uint4 *>(ptrs + T.ptr_base) + lane);                                \
     } while (0)
@@ -806,7 +786,7 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
                     const int u1 = u + 1, r1 = u1 / sch.period, b1 = u1 - r1 * sch.period;
                     if (r1 >= 1 && r1 < sch.rounds && b1 < sch.n_blocks) {
                         const int v0 = b1 * LANE_B, v1 = v0 + LANE_B < c.nv ? v0 + LANE_B : c.nv;
-                        memcpy(ring.data() + lane_ring_offset(LANE_W - 1, u1), wrap + (long long)v0 * 96,
+                        memcpy(ring.data() + LaneRing<W>::offset(W - 1, u1), wrap + (long long)v0 * 96,
                                sizeof(double) * (size_t)(v1 - v0) * 96);
                     }
                 }
@@ -815,6 +795,62 @@ void launch_lane_fill(int variant, int n_tasks, const LaneTask *tasks, const Dev
         for (int lane = 0; lane < 32; ++lane)
             if (geom[lane].active) lane_end_corner(c, geom[lane], endcol + lane, r_elogw[lane], res[lane]);
     }
+}
+#else
+template <int W>
+static void lane_launch(int variant, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs, const DevModel *models,
+                        const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw, const int4 *d_vrow,
+                        const int *d_vlast, unsigned short *ptrs, DevResult *results, double *scratch, long long wrap_doubles,
+                        long long endcol_doubles, long long slot_doubles, int *queue, int n_ctas, cudaStream_t stream) {
+    constexpr int K = LANE_K;
+    const int smem = LaneRing<W>::doubles * (int)sizeof(double) + ((variant & 2) ? STRIP_SMALL_FAS * STRIP_SMALL_FAS * (int)sizeof(double2) : 0);
+#define PG2_LANE_LAUNCH(G, S, WRV)                                                                                                \
+    do {                                                                                                                          \
+        cudaFuncSetAttribute(lane_fill_kernel<K, W, G, S, WRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);               \
+        lane_fill_kernel<K, W, G, S, WRV><<<n_ctas, W * 32, smem, stream>>>(n_tasks, tasks, jobs, graphs, models, d_state, d_off, \
+                                                                            d_estart, d_elogw, d_vrow, d_vlast, ptrs, results,    \
+                                                                            scratch,                                              \
+                                                                            wrap_doubles, endcol_doubles, slot_doubles, queue);   \
+    } while (0)
+    switch (variant & 7) {
+        case 0: PG2_LANE_LAUNCH(false, false, false); break;
+        case 1: PG2_LANE_LAUNCH(true, false, false); break;
+        case 2: PG2_LANE_LAUNCH(false, true, false); break;
+        case 3: PG2_LANE_LAUNCH(true, true, false); break;
+        case 4: PG2_LANE_LAUNCH(false, false, true); break;
+        case 5: PG2_LANE_LAUNCH(true, false, true); break;
+        case 6: PG2_LANE_LAUNCH(false, true, true); break;
+        case 7: PG2_LANE_LAUNCH(true, true, true); break;
+    }
+#undef PG2_LANE_LAUNCH
+}
+#endif
+
+// Launches one group of lane tasks that share the kernel variant, W (LANE_W or LANE_W_WIDE) warps per CTA.
+// `scratch`: n_ctas * lane_cta_doubles(.., W) doubles.
+void launch_lane_fill(int variant, int W, int n_tasks, const LaneTask *tasks, const DevJob *jobs, const DevGraph *graphs,
+                      const DevModel *models, const int *d_state, const int *d_off, const int *d_estart, const float *d_elogw,
+                      const int4 *d_vrow, const int *d_vlast, unsigned short *ptrs, DevResult *results, double *scratch, int max_nv,
+                      int max_lx, int max_slots, int *queue, int n_ctas, cudaStream_t stream) {
+    if (n_tasks <= 0) return;
+    const long long wrap_doubles = (long long)max_nv * 96, endcol_doubles = (long long)max_lx * 96;
+    const long long slot_doubles = (long long)(max_slots + 2) * LANE_SLOT_DOUBLES;
+#ifndef PG2_HOST_EMU
+    cudaMemsetAsync(queue, 0, sizeof(int), stream);
+    if (W == LANE_W_WIDE)
+        lane_launch<LANE_W_WIDE>(variant, n_tasks, tasks, jobs, graphs, models, d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, ptrs, results,
+                                 scratch, wrap_doubles, endcol_doubles, slot_doubles, queue, n_ctas, stream);
+    else
+        lane_launch<LANE_W>(variant, n_tasks, tasks, jobs, graphs, models, d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, ptrs, results,
+                            scratch, wrap_doubles, endcol_doubles, slot_doubles, queue, n_ctas, stream);
+#else
+    (void)queue; (void)n_ctas; (void)stream;
+    if (W == LANE_W_WIDE)
+        lane_emulate<LANE_W_WIDE>(variant, n_tasks, tasks, jobs, graphs, models, d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, ptrs, results,
+                                  scratch, wrap_doubles, endcol_doubles, slot_doubles);
+    else
+        lane_emulate<LANE_W>(variant, n_tasks, tasks, jobs, graphs, models, d_state, d_off, d_estart, d_elogw, d_vrow, d_vlast, ptrs, results,
+                             scratch, wrap_doubles, endcol_doubles, slot_doubles);
 #endif
 }
 

@@ -73,7 +73,10 @@ __host__ __device__ inline long long strip_ptr_index(int nv, int ly, int K, int 
 // Pointer buffer of one task: [strip][virtual row][K/8][lane] uint4, i.e. 8 half-words (8 columns) per lane
 // per 128-bit store, lanes interleaved so that a warp-wide store is one contiguous 512 B segment.
 constexpr int LANE_K = 8;             // columns per lane strip (multiple of 8)
-constexpr int LANE_W = 4;             // warps per CTA = strips of one task in flight
+constexpr int LANE_W = 4;             // warps per CTA = strips of one task in flight (three CTAs per SM: the throughput shape)
+constexpr int LANE_W_WIDE = 10;       // ... of a launch that cannot fill the chip (one CTA per SM: a task ends 2.5 times sooner)
+constexpr int LANE_WIDE_TASKS_PER_SM = 10;  // launches with at most this many tasks per SM take the wide shape (measured on the
+                                      // placement workload: 848 tasks 29.2 -> 19.3 ms, 1 622 tasks 33.8 vs 34.7 ms, 3 175 tasks 56 vs 65 ms)
 #ifndef PG2_LANE_B
 #define PG2_LANE_B 8
 #endif
@@ -96,8 +99,8 @@ __host__ __device__ inline long long lane_ptr_index(int nv, int K, int v, int j,
 // boundary handed from the CTA's last warp to its first), the end column [row][X,Y,M][lane] (what the end
 // corner reads) and per warp n_slots + 2 parked rows (rows that start long-span edges, the row above an open
 // general site, and the pointer accumulators of a site that straddles two pipeline blocks).
-__host__ __device__ inline long long lane_cta_doubles(int max_nv, int max_lx, int n_slots) {
-    return (long long)max_nv * 96 + (long long)max_lx * 96 + (long long)LANE_W * (n_slots + 2) * LANE_SLOT_DOUBLES;
+__host__ __device__ inline long long lane_cta_doubles(int max_nv, int max_lx, int n_slots, int W) {
+    return (long long)max_nv * 96 + (long long)max_lx * 96 + (long long)W * (n_slots + 2) * LANE_SLOT_DOUBLES;
 }
 
 // Decodes one pointer of a strip-kernel half-word into the API encoding (mat | lord<<2 | rord<<8).

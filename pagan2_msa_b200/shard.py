@@ -17,18 +17,56 @@ RECORD_DTYPE = np.dtype([("score", "<f8"), ("end_ptr", "<u4"), ("n_steps", "<i4"
 assert RECORD_DTYPE.itemsize == RECORD_BYTES
 
 
-def partition(cells, world):
-    """Deterministic split of job indices over `world` ranks: contiguous index ranges of the batch after a
-    size-interleaving permutation (jobs sorted by cell count, largest first, dealt round-robin), so that every
-    range carries the same mix of job sizes.  Returns one int64 index array per rank (possibly empty)."""
+def partition(cells, world, groups=None, unit=32):
+    """Deterministic split of job indices over `world` ranks.  Returns one int64 index array per rank (possibly empty).
+
+    groups=None: contiguous index ranges of the batch after a size-interleaving permutation (jobs sorted by cell count,
+    largest first, dealt round-robin), so that every range carries the same mix of job sizes.
+
+    groups = one key per job (placement: the target node a read is aligned against): the jobs of a group stay together.
+    The placement kernel sweeps 32 reads that share their target per task (pg2_lanes.cu), so a cut through a group costs
+    every rank a partly filled task per group -- at 8 ranks and 127 targets that is a quarter of the lanes idle.  Here the
+    groups (largest first) are laid end to end in units of `unit` jobs of similar size and the unit sequence is cut into
+    `world` contiguous ranges of equal cell count: a rank holds whole groups except at its two borders, so it also uploads
+    only the target graphs it needs."""
     cells = np.asarray(cells, dtype=np.int64)
     n = cells.shape[0]
-    order = np.argsort(-cells, kind="stable")
-    perm = np.concatenate([order[r::world] for r in range(world)]) if n else order
-    bounds = [0]
-    for r in range(world):
-        bounds.append(bounds[-1] + len(order[r::world]))
-    return [perm[bounds[r]:bounds[r + 1]] for r in range(world)]
+    if groups is None or n == 0:
+        order = np.argsort(-cells, kind="stable")
+        perm = np.concatenate([order[r::world] for r in range(world)]) if n else order
+        bounds = [0]
+        for r in range(world):
+            bounds.append(bounds[-1] + len(order[r::world]))
+        return [perm[bounds[r]:bounds[r + 1]] for r in range(world)]
+    keys = {}
+    gid = np.empty(n, dtype=np.int64)
+    for t, g in enumerate(groups):  # first-appearance ids: the result does not depend on the key values themselves
+        gid[t] = keys.setdefault(g, len(keys))
+    ng = len(keys)
+    gcells = np.bincount(gid, weights=cells, minlength=ng)
+    grank = np.empty(ng, dtype=np.int64)
+    grank[np.argsort(-gcells, kind="stable")] = np.arange(ng)
+    # jobs ordered by (group, largest first inside the group); units never span two groups
+    order = np.lexsort((np.arange(n), -cells, grank[gid]))
+    og = gid[order]
+    starts = np.flatnonzero(np.concatenate([[True], og[1:] != og[:-1]]))
+    unit_bounds = []
+    for a, b in zip(starts, list(starts[1:]) + [n]):
+        unit_bounds.extend(range(a, b, unit))
+    unit_bounds.append(n)
+    unit_bounds = np.asarray(unit_bounds, dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(cells[order])])
+    ucum = csum[unit_bounds]  # cells before each unit boundary
+    total = int(csum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(ucum, total * r / world, side="left"))
+        k = min(max(k, 0), len(unit_bounds) - 1)
+        if k > 0 and abs(ucum[k - 1] - total * r / world) <= abs(ucum[k] - total * r / world):
+            k -= 1
+        cuts.append(max(int(unit_bounds[k]), cuts[-1]))
+    cuts.append(n)
+    return [order[cuts[r]:cuts[r + 1]] for r in range(world)]
 
 
 def step_capacity(job):

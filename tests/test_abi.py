@@ -43,7 +43,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(abi.Job) == 2 * C.sizeof(abi.Graph) + 8 + 16
     assert C.sizeof(abi.Result) == 40
     assert C.sizeof(abi.Step) == 32
-    assert C.sizeof(abi.Stats) == 4 * 8 + 4 * 8 + 4 * 4 + 8 + 6 * 4
+    assert C.sizeof(abi.Stats) == 4 * 8 + 4 * 8 + 4 * 4 + 8 + 7 * 4 + 4  # (7 trailing int32 + padding to the double's alignment)
 
 
 def test_no_cpu_fallback(lib):

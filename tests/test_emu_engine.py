@@ -77,9 +77,11 @@ def test_golden_pstrip(emu_lib, golden, name, k):
 
 
 @pytest.mark.parametrize("seed,plain_left,n_jobs", [(61, False, 70), (62, True, 40), (63, False, 33), (64, False, 16), (65, True, 100)])
-def test_lane_kernel_shared_target_vs_oracle(emu_lib, seed, plain_left, n_jobs):
+@pytest.mark.parametrize("lane_w", [4, 10])  # three CTAs of 4 warps per SM / one CTA of 10: the throughput and the latency shape
+def test_lane_kernel_shared_target_vs_oracle(emu_lib, monkeypatch, lane_w, seed, plain_left, n_jobs):
     """Jobs that share the left graph are grouped 32 per warp, one alignment per lane (pg2_lanes.cu): every
     variant (plain / general rows, weights on the read edges), ragged read lengths, thin remainders."""
+    monkeypatch.setenv("PG2_LANE_W", str(lane_w))
     rng = np.random.default_rng(seed)
     jobs = []
     for _ in range(3):
@@ -92,12 +94,15 @@ def test_lane_kernel_shared_target_vs_oracle(emu_lib, seed, plain_left, n_jobs):
     assert (res["kernel"][:3 * n_jobs] == 2).all()
     assert (res["kernel"][-5:] == 1).all()
     assert st["jobs_lanes"] == int((res["kernel"] == 2).sum())
+    assert st["jobs_lanes_wide"] == (st["jobs_lanes"] if lane_w == 10 else 0)
 
 
 @pytest.mark.parametrize("seed", [71, 72, 73, 74])
-def test_lane_kernel_schedule_shapes(emu_lib, seed):
+@pytest.mark.parametrize("lane_w", [4, 10])
+def test_lane_kernel_schedule_shapes(emu_lib, monkeypatch, lane_w, seed):
     """Pipeline schedule edge cases: row programs shorter than the pipeline depth, one strip only, many
     rounds (reads of several hundred columns), reads of one site."""
+    monkeypatch.setenv("PG2_LANE_W", str(lane_w))
     rng = np.random.default_rng(seed)
     jobs = []
     for nl, nr_max in ((1, 4), (2, 9), (5, 40), (30, 9), (33, 300), (150, 120), (9, 70)):
@@ -108,8 +113,10 @@ def test_lane_kernel_schedule_shapes(emu_lib, seed):
     assert (res["kernel"] == 2).all()
 
 
-def test_lane_kernel_long_reads_and_bad_job(emu_lib):
+@pytest.mark.parametrize("lane_w", [4, 10])
+def test_lane_kernel_long_reads_and_bad_job(emu_lib, monkeypatch, lane_w):
     """Reads longer than one strip x many strips, and a rejected job inside a task (its lane idles)."""
+    monkeypatch.setenv("PG2_LANE_W", str(lane_w))
     rng = np.random.default_rng(66)
     jobs = randjobs.random_shared_target_jobs(rng, 40, nl=60, nr_max=200)
     jobs = [enginecheck.expect_from_oracle(j) for j in jobs]

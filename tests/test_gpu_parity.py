@@ -116,9 +116,11 @@ def test_placement_uses_register_strip_kernels(eng, eng_nolanes, golden):
 
 
 @pytest.mark.parametrize("seed,plain_left,n_jobs", [(161, False, 70), (162, True, 40), (163, False, 33), (164, False, 16), (165, True, 100)])
-def test_lane_kernel_shared_target_vs_oracle(eng, seed, plain_left, n_jobs):
+@pytest.mark.parametrize("lane_w", [4, 10])  # three CTAs of 4 warps per SM / one CTA of 10: the throughput and the latency shape
+def test_lane_kernel_shared_target_vs_oracle(eng, monkeypatch, lane_w, seed, plain_left, n_jobs):
     """Jobs sharing the left graph run one alignment per lane (pg2_lanes.cu): all template variants, ragged read
     lengths, thin remainders, singletons left to the strip kernel."""
+    monkeypatch.setenv("PG2_LANE_W", str(lane_w))
     rng = np.random.default_rng(seed)
     jobs = []
     for _ in range(6):
@@ -128,9 +130,13 @@ def test_lane_kernel_shared_target_vs_oracle(eng, seed, plain_left, n_jobs):
     res = enginecheck.check_batch(eng, jobs)
     assert (res["kernel"][:6 * n_jobs] == 2).all()
     assert np.isin(res["kernel"][-5:], (1, 3)).all()
+    st = eng.stats()
+    assert st["jobs_lanes_wide"] == (st["jobs_lanes"] if lane_w == 10 else 0)
 
 
-def test_lane_kernel_long_reads_and_bad_job(eng):
+@pytest.mark.parametrize("lane_w", [4, 10])
+def test_lane_kernel_long_reads_and_bad_job(eng, monkeypatch, lane_w):
+    monkeypatch.setenv("PG2_LANE_W", str(lane_w))
     rng = np.random.default_rng(166)
     jobs = randjobs.random_shared_target_jobs(rng, 40, nl=60, nr_max=200)
     jobs = [enginecheck.expect_from_oracle(j) for j in jobs]
