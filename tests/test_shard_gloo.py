@@ -36,6 +36,33 @@ def test_partition_is_a_balanced_permutation():
     assert [len(p) for p in shard.partition([7], 4)] == [1, 0, 0, 0]
 
 
+def test_partition_keeps_groups_together():
+    """groups=: the reads of one target stay on one rank except at the rank borders, units of 32 never mix two targets, the
+    cell counts balance to within one unit, and the result does not depend on the key values."""
+    rng = np.random.default_rng(6)
+    n, ng = 20000, 127
+    g = rng.integers(0, ng, size=n)
+    lens = rng.integers(1400, 3000, size=ng)
+    cells = lens[g] * rng.integers(140, 152, size=n)
+    for world in (1, 2, 4, 8):
+        parts = shard.partition(cells, world, groups=g.tolist())
+        assert len(parts) == world
+        assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+        loads = [int(cells[p].sum()) for p in parts]
+        assert max(loads) - min(loads) <= 2 * 32 * int(cells.max())
+        owners = {}
+        for r, p in enumerate(parts):
+            for k in set(g[p].tolist()):
+                owners.setdefault(k, []).append(r)
+        assert sum(len(v) > 1 for v in owners.values()) <= world - 1  # only a group at a border is cut
+        tasks = sum(int(((np.bincount(g[p], minlength=ng) + 31) // 32).sum()) for p in parts)
+        assert tasks <= int(((np.bincount(g, minlength=ng) + 31) // 32).sum()) + (world - 1)
+        same = shard.partition(cells, world, groups=["t%d" % (ng - k) for k in g.tolist()])
+        assert all((a == b).all() for a, b in zip(parts, same))
+    assert [len(p) for p in shard.partition([], 3, groups=[])] == [0, 0, 0]
+    assert sorted(np.concatenate(shard.partition([5, 3, 9], 2, groups=["a", "b", "a"])).tolist()) == [0, 1, 2]
+
+
 def _worker(rank, world, port, out_path):
     import torch
     import torch.distributed as dist
