@@ -59,6 +59,8 @@ struct LaneCtx {
     int nv, lx, n_slots;
     const float *table;          // global float table (any alphabet)
     const double2 *stab;         // shared {2*lng + ls, lng + ls} table (alphabets up to STRIP_SMALL_FAS)
+    unsigned stab_s;             // its shared-memory address: the kernel loads with ld.shared (through the generic pointer every row
+                                 // re-derives the shared window in the uniform datapath: four issue slots)
     int fas;
     double open, ext, end_ext, lng, lng2;
     bool term, reduced;
@@ -111,9 +113,13 @@ __device__ __forceinline__ void acc_gt(double s, double &best, unsigned &ptr, un
 template <bool SMALLTAB>
 __device__ __forceinline__ void lane_subst(const LaneCtx &c, int rowoff, int tabk, double &mlog, double &xlog) {
     if (SMALLTAB) {
+#ifdef PG2_HOST_EMU
         const double2 v = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(c.stab) + (rowoff + tabk));
         mlog = v.x;
         xlog = v.y;
+#else
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mlog), "=d"(xlog) : "r"(c.stab_s + (unsigned)(rowoff + tabk)));
+#endif
     } else {
         const double ls = (double)__ldg(c.table + rowoff + tabk);
         mlog = __dadd_rn(c.lng2, ls);
@@ -303,11 +309,19 @@ __device__ __forceinline__ void lane_fast_run(const LaneCtx &c, LState<K> &st, c
                                               const double *ring_in, double *out, uint4 *dst) {
     const double ninf = neg_inf();
     constexpr int Q = K / 8;
-    int info_n = __ldg(&c.l_vrow[v].x);
+    // the row states come through a per-thread running pointer, one row ahead and without a test (the row after the run is at
+    // worst the padding entry behind the last row program, pg2_engine.cu): as warp-uniform index arithmetic the fetch costs
+    // nine issue slots per row (measured with the table loads above: 54.3 -> 53.4 ms per 100 000 reads)
+    const int *pinfo = &c.l_vrow[v].x;
+#ifndef PG2_HOST_EMU
+    asm volatile("" : "+l"(pinfo));
+#endif
+    int info_n = __ldg(pinfo);
     PG2_LANE_ROW_UNROLL
     for (int r = 0; r < n; ++r) {
         const int sl = info_n & VR_STATE_MASK;
-        if (r + 1 < n) info_n = __ldg(&c.l_vrow[v + r + 1].x);
+        pinfo += 4;
+        info_n = __ldg(pinfo);
         double rX = ninf, rY = ninf, rM = ninf;
         if (!first) { rX = ring_in[r * 96]; rY = ring_in[r * 96 + 32]; rM = ring_in[r * 96 + 64]; }
         unsigned w[K / 2];
@@ -484,6 +498,7 @@ __device__ __forceinline__ void lane_make_ctx(LaneCtx &c, const LaneTask &T, con
     c.n_slots = GL.n_slots;
     c.table = m.table;
     c.stab = nullptr;
+    c.stab_s = 0;
     c.fas = m.fas;
     c.open = (double)m.open;
     c.ext = (double)m.ext;
@@ -639,6 +654,9 @@ lane_fill_kernel(int n_tasks, const LaneTask *tasks, const DevJob *jobs, const D
                 __syncthreads();
             }
             c.stab = s_tab;
+#ifndef PG2_HOST_EMU
+            c.stab_s = (unsigned)__cvta_generic_to_shared(s_tab);
+#endif
         }
         const int *r_state = d_state + GR.state_base;
         const float *r_elogw = d_elogw + GR.edge_base;
