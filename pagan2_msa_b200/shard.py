@@ -69,6 +69,35 @@ def partition(cells, world, groups=None, unit=32):
     return [order[cuts[r]:cuts[r + 1]] for r in range(world)]
 
 
+GENERAL_VROW_COST = 2.0  # a virtual row of a multi-edge site against a plain row of the placement kernel (measured: the shard that
+                         # holds the root-most targets of the bench tree takes 1.4 - 1.7 times longer per cell than the shard of leaves)
+
+
+def placement_costs(jobs):
+    """Relative device time of placement jobs for partition(): DP columns of the read x (plain rows + GENERAL_VROW_COST x
+    virtual rows of the target's other sites: one per backward edge).  The cell count alone puts the root-most nodes of the
+    reference tree -- a third of their sites carry several edges -- on one rank as if they were leaves."""
+    per_graph = {}
+    out = np.empty(len(jobs), dtype=np.int64)
+    for t, j in enumerate(jobs):
+        g = j.left
+        w = per_graph.get(id(g))
+        if w is None:
+            n = g.n_sites
+            deg = np.diff(g.off)
+            first = g.off[:-1]
+            idx = np.arange(n, dtype=np.int64)
+            has = deg == 1
+            plain = np.zeros(n, dtype=bool)
+            e = first[has]
+            plain[has] = (g.start[e] == idx[has] - 1) & (g.logw.view(np.uint32)[e] == 0)
+            plain[0] = True
+            w = float(plain.sum()) + GENERAL_VROW_COST * float(deg[~plain].sum())
+            per_graph[id(g)] = w
+        out[t] = int(w * max(j.right.n_sites - 1, 1))
+    return out
+
+
 def step_capacity(job):
     """Packed-pointer slots the engine reserves for one job (pg2_engine.cu: left.n_sites + right.n_sites)."""
     return job.left.n_sites + job.right.n_sites
@@ -143,10 +172,16 @@ def assemble(parts, shards, jobs):
     return records, step_off, steps
 
 
-def align_sharded(eng, jobs, dist, rank, world, device, root=0):
+def placement_shards(jobs, world):
+    """The cut of a placement batch: a target's reads stay together, the ranks get equal estimated device time."""
+    return partition(placement_costs(jobs), world, groups=[id(j.left) for j in jobs])
+
+
+def align_sharded(eng, jobs, dist, rank, world, device, root=0, by_target=False):
     """Runs this rank's shard of `jobs` (every rank holds the same job list) and gathers to the root.
-    Returns (records, step_off, steps) on the root, None elsewhere."""
-    shards = partition([j.cells for j in jobs], world)
+    Returns (records, step_off, steps) on the root, None elsewhere.  by_target: placement_shards instead of the
+    size-interleaved cut."""
+    shards = placement_shards(jobs, world) if by_target else partition([j.cells for j in jobs], world)
     mine = [jobs[i] for i in shards[rank]]
     batch = eng.batch(mine)
     try:

@@ -63,6 +63,21 @@ def test_partition_keeps_groups_together():
     assert sorted(np.concatenate(shard.partition([5, 3, 9], 2, groups=["a", "b", "a"])).tolist()) == [0, 1, 2]
 
 
+def test_placement_shards_balance_estimated_time():
+    """placement_costs weighs the virtual rows of multi-edge sites; placement_shards cuts whole targets to equal cost."""
+    jobs = jobio.load_jobs(os.path.join(abi.REPO_ROOT, "tests", "golden", "place_dna.pjob.gz"))
+    costs = shard.placement_costs(jobs)
+    assert costs.shape[0] == len(jobs) and (costs > 0).all()
+    for j, c in zip(jobs, costs):
+        plain_rows = j.left.n_sites  # a general site costs at least its one virtual row
+        assert c >= (plain_rows - 1) * max(j.right.n_sites - 1, 1) * 0.99
+        if j.left.is_plain_chain():
+            assert c == j.left.n_sites * max(j.right.n_sites - 1, 1)
+    for world in (1, 2, 3):
+        parts = shard.placement_shards(jobs, world)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(len(jobs)))
+
+
 def _worker(rank, world, port, out_path):
     import torch
     import torch.distributed as dist

@@ -15,17 +15,21 @@ from pagan2_msa_b200 import engine, shard  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=100000)
 ap.add_argument("--rank", type=int, default=0)
-ap.add_argument("--targets", action="store_true", help="also the target-aware partition (shard.partition(groups=...))")
+ap.add_argument("--targets", action="store_true", help="also the target-aware partitions (shard.partition(groups=...), shard.placement_shards)")
+ap.add_argument("--modes", default="", help="comma-separated subset of cells,targets,cost")
+ap.add_argument("--worlds", default="1,2,4,8")
 args = ap.parse_args()
 jobs, info = bench.build_workload(args.reads, 7, 0)
 eng = engine.Engine(0)
 base = None
-for world in (1, 2, 4, 8):
-    for mode in (("cells", "targets") if args.targets else ("cells",)):
+for world in [int(x) for x in args.worlds.split(",")]:
+    for mode in (args.modes.split(",") if args.modes else (("cells", "targets", "cost") if args.targets else ("cells",))):
         if mode == "cells":
             idx = shard.partition([j.cells for j in jobs], world)[args.rank % world]
-        else:
+        elif mode == "targets":
             idx = shard.partition([j.cells for j in jobs], world, groups=[id(j.left) for j in jobs])[args.rank % world]
+        else:
+            idx = shard.placement_shards(jobs, world)[args.rank % world]
         mine = [jobs[i] for i in idx]
         cells = sum(j.cells for j in mine)
         b = eng.batch(mine)
