@@ -234,6 +234,26 @@ def test_pipelined_align_batch_matches_single_shot(emu_lib, chunks):
         os.environ.pop("PG2_PIPELINE_CHUNKS", None)
 
 
+def test_pipelined_align_batch_dominant_last_job(emu_lib):
+    """A batch of short alignments plus one that holds most of the cells, last in left-graph order: the chunk boundary search
+    lands behind the last job (it used to read one past the permutation there)."""
+    rng = np.random.default_rng(95)
+    jobs = randjobs.random_shared_target_jobs(rng, 40, nl=30, nr_max=40)
+    big = randjobs.random_job(rng, "general")
+    while big.cells < 4 * sum(j.cells for j in jobs):
+        big = abi.FlatJob(randjobs.random_graph(rng, 400, 4, p_extra=0.05), randjobs.random_graph(rng, 400, 4, p_extra=0.05), jobs[0].model, 2)
+    jobs = [enginecheck.expect_from_oracle(j) for j in jobs + [big]]
+    os.environ["PG2_PIPELINE_MIN_JOBS"] = "8"
+    os.environ["PG2_PIPELINE_CHUNKS"] = "4"
+    try:
+        with make_engine(emu_lib, False) as eng:
+            res = enginecheck.check_batch(eng, jobs)
+            assert (res["status"] == 0).all()
+    finally:
+        os.environ.pop("PG2_PIPELINE_MIN_JOBS", None)
+        os.environ.pop("PG2_PIPELINE_CHUNKS", None)
+
+
 def test_compact_chain_form(emu_lib, golden):
     """Plain chains passed in the compact form of pagan2_b200.h (states only, CSR arrays NULL): same results, same packed
     paths, same expanded paths as the explicit form; fewer bytes staged; a compact graph that is no chain is refused."""
