@@ -45,7 +45,7 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-TRAFFIC_PROFILE = "r2_lanes_v10_traffic.json"  # tools/ncu_summary.py output of the committed ncu capture
+TRAFFIC_PROFILE = "r2_lanes_v11_traffic.json"  # tools/ncu_summary.py output of the committed ncu capture
 
 
 def measured_profile(n_reads, fill_launches):
