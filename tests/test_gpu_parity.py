@@ -334,6 +334,40 @@ def test_compact_chain_form_on_device(eng, golden):
             assert oracle_lib.steps_equal(st, job.expected_path, job.expected_path_score) == []
 
 
+def test_lane_shapes_agree_at_scale(eng, monkeypatch):
+    """A shard of the bench workload (the 127 nodes of the reference tree as targets, root-most ancestors with a third of
+    their sites multi-edge) through the lane kernel's throughput shape and its latency shape: every score, status and
+    encoded path identical; the pipelined host-to-host call in the wide shape too; a sample against the oracle."""
+    import bench
+
+    jobs, _ = bench.build_workload(9000, 11, 0)
+    out = {}
+    for w in (4, 10):
+        monkeypatch.setenv("PG2_LANE_W", str(w))
+        with eng.batch(jobs) as b:
+            b.run()
+            st = eng.stats()
+            out[w] = b.fetch()
+        assert st["jobs_lanes"] == len(jobs) and st["jobs_lanes_wide"] == (len(jobs) if w == 10 else 0)
+    monkeypatch.delenv("PG2_LANE_W")
+    ra, sa = out[4]
+    assert (ra["status"] == 0).all()
+    piped = eng.align_prepared(eng.prepare(jobs, pinned=True, compact=True))  # >= 8192 jobs, few tasks: chunks in the wide shape
+    assert eng.stats()["jobs_lanes_wide"] == len(jobs)
+    for rb, sb in (out[10], piped):
+        assert (rb["score"].view(np.uint64) == ra["score"].view(np.uint64)).all()
+        assert (rb["status"] == ra["status"]).all() and (rb["n_steps"] == ra["n_steps"]).all()
+        for k in range(0, len(jobs), 7):
+            x = sb[rb["step_off"][k]: rb["step_off"][k] + rb["n_steps"][k]]
+            y = sa[ra["step_off"][k]: ra["step_off"][k] + ra["n_steps"][k]]
+            assert x.tobytes() == y.tobytes()
+    heavy = sorted(range(len(jobs)), key=lambda k: -jobs[k].left.n_sites)[:3]  # the root-most targets
+    for k in heavy + list(range(0, len(jobs), 3000)):
+        job = enginecheck.expect_from_oracle(jobs[k])
+        stp, _, _ = eng.expand(job, out[10][0][k], out[10][1])
+        assert oracle_lib.steps_equal(stp, job.expected_path, job.expected_path_score) == []
+
+
 def test_pipelined_call_equals_resident_batch_at_scale(eng, golden):
     """12 000 reads against 8 targets: pg2_align_batch takes its chunked, multi-context path by itself (>= 8192 jobs);
     every score, status and encoded path must equal what one resident batch (pg2_batch_create / run / fetch) gives, and
